@@ -1,0 +1,68 @@
+"""Shared test helpers (import-safe on a box with no GPU and no /root/reference)."""
+import os
+import sys
+import contextlib
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, 'ga-gan_b200')
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+TOL = 1e-3   # BASELINE.json north_star: max relative error 1e-3 vs the reference in fp32 / TF32 off
+
+
+def load_golden(name):
+    d = np.load(os.path.join(GOLDEN, name + '.npz'), allow_pickle=False)
+    return {k: d[k] for k in d.files}
+
+
+def t(a, device='cpu', requires_grad=False):
+    if a is None:
+        return None
+    return torch.as_tensor(np.asarray(a), dtype=torch.float32).to(device).requires_grad_(requires_grad)
+
+
+def max_rel_err(a, b):
+    """max|a-b| / max|b| (the north star's metric)."""
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    d = b.abs().max().item()
+    e = (a - b).abs().max().item() if a.numel() else 0.0
+    return e if d == 0 else e / d
+
+
+def assert_close(a, b, tol=TOL, what=''):
+    e = max_rel_err(a, b)
+    assert e <= tol, f'{what}: max-rel-err {e:.3e} > {tol:.1e}'
+    return e
+
+
+@contextlib.contextmanager
+def patched_randn(seed):
+    """Route torch.randn / torch.randn_like through ONE seeded CPU generator.
+
+    The reference (on CPU, when goldens are made), the oracle and the product
+    (on the GPU) then see identical noise as long as they draw in the same order.
+    """
+    g = torch.Generator().manual_seed(seed)
+    orig_randn, orig_like = torch.randn, torch.randn_like
+
+    def randn(*size, device=None, dtype=None, generator=None, **_):
+        if len(size) == 1 and isinstance(size[0], (list, tuple, torch.Size)):
+            size = tuple(size[0])
+        out = orig_randn(tuple(int(s) for s in size), generator=g, dtype=dtype or torch.float32)
+        return out.to(device) if device is not None else out
+
+    def randn_like(x, **_):
+        return randn(*x.shape, device=x.device, dtype=x.dtype)
+
+    torch.randn, torch.randn_like = randn, randn_like
+    try:
+        yield
+    finally:
+        torch.randn, torch.randn_like = orig_randn, orig_like
