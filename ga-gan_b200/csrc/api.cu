@@ -1,0 +1,104 @@
+// C-ABI glue of libgagan_b200.so: error state, argument validation and kernel-family dispatch.
+#include "common.cuh"
+#include <string.h>
+
+namespace gg {
+
+static thread_local char t_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+
+// conv_simt.cu
+int conv2d_simt(const float*, const float*, float*, int, int, int, int, int, int, int, int, int, int, int, int, int, int,
+                const float*, const float*, cudaStream_t);
+int conv2d_wgrad_simt(const float*, const float*, float*, int, int, int, int, int, int, int, int, int, int, int, int, int, int,
+                      const float*, const float*, cudaStream_t);
+// conv_tc.cu (tcgen05 / TMEM / TMA path)
+bool conv2d_tc_eligible(int N, int I, int H, int W, int O, int KH, int KW, int OH, int OW, int stride, int pad_y, int pad_x,
+                        int transposed);
+int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int KH, int KW, int pad_y, int pad_x,
+              int flip_w, int w_is_IO, const float* in_scale, const float* out_scale, int nprod, cudaStream_t st);
+bool wgrad_tc_eligible(int N, int A, int HA, int WA, int B, int HB, int WB, int KH, int KW, int stride, int pad_y, int pad_x);
+int wgrad_tc(const float* a, const float* b, float* dw, int N, int A, int HA, int WA, int B, int KH, int KW, int pad_y, int pad_x,
+             int flip_w, int out_layout, const float* a_scale, const float* b_scale, int nprod, cudaStream_t st);
+
+}  // namespace gg
+
+extern "C" GG_API const char* gg_last_error(void) { return gg::t_err; }
+extern "C" GG_API int gg_version(void) { return 100; }
+extern "C" GG_API int64_t gg_launch_count(void) { return gg::g_launches.load(); }
+
+extern "C" GG_API int gg_device_ok(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    int major = 0, minor = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    return (major == 10 && minor == 0) ? 1 : 0;
+}
+
+extern "C" GG_API int gg_conv2d_f32(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int KH, int KW,
+                             int OH, int OW, int stride, int pad_y, int pad_x, int transposed, int flip_w,
+                             const float* in_scale, const float* out_scale, int prec, int* used_prec, gg_stream_t stream) {
+    GG_REQUIRE(x && w && y, "conv2d: null pointer");
+    GG_REQUIRE(N >= 0 && I >= 1 && H >= 1 && W >= 1 && O >= 1 && KH >= 1 && KW >= 1, "conv2d: bad shape");
+    GG_REQUIRE(stride >= 1 && pad_y >= 0 && pad_x >= 0, "conv2d: bad stride/padding");
+    if (!transposed) {
+        GG_REQUIRE(OH == (H + 2 * pad_y - KH) / stride + 1 && OW == (W + 2 * pad_x - KW) / stride + 1 && OH >= 1 && OW >= 1,
+                   "conv2d: output size mismatch");
+    } else {
+        int bh = (H - 1) * stride - 2 * pad_y + KH, bw = (W - 1) * stride - 2 * pad_x + KW;
+        GG_REQUIRE(OH >= bh && OH < bh + stride && OW >= bw && OW < bw + stride && OH >= 1 && OW >= 1,
+                   "conv_transpose2d: output size mismatch");
+    }
+    GG_REQUIRE((int64_t)N * I * H * W <= 0x7fffffffLL && (int64_t)N * O * OH * OW <= 0x7fffffffLL, "conv2d: tensor is too large");
+    GG_REQUIRE(prec == GG_PREC_AUTO || prec == GG_PREC_FP32_SIMT || prec == GG_PREC_TF32X1 || prec == GG_PREC_TF32X3,
+               "conv2d: unknown precision mode %d", prec);
+    cudaStream_t st = (cudaStream_t)stream;
+    bool tc_ok = gg::conv2d_tc_eligible(N, I, H, W, O, KH, KW, OH, OW, stride, pad_y, pad_x, transposed);
+    if ((prec == GG_PREC_TF32X1 || prec == GG_PREC_TF32X3) && !tc_ok) {
+        gg::set_error("conv2d: shape N=%d I=%d H=%d W=%d O=%d k=%dx%d stride=%d transposed=%d is not served by the tcgen05 path",
+                      N, I, H, W, O, KH, KW, stride, transposed);
+        return GG_EUNSUPPORTED;
+    }
+    int use = (prec == GG_PREC_AUTO) ? (tc_ok ? GG_PREC_TF32X3 : GG_PREC_FP32_SIMT) : prec;
+    if (used_prec) *used_prec = use;
+    if (use == GG_PREC_FP32_SIMT)
+        return gg::conv2d_simt(x, w, y, N, I, H, W, O, KH, KW, OH, OW, stride, pad_y, pad_x, transposed, flip_w, in_scale,
+                               out_scale, st);
+    // stride-1 conv_transpose2d == correlation with the flipped kernel and padding K-1-p; both are
+    // handled inside the tensor-core path through its weight-packing step.
+    return gg::conv2d_tc(x, w, y, N, I, H, W, O, KH, KW, transposed ? KH - 1 - pad_y : pad_y, transposed ? KW - 1 - pad_x : pad_x,
+                         transposed ? !flip_w : flip_w, transposed, in_scale, out_scale, use, st);
+}
+
+extern "C" GG_API int gg_conv2d_wgrad_f32(const float* a, const float* b, float* dw, int N, int A, int HA, int WA, int B, int HB, int WB,
+                                   int KH, int KW, int stride, int pad_y, int pad_x, int flip_w, int out_layout,
+                                   const float* a_scale, const float* b_scale, int prec, int* used_prec, gg_stream_t stream) {
+    GG_REQUIRE(a && b && dw, "conv2d_wgrad: null pointer");
+    GG_REQUIRE(N >= 0 && A >= 1 && B >= 1 && HA >= 1 && WA >= 1 && HB >= 1 && WB >= 1 && KH >= 1 && KW >= 1, "conv2d_wgrad: bad shape");
+    GG_REQUIRE(stride >= 1 && pad_y >= 0 && pad_x >= 0, "conv2d_wgrad: bad stride/padding");
+    GG_REQUIRE((HB - 1) * stride + KH <= HA + 2 * pad_y && (WB - 1) * stride + KW <= WA + 2 * pad_x,
+               "conv2d_wgrad: gradient plane larger than the convolution output");
+    GG_REQUIRE((int64_t)N * A * HA * WA <= 0x7fffffffLL && (int64_t)N * B * HB * WB <= 0x7fffffffLL, "conv2d_wgrad: tensor is too large");
+    GG_REQUIRE(prec == GG_PREC_AUTO || prec == GG_PREC_FP32_SIMT || prec == GG_PREC_TF32X1 || prec == GG_PREC_TF32X3,
+               "conv2d_wgrad: unknown precision mode %d", prec);
+    cudaStream_t st = (cudaStream_t)stream;
+    bool tc_ok = gg::wgrad_tc_eligible(N, A, HA, WA, B, HB, WB, KH, KW, stride, pad_y, pad_x);
+    if ((prec == GG_PREC_TF32X1 || prec == GG_PREC_TF32X3) && !tc_ok) {
+        gg::set_error("conv2d_wgrad: shape is not served by the tcgen05 path");
+        return GG_EUNSUPPORTED;
+    }
+    int use = (prec == GG_PREC_AUTO) ? (tc_ok ? GG_PREC_TF32X3 : GG_PREC_FP32_SIMT) : prec;
+    if (used_prec) *used_prec = use;
+    if (use == GG_PREC_FP32_SIMT)
+        return gg::conv2d_wgrad_simt(a, b, dw, N, A, HA, WA, B, HB, WB, KH, KW, stride, pad_y, pad_x, flip_w, out_layout, a_scale,
+                                     b_scale, st);
+    return gg::wgrad_tc(a, b, dw, N, A, HA, WA, B, KH, KW, pad_y, pad_x, flip_w, out_layout, a_scale, b_scale, use, st);
+}

@@ -1,0 +1,222 @@
+// upfirdn2d for sm_100a: pad -> zero-stuff (up) -> FIR -> decimate (down), per channel plane.
+//
+// Replaces torch_utils/ops/upfirdn2d.cu:29-200 + upfirdn2d.cpp:16-94 of the reference.
+//
+//   y[oy][ox] = sum_{ky,kx} K[ky][kx] * U[oy*downy + ky][ox*downx + kx]
+//   U[uy][ux] = x[(uy-pady0)/upy][(ux-padx0)/upx]  when divisible and inside the image, else 0
+//   K[ky][kx] = gain * (flip ? f[ky][kx] : f[fH-1-ky][fW-1-kx])
+//
+// which is upfirdn2d.py:195-218 (zero-stuff, pad/crop, correlate with the flipped filter, keep every
+// down-th sample).  The path is HBM-bound (4 B*(in+out) per plane, 16 MAC/output for the 4x4 filter):
+//
+//  * fir4_tile<UP,DOWN,PEX,OXT,OYT>: the StyleGAN2 cases (4x4 filter; up2 / down2 / filter-only).  One
+//    CTA stages the input footprint of a (32*OXT)x(8*OYT) output tile in shared memory with coalesced
+//    loads (zero-filled outside the image = the padding), then every thread produces an OXT x OYT
+//    micro-tile from 128/64-bit shared-memory window loads that are reused across the filter taps and
+//    across the micro-tile rows, and writes 128-bit rows.  Polyphase: for UP=2 only the live taps
+//    ((t+kx) parity == PEX) are evaluated.
+//  * upfirdn2d_generic: any filter / factors / padding (separable 12-tap ADA filters, anisotropic
+//    scaling, tiny images): one thread per output, filter in shared memory.
+#include "common.cuh"
+
+namespace {
+
+struct Params {
+    const float* x;
+    const float* f;
+    float* y;
+    int N, C, inH, inW, fH, fW, upx, upy, downx, downy, padx0, pady0, flip;
+    float gain;
+    int outH, outW;
+};
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upfirdn2d_generic(Params p) {
+    extern __shared__ float sK[];
+    const int nf = p.fH * p.fW;
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+        int ky = i / p.fW, kx = i - ky * p.fW;
+        int sy = p.flip ? ky : p.fH - 1 - ky, sx = p.flip ? kx : p.fW - 1 - kx;
+        sK[i] = p.gain * __ldg(p.f + sy * p.fW + sx);
+    }
+    __syncthreads();
+    const int64_t total = (int64_t)p.N * p.C * p.outH * p.outW;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int ox = (int)(idx % p.outW);
+        int64_t r = idx / p.outW;
+        int oy = (int)(r % p.outH);
+        int64_t nc = r / p.outH;
+        const float* xp = p.x + nc * (int64_t)p.inH * p.inW;
+        // first live tap and its input coordinate (exact integer math; bit-exact with the reference's floor_div)
+        int ky0 = gg::posmod(p.pady0 - oy * p.downy, p.upy);
+        int iy0 = (oy * p.downy + ky0 - p.pady0) / p.upy;
+        int kx0 = gg::posmod(p.padx0 - ox * p.downx, p.upx);
+        int ix0 = (ox * p.downx + kx0 - p.padx0) / p.upx;
+        float v = 0.f;
+        for (int ky = ky0, iy = iy0; ky < p.fH; ky += p.upy, ++iy) {
+            if (iy < 0 || iy >= p.inH) continue;
+            for (int kx = kx0, ix = ix0; kx < p.fW; kx += p.upx, ++ix) {
+                if (ix < 0 || ix >= p.inW) continue;
+                v = fmaf(sK[ky * p.fW + kx], __ldg(xp + (int64_t)iy * p.inW + ix), v);
+            }
+        }
+        p.y[idx] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int UP, int DOWN, int OXT, int OYT>
+struct TileGeom {
+    static constexpr int TW = 32 * OXT;                             // output tile width  (one warp = one row strip)
+    static constexpr int TH = 8 * OYT;                              // output tile height (8 warps)
+    static constexpr int WN = (UP == 1) ? (OXT - 1) * DOWN + 4 : 4; // input columns one thread touches per row
+    static constexpr int WNV = (WN + 3) / 4 * 4;                    // ... rounded to whole vector loads
+    static constexpr int LSTEP = OXT * DOWN / UP;                   // per-lane column step inside the tile
+    static constexpr int TC = ((31 * LSTEP + WNV) + 3) / 4 * 4;     // tile columns (pitch), multiple of 4
+    static constexpr int RR = (OYT - 1) * DOWN + 4;                 // u-rows one thread touches
+    static constexpr int TR = ((TH - 1) * DOWN + 3) / UP + 2;       // tile rows
+};
+
+template <int UP, int DOWN, int PEX, int OXT, int OYT>
+__global__ void __launch_bounds__(256) fir4_tile(Params p, int tilesX, int tilesY) {
+    using G = TileGeom<UP, DOWN, OXT, OYT>;
+    __shared__ __align__(16) float tile[G::TR * G::TC];
+    __shared__ float sK[16];
+
+    int64_t bid = blockIdx.x;
+    const int tx = (int)(bid % tilesX); bid /= tilesX;
+    const int ty = (int)(bid % tilesY);
+    const int64_t nc = bid / tilesY;
+    const int ox_t0 = tx * G::TW, oy_t0 = ty * G::TH;
+    const int ix0 = gg::floordiv(ox_t0 * DOWN - p.padx0 + UP - 1, UP);
+    const int iy0 = gg::floordiv(oy_t0 * DOWN - p.pady0 + UP - 1, UP);
+
+    if (threadIdx.x < 16) {
+        int ky = threadIdx.x >> 2, kx = threadIdx.x & 3;
+        int sy = p.flip ? ky : 3 - ky, sx = p.flip ? kx : 3 - kx;
+        sK[threadIdx.x] = p.gain * __ldg(p.f + sy * 4 + sx);
+    }
+    // stage the input footprint (zero outside the image: that is the padding / crop)
+    const float* xp = p.x + nc * (int64_t)p.inH * p.inW;
+    for (int i = threadIdx.x; i < G::TR * G::TC; i += 256) {
+        int r = i / G::TC, c = i - r * G::TC;
+        int gy = iy0 + r, gx = ix0 + c;
+        float v = 0.f;
+        if (gy >= 0 && gy < p.inH && gx >= 0 && gx < p.inW) v = __ldg(xp + (int64_t)gy * p.inW + gx);
+        tile[i] = v;
+    }
+    __syncthreads();
+
+    float K[4][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) K[i >> 2][i & 3] = sK[i];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int oy0 = oy_t0 + warp * OYT;      // first output row of this thread
+    const int ox0 = ox_t0 + lane * OXT;      // first output column of this thread
+    float acc[OYT][OXT];
+#pragma unroll
+    for (int r = 0; r < OYT; ++r)
+#pragma unroll
+        for (int t = 0; t < OXT; ++t) acc[r][t] = 0.f;
+
+    const float* wbase = tile + lane * G::LSTEP;
+#pragma unroll
+    for (int rr = 0; rr < G::RR; ++rr) {
+        const int uy = oy0 * DOWN + rr - p.pady0;
+        if (UP == 2 && (uy & 1)) continue;                 // dead u-row (warp-uniform)
+        const int trow = (UP == 2 ? (uy >> 1) : uy) - iy0;
+        if (trow < 0 || trow >= G::TR) continue;           // only rows that belong to out-of-range outputs
+        const float* src = wbase + trow * G::TC;
+        float w[G::WNV];
+        if (G::LSTEP % 4 == 0) {
+#pragma unroll
+            for (int j = 0; j < G::WNV; j += 4) {
+                float4 v = *reinterpret_cast<const float4*>(src + j);
+                w[j] = v.x; w[j + 1] = v.y; w[j + 2] = v.z; w[j + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < G::WNV; j += 2) {
+                float2 v = *reinterpret_cast<const float2*>(src + j);
+                w[j] = v.x; w[j + 1] = v.y;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < OYT; ++r) {
+            const int ky = rr - r * DOWN;
+            if (ky < 0 || ky > 3) continue;                // compile-time after unrolling
+#pragma unroll
+            for (int t = 0; t < OXT; ++t)
+#pragma unroll
+                for (int kx = 0; kx < 4; ++kx) {
+                    if (UP == 1) {
+                        acc[r][t] = fmaf(K[ky][kx], w[t * DOWN + kx], acc[r][t]);
+                    } else if (((t + kx) & 1) == PEX) {
+                        acc[r][t] = fmaf(K[ky][kx], w[(t + kx - PEX) / 2], acc[r][t]);
+                    }
+                }
+        }
+    }
+
+    float* yp = p.y + nc * (int64_t)p.outH * p.outW;
+    const bool vec = (OXT == 4) && (p.outW % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+#pragma unroll
+    for (int r = 0; r < OYT; ++r) {
+        const int oy = oy0 + r;
+        if (oy >= p.outH) continue;
+        float* dst = yp + (int64_t)oy * p.outW + ox0;
+        if (vec && ox0 + 3 < p.outW) {
+            *reinterpret_cast<float4*>(dst) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        } else {
+#pragma unroll
+            for (int t = 0; t < OXT; ++t)
+                if (ox0 + t < p.outW) dst[t] = acc[r][t];
+        }
+    }
+}
+
+template <int UP, int DOWN, int PEX, int OXT, int OYT>
+int launch_tile(const Params& p, cudaStream_t st) {
+    using G = TileGeom<UP, DOWN, OXT, OYT>;
+    int tilesX = (p.outW + G::TW - 1) / G::TW, tilesY = (p.outH + G::TH - 1) / G::TH;
+    int64_t blocks = (int64_t)tilesX * tilesY * p.N * p.C;
+    if (blocks > 0x7fffffffLL) { gg::set_error("upfirdn2d: grid too large"); return GG_EINVAL; }
+    fir4_tile<UP, DOWN, PEX, OXT, OYT><<<(unsigned)blocks, 256, 0, st>>>(p, tilesX, tilesY);
+    return gg::check_launch("upfirdn2d(fir4_tile)");
+}
+
+}  // namespace
+
+extern "C" GG_API int gg_upfirdn2d_f32(const float* x, const float* f, float* y, int N, int C, int inH, int inW, int fH, int fW,
+                                int upx, int upy, int downx, int downy, int padx0, int padx1, int pady0, int pady1,
+                                int flip, float gain, int outH, int outW, gg_stream_t stream) {
+    GG_REQUIRE(x && f && y, "upfirdn2d: null pointer");
+    GG_REQUIRE(N >= 0 && C >= 0 && inH >= 1 && inW >= 1, "upfirdn2d: x must be rank 4 with non-empty planes");
+    GG_REQUIRE(fH >= 1 && fW >= 1, "upfirdn2d: f must be at least 1x1");                                  // upfirdn2d.cpp:26
+    GG_REQUIRE(upx >= 1 && upy >= 1, "upfirdn2d: upsampling factor must be at least 1");                  // :27
+    GG_REQUIRE(downx >= 1 && downy >= 1, "upfirdn2d: downsampling factor must be at least 1");            // :28
+    const int ew = (inW * upx + padx0 + padx1 - fW + downx) / downx;                                       // :32
+    const int eh = (inH * upy + pady0 + pady1 - fH + downy) / downy;                                       // :33
+    GG_REQUIRE(ew >= 1 && eh >= 1, "upfirdn2d: output must be at least 1x1");                             // :34
+    GG_REQUIRE(ew == outW && eh == outH, "upfirdn2d: output size mismatch (expected %dx%d, got %dx%d)", eh, ew, outH, outW);
+    GG_REQUIRE((int64_t)N * C * inH * inW <= 0x7fffffffLL && (int64_t)N * C * outH * outW <= 0x7fffffffLL,
+               "upfirdn2d: tensor is too large");                                                          // :22,36
+    if ((int64_t)N * C == 0) return GG_OK;
+    Params p{x, f, y, N, C, inH, inW, fH, fW, upx, upy, downx, downy, padx0, pady0, flip, gain, outH, outW};
+    cudaStream_t st = (cudaStream_t)stream;
+
+    const bool f4 = (fH == 4 && fW == 4) && upx == upy && downx == downy && outW >= 48;
+    if (f4 && upx == 1 && downx == 1) return launch_tile<1, 1, 0, 4, 4>(p, st);
+    if (f4 && upx == 1 && downx == 2) return launch_tile<1, 2, 0, 2, 2>(p, st);
+    if (f4 && upx == 2 && downx == 1) {
+        // PEX = parity of (ox0 - padx0) for the first column of any thread (ox0 is a multiple of 4)
+        return (padx0 & 1) ? launch_tile<2, 1, 1, 4, 2>(p, st) : launch_tile<2, 1, 0, 4, 2>(p, st);
+    }
+    GG_REQUIRE((size_t)fH * fW * sizeof(float) <= 48 * 1024, "upfirdn2d: filter too large");
+    int64_t total = (int64_t)N * C * outH * outW;
+    int64_t grid = (total + 255) / 256;
+    if (grid > GG_NUM_SMS * 32) grid = GG_NUM_SMS * 32;
+    upfirdn2d_generic<<<(unsigned)grid, 256, (size_t)fH * fW * sizeof(float), st>>>(p);
+    return gg::check_launch("upfirdn2d(generic)");
+}

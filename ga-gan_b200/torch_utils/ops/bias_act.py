@@ -1,0 +1,184 @@
+"""Fused bias + activation (+ gain, clamp) with first- and second-order gradients, on sm_100a.
+
+Same API as the reference's `torch_utils/ops/bias_act.py` (`activation_funcs` :23-60,
+`bias_act(x, b, dim, act, alpha, gain, clamp, impl)` :88-122) and the same closed autograd
+structure (`BiasActCuda` :181-214, `BiasActCudaGrad` :217-245), over the C-ABI kernel
+`gg_bias_act_f32` (include/gagan_b200.h).  Differences, all deliberate:
+
+  * the bias gradient is produced by the SAME kernel launch as dx (warp-shuffle reduction +
+    atomics) instead of a second full-tensor `dx.sum(...)` pass (reference :211-212, :243);
+  * fp32 only; `impl='cuda'` on a non-CUDA tensor or with a missing library raises -- there is no
+    fallback; `impl='ref'` is not part of the product (the restatement lives in oracle/, which only
+    tests and the CPU-baseline leg of bench.py may import).
+"""
+import numpy as np
+import torch
+
+from .. import custom_ops
+from .. import misc
+
+# ----------------------------------------------------------------------------
+
+activation_funcs = {
+    'linear':   misc.EasyDict(func=lambda x, **_: x,                                          def_alpha=0,   def_gain=1,          cuda_idx=1, ref='',  has_2nd_grad=False),
+    'relu':     misc.EasyDict(func=lambda x, **_: torch.nn.functional.relu(x),                def_alpha=0,   def_gain=np.sqrt(2), cuda_idx=2, ref='y', has_2nd_grad=False),
+    'lrelu':    misc.EasyDict(func=lambda x, alpha, **_: torch.nn.functional.leaky_relu(x, alpha), def_alpha=0.2, def_gain=np.sqrt(2), cuda_idx=3, ref='y', has_2nd_grad=False),
+    'tanh':     misc.EasyDict(func=lambda x, **_: torch.tanh(x),                              def_alpha=0,   def_gain=1,          cuda_idx=4, ref='y', has_2nd_grad=True),
+    'sigmoid':  misc.EasyDict(func=lambda x, **_: torch.sigmoid(x),                           def_alpha=0,   def_gain=1,          cuda_idx=5, ref='y', has_2nd_grad=True),
+    'elu':      misc.EasyDict(func=lambda x, **_: torch.nn.functional.elu(x),                 def_alpha=0,   def_gain=1,          cuda_idx=6, ref='y', has_2nd_grad=True),
+    'selu':     misc.EasyDict(func=lambda x, **_: torch.nn.functional.selu(x),                def_alpha=0,   def_gain=1,          cuda_idx=7, ref='y', has_2nd_grad=True),
+    'softplus': misc.EasyDict(func=lambda x, **_: torch.nn.functional.softplus(x),            def_alpha=0,   def_gain=1,          cuda_idx=8, ref='y', has_2nd_grad=True),
+    'swish':    misc.EasyDict(func=lambda x, **_: torch.sigmoid(x) * x,                       def_alpha=0,   def_gain=np.sqrt(2), cuda_idx=9, ref='x', has_2nd_grad=True),
+}
+
+# ----------------------------------------------------------------------------
+
+_plugin = None
+_null_tensor = torch.empty([0])
+
+
+def _init():
+    """Bind the native library (bias_act.py:70-83).  Raises instead of falling back."""
+    global _plugin
+    if _plugin is None:
+        _plugin = custom_ops.get_plugin('bias_act_plugin', sources=['bias_act.cu'])
+    return True
+
+
+def _null_like(x):
+    return torch.empty([0], dtype=x.dtype, device=x.device)
+
+
+# ----------------------------------------------------------------------------
+
+def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, impl='cuda'):
+    r"""Fused bias and activation function: `clamp(act(x + b) * gain)`.
+
+    Args / semantics identical to the reference (bias_act.py:88-122).  Supports first and second
+    order gradients, not third.
+    """
+    assert isinstance(x, torch.Tensor)
+    assert impl in ['ref', 'cuda']
+    if impl != 'cuda':
+        raise RuntimeError("bias_act: impl='ref' is not shipped in the B200 build (see oracle/ops_ref.py for the CPU restatement)")
+    if x.device.type != 'cuda':
+        raise RuntimeError('bias_act: the B200 build has no CPU path; x must be a CUDA tensor')
+    _init()
+    return _bias_act_cuda(dim=dim, act=act, alpha=alpha, gain=gain, clamp=clamp).apply(x, b)
+
+
+# ----------------------------------------------------------------------------
+
+_bias_act_cuda_cache = dict()
+
+
+def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
+    """Autograd Function factory (bias_act.py:165-251), cached per argument tuple."""
+    assert clamp is None or clamp >= 0
+    spec = activation_funcs[act]
+    alpha = float(alpha if alpha is not None else spec.def_alpha)
+    gain = float(gain if gain is not None else spec.def_gain)
+    clamp = float(clamp if clamp is not None else -1)
+
+    key = (dim, act, alpha, gain, clamp)
+    if key in _bias_act_cuda_cache:
+        return _bias_act_cuda_cache[key]
+
+    is_identity = (act == 'linear' and gain == 1 and clamp < 0)
+
+    def bcast(v, ndim):
+        return v.reshape([-1 if i == dim else 1 for i in range(ndim)])
+
+    # Forward op.
+    class BiasActCuda(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, b):  # pylint: disable=arguments-differ
+            if x.dtype != torch.float32:
+                raise RuntimeError('bias_act: this build serves fp32 only')
+            ctx.memory_format = torch.channels_last if x.ndim > 2 and x.stride()[1] == 1 else torch.contiguous_format
+            x = x.contiguous(memory_format=ctx.memory_format)
+            b = b.contiguous() if b is not None else _null_like(x)
+            null = _null_like(x)
+            y = x
+            if (not is_identity or b.numel() != 0) and x.numel() != 0:
+                y = _plugin.bias_act(x, b, null, null, null, 0, dim, spec.cuda_idx, alpha, gain, clamp)
+            ctx.save_for_backward(
+                x if 'x' in spec.ref or spec.has_2nd_grad else null,
+                b if 'x' in spec.ref or spec.has_2nd_grad else null,
+                y if 'y' in spec.ref else null)
+            ctx.x_ndim = x.ndim
+            ctx.nb = x.shape[dim] if x.ndim > dim else 0
+            return y
+
+        @staticmethod
+        def backward(ctx, dy):  # pylint: disable=arguments-differ
+            dy = dy.contiguous(memory_format=ctx.memory_format)
+            x, b, y = ctx.saved_tensors
+            dx = None
+            db = None
+            if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+                want_db = bool(ctx.needs_input_grad[1])
+                if is_identity:
+                    dx = dy
+                    if want_db:
+                        db = dx.sum([i for i in range(dx.ndim) if i != dim])
+                else:
+                    dx, db = BiasActCudaGrad.apply(dy, x, b, y, want_db)
+                    if not want_db:
+                        db = None
+            return dx, db
+
+    # Backward op: (dx, db) = grad-1 kernel with the bias reduction fused in.
+    class BiasActCudaGrad(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, dy, x, b, y, want_db):  # pylint: disable=arguments-differ
+            ctx.memory_format = torch.channels_last if dy.ndim > 2 and dy.stride()[1] == 1 else torch.contiguous_format
+            null = _null_like(dy)
+            db = torch.zeros([dy.shape[dim]], dtype=dy.dtype, device=dy.device) if want_db else None
+            if dy.numel() != 0:
+                dx = _plugin.bias_act(dy, b, x, y, null, 1, dim, spec.cuda_idx, alpha, gain, clamp, dbias=db)
+            else:
+                dx = torch.empty_like(dy)
+            ctx.save_for_backward(dy if spec.has_2nd_grad else null, x, b, y)
+            ctx.want_db = want_db
+            ctx.shape = tuple(dy.shape)
+            ctx.set_materialize_grads(False)
+            if db is None:
+                db = null
+                ctx.mark_non_differentiable(db)
+            return dx, db
+
+        @staticmethod
+        def backward(ctx, d_dx, d_db):  # pylint: disable=arguments-differ
+            dy, x, b, y = ctx.saved_tensors
+            d_dy = None
+            d_x = None
+            d_b = None
+            d_y = None
+            # (dx, db) is linear in dy:  dx = dy * g,  db = sum(dx)  =>  cotangent of dy = g * (d_dx + bcast(d_db))
+            tot = None
+            if d_dx is not None:
+                tot = d_dx.contiguous(memory_format=ctx.memory_format)
+            if ctx.want_db and d_db is not None:
+                e = bcast(d_db, len(ctx.shape)).expand(ctx.shape)
+                tot = (tot + e) if tot is not None else e.contiguous(memory_format=ctx.memory_format)
+            if tot is None:
+                return None, None, None, None, None
+
+            if ctx.needs_input_grad[0]:
+                d_dy, _ = BiasActCudaGrad.apply(tot, x, b, y, False)
+
+            if spec.has_2nd_grad and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]):
+                null = _null_like(tot)
+                want = bool(ctx.needs_input_grad[2])
+                d_b_buf = torch.zeros([tot.shape[dim]], dtype=tot.dtype, device=tot.device) if want else None
+                d_x = _plugin.bias_act(tot, b, x, y, dy, 2, dim, spec.cuda_idx, alpha, gain, clamp, dbias=d_b_buf)
+                if want:
+                    d_b = d_b_buf
+
+            return d_dy, d_x, d_b, d_y, None
+
+    _bias_act_cuda_cache[key] = BiasActCuda
+    return BiasActCuda
+
+# ----------------------------------------------------------------------------

@@ -1,0 +1,204 @@
+"""`conv2d` / `conv_transpose2d` closed under differentiation, on the library's own sm_100a kernels.
+
+API of the reference's `torch_utils/ops/conv2d_gradfix.py`: module switches `enabled`,
+`weight_gradients_disabled`, `no_weight_gradients()` (:22-32), `conv2d(...)` (:37-46),
+`conv_transpose2d(...)` (:49-58).  The reference wraps cuDNN (`F.conv2d`, `F.conv_transpose2d`,
+`aten::cudnn_convolution_backward_weight`, :141-146,178-188) in two autograd Functions whose backward
+passes are built from each other, so that gradients of any order exist (:126-212).  This module keeps
+exactly that algebra -- forward conv, data gradient = the transposed op, weight gradient = its own op
+whose backward is again {conv, transposed conv} -- but every node runs `gg_conv2d_f32` /
+`gg_conv2d_wgrad_f32` (tcgen05 implicit GEMM with 3xTF32 operands where the shape is eligible, exact
+fp32 FFMA otherwise; see include/gagan_b200.h).
+
+Unlike the reference (:61-81) the custom op is not limited to torch 1.7-1.9 and is always used for
+CUDA tensors; `enabled` is kept for API compatibility.  CPU tensors raise: there is no fallback.
+"""
+import contextlib
+import torch
+
+from .. import custom_ops
+
+# pylint: disable=redefined-builtin
+
+enabled = False                     # kept for API compatibility (training_loop.py:209 sets it to True)
+weight_gradients_disabled = False   # forcefully skip weight gradients (loss.py:98,143 via no_weight_gradients())
+
+
+@contextlib.contextmanager
+def no_weight_gradients():
+    global weight_gradients_disabled
+    old = weight_gradients_disabled
+    weight_gradients_disabled = True
+    yield
+    weight_gradients_disabled = old
+
+
+_plugin = None
+
+
+def _init():
+    global _plugin
+    if _plugin is None:
+        _plugin = custom_ops.get_plugin('conv2d_plugin', sources=['conv_tc.cu', 'conv_simt.cu'])
+    return True
+
+
+def _check_input(input):
+    assert isinstance(input, torch.Tensor)
+    if input.device.type != 'cuda':
+        raise RuntimeError('conv2d_gradfix: the B200 build has no CPU path; input must be a CUDA tensor')
+    if input.dtype != torch.float32:
+        raise RuntimeError('conv2d_gradfix: this build serves fp32 only')
+    _init()
+
+
+def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
+    _check_input(input)
+    return _conv2d_gradfix(transpose=False, weight_shape=weight.shape, stride=stride, padding=padding, output_padding=0,
+                           dilation=dilation, groups=groups).apply(input, weight, bias)
+
+
+def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_padding=0, groups=1, dilation=1):
+    _check_input(input)
+    return _conv2d_gradfix(transpose=True, weight_shape=weight.shape, stride=stride, padding=padding,
+                           output_padding=output_padding, groups=groups, dilation=dilation).apply(input, weight, bias)
+
+
+def _tuple_of_ints(xs, ndim):
+    xs = tuple(xs) if isinstance(xs, (tuple, list)) else (xs,) * ndim
+    assert len(xs) == ndim
+    assert all(isinstance(x, int) for x in xs)
+    return xs
+
+
+# ----------------------------------------------------------------------------
+# Kernel-level helpers: one group at a time (the C ABI serves groups == 1).
+
+
+def _run_conv(x, w, transpose, stride, padding, output_padding, groups):
+    if groups == 1:
+        return _plugin.conv2d(x, w, stride=stride, padding=padding, transposed=transpose, output_padding=output_padding)
+    xs = x.chunk(groups, dim=1)
+    ws = w.chunk(groups, dim=0)
+    return torch.cat([_plugin.conv2d(xg, wg, stride=stride, padding=padding, transposed=transpose,
+                                     output_padding=output_padding) for xg, wg in zip(xs, ws)], dim=1)
+
+
+def _run_wgrad(grad_output, input, weight_shape, transpose, stride, padding, groups):
+    kh, kw = weight_shape[2], weight_shape[3]
+    # y = conv(x, w):   dw[o,i] = sum dy[o] * x[i]      -> a = x,  b = dy
+    # y = convT(x, w):  x' = conv(y', w) is its adjoint  -> a = dy, b = x  (dw comes out as [I,O,kh,kw])
+    a, b = (input, grad_output) if not transpose else (grad_output, input)
+    if groups == 1:
+        return _plugin.conv2d_wgrad(a, b, (kh, kw), stride=stride, padding=padding)
+    a_s = a.chunk(groups, dim=1)
+    b_s = b.chunk(groups, dim=1)
+    return torch.cat([_plugin.conv2d_wgrad(ag, bg, (kh, kw), stride=stride, padding=padding) for ag, bg in zip(a_s, b_s)], dim=0)
+
+
+# ----------------------------------------------------------------------------
+
+_conv2d_gradfix_cache = dict()
+
+
+def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, dilation, groups):
+    ndim = 2
+    weight_shape = tuple(weight_shape)
+    stride = _tuple_of_ints(stride, ndim)
+    padding = _tuple_of_ints(padding, ndim)
+    output_padding = _tuple_of_ints(output_padding, ndim)
+    dilation = _tuple_of_ints(dilation, ndim)
+
+    key = (transpose, weight_shape, stride, padding, output_padding, dilation, groups)
+    if key in _conv2d_gradfix_cache:
+        return _conv2d_gradfix_cache[key]
+
+    # Validate arguments (conv2d_gradfix.py:110-119).
+    assert groups >= 1
+    assert len(weight_shape) == ndim + 2
+    assert all(stride[i] >= 1 for i in range(ndim))
+    assert all(padding[i] >= 0 for i in range(ndim))
+    assert all(dilation[i] >= 0 for i in range(ndim))
+    if not transpose:
+        assert all(output_padding[i] == 0 for i in range(ndim))
+    else:
+        assert all(0 <= output_padding[i] < max(stride[i], dilation[i]) for i in range(ndim))
+    if dilation != (1, 1):
+        raise RuntimeError('conv2d_gradfix: dilation != 1 is not served by the B200 build (the networks never use it)')
+    if stride[0] != stride[1]:
+        raise RuntimeError('conv2d_gradfix: anisotropic stride is not served by the B200 build')
+
+    common_kwargs = dict(stride=stride, padding=padding, dilation=dilation, groups=groups)
+
+    def calc_output_padding(input_shape, output_shape):
+        # conv2d_gradfix.py:124-133
+        if transpose:
+            return [0, 0]
+        return [
+            input_shape[i + 2]
+            - (output_shape[i + 2] - 1) * stride[i]
+            - (1 - 2 * padding[i])
+            - dilation[i] * (weight_shape[i + 2] - 1)
+            for i in range(ndim)
+        ]
+
+    class Conv2d(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, input, weight, bias):
+            assert weight.shape == weight_shape
+            output = _run_conv(input, weight, transpose, stride[0], padding, output_padding, groups)
+            if bias is not None:
+                output = output + bias.reshape(1, -1, 1, 1)
+            ctx.save_for_backward(input, weight)
+            return output
+
+        @staticmethod
+        def backward(ctx, grad_output):
+            input, weight = ctx.saved_tensors
+            grad_input = None
+            grad_weight = None
+            grad_bias = None
+
+            if ctx.needs_input_grad[0]:
+                p = calc_output_padding(input_shape=input.shape, output_shape=grad_output.shape)
+                grad_input = _conv2d_gradfix(transpose=(not transpose), weight_shape=weight_shape, output_padding=p,
+                                             **common_kwargs).apply(grad_output, weight, None)
+                assert grad_input.shape == input.shape
+
+            if ctx.needs_input_grad[1] and not weight_gradients_disabled:
+                grad_weight = Conv2dGradWeight.apply(grad_output, input)
+                assert grad_weight.shape == weight_shape
+
+            if ctx.needs_input_grad[2]:
+                grad_bias = grad_output.sum([0, 2, 3])
+
+            return grad_input, grad_weight, grad_bias
+
+    class Conv2dGradWeight(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, grad_output, input):
+            grad_weight = _run_wgrad(grad_output, input, weight_shape, transpose, stride[0], padding, groups)
+            assert grad_weight.shape == weight_shape
+            ctx.save_for_backward(grad_output, input)
+            return grad_weight
+
+        @staticmethod
+        def backward(ctx, grad2_grad_weight):
+            grad_output, input = ctx.saved_tensors
+            grad2_grad_output = None
+            grad2_input = None
+
+            if ctx.needs_input_grad[0]:
+                grad2_grad_output = Conv2d.apply(input, grad2_grad_weight, None)
+                assert grad2_grad_output.shape == grad_output.shape
+
+            if ctx.needs_input_grad[1]:
+                p = calc_output_padding(input_shape=input.shape, output_shape=grad_output.shape)
+                grad2_input = _conv2d_gradfix(transpose=(not transpose), weight_shape=weight_shape, output_padding=p,
+                                              **common_kwargs).apply(grad_output, grad2_grad_weight, None)
+                assert grad2_input.shape == input.shape
+
+            return grad2_grad_output, grad2_input
+
+    _conv2d_gradfix_cache[key] = Conv2d
+    return Conv2d

@@ -1,0 +1,128 @@
+/*
+ * gagan_b200.h -- C ABI of the B200-native StyleGAN2 conv hot path (libgagan_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry
+ * point names the reference interface it replaces (paths relative to
+ * /root/reference/DissimilarDomains).  All device pointers are fp32, dense, NCHW unless
+ * stated; all kernels are enqueued on `stream` (the caller's current CUDA stream, as the
+ * reference does with at::cuda::getCurrentCUDAStream(), upfirdn2d.cpp:92 / bias_act.cpp:88)
+ * on the CURRENT device and never synchronise.  Inputs are borrowed for the duration of
+ * the enqueued work; outputs are caller-allocated (torch's caching allocator in the
+ * Python host).  The library keeps no per-call state and is re-entrant (autograd worker
+ * threads call it concurrently during backward).
+ *
+ * Return value: 0 on success, negative GG_E* on failure; gg_last_error() returns the
+ * message of the last failure on the calling thread (the reference raises through
+ * TORCH_CHECK; the Python host turns a non-zero code into RuntimeError).
+ * There is no CPU fallback anywhere behind this header.
+ */
+#ifndef GAGAN_B200_H_
+#define GAGAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gg_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define GG_API __attribute__((visibility("default")))
+#else
+#define GG_API
+#endif
+
+enum {
+    GG_OK = 0,
+    GG_EINVAL = -1,      /* bad argument (the reference's TORCH_CHECK failures) */
+    GG_ECUDA = -2,       /* CUDA runtime / launch error */
+    GG_EUNSUPPORTED = -3 /* legal in the reference, not served by this build */
+};
+
+/* Conv arithmetic modes (the reference computes fp32 with TF32 off, training_loop.py:207-208). */
+enum {
+    GG_PREC_FP32_SIMT = 0, /* exact fp32 FFMA kernel (small / odd shapes, and the on-GPU cross-check) */
+    GG_PREC_TF32X1 = 1,    /* tcgen05 kind::tf32, one product per MAC (fast mode, ~3e-4 per layer) */
+    GG_PREC_TF32X3 = 3,    /* tcgen05 kind::tf32, hi/lo split, 3 products per MAC (~4e-7, the parity mode) */
+    GG_PREC_AUTO = -1      /* TF32X3 on tensor cores when the shape is eligible, else FP32_SIMT */
+};
+
+GG_API const char* gg_last_error(void);
+GG_API int gg_version(void);
+/* 1 if the current device is sm_100 (the only target of this library), else 0. */
+GG_API int gg_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------
+ * bias_act -- replaces `_plugin.bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp)`
+ * (torch_utils/ops/bias_act.cpp:32-90, kernel bias_act.cu:23-147).
+ *
+ *   grad=0: y = clamp(act(x + b) * gain)
+ *   grad=1: y = d/dx of the above applied to incoming gradient `x`, using saved `yref` (or `xref`
+ *           for swish); zero where |yref| >= clamp.
+ *   grad=2: second-order term, additionally multiplied by `dy` (has_2nd_grad activations only).
+ *
+ * `x`,`xref`,`yref`,`dy`,`y` hold sizeX elements each (xref/yref/dy/b may be NULL = absent, the
+ * reference's empty tensor).  Bias index of element i is (i / stepB) % sizeB, exactly
+ * bias_act.cu:44 (stepB = x.stride(dim)).  act = the reference's cuda_idx 1..9 (linear, relu,
+ * lrelu, tanh, sigmoid, elu, selu, softplus, swish).  clamp < 0 disables clamping.
+ *
+ * Extension over the reference: if `dbias` is non-NULL (sizeB floats, grad>=1) the kernel also
+ * accumulates dbias[c] += sum of y over all elements with bias index c -- the reference does this
+ * as a second full pass `dx.sum(...)` (bias_act.py:211-212).  dbias must be zero-filled by the
+ * caller (or hold a value to accumulate onto).
+ */
+GG_API int gg_bias_act_f32(const float* x, const float* b, const float* xref, const float* yref, const float* dy,
+                    float* y, float* dbias, int grad, int act, float alpha, float gain, float clamp,
+                    int64_t sizeX, int sizeB, int64_t stepB, gg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * upfirdn2d -- replaces `_plugin.upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1,
+ * flip, gain)` (torch_utils/ops/upfirdn2d.cpp:16-94, kernels upfirdn2d.cu:29-200).
+ *
+ * x: [N,C,inH,inW] dense NCHW; f: [fH,fW] dense fp32; y: [N,C,outH,outW] dense NCHW with
+ *   outW = (inW*upx + padx0 + padx1 - fW + downx) / downx   (upfirdn2d.cpp:32-33; checked here).
+ * Negative padding crops.  flip=0 convolves (filter flipped), flip=1 correlates.
+ */
+GG_API int gg_upfirdn2d_f32(const float* x, const float* f, float* y, int N, int C, int inH, int inW, int fH, int fW,
+                     int upx, int upy, int downx, int downy, int padx0, int padx1, int pady0, int pady1,
+                     int flip, float gain, int outH, int outW, gg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * conv2d -- replaces the ATen/cuDNN calls behind `conv2d_gradfix.conv2d / conv_transpose2d`
+ * (torch_utils/ops/conv2d_gradfix.py:37-58,138-148) and, with the optional per-sample scales, the
+ * multiply passes around them in `modulated_conv2d` (training/networks.py:641-653):
+ *
+ *   y[n,o,:,:] = out_scale[n,o] * sum_i  corr_or_convT( in_scale[n,i] * x[n,i,:,:], w[o,i,:,:] )
+ *
+ * transposed=0: correlation with `stride`, zero padding (pad_y, pad_x); w is [O,I,KH,KW].
+ * transposed=1: conv_transpose2d with `stride`, padding (pad_y,pad_x); w is [I,O,KH,KW]
+ *               (torch layout); OH = (H-1)*stride - 2*pad_y + KH + output_padding (caller passes OH/OW).
+ * flip_w=1 uses w flipped in both spatial axes (conv2d_resample.py:35-36).
+ * in_scale [N,I] / out_scale [N,O] may be NULL (plain conv, the discriminator).
+ * groups == 1 only (grouped convs are split by the host).
+ * prec: GG_PREC_*; AUTO picks the tcgen05 path when eligible.  `used_prec` (nullable) reports the choice.
+ */
+GG_API int gg_conv2d_f32(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int KH, int KW,
+                  int OH, int OW, int stride, int pad_y, int pad_x, int transposed, int flip_w,
+                  const float* in_scale, const float* out_scale, int prec, int* used_prec, gg_stream_t stream);
+
+/* Weight gradient of the op above (replaces aten::cudnn_convolution_backward_weight,
+ * conv2d_gradfix.py:175-191).  For the correlation y = conv(a, w):
+ *   dw[o,i,ky,kx] = sum_{n,oy,ox} (b_scale[n,o]*b[n,o,oy,ox]) * (a_scale[n,i]*a[n,i, oy*stride-pad_y+ky, ox*stride-pad_x+kx])
+ * a: [N,A,HA,WA] (the conv input), b: [N,B,HB,WB] (gradient w.r.t. the conv output), dw: [B,A,KH,KW].
+ * out_layout=1 writes dw transposed as [A,B,KH,KW] (the conv_transpose2d weight layout, roles swapped
+ * by the host).  flip_w=1 writes the spatially flipped gradient.  dw is overwritten.
+ */
+GG_API int gg_conv2d_wgrad_f32(const float* a, const float* b, float* dw, int N, int A, int HA, int WA, int B, int HB, int WB,
+                        int KH, int KW, int stride, int pad_y, int pad_x, int flip_w, int out_layout,
+                        const float* a_scale, const float* b_scale, int prec, int* used_prec, gg_stream_t stream);
+
+/* Number of kernels this library has launched since load (all streams); bench.py reports the delta. */
+GG_API int64_t gg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAGAN_B200_H_ */

@@ -1,0 +1,78 @@
+"""GPU: network-level parity.  The product modules (training/networks.py, training/loss.py) loaded with the
+golden weights must reproduce what the REFERENCE's own Generator / Discriminator / StyleGAN2Loss produced on CPU
+(tests/golden/networks.npz): eval and train forward, and parameter gradients after each of the four loss phases
+(Greg and Dreg are double-backward through every op)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import load_golden, t, assert_close, patched_randn, TOL
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def nets(device):
+    from training import networks
+    g = load_golden('networks')
+    cfg = {kv.split('=')[0]: int(kv.split('=')[1]) for kv in (str(m) for m in g['meta'])}
+    G = networks.Generator(z_dim=cfg['z_dim'], c_dim=0, w_dim=cfg['w_dim'], img_resolution=cfg['res'], img_channels=3,
+                           mapping_kwargs=dict(num_layers=cfg['num_layers']),
+                           synthesis_kwargs=dict(channel_base=cfg['channel_base'], channel_max=cfg['channel_max']))
+    D = networks.Discriminator(c_dim=0, img_resolution=cfg['res'], img_channels=3, channel_base=cfg['channel_base'],
+                               channel_max=cfg['channel_max'], epilogue_kwargs=dict(mbstd_group_size=cfg['mbstd']))
+    G.load_state_dict({k[2:]: t(v) for k, v in g.items() if k.startswith('G.')}, strict=False)
+    D.load_state_dict({k[2:]: t(v) for k, v in g.items() if k.startswith('D.')}, strict=False)
+    return G.to(device), D.to(device), g, cfg
+
+
+def test_eval_forward(nets, device):
+    G, D, g, cfg = nets
+    G.eval(); D.eval()
+    z = t(g['z'], device); c = torch.zeros(z.shape[0], 0, device=device)
+    with torch.no_grad():
+        ws = G.mapping(z, c)
+        assert_close(ws, g['eval.ws'], TOL, 'mapping')
+        img = G.synthesis(ws, noise_mode='const')
+        assert_close(img, g['eval.img'], TOL, 'synthesis')
+        assert_close(G(z, c, truncation_psi=0.7, truncation_cutoff=4, noise_mode='const'), g['eval.img_trunc'], TOL, 'trunc')
+        assert_close(D(t(g['eval.img'], device), c), g['eval.logits'], TOL, 'D')
+
+
+def test_train_forward_random_noise(nets, device):
+    G, D, g, cfg = nets
+    G.train()
+    G.mapping.w_avg_beta = None
+    with torch.no_grad(), patched_randn(7):
+        img = G.synthesis(t(g['eval.ws'], device), noise_mode='random')
+    assert_close(img, g['train.img_randnoise7'], TOL)
+
+
+@pytest.mark.parametrize('phase', ['Gmain', 'Greg', 'Dmain', 'Dreg'])
+def test_loss_phase_parameter_gradients(nets, device, phase):
+    from training.loss import StyleGAN2Loss
+    G, D, g, cfg = nets
+    G.train(); D.train()
+    G.mapping.w_avg_beta = None
+    for p in list(G.parameters()) + list(D.parameters()):
+        p.requires_grad_(True)
+        p.grad = None
+    loss = StyleGAN2Loss(device=device, G_mapping=G.mapping, G_synthesis=G.synthesis, D=D, style_mixing_prob=0,
+                         r1_gamma=10, pl_batch_shrink=2, pl_decay=0.01, pl_weight=2)
+    z = t(g['z'], device); real = t(g['real'], device); c = torch.zeros(z.shape[0], 0, device=device)
+    with patched_randn(11):
+        loss.accumulate_gradients(phase=phase, real_img=real, real_c=c, gen_z=z, gen_c=c, sync=True, gain=1.0)
+    net = G if phase[0] == 'G' else D
+    worst = ('', 0.0)
+    for k, p in net.named_parameters():
+        want = g[f'{phase}.grad.{k}']
+        got = p.grad if p.grad is not None else torch.zeros_like(p)
+        if np.abs(want).max() == 0:
+            assert float(got.abs().max()) <= 1e-6, k
+            continue
+        e = assert_close(got, want, TOL, f'{phase}.{k}')
+        if e > worst[1]:
+            worst = (k, e)
+    if phase == 'Greg':
+        assert_close(loss.pl_mean, g['Greg.pl_mean'], TOL, 'pl_mean')
+    print(f'{phase}: worst max-rel-err {worst[1]:.2e} at {worst[0]}')

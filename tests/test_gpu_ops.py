@@ -1,0 +1,262 @@
+"""GPU parity tests proper: every op of the hot path, called through the product API (-> ctypes -> C ABI ->
+sm_100a kernels), against (a) the committed goldens generated from the live reference and (b) the CPU oracle on
+seeded inputs.  Tolerance: BASELINE.json north_star, max relative error 1e-3 (fp32, TF32 off)."""
+import itertools
+import numpy as np
+import pytest
+import torch
+
+from tests.util import load_golden, t, assert_close, TOL
+from oracle import ops_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _meta(g):
+    return [str(m).split('|') for m in g['meta']]
+
+
+@pytest.fixture(scope='module')
+def ops(device):
+    from torch_utils import custom_ops
+    from torch_utils.ops import upfirdn2d, bias_act, conv2d_resample, conv2d_gradfix, fma
+    from training import networks
+    custom_ops.load_library()
+    import types
+    return types.SimpleNamespace(upfirdn2d=upfirdn2d, bias_act=bias_act, conv2d_resample=conv2d_resample,
+                                 conv2d_gradfix=conv2d_gradfix, fma=fma, networks=networks, custom_ops=custom_ops)
+
+
+# ------------------------------------------------------------------------------------------------ upfirdn2d
+def test_upfirdn2d_golden(ops, device):
+    g = load_golden('upfirdn2d')
+    for name, up, down, pad, flip, gain in _meta(g):
+        up = [int(v) for v in up.split(',')]; down = [int(v) for v in down.split(',')]; pad = [int(v) for v in pad.split(',')]
+        f = t(g[name + '.f'], device) if name + '.f' in g else None
+        x = t(g[name + '.x'], device, requires_grad=True)
+        y = ops.upfirdn2d.upfirdn2d(x, f, up=up, down=down, padding=pad, flip_filter=bool(int(flip)), gain=float(gain))
+        assert_close(y, g[name + '.y'], 1e-5, name)
+        dx, = torch.autograd.grad(y, x, t(g[name + '.dy'], device))
+        assert_close(dx, g[name + '.dx'], 1e-5, name + '.dx')
+    x = t(g['wrap.x'], device)
+    for fname, f in (('2d', t(g['wrap.f2d'], device)), ('1d', t(g['wrap.f1d'], device))):
+        assert_close(ops.upfirdn2d.filter2d(x, f), g[f'wrap.filter2d.{fname}.y'], 1e-5)
+        assert_close(ops.upfirdn2d.upsample2d(x, f), g[f'wrap.upsample2d.{fname}.y'], 1e-5)
+        assert_close(ops.upfirdn2d.downsample2d(x, f), g[f'wrap.downsample2d.{fname}.y'], 1e-5)
+
+
+@pytest.mark.parametrize('case', [
+    # name, shape, up, down, pad  -- the StyleGAN2 call shapes that take the tiled 4x4 kernels (+ ragged edges)
+    ('filt_p1', (2, 3, 129, 129), 1, 1, [1, 1, 1, 1]), ('filt_p2', (2, 3, 128, 128), 1, 1, [2, 2, 2, 2]),
+    ('filt_ragged', (1, 2, 77, 203), 1, 1, [1, 1, 1, 1]), ('up2', (2, 3, 64, 64), 2, 1, [2, 1, 2, 1]),
+    ('up2_oddpad', (1, 2, 50, 70), 2, 1, [1, 2, 3, 0]), ('down2', (2, 3, 128, 128), 1, 2, [1, 1, 1, 1]),
+    ('down2_ragged', (1, 2, 101, 131), 1, 2, [1, 1, 1, 1]), ('filt_crop', (1, 2, 90, 140), 1, 1, [-3, 2, -1, 4]),
+    ('up2_bwd_of_down2', (1, 2, 64, 64), 2, 1, [2, 2, 2, 2]),
+])
+def test_upfirdn2d_tiled_vs_oracle(ops, device, case):
+    name, shape, up, down, pad = case
+    g = torch.Generator().manual_seed(hash(name) % 1000)
+    f = R.setup_filter([1, 3, 3, 1])
+    for flip, gain in ((False, 4.0), (True, 1.0)):
+        x = torch.randn(*shape, generator=g)
+        want = R.upfirdn2d(x, f, up=up, down=down, padding=pad, flip_filter=flip, gain=gain)
+        xg = x.to(device).requires_grad_(True)
+        got = ops.upfirdn2d.upfirdn2d(xg, f.to(device), up=up, down=down, padding=pad, flip_filter=flip, gain=gain)
+        assert got.shape == want.shape
+        assert_close(got, want, 1e-5, name)
+        dy = torch.randn(want.shape, generator=g)
+        bw = R.upfirdn2d_backward_args(x.shape, want.shape, f, up, down, pad)
+        want_dx = R.upfirdn2d(dy, f, flip_filter=(not flip), gain=gain, **bw)
+        got_dx, = torch.autograd.grad(got, xg, dy.to(device))
+        assert_close(got_dx, want_dx, 1e-5, name + '.dx')
+
+
+def test_upfirdn2d_double_backward(ops, device):
+    g = torch.Generator().manual_seed(5)
+    f = R.setup_filter([1, 3, 3, 1]).to(device)
+    x = torch.randn(1, 2, 70, 66, generator=g).to(device).requires_grad_(True)
+    y = ops.upfirdn2d.upsample2d(x, f)
+    dy = torch.randn(y.shape, generator=g).to(device).requires_grad_(True)
+    dx, = torch.autograd.grad(y, x, dy, create_graph=True)
+    v = torch.randn(dx.shape, generator=g).to(device)
+    ddy, = torch.autograd.grad(dx, dy, v)          # linear op: d(dx)/d(dy) applied to v == forward(v)
+    assert_close(ddy, ops.upfirdn2d.upsample2d(v, f), 1e-5)
+
+
+def test_upfirdn2d_errors(ops, device):
+    x = torch.randn(1, 1, 2, 2, device=device)
+    f = R.setup_filter([1, 3, 3, 1]).to(device)
+    with pytest.raises(RuntimeError, match='at least 1x1'):
+        ops.upfirdn2d.upfirdn2d(x, f, padding=0)          # 2 - 4 + 1 < 1
+    with pytest.raises(RuntimeError, match='fp32'):
+        ops.upfirdn2d.upfirdn2d(x.half(), f)
+
+
+# ------------------------------------------------------------------------------------------------ bias_act
+def test_bias_act_golden_all_activations_first_and_second_order(ops, device):
+    g = load_golden('bias_act')
+    for name, act, dim, alpha, gain, clamp in _meta(g):
+        kw = dict(dim=int(dim), act=act, alpha=None if alpha == 'None' else float(alpha),
+                  gain=None if gain == 'None' else float(gain), clamp=None if clamp == 'None' else float(clamp))
+        x = t(g[name + '.x'], device, requires_grad=True)
+        b = t(g[name + '.b'], device, requires_grad=True) if name + '.b' in g else None
+        y = ops.bias_act.bias_act(x, b, **kw)
+        assert_close(y, g[name + '.y'], 1e-5, name)
+        dy = t(g[name + '.dy'], device, requires_grad=True)
+        grads = torch.autograd.grad(y, [x] + ([b] if b is not None else []), dy, create_graph=True)
+        assert_close(grads[0], g[name + '.dx'], 1e-4, name + '.dx')
+        if b is not None:
+            assert_close(grads[1], g[name + '.db'], 1e-4, name + '.db')
+        gg = torch.autograd.grad(grads[0], [dy, x], t(g[name + '.d_dx'], device), allow_unused=True)
+        assert_close(gg[0], g[name + '.gg_dy'], 1e-4, name + '.gg_dy')
+        ggx = gg[1] if gg[1] is not None else torch.zeros_like(x)
+        assert_close(ggx, g[name + '.gg_x'], 2e-4, name + '.gg_x')
+
+
+@pytest.mark.parametrize('shape,dim', [((4, 512), 1), ((2, 32, 64, 64), 1), ((3, 16, 4, 4), 1), ((2, 5, 7, 9), 1),
+                                       ((1, 8, 33, 128), 1), ((2, 512, 16, 16), 1)])
+def test_bias_act_lrelu_shapes_vs_oracle(ops, device, shape, dim):
+    g = torch.Generator().manual_seed(len(shape) * 7 + shape[-1])
+    for clamp, gain in ((None, None), (0.8, 1.0)):
+        x = torch.randn(*shape, generator=g)
+        b = torch.randn(shape[dim], generator=g)
+        dy = torch.randn(*shape, generator=g)
+        xc, bc = x.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        want = R.bias_act(xc, bc, dim=dim, act='lrelu', gain=gain, clamp=clamp)
+        wdx, wdb = torch.autograd.grad(want, [xc, bc], dy)
+        xg, bg = x.to(device).requires_grad_(True), b.to(device).requires_grad_(True)
+        got = ops.bias_act.bias_act(xg, bg, dim=dim, act='lrelu', gain=gain, clamp=clamp)
+        assert_close(got, want, 1e-6)
+        gdx, gdb = torch.autograd.grad(got, [xg, bg], dy.to(device))
+        assert_close(gdx, wdx, 1e-6)
+        assert_close(gdb, wdb, 1e-4)      # fused reduction: fp32 atomics, order differs
+
+
+def test_bias_act_r1_style_double_backward_through_bias(ops, device):
+    # grad-of-grad w.r.t. the bias parameter, as Dreg needs (loss.py:141-152)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 8, 16, 16, generator=g); b = torch.randn(8, generator=g)
+
+    def penalty(bias_act_fn, x, b):
+        x = x.requires_grad_(True)
+        y = bias_act_fn(x * x, b, act='lrelu')
+        gx, = torch.autograd.grad(y.square().sum(), x, create_graph=True)
+        return gx.square().sum()
+
+    bc = b.clone().requires_grad_(True)
+    want, = torch.autograd.grad(penalty(R.bias_act, x.clone(), bc), bc)
+    bg = b.to(device).requires_grad_(True)
+    got, = torch.autograd.grad(penalty(ops.bias_act.bias_act, x.to(device), bg), bg)
+    assert_close(got, want, 1e-4)
+
+
+def test_bias_act_empty_and_errors(ops, device):
+    assert ops.bias_act.bias_act(torch.empty(0, 4, device=device), torch.zeros(4, device=device), act='lrelu').shape == (0, 4)
+    with pytest.raises(RuntimeError, match='wrong number of elements'):
+        ops.bias_act.bias_act(torch.zeros(2, 3, device=device), torch.zeros(4, device=device), act='lrelu')
+
+
+# ------------------------------------------------------------------------------------------------ conv
+def test_conv2d_resample_golden(ops, device):
+    g = load_golden('conv2d_resample')
+    f = t(g['f'], device)
+    for name, up, down, pad, flipw, groups in _meta(g):
+        x = t(g[name + '.x'], device, requires_grad=True); w = t(g[name + '.w'], device, requires_grad=True)
+        y = ops.conv2d_resample.conv2d_resample(x, w, f=f, up=int(up), down=int(down), padding=[int(v) for v in pad.split(',')],
+                                                groups=int(groups), flip_weight=bool(int(flipw)))
+        assert_close(y, g[name + '.y'], TOL, name)
+        dx, dw = torch.autograd.grad(y, [x, w], t(g[name + '.dy'], device))
+        assert_close(dx, g[name + '.dx'], TOL, name + '.dx')
+        assert_close(dw, g[name + '.dw'], TOL, name + '.dw')
+
+
+def _conv_oracle(x, w, stride, pad, transposed, outpad=0):
+    if transposed:
+        return torch.nn.functional.conv_transpose2d(x, w, stride=stride, padding=pad, output_padding=outpad)
+    return torch.nn.functional.conv2d(x, w, stride=stride, padding=pad)
+
+
+@pytest.mark.parametrize('prec', ['simt', 'auto'])
+@pytest.mark.parametrize('case', [
+    # N, I, O, H, W, k, stride, pad, transposed
+    (2, 3, 32, 32, 32, 1, 1, 0, False), (2, 32, 3, 32, 32, 1, 1, 0, False), (3, 16, 16, 4, 4, 3, 1, 1, False),
+    (2, 32, 32, 16, 16, 3, 1, 1, False), (1, 64, 64, 32, 32, 3, 1, 1, False), (2, 128, 64, 16, 16, 3, 1, 1, False),
+    (1, 32, 48, 24, 40, 3, 1, 1, False), (2, 33, 17, 9, 11, 3, 1, 1, False), (2, 16, 32, 17, 17, 3, 2, 0, False),
+    (2, 32, 16, 8, 8, 3, 2, 0, True), (1, 8, 8, 5, 7, 3, 1, 1, True), (1, 513, 16, 4, 4, 3, 1, 1, False),
+    (2, 32, 32, 64, 64, 3, 1, 1, False), (1, 16, 16, 16, 16, 1, 1, 0, False),
+])
+def test_conv2d_fwd_dgrad_wgrad_vs_oracle(ops, device, case, prec):
+    N, I, O, H, W, k, stride, pad, transposed = case
+    g = torch.Generator().manual_seed(N * 1000 + I * 10 + k)
+    x = torch.randn(N, I, H, W, generator=g)
+    wshape = (I, O, k, k) if transposed else (O, I, k, k)
+    w = torch.randn(*wshape, generator=g) / np.sqrt(I * k * k)
+    xc, wc = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    want = _conv_oracle(xc, wc, stride, pad, transposed)
+    dy = torch.randn(want.shape, generator=g)
+    wdx, wdw = torch.autograd.grad(want, [xc, wc], dy)
+    ops.custom_ops.conv_precision = ops.custom_ops.PREC_FP32_SIMT if prec == 'simt' else ops.custom_ops.PREC_AUTO
+    try:
+        xg, wg = x.to(device).requires_grad_(True), w.to(device).requires_grad_(True)
+        fn = ops.conv2d_gradfix.conv_transpose2d if transposed else ops.conv2d_gradfix.conv2d
+        got = fn(xg, wg, stride=stride, padding=pad)
+        assert got.shape == want.shape
+        tol = 2e-5 if prec == 'simt' else 1e-4      # 3xTF32 is ~1e-6; leave headroom, far inside the 1e-3 budget
+        assert_close(got, want, tol, 'fwd')
+        gdx, gdw = torch.autograd.grad(got, [xg, wg], dy.to(device))
+        assert_close(gdx, wdx, tol, 'dgrad')
+        assert_close(gdw, wdw, tol * 5, 'wgrad')
+    finally:
+        ops.custom_ops.conv_precision = ops.custom_ops.PREC_AUTO
+
+
+def test_conv2d_scales_fused(ops, device):
+    # in_scale / out_scale of gg_conv2d_f32 == the multiply passes of modulated_conv2d (networks.py:642,648-651)
+    g = torch.Generator().manual_seed(3)
+    plugin = ops.custom_ops.get_plugin('conv2d_plugin')
+    for (N, I, O, H, k) in [(2, 32, 32, 16, 3), (3, 8, 5, 6, 3), (2, 64, 3, 32, 1)]:
+        x = torch.randn(N, I, H, H, generator=g); w = torch.randn(O, I, k, k, generator=g) / np.sqrt(I * k * k)
+        a = torch.randn(N, I, generator=g); b = torch.randn(N, O, generator=g)
+        want = torch.nn.functional.conv2d(x * a[:, :, None, None], w, padding=k // 2) * b[:, :, None, None]
+        got = plugin.conv2d(x.to(device), w.to(device), padding=(k // 2, k // 2), in_scale=a.to(device), out_scale=b.to(device))
+        assert_close(got, want, 1e-4)
+
+
+def test_conv2d_double_backward_closure(ops, device):
+    # R1-style: gradient of ||d y / d x||^2 w.r.t. the weight goes conv -> dgrad -> (wgrad of dgrad)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 8, 12, 12, generator=g); w = torch.randn(6, 8, 3, 3, generator=g) * 0.2
+
+    def pen(conv, x, w):
+        x = x.requires_grad_(True)
+        y = conv(x, w)
+        gx, = torch.autograd.grad((y * y).sum(), x, create_graph=True)
+        return gx.square().sum()
+
+    wc = w.clone().requires_grad_(True)
+    want, = torch.autograd.grad(pen(lambda a, b: torch.nn.functional.conv2d(a, b, padding=1), x.clone(), wc), wc)
+    wg = w.to(device).requires_grad_(True)
+    got, = torch.autograd.grad(pen(lambda a, b: ops.conv2d_gradfix.conv2d(a, b, padding=1), x.to(device), wg), wg)
+    assert_close(got, want, 1e-4)
+    with ops.conv2d_gradfix.no_weight_gradients():
+        xg = x.to(device).requires_grad_(True)
+        y = ops.conv2d_gradfix.conv2d(xg, wg, padding=1)
+        gx, gw = torch.autograd.grad(y.sum(), [xg, wg], allow_unused=True)
+        assert gw is None and gx is not None
+
+
+# ------------------------------------------------------------------------------------------------ modconv
+def test_modulated_conv2d_golden(ops, device):
+    g = load_golden('modconv')
+    f = t(g['f'], device)
+    for name, k, up, demod, noise_kind, fused in _meta(g):
+        x = t(g[name + '.x'], device, requires_grad=True); w = t(g[name + '.w'], device, requires_grad=True)
+        s = t(g[name + '.s'], device, requires_grad=True)
+        noise = t(g[name + '.noise'], device, requires_grad=True) if name + '.noise' in g else None
+        y = ops.networks.modulated_conv2d(x=x, weight=w, styles=s, noise=noise, up=int(up), padding=int(k) // 2,
+                                          resample_filter=f, demodulate=bool(int(demod)), flip_weight=(int(up) == 1),
+                                          fused_modconv=bool(int(fused)))
+        assert_close(y, g[name + '.y'], TOL, name)
+        grads = torch.autograd.grad(y, [x, w, s] + ([noise] if noise is not None else []), t(g[name + '.dy'], device))
+        for gname, got in zip(['dx', 'dw', 'ds', 'dnoise'], grads):
+            assert_close(got, g[f'{name}.{gname}'], TOL, f'{name}.{gname}')

@@ -1,0 +1,121 @@
+"""CPU: host-side logic of the product -- integer pad/branch bookkeeping (bit-exact against the oracle),
+the C-ABI library (loads, exports every symbol the header declares), and the no-fallback contract."""
+import os
+import re
+import ctypes
+import itertools
+import pytest
+import torch
+
+from tests.util import ROOT, PKG
+from oracle import ops_ref as R
+
+from torch_utils import custom_ops
+from torch_utils.ops import upfirdn2d, bias_act, conv2d_resample, conv2d_gradfix, fma
+from training import networks
+
+
+def test_conv2d_resample_plan_bit_exact():
+    f4 = R.setup_filter([1, 3, 3, 1]); f12 = R.setup_filter(list(range(1, 13))); f3 = R.setup_filter([1, 2, 1])
+    n = 0
+    for k, up, down, f, pad in itertools.product([1, 3, 5], [1, 2, 4], [1, 2, 3], [None, f4, f12, f3],
+                                                 [0, 1, 2, [1, 0], [0, 1, 2, 3], [-1, 1, 0, 2]]):
+        got = conv2d_resample.plan((8, 4, k, k), f, up, down, pad)
+        want = R.conv2d_resample_plan((8, 4, k, k), f, up, down, pad)
+        assert got == want, (k, up, down, pad, got, want)
+        n += 1
+    assert n == 3 * 3 * 3 * 4 * 6
+
+
+def test_padding_helpers_and_filter():
+    for pad in [0, 3, [1, 2], [1, 2, 3, 4], [-1, 0, 2, -3]]:
+        assert upfirdn2d._parse_padding(pad) == R.parse_padding(pad)
+    for s in [1, 3, [2, 1]]:
+        assert upfirdn2d._parse_scaling(s) == R.parse_scaling(s)
+    for spec, kw in [([1, 3, 3, 1], {}), ([1, 2, 1], dict(gain=4)), (list(range(1, 13)), {}), ([1, 3, 3, 1], dict(flip_filter=True, normalize=False)),
+                     (None, {}), (2.0, {}), ([1, 3, 3, 1], dict(separable=True))]:
+        a = upfirdn2d.setup_filter(spec, **kw); b = R.setup_filter(spec, **kw)
+        assert a.shape == b.shape and torch.equal(a, b)
+    assert upfirdn2d._get_filter_size(None) == (1, 1)
+    assert upfirdn2d._get_filter_size(torch.zeros(3, 5)) == (5, 3)
+
+
+def test_activation_table_matches_reference_values():
+    for name, (alpha, gain, idx, ref, has2) in R.ACTIVATIONS.items():
+        s = bias_act.activation_funcs[name]
+        assert (s.def_alpha, float(s.def_gain), s.cuda_idx, s.ref, s.has_2nd_grad) == (alpha, float(gain), idx, ref, has2)
+
+
+def test_cabi_library_loads_and_exports_header_symbols():
+    header = open(os.path.join(ROOT, 'include', 'gagan_b200.h')).read()
+    declared = re.findall(r'GG_API\s+[\w\s\*]+?\b(gg_\w+)\s*\(', header)
+    assert len(declared) >= 8
+    lib = custom_ops.load_library()                     # builds with nvcc if the .so is missing; no GPU needed
+    for sym in declared:
+        assert hasattr(lib, sym), f'{sym} declared in include/gagan_b200.h but not exported by libgagan_b200.so'
+    assert set(declared) == set(custom_ops.EXPORTED_SYMBOLS)
+    assert lib.gg_version() == 100
+    assert isinstance(lib.gg_launch_count(), int)
+    # argument validation runs before any CUDA call: usable without a device
+    rc = lib.gg_bias_act_f32(None, None, None, None, None, None, None, 0, 3, 0.2, 1.0, -1.0, 16, 1, 1, None)
+    assert rc == -1 and b'non-null' in lib.gg_last_error()
+    rc = lib.gg_upfirdn2d_f32(ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), 1, 1, 4, 4, 4, 4, 0, 1, 1, 1, 0, 0, 0, 0, 0, 1.0, 1, 1, None)
+    assert rc == -1 and b'upsampling factor' in lib.gg_last_error()
+
+
+def test_no_cpu_fallback_and_no_ref_impl():
+    x = torch.randn(2, 3, 8, 8)
+    f = upfirdn2d.setup_filter([1, 3, 3, 1])
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        bias_act.bias_act(x, torch.zeros(3))
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        upfirdn2d.upfirdn2d(x, f)
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        conv2d_gradfix.conv2d(x, torch.randn(4, 3, 3, 3), padding=1)
+    with pytest.raises(RuntimeError, match="impl='ref'"):
+        bias_act.bias_act(x, impl='ref')
+    with pytest.raises(RuntimeError, match="impl='ref'"):
+        upfirdn2d.upsample2d(x, f, impl='ref')
+    with pytest.raises(RuntimeError):
+        custom_ops.get_plugin('no_such_plugin')
+    # the product never imports the oracle
+    for dirpath, _, files in os.walk(PKG):
+        for fn in files:
+            if fn.endswith('.py'):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert 'import oracle' not in src and 'from oracle' not in src, fn
+
+
+def test_fma_matches_oracle_on_cpu():
+    # fma is plain torch (no kernel): check forward and the hand-written broadcast-aware backward
+    g = torch.Generator().manual_seed(1)
+    a = torch.randn(2, 4, 5, 5, generator=g, requires_grad=True)
+    b = torch.randn(2, 4, 1, 1, generator=g, requires_grad=True)
+    c = torch.randn(2, 1, 5, 5, generator=g, requires_grad=True)
+    y = fma.fma(a, b, c)
+    yo = R.fma(a, b, c)
+    assert torch.allclose(y, yo)
+    dy = torch.randn(y.shape, generator=g)
+    for u, v in zip(torch.autograd.grad(y, [a, b, c], dy), torch.autograd.grad(yo, [a, b, c], dy)):
+        assert torch.allclose(u, v, atol=1e-6)
+
+
+def test_network_state_dict_names_match_golden_weights():
+    from tests.util import load_golden
+    g = load_golden('networks')
+    cfg = {kv.split('=')[0]: int(kv.split('=')[1]) for kv in (str(m) for m in g['meta'])}
+    G = networks.Generator(z_dim=cfg['z_dim'], c_dim=0, w_dim=cfg['w_dim'], img_resolution=cfg['res'], img_channels=3,
+                           mapping_kwargs=dict(num_layers=cfg['num_layers']),
+                           synthesis_kwargs=dict(channel_base=cfg['channel_base'], channel_max=cfg['channel_max']))
+    D = networks.Discriminator(c_dim=0, img_resolution=cfg['res'], img_channels=3, channel_base=cfg['channel_base'],
+                               channel_max=cfg['channel_max'], epilogue_kwargs=dict(mbstd_group_size=cfg['mbstd']))
+    for net, pre in ((G, 'G.'), (D, 'D.')):
+        sd = {k: v for k, v in net.state_dict().items() if not k.endswith('resample_filter')}
+        gold = {k[2:]: v for k, v in g.items() if k.startswith(pre)}
+        assert set(sd) == set(gold), (set(sd) ^ set(gold))
+        for k in sd:
+            assert tuple(sd[k].shape) == tuple(gold[k].shape), k
+    # parameter counts of the real configs: cfg-f 1024^2 G 30.37 M / D 29.01 M
+    Gf = networks.Generator(512, 0, 512, 1024, 3, mapping_kwargs=dict(num_layers=8), synthesis_kwargs=dict(channel_base=32768))
+    assert sum(p.numel() for p in Gf.parameters()) == 30370060
+    assert Gf.num_ws == 18
