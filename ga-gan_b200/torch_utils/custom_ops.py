@@ -171,7 +171,7 @@ class _Plugin:
             raise RuntimeError('b has wrong number of elements')
         if grad < 0:
             raise RuntimeError('grad must be non-negative')
-        if not x.is_non_overlapping_and_dense():
+        if not (x.is_contiguous() or (x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last))):
             raise RuntimeError('x must be non-overlapping and dense')
         if not b.is_contiguous():
             raise RuntimeError('b must be contiguous')

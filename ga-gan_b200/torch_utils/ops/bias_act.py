@@ -105,9 +105,7 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
             ctx.save_for_backward(
                 x if 'x' in spec.ref or spec.has_2nd_grad else null,
                 b if 'x' in spec.ref or spec.has_2nd_grad else null,
-                y if 'y' in spec.ref else null)
-            ctx.x_ndim = x.ndim
-            ctx.nb = x.shape[dim] if x.ndim > dim else 0
+                y if ('y' in spec.ref or clamp >= 0) else null)   # the clamp mask needs y even for 'linear'
             return y
 
         @staticmethod

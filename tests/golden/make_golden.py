@@ -61,7 +61,7 @@ def pin(name, got, want, tol=PIN_TOL):
 
 
 def npy(t):
-    return None if t is None else t.detach().cpu().numpy()
+    return None if t is None else t.detach().cpu().numpy().copy()
 
 
 def save(name, **arrays):
