@@ -101,9 +101,15 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_ma
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// 3xTF32 operand split.  Both parts are rounded to nearest tf32 (cvt.rna) rather than left to the tensor core's
+// truncation: |lo| <= 2^-12 |v| and lo itself carries a 2^-12 relative rounding error, so hi*hi + hi*lo + lo*hi
+// reproduces the fp32 product to ~2^-22 (the dropped lo*lo term is 2^-24).
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-    hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);   // exactly representable in tf32 (10 explicit mantissa bits)
-    lo = v - hi;                                              // exact in fp32; the tensor core keeps its top 10 bits
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    hi = __uint_as_float(h);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+    lo = __uint_as_float(l);
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
