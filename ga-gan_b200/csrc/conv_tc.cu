@@ -1,25 +1,32 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a, fp32 accuracy through 3xTF32.
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a, fp32-faithful through 3xTF32 + chunked accumulation.
 //
-// Serves the stride-1 convolutions of the StyleGAN2 hot path (3x3 pad 1 and 1x1: SynthesisLayer conv1, ToRGB-sized
-// 1x1s with O>=16, Discriminator conv0, and their data gradients, which are stride-1 correlations with the transposed,
-// flipped kernel), i.e. the cuDNN calls behind conv2d_gradfix (torch_utils/ops/conv2d_gradfix.py:141-146) plus the
-// modulated_conv2d scale passes (training/networks.py:642,648-651) folded into the operand conversion (in_scale) and
-// the epilogue (out_scale).
+// Serves every stride-1 correlation of the StyleGAN2 hot path with a k x k kernel, k in {1,2,3}: SynthesisLayer conv1,
+// Discriminator conv0, 1x1 layers with >= 16 channels, their data gradients (stride-1 correlations with the transposed,
+// flipped kernel) and -- through the phase-major (space-to-depth) formulation in torch_utils/ops/conv2d_resample.py --
+// the stride-2 up/down layers, i.e. the cuDNN calls behind conv2d_gradfix (torch_utils/ops/conv2d_gradfix.py:141-146)
+// plus the modulated_conv2d scale passes (training/networks.py:642,648-651) folded into the operand conversion
+// (in_scale) and the epilogue (out_scale).
 //
 // GEMM view      D[m = output pixel, n = out channel] = sum_{k = (tap, in channel)} A[m,k] * B[n,k]
-// CTA tile       16x16 output pixels (two 8x16 UMMA M-tiles of 128 pixels) x NT<=128 output channels.
-// A operand      the input halo tile (18x20 pixels x 16 channels per K-block) arrives by ONE 4-D TMA box load with
-//                hardware zero fill outside the image (= the conv padding), is converted ONCE by four SIMT warps
-//                (x in_scale, split into tf32 hi + lo) into the UMMA no-swizzle K-major layout
-//                [chunk of 4 channels][pixel][4 channels]; in that layout rows (pixels) are 16 B apart, so each of the
-//                nine filter taps is just a different descriptor START ADDRESS into the same tile -- the im2col is free
-//                and every input element is converted once, not nine times.
-// B operand      weights pre-split (hi/lo) and pre-packed per (n-tile, K-block, tap) by pack_weights_kernel into the
-//                exact shared-memory image, streamed by 1-D bulk TMA copies through a 4-stage ring.
-// MMA            tcgen05.mma.cta_group::1.kind::tf32, M=128, N=NT, K=8; accumulators in TMEM (2 x NT columns);
-//                3 products per MAC (hi*hi + hi*lo + lo*hi) reproduce fp32 to ~1e-6.
-// Epilogue       tcgen05.ld 32x32b -> registers -> x out_scale -> NCHW stores (32 B runs per lane group).
-// Warp roles     w0 TMA(x)  w1 TMA(weights)  w2 MMA issue + TMEM alloc  w3..w6 convert, then epilogue.
+// CTA            persistent (one per SM), walks 16x16-pixel x NT-channel output tiles; NT in {32,64,128}.
+// A operand      the input halo tile ((16+k-1)^2 pixels x 16 channels per K-block) arrives by ONE 4-D TMA box load with
+//                hardware zero fill outside the image (= the conv padding), is converted ONCE by the consumer warps
+//                (x in_scale, split into tf32 hi + lo, cvt.rna) into the UMMA no-swizzle K-major layout
+//                [chunk of 4 channels][pixel][4 channels]; rows (pixels) are 16 B apart, so each filter tap is just a
+//                different descriptor START ADDRESS into the same tile -- the im2col is free and every input element
+//                is converted once, not k*k times.
+// B operand      weights pre-split (hi/lo) and pre-packed per (n-tile, K-block, tap) by pack_weights_kernel into the exact
+//                shared-memory image, streamed by 1-D bulk TMA copies through a 4-stage ring.  pack_weights_kernel also
+//                flags all-zero (n-tile, K-block, tap) blocks; they are skipped by every role (the phase-major stride-2
+//                formulation has 7 structurally zero blocks out of 16).
+// MMA            tcgen05.mma.cta_group::1.kind::tf32, M=128, N=NT, K=8; 3 products per MAC (hi*hi + hi*lo + lo*hi).
+// Accumulation   The tensor core adds into its fp32 accumulator with truncation toward zero (measured:
+//                tools/tc_rounding.py), a systematic error growing with the chain length.  So only ONE K-block
+//                (<= 54 MMA steps) is accumulated in TMEM; two TMEM accumulator sets ping-pong, and the consumer warps
+//                drain each finished partial sum (tcgen05.ld) into fp32 REGISTERS with round-to-nearest adds while the
+//                tensor core works on the next K-block / the next tile.  The epilogue (x out_scale) runs from registers.
+// Warp roles     w0 TMA(x)  w1 TMA(weights)  w2 MMA issue + TMEM alloc  (w3 idle)  w4..w11 convert + drain + epilogue;
+//                setmaxnreg moves registers from the producer warpgroup to the two consumer warpgroups (128 accumulators/thread).
 #include "common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
@@ -90,10 +97,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 // UMMA shared-memory descriptor, SWIZZLE_NONE ("interleave") canonical layouts (cute/arch/mma_sm100_desc.hpp):
 // bits [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout type 0.
 //   K-major : ((8,m),(4,2)) : rows 16 B apart inside a core matrix, SBO between 8-row groups, LBO between the 16-byte K chunks.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
 // Instruction descriptor (UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format TF32 (2) @7/@10, a/b major @15/@16 (0 = K),
 // N>>3 @17, M>>4 @24.
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
@@ -113,14 +116,16 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
-constexpr int KB_CH = 16;   // input channels per K-block (two UMMA K=8 steps)
+constexpr int KB_CH = 16;      // input channels per K-block (two UMMA K=8 steps)
+constexpr int MAX_KB = 128;    // K-blocks per conv (I <= 2048); zero-block masks live in 4 registers per lane
 
 struct PackP {
-    const float* w; float* wp;
+    const float* w; float* wp; uint32_t* mask;
     int O, I, K, NT, n_tiles, num_kb, flip, w_is_IO;
 };
 
 // wp[n_tile][kb][tap][half: hi,lo][chunk 0..3][n 0..NT-1][4 channels]  -- per (n_tile,kb,tap) exactly the smem image
+// mask[n_tile][kb] bit tap = 1 iff the block holds a non-zero weight
 __global__ void pack_weights_kernel(PackP p) {
     const int KK = p.K * p.K;
     const int64_t total = (int64_t)p.n_tiles * p.num_kb * KK * 4 * p.NT;     // one thread = one (chunk, n) = 4 channels, hi and lo
@@ -133,6 +138,7 @@ __global__ void pack_weights_kernel(PackP p) {
         int ky = tap / p.K, kx = tap - ky * p.K;
         if (p.flip) { ky = p.K - 1 - ky; kx = p.K - 1 - kx; }
         float hi[4], lo[4];
+        bool nz = false;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int i = kb * KB_CH + chunk * 4 + j;
@@ -141,55 +147,107 @@ __global__ void pack_weights_kernel(PackP p) {
                 int64_t src = p.w_is_IO ? (((int64_t)i * p.O + o) * p.K + ky) * p.K + kx : (((int64_t)o * p.I + i) * p.K + ky) * p.K + kx;
                 v = __ldg(p.w + src);
             }
+            nz |= (v != 0.f);
             split_tf32(v, hi[j], lo[j]);
         }
         int64_t blk = (((int64_t)nt * p.num_kb + kb) * KK + tap) * (2 * 4 * p.NT * 4);
         int64_t off = ((int64_t)chunk * p.NT + n) * 4;
         *reinterpret_cast<float4*>(p.wp + blk + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<float4*>(p.wp + blk + 4 * p.NT * 4 + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        // NT is a multiple of 32 and `total` a multiple of 32: the 32 lanes of a warp always share (nt, kb, tap, chunk)
+        const unsigned any = __ballot_sync(0xffffffffu, nz);
+        if (any != 0u && (threadIdx.x & 31) == 0) atomicOr(p.mask + (int64_t)nt * p.num_kb + kb, 1u << tap);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ the conv kernel
-constexpr int TILE_W = 16, TILE_H = 16;   // output pixels per CTA: two 8x16 UMMA M-tiles side by side
+constexpr int TILE_W = 16, TILE_H = 16;   // output pixels per tile: two 8x16 UMMA M-tiles side by side
 constexpr int W_STAGES = 4;
-constexpr int NUM_THREADS = 7 * 32;
-constexpr int CVT_THREADS = 128;
+constexpr int CONS_WARPS = 8;
+constexpr int CONS_THREADS = CONS_WARPS * 32;
+constexpr int PROD_WARPS = 4;           // one warpgroup: TMA(x), TMA(weights), MMA, idle -- so that setmaxnreg can shift registers
+constexpr int NUM_THREADS = (PROD_WARPS + CONS_WARPS) * 32;
+constexpr int MAX_SCALE_CH = MAX_KB * KB_CH;
+constexpr int CVT_ITEMS = (4 * 20 * 18 + CONS_THREADS - 1) / CONS_THREADS;   // (chunk, pixel) items per consumer thread, worst case
 
 struct TcP {
-    const float* wp; float* y; const float* in_scale; const float* out_scale;
+    const float* wp; const uint32_t* mask; float* y; const float* in_scale; const float* out_scale;
     int Nimg, I, O, OH, OW, K, pad_y, pad_x;
-    int tiles_x, tiles_y, NT, num_kb, nprod;
+    int tiles_x, tiles_y, n_tiles, num_kb, nprod, total_tiles;
     int boxW, boxH;            // converted halo tile in pixels; boxW is its smem pixel pitch
     int rawW;                  // width of the raw TMA box (>= boxW: the box must start on a 16-byte boundary in global memory)
-    uint32_t tmem_cols;
-    int dbg;                   // GG_TC_DBG bitmask (debug experiments only)
 };
 
-struct SmemLayout {   // byte offsets from the 128-byte aligned dynamic smem base
-    uint32_t raw[2], cvt[2][2], wst[W_STAGES], bars, tmem_slot, total;
+struct SmemLayout {   // byte offsets from the 128-byte aligned dynamic smem base (arithmetic, so that stage indices stay in registers)
+    uint32_t raw0, rtile, cvt0, tile, w0, wbytes, scale, bars, tmem_slot, total;
+    __host__ __device__ uint32_t raw(int s) const { return raw0 + (uint32_t)s * rtile; }
+    __host__ __device__ uint32_t cvt(int s, int h) const { return cvt0 + (uint32_t)(2 * s + h) * tile; }
+    __host__ __device__ uint32_t wst(int s) const { return w0 + (uint32_t)s * wbytes; }
 };
 
 __host__ __device__ inline SmemLayout make_layout(int boxW, int boxH, int rawW, int NT) {
     SmemLayout L;
-    uint32_t tile = (uint32_t)(KB_CH * boxW * boxH * 4), rtile = (uint32_t)(KB_CH * rawW * boxH * 4);
-    tile = (tile + 127) & ~127u;
-    rtile = (rtile + 127) & ~127u;
+    L.tile = ((uint32_t)(KB_CH * boxW * boxH * 4) + 127) & ~127u;
+    L.rtile = ((uint32_t)(KB_CH * rawW * boxH * 4) + 127) & ~127u;
+    L.wbytes = (uint32_t)(2 * 4 * NT * 16);
     uint32_t off = 0;
-    for (int s = 0; s < 2; ++s) { L.raw[s] = off; off += rtile; }
-    for (int s = 0; s < 2; ++s) for (int h = 0; h < 2; ++h) { L.cvt[s][h] = off; off += tile; }
-    for (int s = 0; s < W_STAGES; ++s) { L.wst[s] = off; off += (uint32_t)(2 * 4 * NT * 16); }
-    L.bars = off; off += 256;          // 2 raw_full, 2 raw_empty, 2 cvt_full, 2 cvt_empty, W_STAGES w_full, W_STAGES w_empty, acc_full
+    L.raw0 = off; off += 2 * L.rtile;
+    L.cvt0 = off; off += 4 * L.tile;
+    L.w0 = off; off += W_STAGES * L.wbytes;
+    L.scale = off; off += MAX_SCALE_CH * 4;
+    L.bars = off; off += 256;
     L.tmem_slot = off; off += 16;
     L.total = off;
     return L;
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+struct TileCoord { int tx, ty, img, nt; };
+__device__ __forceinline__ TileCoord decode_tile(int t, const TcP& p) {
+    TileCoord c;
+    c.tx = t % p.tiles_x; t /= p.tiles_x;
+    c.ty = t % p.tiles_y; t /= p.tiles_y;
+    c.img = t % p.Nimg;
+    c.nt = t / p.Nimg;
+    return c;
+}
+
+// Zero-block masks of one n-tile, spread over the lanes of a warp: lane l holds kb = l + 32*i in mk[i].
+struct KbMasks {
+    uint32_t mk[MAX_KB / 32];
+    int last_kb;            // highest K-block with any live tap, -1 if the whole n-tile is zero
+    __device__ __forceinline__ void load(const TcP& p, int nt, int lane) {
+        last_kb = -1;
+#pragma unroll
+        for (int i = 0; i < MAX_KB / 32; ++i) {
+            const int kb = lane + 32 * i;
+            uint32_t m = 0u;
+            if (kb < p.num_kb) m = p.mask ? __ldg(p.mask + (size_t)nt * p.num_kb + kb) : 0x1FFu;
+            mk[i] = m;
+            const unsigned b = __ballot_sync(0xffffffffu, m != 0u);
+            if (b) last_kb = 32 * i + 31 - __clz(b);
+        }
+    }
+    __device__ __forceinline__ uint32_t get(int kb) const {
+        uint32_t v = 0;
+#pragma unroll
+        for (int i = 0; i < MAX_KB / 32; ++i) {
+            const uint32_t t = __shfl_sync(0xffffffffu, mk[i], kb & 31);
+            if ((kb >> 5) == i) v = t;
+        }
+        return v;
+    }
+};
+
+template <int NT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, TcP p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-    const SmemLayout L = make_layout(p.boxW, p.boxH, p.rawW, p.NT);
+    const SmemLayout L = make_layout(p.boxW, p.boxH, p.rawW, NT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const uint32_t bar0 = base + L.bars;
@@ -197,195 +255,285 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     auto BAR_RAW_EMPTY = [&](int s) { return bar0 + 8u * (2 + s); };
     auto BAR_CVT_FULL = [&](int s) { return bar0 + 8u * (4 + s); };
     auto BAR_CVT_EMPTY = [&](int s) { return bar0 + 8u * (6 + s); };
-    auto BAR_W_FULL = [&](int s) { return bar0 + 8u * (8 + s); };
-    auto BAR_W_EMPTY = [&](int s) { return bar0 + 8u * (8 + W_STAGES + s); };
-    const uint32_t BAR_ACC_FULL = bar0 + 8u * (8 + 2 * W_STAGES);
+    auto BAR_ACC_FULL = [&](int s) { return bar0 + 8u * (8 + s); };
+    auto BAR_ACC_EMPTY = [&](int s) { return bar0 + 8u * (10 + s); };
+    auto BAR_W_FULL = [&](int s) { return bar0 + 8u * (12 + s); };
+    auto BAR_W_EMPTY = [&](int s) { return bar0 + 8u * (12 + W_STAGES + s); };
 
-    // tile coordinates
-    int bid = blockIdx.x;
-    const int tx = bid % p.tiles_x; bid /= p.tiles_x;
-    const int ty = bid % p.tiles_y;
-    const int img = bid / p.tiles_y;
-    const int nt = blockIdx.y;
-    const int ox0 = tx * TILE_W, oy0 = ty * TILE_H;
     const int KK = p.K * p.K;
     const int npix = p.boxW * p.boxH;
     const int rpix = p.rawW * p.boxH;
     const uint32_t raw_bytes = (uint32_t)(KB_CH * rpix * 4);
-    // TMA box origin: x aligned down to 4 floats (16 B) and both clamped to >= 0; the converter undoes the shift
-    const int cx = max((ox0 - p.pad_x) & ~3, 0), cy = max(oy0 - p.pad_y, 0);
-    const uint32_t w_bytes = (uint32_t)(2 * 4 * p.NT * 16);
+    constexpr uint32_t w_bytes = (uint32_t)(2 * 4 * NT * 16);
+    constexpr uint32_t TMEM_COLS = 4 * NT;      // 2 accumulator sets x 2 sub-tiles x NT columns
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(BAR_RAW_FULL(s), 1); mbar_init(BAR_RAW_EMPTY(s), CVT_THREADS);
-            mbar_init(BAR_CVT_FULL(s), CVT_THREADS); mbar_init(BAR_CVT_EMPTY(s), 1);
+            mbar_init(BAR_RAW_FULL(s), 1); mbar_init(BAR_RAW_EMPTY(s), CONS_WARPS);
+            mbar_init(BAR_CVT_FULL(s), CONS_WARPS); mbar_init(BAR_CVT_EMPTY(s), 1);
+            mbar_init(BAR_ACC_FULL(s), 1); mbar_init(BAR_ACC_EMPTY(s), CONS_WARPS);
         }
         for (int s = 0; s < W_STAGES; ++s) { mbar_init(BAR_W_FULL(s), 1); mbar_init(BAR_W_EMPTY(s), 1); }
-        mbar_init(BAR_ACC_FULL, 1);
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(base + L.tmem_slot, p.tmem_cols);
+    if (warp == 2) tmem_alloc(base + L.tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + L.tmem_slot);
 
+    if (warp < PROD_WARPS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
-        // ===== x producer: one 4-D TMA box per K-block.  Boxes that stick out on the right / bottom are zero-filled by the
-        // TMA unit (= the conv padding).  The innermost start coordinate must land on a 16-byte boundary (an unaligned or
-        // negative one faults with "illegal instruction"), so the box starts at the aligned, clamped (cx, cy) and the
+        // ===== x producer: one 4-D TMA box per live K-block.  Boxes that stick out on the right / bottom are zero-filled by
+        // the TMA unit (= the conv padding).  The innermost start coordinate must land on a 16-byte boundary (an unaligned
+        // or negative one faults with "illegal instruction"), so the box starts at the aligned, clamped (cx, cy) and the
         // converter shifts it back and re-creates the left / top padding (see cvt_src below).
-        if (lane == 0) {
+        KbMasks M; int cur_nt = -1;
+        uint32_t kbc = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const TileCoord tc = decode_tile(t, p);
+            if (tc.nt != cur_nt) { M.load(p, tc.nt, lane); cur_nt = tc.nt; }
+            const int cx = max((tc.tx * TILE_W - p.pad_x) & ~3, 0), cy = max(tc.ty * TILE_H - p.pad_y, 0);
             for (int kb = 0; kb < p.num_kb; ++kb) {
-                const int s = kb & 1;
-                mbar_wait(BAR_RAW_EMPTY(s), ((kb >> 1) & 1) ^ 1);
-                if (p.dbg & 16) { mbar_arrive(BAR_RAW_FULL(s)); continue; }
-                mbar_expect_tx(BAR_RAW_FULL(s), raw_bytes);
-                tma_load_4d(base + L.raw[s], &xmap, BAR_RAW_FULL(s), cx, cy, kb * KB_CH, img);
+                if (M.get(kb) == 0u) continue;
+                const int s = kbc & 1;
+                mbar_wait(BAR_RAW_EMPTY(s), ((kbc >> 1) & 1) ^ 1);
+                if (lane == 0) {
+                    mbar_expect_tx(BAR_RAW_FULL(s), raw_bytes);
+                    tma_load_4d(base + L.raw(s), &xmap, BAR_RAW_FULL(s), cx, cy, kb * KB_CH, tc.img);
+                }
+                __syncwarp();
+                ++kbc;
             }
         }
     } else if (warp == 1) {
-        // ===== weight producer: one bulk copy (hi+lo image of this tap) per ring stage
-        if (lane == 0) {
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wp) + (size_t)nt * p.num_kb * KK * w_bytes;
-            const int total = p.num_kb * KK;
-            for (int g = 0; g < total; ++g) {
-                const int s = g % W_STAGES;
-                mbar_wait(BAR_W_EMPTY(s), ((g / W_STAGES) & 1) ^ 1);
-                mbar_expect_tx(BAR_W_FULL(s), w_bytes);
-                bulk_load(base + L.wst[s], src + (size_t)g * w_bytes, w_bytes, BAR_W_FULL(s));
+        // ===== weight producer: one bulk copy (hi+lo image of one live tap) per ring stage
+        KbMasks M; int cur_nt = -1;
+        uint32_t g = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const TileCoord tc = decode_tile(t, p);
+            if (tc.nt != cur_nt) { M.load(p, tc.nt, lane); cur_nt = tc.nt; }
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wp) + (size_t)tc.nt * p.num_kb * KK * w_bytes;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                const uint32_t m = M.get(kb);
+                if (m == 0u) continue;
+                for (int tap = 0; tap < KK; ++tap) {
+                    if (!((m >> tap) & 1u)) continue;
+                    const int s = g % W_STAGES;
+                    mbar_wait(BAR_W_EMPTY(s), ((g / W_STAGES) & 1) ^ 1);
+                    if (lane == 0) {
+                        mbar_expect_tx(BAR_W_FULL(s), w_bytes);
+                        bulk_load(base + L.wst(s), src + (size_t)(kb * KK + tap) * w_bytes, w_bytes, BAR_W_FULL(s));
+                    }
+                    __syncwarp();
+                    ++g;
+                }
             }
         }
     } else if (warp == 2) {
-        // ===== MMA issuer (one thread)
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(128, p.NT, 0, 0);
-            const uint32_t a_lbo = (uint32_t)npix * 16u, a_sbo = (uint32_t)p.boxW * 16u;
-            const uint32_t b_lbo = (uint32_t)p.NT * 16u, b_sbo = 128u;
-            int g = 0;
+        // ===== MMA issuer (lane 0 issues; the whole warp walks the loop so that the mask shuffles stay convergent)
+        KbMasks M; int cur_nt = -1;
+        uint32_t kbc = 0, g = 0;
+        const uint32_t idesc = umma_idesc_tf32(128, NT, 0, 0);
+        // descriptor words: lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version 1 (bit 46)
+        const uint32_t a_lbo16 = (uint32_t)npix, a_sbo16 = (uint32_t)p.boxW;            // in 16-byte units
+        const uint32_t a_lo_w = (a_lbo16 & 0x3FFFu) << 16, a_hi_w = (a_sbo16 & 0x3FFFu) | (1u << 14);
+        const uint32_t b_lo_w = ((uint32_t)NT & 0x3FFFu) << 16, b_hi_w = 8u | (1u << 14);   // LBO = NT*16 B, SBO = 128 B
+        auto mk_desc = [](uint32_t lo_w, uint32_t hi_w, uint32_t addr16) -> uint64_t {
+            return ((uint64_t)hi_w << 32) | (uint64_t)(lo_w | (addr16 & 0x3FFFu));
+        };
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const TileCoord tc = decode_tile(t, p);
+            if (tc.nt != cur_nt) { M.load(p, tc.nt, lane); cur_nt = tc.nt; }
             for (int kb = 0; kb < p.num_kb; ++kb) {
-                const int cs = kb & 1;
-                mbar_wait(BAR_CVT_FULL(cs), (kb >> 1) & 1);
+                const uint32_t m = M.get(kb);
+                if (m == 0u) continue;
+                const int cs = kbc & 1;
+                mbar_wait(BAR_CVT_FULL(cs), (kbc >> 1) & 1);
+                mbar_wait(BAR_ACC_EMPTY(cs), ((kbc >> 1) & 1) ^ 1);       // accumulator set cs was drained (two K-blocks ago)
                 tc_fence_after();
-                const uint32_t a_hi0 = base + L.cvt[cs][0], a_lo0 = base + L.cvt[cs][1];
-                for (int tap = 0; tap < KK; ++tap, ++g) {
+                const uint32_t a_hi16 = (base + L.cvt(cs, 0)) >> 4, a_lo16 = (base + L.cvt(cs, 1)) >> 4;
+                const uint32_t d0 = tmem_base + (uint32_t)(cs * 2 * NT);
+                bool first = true;
+                for (int tap = 0; tap < KK; ++tap) {
+                    if (!((m >> tap) & 1u)) continue;
                     const int ws = g % W_STAGES;
                     mbar_wait(BAR_W_FULL(ws), (g / W_STAGES) & 1);
                     tc_fence_after();
-                    const int ky = tap / p.K, kx = tap - ky * p.K;
-                    const uint32_t b_hi0 = base + L.wst[ws], b_lo0 = b_hi0 + 4u * p.NT * 16u;
+                    if (lane == 0) {
+                        const int ky = tap / p.K, kx = tap - ky * p.K;
+                        const uint32_t tapoff = (uint32_t)(ky * p.boxW + kx);
+                        const uint32_t b_hi16 = (base + L.wst(ws)) >> 4, b_lo16 = b_hi16 + 4u * NT;
 #pragma unroll
-                    for (int sub = 0; sub < 2; ++sub) {
+                        for (int sub = 0; sub < 2; ++sub) {
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
-                            const uint32_t a_off = (uint32_t)(((p.dbg & 1) ? 8 * sub : (ky * p.boxW + 8 * sub + kx)) * 16) + (uint32_t)(2 * ks) * a_lbo;
-                            const uint32_t b_off = (uint32_t)(2 * ks) * b_lbo;
-                            const uint64_t a_hi = umma_desc(a_hi0 + a_off, a_lbo, a_sbo);
-                            const uint64_t b_hi = umma_desc(b_hi0 + b_off, b_lbo, b_sbo);
-                            const uint32_t d = tmem_base + (uint32_t)(sub * p.NT);
-                            if (p.dbg & 8) continue;
-                            umma_tf32(d, a_hi, b_hi, idesc, (kb | tap | ks) != 0 ? 1u : 0u);
-                            if (p.nprod == 3) {
-                                const uint64_t a_lo = umma_desc(a_lo0 + a_off, a_lbo, a_sbo);
-                                const uint64_t b_lo = umma_desc(b_lo0 + b_off, b_lbo, b_sbo);
-                                umma_tf32(d, a_hi, b_lo, idesc, 1u);
-                                umma_tf32(d, a_lo, b_hi, idesc, 1u);
+                            for (int ks = 0; ks < 2; ++ks) {
+                                const uint32_t a_off = tapoff + 8u * sub + (uint32_t)(2 * ks) * a_lbo16;
+                                const uint32_t b_off = (uint32_t)(2 * ks) * NT;
+                                const uint64_t a_hi = mk_desc(a_lo_w, a_hi_w, a_hi16 + a_off);
+                                const uint64_t b_hi = mk_desc(b_lo_w, b_hi_w, b_hi16 + b_off);
+                                const uint32_t d = d0 + (uint32_t)(sub * NT);
+                                umma_tf32(d, a_hi, b_hi, idesc, (first && ks == 0) ? 0u : 1u);
+                                if (p.nprod == 3) {
+                                    const uint64_t a_lo = mk_desc(a_lo_w, a_hi_w, a_lo16 + a_off);
+                                    const uint64_t b_lo = mk_desc(b_lo_w, b_hi_w, b_lo16 + b_off);
+                                    umma_tf32(d, a_hi, b_lo, idesc, 1u);
+                                    umma_tf32(d, a_lo, b_hi, idesc, 1u);
+                                }
                             }
                         }
+                        umma_commit(BAR_W_EMPTY(ws));      // frees the weight stage when these MMAs have read it
                     }
-                    umma_commit(BAR_W_EMPTY(ws));      // frees the weight stage when these MMAs have read it
+                    __syncwarp();
+                    first = false;
+                    ++g;
                 }
-                umma_commit(BAR_CVT_EMPTY(cs));        // frees the converted tile
+                if (lane == 0) {
+                    umma_commit(BAR_CVT_EMPTY(cs));        // frees the converted tile
+                    umma_commit(BAR_ACC_FULL(cs));         // this K-block's partial sums are complete in TMEM set cs
+                }
+                __syncwarp();
+                ++kbc;
             }
-            umma_commit(BAR_ACC_FULL);
         }
+    }
     } else {
-        // ===== converter warps (w3..w6), then epilogue
-        const int ct = threadIdx.x - 3 * 32;            // 0..127
-        const float* sc = p.in_scale ? p.in_scale + (size_t)img * p.I : nullptr;
-        // source index inside the raw box for each converted pixel this thread owns (-1 = conv padding -> 0)
-        constexpr int MAXPX = 4;
-        int cvt_src[MAXPX];
-        {
-            const int dx = (ox0 - p.pad_x) - cx, dy = (oy0 - p.pad_y) - cy;     // converted (r,c) <- raw (r+dy, c+dx)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        // ===== consumer warps (w4..w11): convert K-block j, then drain the partial sums of K-block j-1 into registers
+        // (and store the finished tile) while the tensor core works on K-block j.
+        const int cw = warp - PROD_WARPS;               // 0..7
+        const int ct = threadIdx.x - PROD_WARPS * 32;   // 0..255
+        const int q = warp & 3;                         // TMEM lane quarter this warp may access
+        const int hcol = cw >> 2;                       // which half of the NT accumulator columns this warp owns
+        constexpr int HN = NT / 2;
+        float acc[2][HN];
 #pragma unroll
-            for (int t = 0; t < MAXPX; ++t) {
-                const int px = ct + t * CVT_THREADS;
-                const int rr = px / p.boxW + dy, cc = px % p.boxW + dx;
-                cvt_src[t] = (px < npix && rr >= 0 && cc >= 0 && rr < p.boxH && cc < p.rawW) ? rr * p.rawW + cc : -1;
-            }
-        }
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-            const int s = kb & 1;
-            mbar_wait(BAR_RAW_FULL(s), (kb >> 1) & 1);
-            mbar_wait(BAR_CVT_EMPTY(s), ((kb >> 1) & 1) ^ 1);
-            const float* raw = reinterpret_cast<const float*>(gbase + L.raw[s]);
-            float4* hi = reinterpret_cast<float4*>(gbase + L.cvt[s][0]);
-            float4* lo = reinterpret_cast<float4*>(gbase + L.cvt[s][1]);
-#pragma unroll 1
-            for (int chunk = 0; chunk < 4; ++chunk) {
-                float s0 = 1.f, s1 = 1.f, s2 = 1.f, s3 = 1.f;
-                if (sc) {
-                    const int c = kb * KB_CH + chunk * 4;
-                    s0 = (c + 0 < p.I) ? __ldg(sc + c + 0) : 0.f; s1 = (c + 1 < p.I) ? __ldg(sc + c + 1) : 0.f;
-                    s2 = (c + 2 < p.I) ? __ldg(sc + c + 2) : 0.f; s3 = (c + 3 < p.I) ? __ldg(sc + c + 3) : 0.f;
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int j = 0; j < HN; ++j) acc[s][j] = 0.f;
+        float* sc_s = reinterpret_cast<float*>(gbase + L.scale);
+        KbMasks M; int cur_nt = -1, cur_img = -1;
+        uint32_t kbc = 0;
+        bool pend = false, pend_last = false;
+        uint32_t pend_kbc = 0;
+        TileCoord pend_tc{0, 0, 0, 0};
+        const size_t plane = (size_t)p.OH * p.OW;
+
+        auto store_tile = [&](const TileCoord& tc) {
+            const int m = q * 32 + lane;                // accumulator row = pixel inside the 8x16 sub-tile
+            const int r = m >> 3, c = m & 7;
+            const int oy = tc.ty * TILE_H + r;
+            const int n0 = tc.nt * NT + hcol * HN;
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+                const int ox = tc.tx * TILE_W + 8 * sub + c;
+                const bool pix_ok = (oy < p.OH) && (ox < p.OW);
+                float* yp = p.y + ((size_t)tc.img * p.O + n0) * plane + (size_t)oy * p.OW + ox;
+                const float* os = p.out_scale ? p.out_scale + (size_t)tc.img * p.O + n0 : nullptr;
+                const int nvalid = pix_ok ? min(HN, p.O - n0) : 0;
+#pragma unroll
+                for (int j = 0; j < HN; ++j) {
+                    if (j < nvalid) {
+                        float val = acc[sub][j];
+                        if (os) val *= __ldg(os + j);
+                        *yp = val;
+                    }
+                    yp += plane;                        // running pointer: one live address instead of HN
+                    acc[sub][j] = 0.f;
                 }
-                const float* r0 = raw + (chunk * 4) * rpix;
+            }
+        };
+        auto drain = [&](uint32_t k) {
+            const int s = k & 1;
+            mbar_wait(BAR_ACC_FULL(s), (k >> 1) & 1);
+            tc_fence_after();
 #pragma unroll
-                for (int t = 0; t < MAXPX; ++t) {
-                    const int px = ct + t * CVT_THREADS;
-                    if (px >= npix) break;
-                    const int src = cvt_src[t];
+            for (int sub = 0; sub < 2; ++sub) {
+#pragma unroll
+                for (int cb = 0; cb < HN; cb += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 2 * NT + sub * NT + hcol * HN + cb), v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[sub][cb + j] += __uint_as_float(v[j]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR_ACC_EMPTY(s));
+        };
+
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const TileCoord tc = decode_tile(t, p);
+            if (tc.nt != cur_nt) { M.load(p, tc.nt, lane); cur_nt = tc.nt; }
+            if (M.last_kb < 0) {                        // the whole n-tile of weights is zero: the output tile is zero
+                if (pend) { drain(pend_kbc); if (pend_last) store_tile(pend_tc); pend = false; }
+                store_tile(tc);
+                continue;
+            }
+            if (p.in_scale && tc.img != cur_img) {      // stage this image's per-channel input scales (styles)
+                named_bar_sync(1, CONS_THREADS);
+                for (int i = ct; i < p.num_kb * KB_CH; i += CONS_THREADS)
+                    sc_s[i] = (i < p.I) ? __ldg(p.in_scale + (size_t)tc.img * p.I + i) : 0.f;
+                named_bar_sync(1, CONS_THREADS);
+                cur_img = tc.img;
+            }
+            // source index inside the raw box for each converted (chunk, pixel) item this thread owns (-1 = padding -> 0)
+            const int ox0 = tc.tx * TILE_W, oy0 = tc.ty * TILE_H;
+            const int cx = max((ox0 - p.pad_x) & ~3, 0), cy = max(oy0 - p.pad_y, 0);
+            const int dx = (ox0 - p.pad_x) - cx, dy = (oy0 - p.pad_y) - cy;       // converted (r,c) <- raw (r+dy, c+dx)
+            int cvt_src[CVT_ITEMS];
+#pragma unroll
+            for (int it = 0; it < CVT_ITEMS; ++it) {
+                const int idx = ct + it * CONS_THREADS;
+                const int chunk = idx / npix, px = idx - chunk * npix;
+                const int rr = px / p.boxW + dy, cc = px % p.boxW + dx;
+                cvt_src[it] = (chunk < 4 && rr >= 0 && cc >= 0 && rr < p.boxH && cc < p.rawW) ? (chunk * 4) * rpix + rr * p.rawW + cc
+                                                                                               : (chunk < 4 ? -1 : -2);
+            }
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                if (M.get(kb) == 0u) continue;
+                const int s = kbc & 1;
+                mbar_wait(BAR_RAW_FULL(s), (kbc >> 1) & 1);
+                mbar_wait(BAR_CVT_EMPTY(s), ((kbc >> 1) & 1) ^ 1);
+                const float* raw = reinterpret_cast<const float*>(gbase + L.raw(s));
+                float4* hi = reinterpret_cast<float4*>(gbase + L.cvt(s, 0));
+                float4* lo = reinterpret_cast<float4*>(gbase + L.cvt(s, 1));
+#pragma unroll
+                for (int it = 0; it < CVT_ITEMS; ++it) {
+                    const int src = cvt_src[it];
+                    if (src == -2) continue;            // past the end of the tile
+                    const int idx = ct + it * CONS_THREADS;
                     float4 h = make_float4(0.f, 0.f, 0.f, 0.f), l = h;
                     if (src >= 0) {
-                        split_tf32(r0[src] * s0, h.x, l.x);
-                        split_tf32(r0[rpix + src] * s1, h.y, l.y);
-                        split_tf32(r0[2 * rpix + src] * s2, h.z, l.z);
-                        split_tf32(r0[3 * rpix + src] * s3, h.w, l.w);
+                        float v0 = raw[src], v1 = raw[src + rpix], v2 = raw[src + 2 * rpix], v3 = raw[src + 3 * rpix];
+                        if (p.in_scale) {
+                            const int chunk = idx / npix;
+                            const float4 sv = *reinterpret_cast<const float4*>(sc_s + kb * KB_CH + chunk * 4);
+                            v0 *= sv.x; v1 *= sv.y; v2 *= sv.z; v3 *= sv.w;
+                        }
+                        split_tf32(v0, h.x, l.x); split_tf32(v1, h.y, l.y);
+                        split_tf32(v2, h.z, l.z); split_tf32(v3, h.w, l.w);
                     }
-                    hi[chunk * npix + px] = h;
-                    lo[chunk * npix + px] = l;
+                    hi[idx] = h;
+                    lo[idx] = l;
+                    if (NT == 128 && (it & 1)) asm volatile("" ::: "memory");   // bound the live range: 128 accumulators are resident
                 }
-            }
-            fence_proxy_async();                        // generic-proxy writes -> visible to the tensor core (async proxy)
-            mbar_arrive(BAR_CVT_FULL(s));
-            mbar_arrive(BAR_RAW_EMPTY(s));
-        }
-
-        // epilogue: this warp may touch TMEM lanes 32*(warp%4) .. +31
-        mbar_wait(BAR_ACC_FULL, 0);
-        tc_fence_after();
-        const int q = warp & 3;
-        const int m = q * 32 + lane;                    // accumulator row = pixel inside the 8x16 sub-tile
-        const int r = m >> 3, c = m & 7;
-        const int oy = oy0 + r;
-        const int n0 = nt * p.NT;
-        const size_t plane = (size_t)p.OH * p.OW;
-        for (int sub = 0; sub < 2; ++sub) {
-            const int ox = ox0 + 8 * sub + c;
-            const bool pix_ok = (oy < p.OH) && (ox < p.OW);
-            float* yp = p.y + ((size_t)img * p.O + n0) * plane + (size_t)oy * p.OW + ox;
-            for (int cb = 0; cb < p.NT; cb += 16) {
-                uint32_t v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * p.NT + cb), v);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int o = n0 + cb + j;
-                    if (pix_ok && o < p.O) {
-                        float val = __uint_as_float(v[j]);
-                        if (p.out_scale) val *= __ldg(p.out_scale + (size_t)img * p.O + o);
-                        yp[(size_t)(cb + j) * plane] = val;
-                    }
-                }
+                fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(BAR_CVT_FULL(s)); mbar_arrive(BAR_RAW_EMPTY(s)); }
+                if (pend) { drain(pend_kbc); if (pend_last) store_tile(pend_tc); }
+                pend = true; pend_kbc = kbc; pend_last = (kb == M.last_kb); pend_tc = tc;
+                ++kbc;
             }
         }
+        if (pend) { drain(pend_kbc); if (pend_last) store_tile(pend_tc); }
         tc_fence_before();
     }
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, p.tmem_cols);
+        tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -407,17 +555,34 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+template <int NT>
+int launch_conv_tc(const CUtensorMap& xmap, const TcP& p, cudaStream_t st) {
+    const SmemLayout L = make_layout(p.boxW, p.boxH, p.rawW, NT);
+    const size_t smem = L.total + 128;
+    if (smem > 227 * 1024) { gg::set_error("conv2d(tc): shared-memory layout of %zu bytes does not fit", smem); return GG_EUNSUPPORTED; }
+    static std::atomic<int> attr_set{0};
+    if (!attr_set.load()) {
+        GG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set.store(1);
+    }
+    const int grid = p.total_tiles < GG_NUM_SMS ? p.total_tiles : GG_NUM_SMS;
+    conv_tc_kernel<NT><<<grid, NUM_THREADS, smem, st>>>(xmap, p);
+    return gg::check_launch("conv2d(tc)");
+}
+
 }  // namespace
 
 namespace gg {
 
 bool conv2d_tc_eligible(int N, int I, int H, int W, int O, int KH, int KW, int OH, int OW, int stride, int pad_y, int pad_x,
                         int transposed) {
-    if (stride != 1 || KH != KW || (KH != 1 && KH != 3)) return false;
-    if (transposed && (pad_y > KH - 1 || pad_x > KW - 1)) return false;
+    if (stride != 1 || KH != KW || KH < 1 || KH > 3) return false;
+    if (pad_y > KH - 1 || pad_x > KW - 1) return false;
     if (N < 1 || I < 16 || O < 16) return false;       // 3-channel fromRGB / ToRGB stay on the FFMA path (HBM-bound, AI ~ 1.4)
+    if (I > MAX_KB * KB_CH) return false;
     if (W % 4 != 0) return false;                      // TMA global strides must be multiples of 16 bytes
-    if (OW < 16 || OH < 16) return false;              // 4x4 / 8x8 maps: < 0.3 % of the FLOPs, served by the FFMA kernel
+    if (OW < 8 || OH < 8) return false;                // 4x4 maps: < 0.1 % of the FLOPs, served by the FFMA kernel
+    (void)H; (void)transposed;
     return true;
 }
 
@@ -425,20 +590,21 @@ int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int
               int flip_w, int w_is_IO, const float* in_scale, const float* out_scale, int nprod, cudaStream_t st) {
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) { set_error("conv2d(tc): x must be 16-byte aligned"); return GG_EINVAL; }
     const int OH = H + 2 * pad_y - K + 1, OW = W + 2 * pad_x - K + 1;
-    const int NT = O >= 128 ? 128 : ((O + 15) / 16) * 16;
+    const int NT = O > 64 ? 128 : (O > 32 ? 64 : 32);
     const int n_tiles = (O + NT - 1) / NT;
     const int num_kb = (I + KB_CH - 1) / KB_CH;
     const int KK = K * K;
-    const char* dbg_env = getenv("GG_TC_DBG");
-    const int dbg = dbg_env ? atoi(dbg_env) : 0;
     const int boxW = ((TILE_W + K - 1) + 3) / 4 * 4, boxH = TILE_H + K - 1;
     const int rawW = (TILE_W + K - 1 + ((4 - pad_x % 4) % 4) + 3) / 4 * 4;   // aligned-down start => up to 3 extra columns
 
-    // 1. pack + split the weights (tiny; stream-ordered scratch)
+    // 1. pack + split the weights, flag the all-zero blocks (tiny; stream-ordered scratch)
     const size_t wp_floats = (size_t)n_tiles * num_kb * KK * 2 * 4 * NT * 4;
+    const size_t mask_words = (size_t)n_tiles * num_kb;
     float* wp = nullptr;
-    GG_CUDA(cudaMallocAsync(&wp, wp_floats * sizeof(float), st));
-    PackP pp{w, wp, O, I, K, NT, n_tiles, num_kb, flip_w, w_is_IO};
+    GG_CUDA(cudaMallocAsync(&wp, wp_floats * sizeof(float) + mask_words * sizeof(uint32_t), st));
+    uint32_t* mask = reinterpret_cast<uint32_t*>(wp + wp_floats);
+    cudaMemsetAsync(mask, 0, mask_words * sizeof(uint32_t), st);
+    PackP pp{w, wp, mask, O, I, K, NT, n_tiles, num_kb, flip_w, w_is_IO};
     {
         int64_t threads = (int64_t)n_tiles * num_kb * KK * 4 * NT;
         int grid = (int)((threads + 255) / 256);
@@ -448,7 +614,7 @@ int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int
         if (rc != GG_OK) { cudaFreeAsync(wp, st); return rc; }
     }
 
-    // 2. TMA descriptor of x as a 4-D tensor {W, H, C, N}; box {boxW, boxH, 16, 1}; OOB elements read as zero
+    // 2. TMA descriptor of x as a 4-D tensor {W, H, C, N}; box {rawW, boxH, 16, 1}; OOB elements read as zero
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) { cudaFreeAsync(wp, st); set_error("conv2d(tc): cuTensorMapEncodeTiled is unavailable"); return GG_ECUDA; }
     CUtensorMap xmap;
@@ -461,22 +627,20 @@ int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { cudaFreeAsync(wp, st); set_error("conv2d(tc): cuTensorMapEncodeTiled failed (%d)", (int)cr); return GG_ECUDA; }
 
-    // 3. launch
-    TcP p{wp, y, in_scale, out_scale, N, I, O, OH, OW, K, pad_y, pad_x, (OW + TILE_W - 1) / TILE_W, (OH + TILE_H - 1) / TILE_H,
-          NT, num_kb, (nprod == GG_PREC_TF32X1 || (dbg & 2)) ? 1 : 3, boxW, boxH, rawW, 0, dbg};
-    uint32_t cols = 32;
-    while (cols < (uint32_t)(2 * NT)) cols <<= 1;
-    p.tmem_cols = cols;
-    const SmemLayout L = make_layout(boxW, boxH, rawW, NT);
-    const size_t smem = L.total + 128;
-    static std::atomic<int> attr_set{0};
-    if (!attr_set.load()) {
-        GG_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set.store(1);
-    }
-    dim3 grid((unsigned)((size_t)p.tiles_x * p.tiles_y * N), (unsigned)n_tiles);
-    conv_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(xmap, p);
-    int rc = check_launch("conv2d(tc)");
+    // 3. launch (persistent: one CTA per SM walks the tiles, n-tile slowest so that concurrent CTAs share weights in L2)
+    TcP p{};
+    p.wp = wp; p.mask = mask; p.y = y; p.in_scale = in_scale; p.out_scale = out_scale;
+    p.Nimg = N; p.I = I; p.O = O; p.OH = OH; p.OW = OW; p.K = K; p.pad_y = pad_y; p.pad_x = pad_x;
+    p.tiles_x = (OW + TILE_W - 1) / TILE_W; p.tiles_y = (OH + TILE_H - 1) / TILE_H; p.n_tiles = n_tiles; p.num_kb = num_kb;
+    p.nprod = (nprod == GG_PREC_TF32X1) ? 1 : 3;
+    const int64_t total = (int64_t)p.tiles_x * p.tiles_y * N * n_tiles;
+    if (total > 0x7fffffffLL) { cudaFreeAsync(wp, st); set_error("conv2d(tc): too many tiles"); return GG_EINVAL; }
+    p.total_tiles = (int)total;
+    p.boxW = boxW; p.boxH = boxH; p.rawW = rawW;
+    int rc;
+    if (NT == 128) rc = launch_conv_tc<128>(xmap, p, st);
+    else if (NT == 64) rc = launch_conv_tc<64>(xmap, p, st);
+    else rc = launch_conv_tc<32>(xmap, p, st);
     cudaFreeAsync(wp, st);
     return rc;
 }
