@@ -22,8 +22,8 @@ int conv2d_wgrad_simt(const float*, const float*, float*, int, int, int, int, in
 // conv_tc.cu (tcgen05 / TMEM / TMA path)
 bool conv2d_tc_eligible(int N, int I, int H, int W, int O, int KH, int KW, int OH, int OW, int stride, int pad_y, int pad_x,
                         int transposed);
-int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int KH, int KW, int pad_y, int pad_x,
-              int flip_w, int w_is_IO, const float* in_scale, const float* out_scale, int nprod, cudaStream_t st);
+int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int KH, int KW, int OH, int OW, int pad_y,
+              int pad_x, int flip_w, int w_is_IO, const float* in_scale, const float* out_scale, int nprod, cudaStream_t st);
 bool wgrad_tc_eligible(int N, int A, int HA, int WA, int B, int HB, int WB, int KH, int KW, int stride, int pad_y, int pad_x);
 int wgrad_tc(const float* a, const float* b, float* dw, int N, int A, int HA, int WA, int B, int KH, int KW, int pad_y, int pad_x,
              int flip_w, int out_layout, const float* a_scale, const float* b_scale, int nprod, cudaStream_t st);
@@ -49,13 +49,14 @@ extern "C" GG_API int gg_conv2d_f32(const float* x, const float* w, float* y, in
     GG_REQUIRE(x && w && y, "conv2d: null pointer");
     GG_REQUIRE(N >= 0 && I >= 1 && H >= 1 && W >= 1 && O >= 1 && KH >= 1 && KW >= 1, "conv2d: bad shape");
     GG_REQUIRE(stride >= 1 && pad_y >= 0 && pad_x >= 0, "conv2d: bad stride/padding");
-    if (!transposed) {
-        GG_REQUIRE(OH == (H + 2 * pad_y - KH) / stride + 1 && OW == (W + 2 * pad_x - KW) / stride + 1 && OH >= 1 && OW >= 1,
-                   "conv2d: output size mismatch");
-    } else {
-        int bh = (H - 1) * stride - 2 * pad_y + KH, bw = (W - 1) * stride - 2 * pad_x + KW;
-        GG_REQUIRE(OH >= bh && OH < bh + stride && OW >= bw && OW < bw + stride && OH >= 1 && OW >= 1,
-                   "conv_transpose2d: output size mismatch");
+    GG_REQUIRE(OH >= 1 && OW >= 1, "conv2d: output must be at least 1x1");
+    if (stride != 1) {   // stride 1: the output extent is free (positions that read outside x see zeros)
+        if (!transposed) {
+            GG_REQUIRE(OH == (H + 2 * pad_y - KH) / stride + 1 && OW == (W + 2 * pad_x - KW) / stride + 1, "conv2d: output size mismatch");
+        } else {
+            int bh = (H - 1) * stride - 2 * pad_y + KH, bw = (W - 1) * stride - 2 * pad_x + KW;
+            GG_REQUIRE(OH >= bh && OH < bh + stride && OW >= bw && OW < bw + stride, "conv_transpose2d: output size mismatch");
+        }
     }
     GG_REQUIRE((int64_t)N * I * H * W <= 0x7fffffffLL && (int64_t)N * O * OH * OW <= 0x7fffffffLL, "conv2d: tensor is too large");
     GG_REQUIRE(prec == GG_PREC_AUTO || prec == GG_PREC_FP32_SIMT || prec == GG_PREC_TF32X1 || prec == GG_PREC_TF32X3,
@@ -74,7 +75,7 @@ extern "C" GG_API int gg_conv2d_f32(const float* x, const float* w, float* y, in
                                out_scale, st);
     // stride-1 conv_transpose2d == correlation with the flipped kernel and padding K-1-p; both are
     // handled inside the tensor-core path through its weight-packing step.
-    return gg::conv2d_tc(x, w, y, N, I, H, W, O, KH, KW, transposed ? KH - 1 - pad_y : pad_y, transposed ? KW - 1 - pad_x : pad_x,
+    return gg::conv2d_tc(x, w, y, N, I, H, W, O, KH, KW, OH, OW, transposed ? KH - 1 - pad_y : pad_y, transposed ? KW - 1 - pad_x : pad_x,
                          transposed ? !flip_w : flip_w, transposed, in_scale, out_scale, use, st);
 }
 
@@ -84,8 +85,6 @@ extern "C" GG_API int gg_conv2d_wgrad_f32(const float* a, const float* b, float*
     GG_REQUIRE(a && b && dw, "conv2d_wgrad: null pointer");
     GG_REQUIRE(N >= 0 && A >= 1 && B >= 1 && HA >= 1 && WA >= 1 && HB >= 1 && WB >= 1 && KH >= 1 && KW >= 1, "conv2d_wgrad: bad shape");
     GG_REQUIRE(stride >= 1 && pad_y >= 0 && pad_x >= 0, "conv2d_wgrad: bad stride/padding");
-    GG_REQUIRE((HB - 1) * stride + KH <= HA + 2 * pad_y && (WB - 1) * stride + KW <= WA + 2 * pad_x,
-               "conv2d_wgrad: gradient plane larger than the convolution output");
     GG_REQUIRE((int64_t)N * A * HA * WA <= 0x7fffffffLL && (int64_t)N * B * HB * WB <= 0x7fffffffLL, "conv2d_wgrad: tensor is too large");
     GG_REQUIRE(prec == GG_PREC_AUTO || prec == GG_PREC_FP32_SIMT || prec == GG_PREC_TF32X1 || prec == GG_PREC_TF32X3,
                "conv2d_wgrad: unknown precision mode %d", prec);

@@ -27,93 +27,12 @@
 //                tensor core works on the next K-block / the next tile.  The epilogue (x out_scale) runs from registers.
 // Warp roles     w0 TMA(x)  w1 TMA(weights)  w2 MMA issue + TMEM alloc  (w3 idle)  w4..w11 convert + drain + epilogue;
 //                setmaxnreg moves registers from the producer warpgroup to the two consumer warpgroups (128 accumulators/thread).
-#include "common.cuh"
-#include <cuda.h>
+#include "tc_common.cuh"
 #include <stdlib.h>
 
+using namespace ggtc;
+
 namespace {
-
-// ------------------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    const long long t0 = clock64();
-    for (;;) {
-        uint32_t ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (ok) return;
-        if (clock64() - t0 > 4000000000LL) {   // ~2 s: a pipeline bug must not hang the GPU
-            // distinguishable from a hardware fault: a watchdog expiry shows up as "illegal memory access" (null store)
-            *reinterpret_cast<volatile int*>(8) = (int)bar;
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// UMMA shared-memory descriptor, SWIZZLE_NONE ("interleave") canonical layouts (cute/arch/mma_sm100_desc.hpp):
-// bits [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout type 0.
-//   K-major : ((8,m),(4,2)) : rows 16 B apart inside a core matrix, SBO between 8-row groups, LBO between the 16-byte K chunks.
-// Instruction descriptor (UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format TF32 (2) @7/@10, a/b major @15/@16 (0 = K),
-// N>>3 @17, M>>4 @24.
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// 3xTF32 operand split.  Both parts are rounded to nearest tf32 (cvt.rna) rather than left to the tensor core's
-// truncation: |lo| <= 2^-12 |v| and lo itself carries a 2^-12 relative rounding error, so hi*hi + hi*lo + lo*hi
-// reproduces the fp32 product to ~2^-22 (the dropped lo*lo term is 2^-24).
-__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-    uint32_t h, l;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-    hi = __uint_as_float(h);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
-    lo = __uint_as_float(l);
-}
 
 // ------------------------------------------------------------------------------------------------ weight packing
 constexpr int KB_CH = 16;      // input channels per K-block (two UMMA K=8 steps)
@@ -126,37 +45,42 @@ struct PackP {
 
 // wp[n_tile][kb][tap][half: hi,lo][chunk 0..3][n 0..NT-1][4 channels]  -- per (n_tile,kb,tap) exactly the smem image
 // mask[n_tile][kb] bit tap = 1 iff the block holds a non-zero weight
+// One thread = one (n, chunk, kb, n_tile) = 4 channels x all taps: for the [O,I,k,k] layout that is one contiguous run of
+// 4*k*k floats, for [I,O,k,k] the lanes of a warp (consecutive n) read consecutive k*k-float runs.
 __global__ void pack_weights_kernel(PackP p) {
     const int KK = p.K * p.K;
-    const int64_t total = (int64_t)p.n_tiles * p.num_kb * KK * 4 * p.NT;     // one thread = one (chunk, n) = 4 channels, hi and lo
+    const int64_t total = (int64_t)p.n_tiles * p.num_kb * 4 * p.NT;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         int n = (int)(idx % p.NT); int64_t r = idx / p.NT;
         int chunk = (int)(r % 4); r /= 4;
-        int tap = (int)(r % KK); r /= KK;
         int kb = (int)(r % p.num_kb); int nt = (int)(r / p.num_kb);
-        int o = nt * p.NT + n;
-        int ky = tap / p.K, kx = tap - ky * p.K;
-        if (p.flip) { ky = p.K - 1 - ky; kx = p.K - 1 - kx; }
-        float hi[4], lo[4];
-        bool nz = false;
+        const int o = nt * p.NT + n;
+        const int i0 = kb * KB_CH + chunk * 4;
+        uint32_t live = 0u;
+        for (int tap = 0; tap < KK; ++tap) {
+            int ky = tap / p.K, kx = tap - ky * p.K;
+            if (p.flip) { ky = p.K - 1 - ky; kx = p.K - 1 - kx; }
+            float hi[4], lo[4];
+            bool nz = false;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int i = kb * KB_CH + chunk * 4 + j;
-            float v = 0.f;
-            if (o < p.O && i < p.I) {
-                int64_t src = p.w_is_IO ? (((int64_t)i * p.O + o) * p.K + ky) * p.K + kx : (((int64_t)o * p.I + i) * p.K + ky) * p.K + kx;
-                v = __ldg(p.w + src);
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + j;
+                float v = 0.f;
+                if (o < p.O && i < p.I) {
+                    int64_t src = p.w_is_IO ? (((int64_t)i * p.O + o) * p.K + ky) * p.K + kx : (((int64_t)o * p.I + i) * p.K + ky) * p.K + kx;
+                    v = __ldg(p.w + src);
+                }
+                nz |= (v != 0.f);
+                split_tf32(v, hi[j], lo[j]);
             }
-            nz |= (v != 0.f);
-            split_tf32(v, hi[j], lo[j]);
+            int64_t blk = (((int64_t)nt * p.num_kb + kb) * KK + tap) * (2 * 4 * p.NT * 4);
+            int64_t off = ((int64_t)chunk * p.NT + n) * 4;
+            *reinterpret_cast<float4*>(p.wp + blk + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(p.wp + blk + 4 * p.NT * 4 + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            // NT is a multiple of 32: the 32 lanes of a warp always share (nt, kb, chunk)
+            if (__ballot_sync(0xffffffffu, nz) != 0u) live |= 1u << tap;
         }
-        int64_t blk = (((int64_t)nt * p.num_kb + kb) * KK + tap) * (2 * 4 * p.NT * 4);
-        int64_t off = ((int64_t)chunk * p.NT + n) * 4;
-        *reinterpret_cast<float4*>(p.wp + blk + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(p.wp + blk + 4 * p.NT * 4 + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        // NT is a multiple of 32 and `total` a multiple of 32: the 32 lanes of a warp always share (nt, kb, tap, chunk)
-        const unsigned any = __ballot_sync(0xffffffffu, nz);
-        if (any != 0u && (threadIdx.x & 31) == 0) atomicOr(p.mask + (int64_t)nt * p.num_kb + kb, 1u << tap);
+        if (live != 0u && (threadIdx.x & 31) == 0) atomicOr(p.mask + (int64_t)nt * p.num_kb + kb, live);
     }
 }
 
@@ -285,116 +209,112 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     if (warp < PROD_WARPS) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
-        // ===== x producer: one 4-D TMA box per live K-block.  Boxes that stick out on the right / bottom are zero-filled by
-        // the TMA unit (= the conv padding).  The innermost start coordinate must land on a 16-byte boundary (an unaligned
-        // or negative one faults with "illegal instruction"), so the box starts at the aligned, clamped (cx, cy) and the
-        // converter shifts it back and re-creates the left / top padding (see cvt_src below).
-        KbMasks M; int cur_nt = -1;
-        uint32_t kbc = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            const TileCoord tc = decode_tile(t, p);
-            if (tc.nt != cur_nt) { M.load(p, tc.nt, lane); cur_nt = tc.nt; }
-            const int cx = max((tc.tx * TILE_W - p.pad_x) & ~3, 0), cy = max(tc.ty * TILE_H - p.pad_y, 0);
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                if (M.get(kb) == 0u) continue;
-                const int s = kbc & 1;
-                mbar_wait(BAR_RAW_EMPTY(s), ((kbc >> 1) & 1) ^ 1);
-                if (lane == 0) {
+        // ===== x producer (one thread): one 4-D TMA box per live K-block.  Boxes that stick out on the right / bottom are
+        // zero-filled by the TMA unit (= the conv padding).  The innermost start coordinate must land on a 16-byte boundary
+        // (an unaligned or negative one faults with "illegal instruction"), so the box starts at the aligned, clamped
+        // (cx, cy) and the converter shifts it back and re-creates the left / top padding (see cvt_src below).
+        if (lane == 0) {
+            uint32_t kbc = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(t, p);
+                const uint32_t* mrow = p.mask + (size_t)tc.nt * p.num_kb;
+                const int cx = max((tc.tx * TILE_W - p.pad_x) & ~3, 0), cy = max(tc.ty * TILE_H - p.pad_y, 0);
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    if (__ldg(mrow + kb) == 0u) continue;
+                    const int s = kbc & 1;
+                    mbar_wait(BAR_RAW_EMPTY(s), ((kbc >> 1) & 1) ^ 1);
                     mbar_expect_tx(BAR_RAW_FULL(s), raw_bytes);
                     tma_load_4d(base + L.raw(s), &xmap, BAR_RAW_FULL(s), cx, cy, kb * KB_CH, tc.img);
+                    ++kbc;
                 }
-                __syncwarp();
-                ++kbc;
             }
         }
     } else if (warp == 1) {
-        // ===== weight producer: one bulk copy (hi+lo image of one live tap) per ring stage
-        KbMasks M; int cur_nt = -1;
-        uint32_t g = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            const TileCoord tc = decode_tile(t, p);
-            if (tc.nt != cur_nt) { M.load(p, tc.nt, lane); cur_nt = tc.nt; }
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wp) + (size_t)tc.nt * p.num_kb * KK * w_bytes;
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                const uint32_t m = M.get(kb);
-                if (m == 0u) continue;
-                for (int tap = 0; tap < KK; ++tap) {
-                    if (!((m >> tap) & 1u)) continue;
-                    const int s = g % W_STAGES;
-                    mbar_wait(BAR_W_EMPTY(s), ((g / W_STAGES) & 1) ^ 1);
-                    if (lane == 0) {
-                        mbar_expect_tx(BAR_W_FULL(s), w_bytes);
-                        bulk_load(base + L.wst(s), src + (size_t)(kb * KK + tap) * w_bytes, w_bytes, BAR_W_FULL(s));
+        // ===== weight producer (one thread): one bulk copy (hi+lo image of one live tap) per ring stage
+        if (lane == 0) {
+            uint32_t ws = 0, wph = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(t, p);
+                const uint32_t* mrow = p.mask + (size_t)tc.nt * p.num_kb;
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wp) + (size_t)tc.nt * p.num_kb * KK * w_bytes;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    const uint32_t m = __ldg(mrow + kb);
+                    for (int tap = 0; tap < KK; ++tap) {
+                        if (!((m >> tap) & 1u)) continue;
+                        mbar_wait(BAR_W_EMPTY(ws), wph ^ 1);
+                        mbar_expect_tx(BAR_W_FULL(ws), w_bytes);
+                        bulk_load(base + L.wst(ws), src + (size_t)(kb * KK + tap) * w_bytes, w_bytes, BAR_W_FULL(ws));
+                        if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
                     }
-                    __syncwarp();
-                    ++g;
                 }
             }
         }
     } else if (warp == 2) {
-        // ===== MMA issuer (lane 0 issues; the whole warp walks the loop so that the mask shuffles stay convergent)
-        KbMasks M; int cur_nt = -1;
-        uint32_t kbc = 0, g = 0;
-        const uint32_t idesc = umma_idesc_tf32(128, NT, 0, 0);
-        // descriptor words: lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version 1 (bit 46)
-        const uint32_t a_lbo16 = (uint32_t)npix, a_sbo16 = (uint32_t)p.boxW;            // in 16-byte units
-        const uint32_t a_lo_w = (a_lbo16 & 0x3FFFu) << 16, a_hi_w = (a_sbo16 & 0x3FFFu) | (1u << 14);
-        const uint32_t b_lo_w = ((uint32_t)NT & 0x3FFFu) << 16, b_hi_w = 8u | (1u << 14);   // LBO = NT*16 B, SBO = 128 B
-        auto mk_desc = [](uint32_t lo_w, uint32_t hi_w, uint32_t addr16) -> uint64_t {
-            return ((uint64_t)hi_w << 32) | (uint64_t)(lo_w | (addr16 & 0x3FFFu));
-        };
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            const TileCoord tc = decode_tile(t, p);
-            if (tc.nt != cur_nt) { M.load(p, tc.nt, lane); cur_nt = tc.nt; }
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                const uint32_t m = M.get(kb);
-                if (m == 0u) continue;
-                const int cs = kbc & 1;
-                mbar_wait(BAR_CVT_FULL(cs), (kbc >> 1) & 1);
-                mbar_wait(BAR_ACC_EMPTY(cs), ((kbc >> 1) & 1) ^ 1);       // accumulator set cs was drained (two K-blocks ago)
-                tc_fence_after();
-                const uint32_t a_hi16 = (base + L.cvt(cs, 0)) >> 4, a_lo16 = (base + L.cvt(cs, 1)) >> 4;
-                const uint32_t d0 = tmem_base + (uint32_t)(cs * 2 * NT);
-                bool first = true;
-                for (int tap = 0; tap < KK; ++tap) {
-                    if (!((m >> tap) & 1u)) continue;
-                    const int ws = g % W_STAGES;
-                    mbar_wait(BAR_W_FULL(ws), (g / W_STAGES) & 1);
+        // ===== MMA issuer (one thread).  Descriptors are 64-bit adds on per-K-block bases: the issue loop has to stay well
+        // under the 64-cycle tensor-core time of one M=128 x N=128 x K=8 instruction.
+        if (lane == 0) {
+            uint32_t kbc = 0, ws = 0, wph = 0;
+            const uint32_t idesc = umma_idesc_tf32(128, NT, 0, 0);
+            // descriptor: bits [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, bit 46 = version 1
+            //   A: LBO = npix*16 B (between 4-channel chunks), SBO = boxW*16 B (next pixel row = next 8-row group)
+            //   B: LBO = NT*16 B, SBO = 128 B
+            const uint64_t a_word = ((uint64_t)(((uint32_t)p.boxW & 0x3FFFu) | (1u << 14)) << 32) | (((uint32_t)npix & 0x3FFFu) << 16);
+            const uint64_t b_word = ((uint64_t)(8u | (1u << 14)) << 32) | (((uint32_t)NT & 0x3FFFu) << 16);
+            const uint32_t a_ks = 2u * (uint32_t)npix;          // second K=8 step: two 4-channel chunks further (16-byte units)
+            constexpr uint32_t b_ks = 2u * NT, b_lo_off = 4u * NT;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(t, p);
+                const uint32_t* mrow = p.mask + (size_t)tc.nt * p.num_kb;
+                uint32_t m_next = __ldg(mrow);
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    const uint32_t m = m_next;
+                    if (kb + 1 < p.num_kb) m_next = __ldg(mrow + kb + 1);
+                    if (m == 0u) continue;
+                    const uint32_t cs = kbc & 1, cph = (kbc >> 1) & 1;
+                    mbar_wait(BAR_CVT_FULL(cs), cph);
+                    mbar_wait(BAR_ACC_EMPTY(cs), cph ^ 1);             // accumulator set cs was drained (two K-blocks ago)
                     tc_fence_after();
-                    if (lane == 0) {
-                        const int ky = tap / p.K, kx = tap - ky * p.K;
-                        const uint32_t tapoff = (uint32_t)(ky * p.boxW + kx);
-                        const uint32_t b_hi16 = (base + L.wst(ws)) >> 4, b_lo16 = b_hi16 + 4u * NT;
-#pragma unroll
-                        for (int sub = 0; sub < 2; ++sub) {
-#pragma unroll
-                            for (int ks = 0; ks < 2; ++ks) {
-                                const uint32_t a_off = tapoff + 8u * sub + (uint32_t)(2 * ks) * a_lbo16;
-                                const uint32_t b_off = (uint32_t)(2 * ks) * NT;
-                                const uint64_t a_hi = mk_desc(a_lo_w, a_hi_w, a_hi16 + a_off);
-                                const uint64_t b_hi = mk_desc(b_lo_w, b_hi_w, b_hi16 + b_off);
-                                const uint32_t d = d0 + (uint32_t)(sub * NT);
-                                umma_tf32(d, a_hi, b_hi, idesc, (first && ks == 0) ? 0u : 1u);
-                                if (p.nprod == 3) {
-                                    const uint64_t a_lo = mk_desc(a_lo_w, a_hi_w, a_lo16 + a_off);
-                                    const uint64_t b_lo = mk_desc(b_lo_w, b_hi_w, b_lo16 + b_off);
-                                    umma_tf32(d, a_hi, b_lo, idesc, 1u);
-                                    umma_tf32(d, a_lo, b_hi, idesc, 1u);
-                                }
+                    const uint64_t a_hi0 = a_word + ((base + L.cvt(cs, 0)) >> 4), a_lo0 = a_word + ((base + L.cvt(cs, 1)) >> 4);
+                    const uint32_t d0 = tmem_base + cs * 2u * NT, d1 = d0 + NT;
+                    uint32_t accf = 0u;                               // first MMA of the K-block overwrites the accumulator
+                    uint32_t tap = 0;
+                    for (int ky = 0; ky < p.K; ++ky) {
+                        for (int kx = 0; kx < p.K; ++kx, ++tap) {
+                            if (!((m >> tap) & 1u)) continue;
+                            mbar_wait(BAR_W_FULL(ws), wph);
+                            tc_fence_after();
+                            const uint32_t toff = (uint32_t)(ky * p.boxW + kx);
+                            const uint64_t b_hi0 = b_word + ((base + L.wst(ws)) >> 4), b_lo0 = b_hi0 + b_lo_off;
+                            const uint64_t ah0 = a_hi0 + toff, al0 = a_lo0 + toff;
+                            if (p.nprod == 3) {
+                                // sub-tile 0 (x offset 0), K steps 0 and 1; then sub-tile 1 (x offset 8 pixels)
+                                umma_tf32(d0, ah0, b_hi0, idesc, accf);
+                                umma_tf32(d0, ah0, b_lo0, idesc, 1u);
+                                umma_tf32(d0, al0, b_hi0, idesc, 1u);
+                                umma_tf32(d0, ah0 + a_ks, b_hi0 + b_ks, idesc, 1u);
+                                umma_tf32(d0, ah0 + a_ks, b_lo0 + b_ks, idesc, 1u);
+                                umma_tf32(d0, al0 + a_ks, b_hi0 + b_ks, idesc, 1u);
+                                umma_tf32(d1, ah0 + 8u, b_hi0, idesc, accf);
+                                umma_tf32(d1, ah0 + 8u, b_lo0, idesc, 1u);
+                                umma_tf32(d1, al0 + 8u, b_hi0, idesc, 1u);
+                                umma_tf32(d1, ah0 + 8u + a_ks, b_hi0 + b_ks, idesc, 1u);
+                                umma_tf32(d1, ah0 + 8u + a_ks, b_lo0 + b_ks, idesc, 1u);
+                                umma_tf32(d1, al0 + 8u + a_ks, b_hi0 + b_ks, idesc, 1u);
+                            } else {
+                                umma_tf32(d0, ah0, b_hi0, idesc, accf);
+                                umma_tf32(d0, ah0 + a_ks, b_hi0 + b_ks, idesc, 1u);
+                                umma_tf32(d1, ah0 + 8u, b_hi0, idesc, accf);
+                                umma_tf32(d1, ah0 + 8u + a_ks, b_hi0 + b_ks, idesc, 1u);
                             }
+                            umma_commit(BAR_W_EMPTY(ws));          // frees the weight stage when these MMAs have read it
+                            if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+                            accf = 1u;
                         }
-                        umma_commit(BAR_W_EMPTY(ws));      // frees the weight stage when these MMAs have read it
                     }
-                    __syncwarp();
-                    first = false;
-                    ++g;
+                    umma_commit(BAR_CVT_EMPTY(cs));                // frees the converted tile
+                    umma_commit(BAR_ACC_FULL(cs));                 // this K-block's partial sums are complete in TMEM set cs
+                    ++kbc;
                 }
-                if (lane == 0) {
-                    umma_commit(BAR_CVT_EMPTY(cs));        // frees the converted tile
-                    umma_commit(BAR_ACC_FULL(cs));         // this K-block's partial sums are complete in TMEM set cs
-                }
-                __syncwarp();
-                ++kbc;
             }
         }
     }
@@ -555,6 +475,21 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+// The stream-ordered scratch comes from the device's default memory pool.  Its default release threshold of 0 hands the
+// memory back to the driver at every synchronisation, which makes the next cudaMallocAsync cost ~1 ms; keep it cached.
+void keep_pool_memory() {
+    static std::atomic<uint64_t> done{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    if (done.load() & (1ull << dev)) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done.fetch_or(1ull << dev);
+}
+
 template <int NT>
 int launch_conv_tc(const CUtensorMap& xmap, const TcP& p, cudaStream_t st) {
     const SmemLayout L = make_layout(p.boxW, p.boxH, p.rawW, NT);
@@ -586,10 +521,9 @@ bool conv2d_tc_eligible(int N, int I, int H, int W, int O, int KH, int KW, int O
     return true;
 }
 
-int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int K, int /*KW*/, int pad_y, int pad_x,
-              int flip_w, int w_is_IO, const float* in_scale, const float* out_scale, int nprod, cudaStream_t st) {
+int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int K, int /*KW*/, int OH, int OW, int pad_y,
+              int pad_x, int flip_w, int w_is_IO, const float* in_scale, const float* out_scale, int nprod, cudaStream_t st) {
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) { set_error("conv2d(tc): x must be 16-byte aligned"); return GG_EINVAL; }
-    const int OH = H + 2 * pad_y - K + 1, OW = W + 2 * pad_x - K + 1;
     const int NT = O > 64 ? 128 : (O > 32 ? 64 : 32);
     const int n_tiles = (O + NT - 1) / NT;
     const int num_kb = (I + KB_CH - 1) / KB_CH;
@@ -598,6 +532,7 @@ int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int
     const int rawW = (TILE_W + K - 1 + ((4 - pad_x % 4) % 4) + 3) / 4 * 4;   // aligned-down start => up to 3 extra columns
 
     // 1. pack + split the weights, flag the all-zero blocks (tiny; stream-ordered scratch)
+    keep_pool_memory();
     const size_t wp_floats = (size_t)n_tiles * num_kb * KK * 2 * 4 * NT * 4;
     const size_t mask_words = (size_t)n_tiles * num_kb;
     float* wp = nullptr;
@@ -606,7 +541,7 @@ int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int
     cudaMemsetAsync(mask, 0, mask_words * sizeof(uint32_t), st);
     PackP pp{w, wp, mask, O, I, K, NT, n_tiles, num_kb, flip_w, w_is_IO};
     {
-        int64_t threads = (int64_t)n_tiles * num_kb * KK * 4 * NT;
+        int64_t threads = (int64_t)n_tiles * num_kb * 4 * NT;
         int grid = (int)((threads + 255) / 256);
         if (grid > GG_NUM_SMS * 8) grid = GG_NUM_SMS * 8;
         pack_weights_kernel<<<grid, 256, 0, st>>>(pp);

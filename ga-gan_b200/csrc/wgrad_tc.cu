@@ -1,0 +1,359 @@
+// tcgen05 / TMEM weight-gradient kernel for sm_100a (stride-1 convolutions, k in {1,2,3}), fp32-faithful 3xTF32.
+//
+// Replaces aten::cudnn_convolution_backward_weight behind conv2d_gradfix.Conv2dGradWeight (torch_utils/ops/
+// conv2d_gradfix.py:175-191) for every stride-1 layer and, through the phase-major formulation of conv2d_resample.py,
+// for the stride-2 layers as well:
+//
+//   dw[b,a,ky,kx] = sum_{n,y,x} (gs[n,b] * G[n,b,y,x]) * (xs[n,a] * X[n,a,y+ky-py,x+kx-px])          X == 0 outside its extent
+//
+// GEMM view     D_ky[m = (kx slot, grad channel b), n = input channel a] += sum_{pixels} Gshift[m, pix] * X_ky[n, pix]
+//               The reduction dimension is the PIXEL axis, which is the contiguous axis of both NCHW operands, so both
+//               are K-major UMMA operands: shared-memory image [4-pixel chunk][row][4 pixels] (no-swizzle canonical layout).
+//               A ky shift of X is a different row of the X ring (= a different descriptor start address); a kx shift
+//               cannot be expressed by a descriptor (it breaks the 16-byte chunk alignment), so the G operand is stored
+//               once per kx with the shift applied while it is converted -- with few channels several kx copies are
+//               stacked into the 128 rows of one MMA (32 channels: 3 copies, 64: 2, >= 128: one kx per CTA group).
+// Work unit     one (tile, strip): tile = (128 rows of (kx,b)) x (NTA input channels) x (all ky); strip = RR image rows x
+//               16 image columns of one sample.  A persistent CTA walks a contiguous range of units.
+// Pipeline      converter warps load G / X rows straight from global memory (coalesced 64-byte runs, 128-bit loads when
+//               aligned), apply the per-sample scales, split into tf32 hi/lo (cvt.rna) and fill two shared-memory rings;
+//               one thread issues tcgen05.mma.kind::tf32 (M=128, N=NTA, K=8; hi*hi + hi*lo + lo*hi) into TMEM.
+// Accumulation  as in conv_tc.cu the tensor core's truncating fp32 accumulator is only trusted for one strip
+//               (<= 32 rows x 2 steps x 3 products); two TMEM sets ping-pong and the converter warps drain every finished
+//               strip into fp32 REGISTERS (round-to-nearest).  A tile's partial sum leaves the CTA once, with fp32 atomics
+//               into the zero-initialised dw (a handful of partials per tile: one per CTA that worked on it).
+#include "tc_common.cuh"
+
+using namespace ggtc;
+
+namespace {
+
+constexpr int WG_CONS_WARPS = 8;
+constexpr int WG_CONS_THREADS = WG_CONS_WARPS * 32;
+constexpr int WG_THREADS = (1 + WG_CONS_WARPS) * 32;     // w0 = MMA issuer + TMEM owner, w1..w8 = convert + drain + flush
+constexpr int UW = 16;                                   // image columns per strip (two K=8 steps)
+constexpr int GS = 3;                                    // G-row ring slots
+constexpr int XS = 5;                                    // X-row ring slots (k live rows + rows in flight)
+constexpr uint32_t LBO_A = 128 * 16 + 32;                // chunk pitch of the G image (+32 B: conflict-free 128-bit stores)
+
+struct WgP {
+    const float* X; const float* G; float* dw; const float* xs; const float* gs;
+    int N, A, HA, WA, B, HB, WB, K, pad_y, pad_x, flip_w, out_layout;
+    int RB, rb_shift, nshift, zgroups, btiles, atiles;
+    int RR, ustrips, rstrips, S;
+    int total_units, units_per_cta, nprod, vecX, vecG;
+};
+
+struct Unit { int n, r0, rows, u0, b0, a0, kx0, ns, tile; };
+
+__device__ __forceinline__ Unit decode_unit(int unit, const WgP& p, int NTA) {
+    Unit u;
+    u.tile = unit / p.S;
+    int strip = unit - u.tile * p.S;
+    int us = strip % p.ustrips; strip /= p.ustrips;
+    int rs = strip % p.rstrips;
+    u.n = strip / p.rstrips;
+    u.u0 = us * UW;
+    u.r0 = rs * p.RR;
+    u.rows = min(p.RR, p.HB - u.r0);
+    int t = u.tile;
+    int gz = t % p.zgroups; t /= p.zgroups;
+    int at = t % p.atiles;
+    int bt = t / p.atiles;
+    u.b0 = bt * p.RB; u.a0 = at * NTA;
+    u.kx0 = gz * p.nshift;
+    u.ns = min(p.nshift, p.K - u.kx0);
+    return u;
+}
+
+template <int NTA>
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    constexpr uint32_t LBO_B = NTA * 16 + 32;
+    constexpr uint32_t G_HALF = 4 * LBO_A, G_SLOT = 2 * G_HALF;          // hi image, lo image
+    constexpr uint32_t X_HALF = 4 * LBO_B, X_SLOT = 2 * X_HALF;
+    constexpr uint32_t OFF_G = 0, OFF_X = OFF_G + GS * G_SLOT, OFF_BAR = OFF_X + XS * X_SLOT, OFF_SLOT = OFF_BAR + 256;
+    constexpr uint32_t ACC_STRIDE = 3 * NTA;                             // TMEM columns of one accumulator set (ky-major)
+    constexpr uint32_t TMEM_COLS = (2 * ACC_STRIDE <= 256) ? 256 : 512;
+
+    const uint32_t bar0 = base + OFF_BAR;
+    auto BAR_G_FULL = [&](int s) { return bar0 + 8u * s; };
+    auto BAR_G_EMPTY = [&](int s) { return bar0 + 8u * (GS + s); };
+    auto BAR_X_FULL = [&](int s) { return bar0 + 8u * (2 * GS + s); };
+    auto BAR_X_EMPTY = [&](int s) { return bar0 + 8u * (2 * GS + XS + s); };
+    auto BAR_ACC_FULL = [&](int s) { return bar0 + 8u * (2 * GS + 2 * XS + s); };
+    auto BAR_ACC_EMPTY = [&](int s) { return bar0 + 8u * (2 * GS + 2 * XS + 2 + s); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < GS; ++s) { mbar_init(BAR_G_FULL(s), WG_CONS_WARPS); mbar_init(BAR_G_EMPTY(s), 1); }
+        for (int s = 0; s < XS; ++s) { mbar_init(BAR_X_FULL(s), WG_CONS_WARPS); mbar_init(BAR_X_EMPTY(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(BAR_ACC_FULL(s), 1); mbar_init(BAR_ACC_EMPTY(s), WG_CONS_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(base + OFF_SLOT, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + OFF_SLOT);
+
+    const int unit_beg = blockIdx.x * p.units_per_cta;
+    const int unit_end = min(p.total_units, unit_beg + p.units_per_cta);
+    const int K = p.K;
+
+    if (warp == 0) {
+        // ===== MMA issuer (one thread)
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(128, NTA, 0, 0);
+            const uint64_t a_word = ((uint64_t)(8u | (1u << 14)) << 32) | ((uint64_t)(LBO_A >> 4) << 16);   // SBO 128 B, LBO
+            const uint64_t b_word = ((uint64_t)(8u | (1u << 14)) << 32) | ((uint64_t)(LBO_B >> 4) << 16);
+            constexpr uint32_t a_ks = 2 * (LBO_A >> 4), b_ks = 2 * (LBO_B >> 4);
+            uint32_t gc = 0, xc = 0, sc = 0;        // running G-row, X-row and strip counters (ring positions)
+            for (int unit = unit_beg; unit < unit_end; ++unit) {
+                const Unit u = decode_unit(unit, p, NTA);
+                const uint32_t buf = sc & 1;
+                mbar_wait(BAR_ACC_EMPTY(buf), ((sc >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + buf * ACC_STRIDE;
+                for (int i = 0; i < u.rows; ++i) {
+                    const uint32_t gslot = gc % GS;
+                    mbar_wait(BAR_G_FULL(gslot), (gc / GS) & 1);
+                    for (int j = (i == 0 ? 0 : K - 1); j < K; ++j) {           // X rows i .. i+K-1 must have landed
+                        const uint32_t c = xc + i + j;
+                        mbar_wait(BAR_X_FULL(c % XS), (c / XS) & 1);
+                    }
+                    tc_fence_after();
+                    const uint64_t g_hi = a_word + ((base + OFF_G + gslot * G_SLOT) >> 4), g_lo = g_hi + (G_HALF >> 4);
+                    for (int ky = 0; ky < K; ++ky) {
+                        const uint32_t xslot = (xc + i + ky) % XS;
+                        const uint64_t x_hi = b_word + ((base + OFF_X + xslot * X_SLOT) >> 4), x_lo = x_hi + (X_HALF >> 4);
+                        const uint32_t d = d0 + (uint32_t)ky * NTA;
+                        const uint32_t accf = i > 0 ? 1u : 0u;
+                        if (p.nprod == 3) {
+                            umma_tf32(d, g_hi, x_hi, idesc, accf);
+                            umma_tf32(d, g_hi, x_lo, idesc, 1u);
+                            umma_tf32(d, g_lo, x_hi, idesc, 1u);
+                            umma_tf32(d, g_hi + a_ks, x_hi + b_ks, idesc, 1u);
+                            umma_tf32(d, g_hi + a_ks, x_lo + b_ks, idesc, 1u);
+                            umma_tf32(d, g_lo + a_ks, x_hi + b_ks, idesc, 1u);
+                        } else {
+                            umma_tf32(d, g_hi, x_hi, idesc, accf);
+                            umma_tf32(d, g_hi + a_ks, x_hi + b_ks, idesc, 1u);
+                        }
+                    }
+                    umma_commit(BAR_G_EMPTY(gslot));
+                    umma_commit(BAR_X_EMPTY((xc + i) % XS));                 // X row i is not needed by later G rows
+                    ++gc;
+                }
+                for (int j = 0; j < K - 1; ++j) umma_commit(BAR_X_EMPTY((xc + u.rows + j) % XS));   // the strip's bottom halo rows
+                xc += u.rows + K - 1;
+                umma_commit(BAR_ACC_FULL(buf));
+                ++sc;
+            }
+        }
+    } else {
+        // ===== converter warps: fill the rings for strip s, then drain strip s-1 from TMEM into registers
+        const int ct = threadIdx.x - 32;                // 0..255
+        const int q = warp & 3;                         // TMEM lane quarter
+        const int half = (warp - 1) >> 2;               // which half of the accumulator columns this warp owns
+        constexpr int HC = 3 * NTA / 2;                 // accumulator columns per thread (K = 3); K < 3 uses a prefix
+        float acc[HC];
+#pragma unroll
+        for (int j = 0; j < HC; ++j) acc[j] = 0.f;
+        const int hcols = K * NTA / 2;                  // live columns per half
+        uint32_t gc = 0, xc = 0, sc = 0;
+        bool pend = false;
+        Unit pu{};
+        uint32_t pend_sc = 0;
+
+        auto fill_x_row = [&](const Unit& u, int j) {   // local X row j  <->  image row v
+            const int v = u.r0 - p.pad_y + j;
+            const uint32_t slot = xc % XS;
+            mbar_wait(BAR_X_EMPTY(slot), ((xc / XS) & 1) ^ 1);
+            uint8_t* sb = gbase + OFF_X + slot * X_SLOT;
+            for (int id = ct; id < NTA * 4; id += WG_CONS_THREADS) {
+                const int c = id & 3, r = id >> 2;
+                const int ac = u.a0 + r, col = u.u0 + 4 * c;
+                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (v >= 0 && v < p.HA && ac < p.A && col < p.WA) {
+                    const float* src = p.X + (((size_t)u.n * p.A + ac) * p.HA + v) * p.WA + col;
+                    if (p.vecX && col + 3 < p.WA) {
+                        val = __ldg(reinterpret_cast<const float4*>(src));
+                    } else {
+                        val.x = __ldg(src);
+                        if (col + 1 < p.WA) val.y = __ldg(src + 1);
+                        if (col + 2 < p.WA) val.z = __ldg(src + 2);
+                        if (col + 3 < p.WA) val.w = __ldg(src + 3);
+                    }
+                    if (p.xs) { const float s = __ldg(p.xs + (size_t)u.n * p.A + ac); val.x *= s; val.y *= s; val.z *= s; val.w *= s; }
+                }
+                float4 h, l;
+                split_tf32(val.x, h.x, l.x); split_tf32(val.y, h.y, l.y); split_tf32(val.z, h.z, l.z); split_tf32(val.w, h.w, l.w);
+                *reinterpret_cast<float4*>(sb + c * LBO_B + r * 16) = h;
+                *reinterpret_cast<float4*>(sb + X_HALF + c * LBO_B + r * 16) = l;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR_X_FULL(slot));
+            ++xc;
+        };
+        auto fill_g_row = [&](const Unit& u, int i) {
+            const int y = u.r0 + i;
+            const uint32_t slot = gc % GS;
+            mbar_wait(BAR_G_EMPTY(slot), ((gc / GS) & 1) ^ 1);
+            uint8_t* sb = gbase + OFF_G + slot * G_SLOT;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int id = ct + t * WG_CONS_THREADS;                       // 512 items: (row m, chunk c)
+                const int c = id & 3, m = id >> 2;
+                const int s = m >> p.rb_shift, bc = u.b0 + (m & (p.RB - 1));
+                const int x0 = u.u0 + 4 * c - (u.kx0 + s - p.pad_x);           // G column of the chunk's first pixel
+                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (s < u.ns && bc < p.B && x0 + 3 >= 0 && x0 < p.WB) {
+                    const float* src = p.G + (((size_t)u.n * p.B + bc) * p.HB + y) * p.WB;
+                    if (p.vecG && (x0 & 3) == 0 && x0 >= 0 && x0 + 3 < p.WB) {
+                        val = __ldg(reinterpret_cast<const float4*>(src + x0));
+                    } else {
+                        if (x0 >= 0) val.x = __ldg(src + x0);
+                        if (x0 + 1 >= 0 && x0 + 1 < p.WB) val.y = __ldg(src + x0 + 1);
+                        if (x0 + 2 >= 0 && x0 + 2 < p.WB) val.z = __ldg(src + x0 + 2);
+                        if (x0 + 3 < p.WB) val.w = __ldg(src + x0 + 3);
+                    }
+                    if (p.gs) { const float sg = __ldg(p.gs + (size_t)u.n * p.B + bc); val.x *= sg; val.y *= sg; val.z *= sg; val.w *= sg; }
+                }
+                float4 h, l;
+                split_tf32(val.x, h.x, l.x); split_tf32(val.y, h.y, l.y); split_tf32(val.z, h.z, l.z); split_tf32(val.w, h.w, l.w);
+                *reinterpret_cast<float4*>(sb + c * LBO_A + m * 16) = h;
+                *reinterpret_cast<float4*>(sb + G_HALF + c * LBO_A + m * 16) = l;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR_G_FULL(slot));
+            ++gc;
+        };
+        auto drain = [&](uint32_t k) {                  // TMEM accumulator set of strip k -> registers (RN adds)
+            const uint32_t buf = k & 1;
+            mbar_wait(BAR_ACC_FULL(buf), (k >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int cb = 0; cb < HC; cb += 16) {
+                if (cb < hcols) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_STRIDE + (uint32_t)(half * hcols + cb), v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[cb + j] += __uint_as_float(v[j]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR_ACC_EMPTY(buf));
+        };
+        auto flush = [&](const Unit& u) {               // registers -> dw (fp32 atomics; dw was zero-filled by the host)
+            const int m = q * 32 + lane;
+            const int s = m >> p.rb_shift, bc = u.b0 + (m & (p.RB - 1));
+            const bool row_ok = s < u.ns && bc < p.B;
+            int kx = u.kx0 + s;
+            if (p.flip_w) kx = K - 1 - kx;
+#pragma unroll
+            for (int j = 0; j < HC; ++j) {
+                if (j < hcols) {
+                    const int col = half * hcols + j;
+                    int ky = col / NTA;
+                    const int ac = u.a0 + (col - ky * NTA);
+                    if (p.flip_w) ky = K - 1 - ky;
+                    if (row_ok && ac < p.A) {
+                        const size_t idx = p.out_layout ? ((((size_t)ac * p.B + bc) * K + ky) * K + kx)
+                                                        : ((((size_t)bc * p.A + ac) * K + ky) * K + kx);
+                        atomicAdd(p.dw + idx, acc[j]);
+                    }
+                }
+                acc[j] = 0.f;
+            }
+        };
+
+        for (int unit = unit_beg; unit < unit_end; ++unit) {
+            const Unit u = decode_unit(unit, p, NTA);
+            for (int j = 0; j < K - 1; ++j) fill_x_row(u, j);
+            for (int i = 0; i < u.rows; ++i) {
+                fill_x_row(u, i + K - 1);
+                fill_g_row(u, i);
+            }
+            if (pend) {
+                drain(pend_sc);
+                if (pu.tile != u.tile) flush(pu);
+            }
+            pend = true; pu = u; pend_sc = sc;
+            ++sc;
+        }
+        if (pend) { drain(pend_sc); flush(pu); }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int NTA>
+int launch_wgrad(const WgP& p, int grid, cudaStream_t st) {
+    constexpr uint32_t LBO_B = NTA * 16 + 32;
+    const size_t smem = GS * 2 * 4 * LBO_A + XS * 2 * 4 * LBO_B + 256 + 16 + 128;
+    static std::atomic<int> attr_set{0};
+    if (!attr_set.load()) {
+        GG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<NTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set.store(1);
+    }
+    wgrad_tc_kernel<NTA><<<grid, WG_THREADS, smem, st>>>(p);
+    return gg::check_launch("conv2d_wgrad(tc)");
+}
+
+}  // namespace
+
+namespace gg {
+
+bool wgrad_tc_eligible(int N, int A, int HA, int WA, int B, int HB, int WB, int KH, int KW, int stride, int pad_y, int pad_x) {
+    if (stride != 1 || KH != KW || KH < 1 || KH > 3) return false;
+    if (pad_y > KH - 1 || pad_x > KW - 1) return false;
+    if (N < 1 || A < 1 || B < 1) return false;
+    if ((int64_t)A * B < 256) return false;            // 3x3-channel corner cases: nothing to gain
+    if ((int64_t)N * HB * WB < 256) return false;      // 4x4 maps: launch-latency bound either way, keep the exact FFMA kernel
+    (void)HA; (void)WA;
+    return true;
+}
+
+int wgrad_tc(const float* a, const float* b, float* dw, int N, int A, int HA, int WA, int B, int HB, int WB, int K, int /*KW*/,
+             int pad_y, int pad_x, int flip_w, int out_layout, const float* a_scale, const float* b_scale, int nprod, cudaStream_t st) {
+    WgP p{};
+    p.X = a; p.G = b; p.dw = dw; p.xs = a_scale; p.gs = b_scale;
+    p.N = N; p.A = A; p.HA = HA; p.WA = WA; p.B = B; p.HB = HB; p.WB = WB; p.K = K; p.pad_y = pad_y; p.pad_x = pad_x;
+    p.flip_w = flip_w; p.out_layout = out_layout;
+    p.RB = B > 64 ? 128 : (B > 32 ? 64 : 32);
+    p.rb_shift = p.RB == 128 ? 7 : (p.RB == 64 ? 6 : 5);
+    p.nshift = 128 / p.RB < K ? 128 / p.RB : K;
+    p.zgroups = (K + p.nshift - 1) / p.nshift;
+    const int NTA = A > 32 ? 64 : 32;
+    p.btiles = (B + p.RB - 1) / p.RB;
+    p.atiles = (A + NTA - 1) / NTA;
+    p.RR = HB < 32 ? HB : 32;
+    p.ustrips = (WA + UW - 1) / UW;
+    p.rstrips = (HB + p.RR - 1) / p.RR;
+    const int64_t S = (int64_t)N * p.ustrips * p.rstrips;
+    const int64_t total = S * p.btiles * p.atiles * p.zgroups;
+    if (total > 0x7fffffffLL) { set_error("conv2d_wgrad(tc): too many work units"); return GG_EINVAL; }
+    p.S = (int)S; p.total_units = (int)total;
+    int grid = total < GG_NUM_SMS ? (int)total : GG_NUM_SMS;
+    p.units_per_cta = (int)((total + grid - 1) / grid);
+    grid = (int)((total + p.units_per_cta - 1) / p.units_per_cta);
+    p.nprod = (nprod == GG_PREC_TF32X1) ? 1 : 3;
+    p.vecX = ((reinterpret_cast<uintptr_t>(a) & 15) == 0 && WA % 4 == 0) ? 1 : 0;
+    p.vecG = ((reinterpret_cast<uintptr_t>(b) & 15) == 0 && WB % 4 == 0) ? 1 : 0;
+    GG_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)A * B * K * K, st));
+    if (NTA == 64) return launch_wgrad<64>(p, grid, st);
+    return launch_wgrad<32>(p, grid, st);
+}
+
+}  // namespace gg

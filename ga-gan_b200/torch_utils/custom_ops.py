@@ -220,7 +220,7 @@ class _Plugin:
 
     # replaces torch.nn.functional.conv2d / conv_transpose2d (conv2d_gradfix.py:141-146), groups == 1
     def conv2d(self, x, w, stride=1, padding=(0, 0), transposed=False, output_padding=(0, 0), flip_w=False,
-               in_scale=None, out_scale=None, prec=None):
+               in_scale=None, out_scale=None, prec=None, out_hw=None, flop_scale=1.0):
         _require_cuda(x, 'input')
         _require_cuda(w, 'weight')
         _check_device(x)
@@ -235,6 +235,10 @@ class _Plugin:
             wi, O, KH, KW = w.shape
             OH = (H - 1) * stride - 2 * padding[0] + KH + output_padding[0]
             OW = (W - 1) * stride - 2 * padding[1] + KW + output_padding[1]
+        if out_hw is not None:          # stride-1 only: crop / extend the output into the zero region (include/gagan_b200.h)
+            if stride != 1:
+                raise RuntimeError('conv2d: out_hw needs stride 1')
+            OH, OW = int(out_hw[0]), int(out_hw[1])
         if wi != I:
             raise RuntimeError(f'conv2d: weight expects {wi} input channels, input has {I}')
         if OH < 1 or OW < 1:
@@ -255,12 +259,12 @@ class _Plugin:
                                           _stream(x)), 'conv2d')
         self.last_conv_prec = used.value
         # algorithmic FLOPs: 2*N*O*I*kh*kw*Hout*Wout, transposed: *Hin*Win
-        _prof_end(x, ev0, 'convT' if transposed else 'conv', 2.0 * N * O * I * KH * KW * (H * W if transposed else OH * OW), used.value)
+        _prof_end(x, ev0, 'convT' if transposed else 'conv', flop_scale * 2.0 * N * O * I * KH * KW * (H * W if (transposed and stride != 1) else OH * OW), used.value)
         return y
 
     # replaces aten::cudnn_convolution(_transpose)_backward_weight (conv2d_gradfix.py:178-188)
     def conv2d_wgrad(self, a, b, kernel_size, stride=1, padding=(0, 0), flip_w=False, out_layout=0, a_scale=None,
-                     b_scale=None, prec=None):
+                     b_scale=None, prec=None, flop_scale=1.0):
         _require_cuda(a, 'input')
         _require_cuda(b, 'grad_output')
         _check_device(a)
@@ -281,7 +285,7 @@ class _Plugin:
                                                 _ptr(a_scale), _ptr(b_scale), int(conv_precision if prec is None else prec),
                                                 ctypes.byref(used), _stream(a)), 'conv2d_wgrad')
         self.last_wgrad_prec = used.value
-        _prof_end(a, ev0, 'wgrad', 2.0 * N * A * B * KH * KW * HB * WB, used.value)
+        _prof_end(a, ev0, 'wgrad', flop_scale * 2.0 * N * A * B * KH * KW * HB * WB, used.value)
         return dw
 
 

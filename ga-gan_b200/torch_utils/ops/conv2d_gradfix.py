@@ -52,14 +52,29 @@ def _check_input(input):
     _init()
 
 
+def _is_s1(weight, stride, padding, dilation, groups, output_padding=0):
+    k = (int(weight.shape[2]), int(weight.shape[3]))
+    pad = _tuple_of_ints(padding, 2)
+    return (_tuple_of_ints(stride, 2) == (1, 1) and _tuple_of_ints(dilation, 2) == (1, 1) and groups == 1
+            and _tuple_of_ints(output_padding, 2) == (0, 0) and pad[0] <= k[0] - 1 and pad[1] <= k[1] - 1)
+
+
 def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
     _check_input(input)
+    if _is_s1(weight, stride, padding, dilation, groups):
+        y = conv2d_s1(input, weight, padding=padding)
+        return y if bias is None else y + bias.reshape(1, -1, 1, 1)
     return _conv2d_gradfix(transpose=False, weight_shape=weight.shape, stride=stride, padding=padding, output_padding=0,
                            dilation=dilation, groups=groups).apply(input, weight, bias)
 
 
 def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_padding=0, groups=1, dilation=1):
     _check_input(input)
+    if _is_s1(weight, stride, padding, dilation, groups, output_padding):
+        # stride-1 transposed conv == correlation with the transposed, flipped kernel and padding k-1-p
+        pad = _tuple_of_ints(padding, 2)
+        y = conv2d_s1(input, weight, padding=(weight.shape[2] - 1 - pad[0], weight.shape[3] - 1 - pad[1]), io=True, flip=True)
+        return y if bias is None else y + bias.reshape(1, -1, 1, 1)
     return _conv2d_gradfix(transpose=True, weight_shape=weight.shape, stride=stride, padding=padding,
                            output_padding=output_padding, groups=groups, dilation=dilation).apply(input, weight, bias)
 
@@ -94,6 +109,82 @@ def _run_wgrad(grad_output, input, weight_shape, transpose, stride, padding, gro
     a_s = a.chunk(groups, dim=1)
     b_s = b.chunk(groups, dim=1)
     return torch.cat([_plugin.conv2d_wgrad(ag, bg, (kh, kw), stride=stride, padding=padding) for ag, bg in zip(a_s, b_s)], dim=0)
+
+
+# ----------------------------------------------------------------------------
+# The stride-1 primitive every tensor-core convolution goes through.
+#
+#   y[n,o,Y,X] = sum_{i,a,b} x[n,i,Y-py+a,X-px+b] * v[o,i,a,b],   Y < OH, X < OW, x == 0 outside its extent
+#
+# where v is `w` read as [out,in,kh,kw] (io=False) or [in,out,kh,kw] (io=True), spatially flipped when flip=True.
+# The output size is a free parameter (cropping / extending into the zero region), which makes the op closed under
+# differentiation without any tensor copies:  d/dx = the same op with (io, flip) toggled, pad -> k-1-pad and
+# out_hw = x's extent;  d/dw = `gg_conv2d_wgrad_f32`, whose own gradients are again this op (conv2d_gradfix.py:126-212
+# is the template).  conv2d_resample's phase-major up/down paths and the plain stride-1 layers all use it.
+
+_conv2d_s1_cache = dict()
+
+
+def conv2d_s1(x, w, padding=(0, 0), out_hw=None, io=False, flip=False, live=1.0):
+    _check_input(x)
+    kh, kw = int(w.shape[2]), int(w.shape[3])
+    padding = _tuple_of_ints(padding, 2)
+    if out_hw is None:
+        out_hw = (x.shape[2] + 2 * padding[0] - kh + 1, x.shape[3] + 2 * padding[1] - kw + 1)
+    return _conv2d_s1(tuple(w.shape), padding, (int(out_hw[0]), int(out_hw[1])), bool(io), bool(flip), float(live)).apply(x, w)
+
+
+def _conv2d_s1(weight_shape, padding, out_hw, io, flip, live=1.0):
+    # `live` = fraction of structurally non-zero weight blocks (9/16 for the phase-major stride-2 forms); it only scales
+    # the algorithmic-FLOP accounting of bench.py so that skipped zero blocks are never counted as work.
+    key = (weight_shape, padding, out_hw, io, flip, live)
+    if key in _conv2d_s1_cache:
+        return _conv2d_s1_cache[key]
+    kh, kw = weight_shape[2], weight_shape[3]
+    assert 0 <= padding[0] <= kh - 1 and 0 <= padding[1] <= kw - 1, 'conv2d_s1: padding must be within [0, k-1]'
+    assert out_hw[0] >= 1 and out_hw[1] >= 1
+    dpad = (kh - 1 - padding[0], kw - 1 - padding[1])
+
+    def run(x, w):
+        if not io:
+            return _plugin.conv2d(x, w, stride=1, padding=padding, transposed=False, flip_w=flip, out_hw=out_hw, flop_scale=live)
+        return _plugin.conv2d(x, w, stride=1, padding=dpad, transposed=True, flip_w=(not flip), out_hw=out_hw, flop_scale=live)
+
+    class ConvS1(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, w):
+            assert tuple(w.shape) == weight_shape
+            ctx.save_for_backward(x, w)
+            return run(x, w)
+
+        @staticmethod
+        def backward(ctx, dy):
+            x, w = ctx.saved_tensors
+            dx = dw = None
+            if ctx.needs_input_grad[0]:
+                dx = _conv2d_s1(weight_shape, dpad, (x.shape[2], x.shape[3]), not io, not flip, live).apply(dy, w)
+            if ctx.needs_input_grad[1] and not weight_gradients_disabled:
+                dw = WgradS1.apply(dy, x)
+            return dx, dw
+
+    class WgradS1(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, dy, x):
+            ctx.save_for_backward(dy, x)
+            return _plugin.conv2d_wgrad(x, dy, (kh, kw), stride=1, padding=padding, flip_w=flip, out_layout=(1 if io else 0), flop_scale=live)
+
+        @staticmethod
+        def backward(ctx, ggw):
+            dy, x = ctx.saved_tensors
+            g_dy = g_x = None
+            if ctx.needs_input_grad[0]:
+                g_dy = _conv2d_s1(weight_shape, padding, (dy.shape[2], dy.shape[3]), io, flip, live).apply(x, ggw)
+            if ctx.needs_input_grad[1]:
+                g_x = _conv2d_s1(weight_shape, dpad, (x.shape[2], x.shape[3]), not io, not flip, live).apply(dy, ggw)
+            return g_dy, g_x
+
+    _conv2d_s1_cache[key] = ConvS1
+    return ConvS1
 
 
 # ----------------------------------------------------------------------------

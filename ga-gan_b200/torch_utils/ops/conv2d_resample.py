@@ -29,6 +29,75 @@ def _conv2d_wrapper(x, w, stride=1, padding=0, groups=1, transpose=False, flip_w
     return op(x, w, stride=stride, padding=padding, groups=groups)
 
 
+# ----------------------------------------------------------------------------
+# Phase-major ("space-to-depth") form of the stride-2 layers.
+#
+#   x_pm[n, (py,px,c), Y, X] = x[n, c, 2Y+py, 2X+px]
+#
+# A 3x3 stride-2 correlation is a 2x2 stride-1 correlation over the 4C phase channels, a 3x3 stride-2 transposed
+# convolution is a 2x2 stride-1 correlation producing the 4O output phases (weights below; 7 of the 16 (phase, tap)
+# blocks are structurally zero and are skipped by the tcgen05 kernel, so the MAC count equals the reference's).  That
+# way every dense contraction of the networks -- forward, data gradient and weight gradient -- runs through the ONE
+# stride-1 tensor-core kernel (conv2d_gradfix.conv2d_s1), with the same results as conv2d_resample.py:119-142.
+
+_PM_LIVE = 9.0 / 16.0
+
+
+def phase_major_weight_down(w):
+    """[O,I,kh,kw] (kh,kw <= 4) -> [O,4I,2,2]:  W2[o,(py,px,i),a,b] = w[o,i,2a+py,2b+px]  (0 beyond the kernel)."""
+    O, I, kh, kw = w.shape
+    wp = torch.nn.functional.pad(w, (0, 4 - kw, 0, 4 - kh)).reshape(O, I, 2, 2, 2, 2)      # [O,I,a,py,b,px]
+    return wp.permute(0, 3, 5, 1, 2, 4).reshape(O, 4 * I, 2, 2)
+
+
+def phase_major_weight_up(w):
+    """[O,I,kh,kw] -> [4O,I,2,2]:  W2[(py,px,o),i,a,b] = w[o,i,py+2(1-a),px+2(1-b)]  (conv_transpose2d, stride 2, pad 0)."""
+    O, I, kh, kw = w.shape
+    wp = torch.nn.functional.pad(w, (0, 4 - kw, 0, 4 - kh)).reshape(O, I, 2, 2, 2, 2).flip([2, 4])
+    return wp.permute(3, 5, 0, 1, 2, 4).reshape(4 * O, I, 2, 2)
+
+
+def space_to_depth(x, ys, xs):
+    """[N,C,H,W] -> [N,4C,ys,xs] phase-major, zero-padded (or cropped) to 2ys x 2xs first."""
+    N, C, H, W = x.shape
+    x = torch.nn.functional.pad(x, (0, 2 * xs - W, 0, 2 * ys - H))
+    return x.reshape(N, C, ys, 2, xs, 2).permute(0, 3, 5, 1, 2, 4).reshape(N, 4 * C, ys, xs)
+
+
+def depth_to_space(z):
+    """[N,4O,ys,xs] phase-major -> [N,O,2ys,2xs]."""
+    N, C4, ys, xs = z.shape
+    return z.reshape(N, 2, 2, C4 // 4, ys, xs).permute(0, 3, 4, 1, 5, 2).reshape(N, C4 // 4, 2 * ys, 2 * xs)
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def down2_phase_major(x, w, f, fir_pad, flip_weight, flip_filter, conv_s1, fir):
+    """conv2d_resample.py:119-122 (FIR, then stride-2 conv) with the conv in phase-major form.
+    `conv_s1(x, w, padding, out_hw, live)` and `fir(x, f, padding, flip_filter)` are injected (tests pass torch stand-ins)."""
+    kh, kw = int(w.shape[2]), int(w.shape[3])
+    x = fir(x, f, fir_pad, flip_filter)
+    oh, ow = (x.shape[2] - kh) // 2 + 1, (x.shape[3] - kw) // 2 + 1
+    if not flip_weight:
+        w = w.flip([2, 3])
+    xs = space_to_depth(x, oh + 1, _round_up(ow + 1, 4))     # width multiple of 4: TMA row pitch must be 16-byte aligned
+    return conv_s1(xs, phase_major_weight_down(w), (0, 0), (oh, ow), _PM_LIVE)
+
+
+def up2_phase_major(x, w, f, fir_pad, flip_weight, flip_filter, conv_s1, fir):
+    """conv2d_resample.py:125-139 (stride-2 transposed conv with pad 0, then FIR with gain 4) in phase-major form."""
+    N, I, H, W = x.shape
+    if flip_weight:                      # the reference hands `not flip_weight` to the transposed conv (:138)
+        w = w.flip([2, 3])
+    xs_w = _round_up(W + 1, 4)           # the gradient of this tensor is a TMA source in backward: keep the width aligned
+    z = conv_s1(x, phase_major_weight_up(w), (1, 1), (H + 1, xs_w), _PM_LIVE)
+    z = depth_to_space(z)                # [N,O,2H+2,2xs_w]; rows/cols beyond 2H+1 / 2W+1 are exact zeros
+    px0, px1, py0, py1 = fir_pad
+    return fir(z, f, [px0, px1 - (2 * xs_w - (2 * W + 1)), py0, py1 - 1], flip_filter, 4)
+
+
 def plan(w_shape, f, up, down, padding):
     """Branch + pads chosen by conv2d_resample.py:86-154 for a weight of shape `w_shape`."""
     _, _, kh, kw = [int(v) for v in w_shape]
@@ -57,6 +126,14 @@ def plan(w_shape, f, up, down, padding):
     return dict(branch='generic', fir_pad=[px0, px1, py0, py1])
 
 
+def _conv_s1(x, w, padding, out_hw, live):
+    return conv2d_gradfix.conv2d_s1(x, w, padding=padding, out_hw=out_hw, live=live)
+
+
+def _fir(x, f, padding, flip_filter, gain=1):
+    return upfirdn2d.upfirdn2d(x=x, f=f, padding=padding, flip_filter=flip_filter, gain=gain)
+
+
 @misc.profiled_function
 def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False):
     r"""2D convolution with optional up/downsampling; padding is applied once, up front.
@@ -83,10 +160,14 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
         return upfirdn2d.upfirdn2d(x=x, f=f, up=up, padding=pl['fir_pad'], gain=up ** 2, flip_filter=flip_filter)
 
     if branch == 'down':          # FIR at full resolution, then a strided conv
+        if down == 2 and groups == 1 and kh <= 4 and kw <= 4:
+            return down2_phase_major(x, w, f, pl['fir_pad'], flip_weight, flip_filter, _conv_s1, _fir)
         x = upfirdn2d.upfirdn2d(x=x, f=f, padding=pl['fir_pad'], flip_filter=flip_filter)
         return _conv2d_wrapper(x=x, w=w, stride=down, groups=groups, flip_weight=flip_weight)
 
     if branch == 'up':            # transposed strided conv, then FIR (then optional decimation)
+        if up == 2 and down == 1 and groups == 1 and kh <= 4 and kw <= 4 and pl['conv_pad'] == [0, 0]:
+            return up2_phase_major(x, w, f, pl['fir_pad'], flip_weight, flip_filter, _conv_s1, _fir)
         if groups == 1:
             w = w.transpose(0, 1)
         else:

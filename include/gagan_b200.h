@@ -99,6 +99,9 @@ GG_API int gg_upfirdn2d_f32(const float* x, const float* f, float* y, int N, int
  * transposed=0: correlation with `stride`, zero padding (pad_y, pad_x); w is [O,I,KH,KW].
  * transposed=1: conv_transpose2d with `stride`, padding (pad_y,pad_x); w is [I,O,KH,KW]
  *               (torch layout); OH = (H-1)*stride - 2*pad_y + KH + output_padding (caller passes OH/OW).
+ * stride == 1:  OH/OW are free -- (pad_y,pad_x) is the top/left padding and every position that reads outside
+ *               x sees zeros, so a caller may crop or extend the output (this is what makes the op closed
+ *               under differentiation without copies; conv2d_gradfix.conv2d_s1 in the Python host).
  * flip_w=1 uses w flipped in both spatial axes (conv2d_resample.py:35-36).
  * in_scale [N,I] / out_scale [N,O] may be NULL (plain conv, the discriminator).
  * groups == 1 only (grouped convs are split by the host).
@@ -113,7 +116,8 @@ GG_API int gg_conv2d_f32(const float* x, const float* w, float* y, int N, int I,
  *   dw[o,i,ky,kx] = sum_{n,oy,ox} (b_scale[n,o]*b[n,o,oy,ox]) * (a_scale[n,i]*a[n,i, oy*stride-pad_y+ky, ox*stride-pad_x+kx])
  * a: [N,A,HA,WA] (the conv input), b: [N,B,HB,WB] (gradient w.r.t. the conv output), dw: [B,A,KH,KW].
  * out_layout=1 writes dw transposed as [A,B,KH,KW] (the conv_transpose2d weight layout, roles swapped
- * by the host).  flip_w=1 writes the spatially flipped gradient.  dw is overwritten.
+ * by the host).  flip_w=1 writes the spatially flipped gradient.  dw is overwritten.  Positions of `a` outside
+ * its extent count as zeros (b may be smaller or larger than the natural correlation output).
  */
 GG_API int gg_conv2d_wgrad_f32(const float* a, const float* b, float* dw, int N, int A, int HA, int WA, int B, int HB, int WB,
                         int KH, int KW, int stride, int pad_y, int pad_x, int flip_w, int out_layout,

@@ -119,3 +119,42 @@ def test_network_state_dict_names_match_golden_weights():
     Gf = networks.Generator(512, 0, 512, 1024, 3, mapping_kwargs=dict(num_layers=8), synthesis_kwargs=dict(channel_base=32768))
     assert sum(p.numel() for p in Gf.parameters()) == 30370060
     assert Gf.num_ws == 18
+
+
+def test_phase_major_forms_of_the_stride2_layers_match_the_oracle():
+    """Host algebra of conv2d_resample's up=2 / down=2 paths: with torch stand-ins for the two device ops, the
+    phase-major (space-to-depth) formulation must reproduce the oracle's conv2d_resample (conv2d_resample.py:119-142)."""
+    import torch
+    import torch.nn.functional as F
+    from torch_utils.ops import conv2d_resample as cr
+    from oracle import ops_ref as R
+
+    def conv_s1(x, w, padding, out_hw, live):
+        # y[Y,X] = sum x[Y-py+a, X-px+b] w[a,b], zero outside x, free output extent
+        kh, kw = w.shape[2:]
+        py, px = padding
+        H, W = x.shape[2:]
+        need_h, need_w = out_hw[0] + kh - 1, out_hw[1] + kw - 1
+        xp = F.pad(x, (px, max(need_w - W - px, 0), py, max(need_h - H - py, 0)))[:, :, :need_h, :need_w]
+        return F.conv2d(xp, w)
+
+    def fir(x, f, padding, flip_filter, gain=1):
+        return R.upfirdn2d(x, f, padding=padding, flip_filter=flip_filter, gain=gain)
+
+    g = torch.Generator().manual_seed(11)
+    f = R.setup_filter([1, 3, 3, 1])
+    for (N, I, O, H, W, flip_weight) in [(2, 5, 7, 8, 8, True), (1, 4, 6, 16, 12, False), (2, 3, 4, 5, 9, True)]:
+        x = torch.randn(N, I, H, W, generator=g, dtype=torch.float64)
+        w = torch.randn(O, I, 3, 3, generator=g, dtype=torch.float64)
+        for up, down in [(2, 1), (1, 2)]:
+            want = R.conv2d_resample(x, w, f=f, up=up, down=down, padding=1, flip_weight=flip_weight)
+            pl = cr.plan(w.shape, f, up, down, 1)
+            fn = cr.up2_phase_major if up == 2 else cr.down2_phase_major
+            got = fn(x, w, f, pl['fir_pad'], flip_weight, False, conv_s1, fir)
+            assert got.shape == want.shape, (got.shape, want.shape)
+            assert float((got - want).abs().max()) < 1e-12, (up, down, flip_weight)
+    # 7 of the 16 (phase, tap) blocks of the phase-major weights are structurally zero
+    w2 = cr.phase_major_weight_down(torch.ones(2, 3, 3, 3)).reshape(2, 4, 3, 4)
+    assert int((w2.abs().sum(dim=(0, 2)) == 0).sum()) == 7
+    w2 = cr.phase_major_weight_up(torch.ones(2, 3, 3, 3)).reshape(4, 2, 3, 4)
+    assert int((w2.abs().sum(dim=(1, 2)) == 0).sum()) == 7
