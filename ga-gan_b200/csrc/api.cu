@@ -19,14 +19,23 @@ int conv2d_simt(const float*, const float*, float*, int, int, int, int, int, int
                 const float*, const float*, cudaStream_t);
 int conv2d_wgrad_simt(const float*, const float*, float*, int, int, int, int, int, int, int, int, int, int, int, int, int, int,
                       const float*, const float*, cudaStream_t);
+// conv_thin.cu (HBM-streaming 1x1 kernels with <= 4 channels on one side: ToRGB / fromRGB)
+bool conv1x1_thin_eligible(const float* x, const float* y, int N, int I, int H, int W, int O, int KH, int KW, int OH, int OW,
+                           int stride, int pad_y, int pad_x);
+int conv1x1_thin(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int w_io, const float* in_scale,
+                 const float* out_scale, cudaStream_t st);
+bool wgrad1x1_thin_eligible(const float* a, const float* b, int N, int A, int HA, int WA, int B, int HB, int WB, int KH, int KW,
+                            int stride, int pad_y, int pad_x);
+int wgrad1x1_thin(const float* a, const float* b, float* dw, int N, int A, int HA, int WA, int B, int out_layout,
+                  const float* a_scale, const float* b_scale, cudaStream_t st);
 // conv_tc.cu (tcgen05 / TMEM / TMA path)
 bool conv2d_tc_eligible(int N, int I, int H, int W, int O, int KH, int KW, int OH, int OW, int stride, int pad_y, int pad_x,
                         int transposed);
 int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int KH, int KW, int OH, int OW, int pad_y,
               int pad_x, int flip_w, int w_is_IO, const float* in_scale, const float* out_scale, int nprod, cudaStream_t st);
 bool wgrad_tc_eligible(int N, int A, int HA, int WA, int B, int HB, int WB, int KH, int KW, int stride, int pad_y, int pad_x);
-int wgrad_tc(const float* a, const float* b, float* dw, int N, int A, int HA, int WA, int B, int KH, int KW, int pad_y, int pad_x,
-             int flip_w, int out_layout, const float* a_scale, const float* b_scale, int nprod, cudaStream_t st);
+int wgrad_tc(const float* a, const float* b, float* dw, int N, int A, int HA, int WA, int B, int HB, int WB, int KH, int KW,
+             int pad_y, int pad_x, int flip_w, int out_layout, const float* a_scale, const float* b_scale, int nprod, cudaStream_t st);
 
 }  // namespace gg
 
@@ -68,8 +77,11 @@ extern "C" GG_API int gg_conv2d_f32(const float* x, const float* w, float* y, in
                       N, I, H, W, O, KH, KW, stride, transposed);
         return GG_EUNSUPPORTED;
     }
-    int use = (prec == GG_PREC_AUTO) ? (tc_ok ? GG_PREC_TF32X3 : GG_PREC_FP32_SIMT) : prec;
+    const bool thin_ok = N > 0 && gg::conv1x1_thin_eligible(x, y, N, I, H, W, O, KH, KW, OH, OW, stride, pad_y, pad_x);
+    int use = (prec == GG_PREC_AUTO) ? ((tc_ok && !thin_ok) ? GG_PREC_TF32X3 : GG_PREC_FP32_SIMT) : prec;
     if (used_prec) *used_prec = use;
+    if (use == GG_PREC_FP32_SIMT && thin_ok)
+        return gg::conv1x1_thin(x, w, y, N, I, H, W, O, transposed, in_scale, out_scale, st);
     if (use == GG_PREC_FP32_SIMT)
         return gg::conv2d_simt(x, w, y, N, I, H, W, O, KH, KW, OH, OW, stride, pad_y, pad_x, transposed, flip_w, in_scale,
                                out_scale, st);
@@ -94,10 +106,13 @@ extern "C" GG_API int gg_conv2d_wgrad_f32(const float* a, const float* b, float*
         gg::set_error("conv2d_wgrad: shape is not served by the tcgen05 path");
         return GG_EUNSUPPORTED;
     }
-    int use = (prec == GG_PREC_AUTO) ? (tc_ok ? GG_PREC_TF32X3 : GG_PREC_FP32_SIMT) : prec;
+    const bool thin_ok = N > 0 && gg::wgrad1x1_thin_eligible(a, b, N, A, HA, WA, B, HB, WB, KH, KW, stride, pad_y, pad_x);
+    int use = (prec == GG_PREC_AUTO) ? ((tc_ok && !thin_ok) ? GG_PREC_TF32X3 : GG_PREC_FP32_SIMT) : prec;
     if (used_prec) *used_prec = use;
+    if (use == GG_PREC_FP32_SIMT && thin_ok)
+        return gg::wgrad1x1_thin(a, b, dw, N, A, HA, WA, B, out_layout, a_scale, b_scale, st);
     if (use == GG_PREC_FP32_SIMT)
         return gg::conv2d_wgrad_simt(a, b, dw, N, A, HA, WA, B, HB, WB, KH, KW, stride, pad_y, pad_x, flip_w, out_layout, a_scale,
                                      b_scale, st);
-    return gg::wgrad_tc(a, b, dw, N, A, HA, WA, B, KH, KW, pad_y, pad_x, flip_w, out_layout, a_scale, b_scale, use, st);
+    return gg::wgrad_tc(a, b, dw, N, A, HA, WA, B, HB, WB, KH, KW, pad_y, pad_x, flip_w, out_layout, a_scale, b_scale, use, st);
 }

@@ -580,11 +580,4 @@ int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int
     return rc;
 }
 
-bool wgrad_tc_eligible(int, int, int, int, int, int, int, int, int, int, int, int) { return false; }
-int wgrad_tc(const float*, const float*, float*, int, int, int, int, int, int, int, int, int, int, int, const float*, const float*,
-             int, cudaStream_t) {
-    set_error("wgrad(tc): not built yet");
-    return GG_EUNSUPPORTED;
-}
-
 }  // namespace gg

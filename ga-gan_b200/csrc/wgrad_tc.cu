@@ -19,7 +19,7 @@
 //               aligned), apply the per-sample scales, split into tf32 hi/lo (cvt.rna) and fill two shared-memory rings;
 //               one thread issues tcgen05.mma.kind::tf32 (M=128, N=NTA, K=8; hi*hi + hi*lo + lo*hi) into TMEM.
 // Accumulation  as in conv_tc.cu the tensor core's truncating fp32 accumulator is only trusted for one strip
-//               (<= 32 rows x 2 steps x 3 products); two TMEM sets ping-pong and the converter warps drain every finished
+//               (<= 16 rows x 2 steps x 3 products); two TMEM sets ping-pong and the converter warps drain every finished
 //               strip into fp32 REGISTERS (round-to-nearest).  A tile's partial sum leaves the CTA once, with fp32 atomics
 //               into the zero-initialised dw (a handful of partials per tile: one per CTA that worked on it).
 #include "tc_common.cuh"
@@ -30,7 +30,8 @@ namespace {
 
 constexpr int WG_CONS_WARPS = 8;
 constexpr int WG_CONS_THREADS = WG_CONS_WARPS * 32;
-constexpr int WG_THREADS = (1 + WG_CONS_WARPS) * 32;     // w0 = MMA issuer + TMEM owner, w1..w8 = convert + drain + flush
+constexpr int WG_PROD_WARPS = 4;                         // one warpgroup (w0 = MMA issuer + TMEM owner, w1..w3 idle) so that setmaxnreg applies
+constexpr int WG_THREADS = (WG_PROD_WARPS + WG_CONS_WARPS) * 32;   // w4..w11 = convert + drain + flush
 constexpr int UW = 16;                                   // image columns per strip (two K=8 steps)
 constexpr int GS = 3;                                    // G-row ring slots
 constexpr int XS = 5;                                    // X-row ring slots (k live rows + rows in flight)
@@ -104,9 +105,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
     const int unit_end = min(p.total_units, unit_beg + p.units_per_cta);
     const int K = p.K;
 
-    if (warp == 0) {
+    if (warp < WG_PROD_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         // ===== MMA issuer (one thread)
-        if (lane == 0) {
+        if (warp == 0 && lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(128, NTA, 0, 0);
             const uint64_t a_word = ((uint64_t)(8u | (1u << 14)) << 32) | ((uint64_t)(LBO_A >> 4) << 16);   // SBO 128 B, LBO
             const uint64_t b_word = ((uint64_t)(8u | (1u << 14)) << 32) | ((uint64_t)(LBO_B >> 4) << 16);
@@ -155,30 +157,43 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
             }
         }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         // ===== converter warps: fill the rings for strip s, then drain strip s-1 from TMEM into registers
-        const int ct = threadIdx.x - 32;                // 0..255
-        const int q = warp & 3;                         // TMEM lane quarter
-        const int half = (warp - 1) >> 2;               // which half of the accumulator columns this warp owns
-        constexpr int HC = 3 * NTA / 2;                 // accumulator columns per thread (K = 3); K < 3 uses a prefix
+        const int ct = threadIdx.x - WG_PROD_WARPS * 32;   // 0..255
+        const int q = warp & 3;                            // TMEM lane quarter
+        const int half = (warp - WG_PROD_WARPS) >> 2;      // which half of the accumulator columns this warp owns
+        constexpr int HN = NTA / 2;                     // input channels per thread and ky
+        constexpr int HC = 3 * HN;                      // accumulator registers per thread
         float acc[HC];
 #pragma unroll
         for (int j = 0; j < HC; ++j) acc[j] = 0.f;
-        const int hcols = K * NTA / 2;                  // live columns per half
         uint32_t gc = 0, xc = 0, sc = 0;
         bool pend = false;
         Unit pu{};
         uint32_t pend_sc = 0;
 
-        auto fill_x_row = [&](const Unit& u, int j) {   // local X row j  <->  image row v
-            const int v = u.r0 - p.pad_y + j;
-            const uint32_t slot = xc % XS;
-            mbar_wait(BAR_X_EMPTY(slot), ((xc / XS) & 1) ^ 1);
-            uint8_t* sb = gbase + OFF_X + slot * X_SLOT;
-            for (int id = ct; id < NTA * 4; id += WG_CONS_THREADS) {
-                const int c = id & 3, r = id >> 2;
-                const int ac = u.a0 + r, col = u.u0 + 4 * c;
+        // One converter task = local X row j of a unit (image row r0 - pad_y + j) plus, for j >= K-1, G row j-(K-1).
+        // Loads are issued THREE tasks ahead of their conversion (global/L2 latency is ~1-2 us, a task ~0.3 us).
+        constexpr int XI = (NTA * 4 + WG_CONS_THREADS - 1) / WG_CONS_THREADS;     // X items per thread (1)
+        struct Task { Unit u; int unit, j; bool valid; };   // a cursor into the CTA's task sequence
+        struct Regs { float4 x[XI]; float4 g[2]; };
+        auto task_begin = [&](Task& t, int unit) {
+            t.unit = unit; t.j = 0; t.valid = unit < unit_end;
+            if (t.valid) t.u = decode_unit(unit, p, NTA);
+        };
+        auto task_advance = [&](Task& t) {
+            if (t.valid && ++t.j == t.u.rows + K - 1) task_begin(t, t.unit + 1);
+        };
+        auto load_task = [&](const Task& t, Regs& r) {
+            const Unit& u = t.u;
+            const int v = u.r0 - p.pad_y + t.j;
+#pragma unroll
+            for (int k = 0; k < XI; ++k) {
+                const int id = ct + k * WG_CONS_THREADS;
+                const int c = id & 3, row = id >> 2;
+                const int ac = u.a0 + row, col = u.u0 + 4 * c;
                 float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (v >= 0 && v < p.HA && ac < p.A && col < p.WA) {
+                if (row < NTA && v >= 0 && v < p.HA && ac < p.A && col < p.WA) {
                     const float* src = p.X + (((size_t)u.n * p.A + ac) * p.HA + v) * p.WA + col;
                     if (p.vecX && col + 3 < p.WA) {
                         val = __ldg(reinterpret_cast<const float4*>(src));
@@ -188,32 +203,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
                         if (col + 2 < p.WA) val.z = __ldg(src + 2);
                         if (col + 3 < p.WA) val.w = __ldg(src + 3);
                     }
-                    if (p.xs) { const float s = __ldg(p.xs + (size_t)u.n * p.A + ac); val.x *= s; val.y *= s; val.z *= s; val.w *= s; }
+                    if (p.xs) { const float sx = __ldg(p.xs + (size_t)u.n * p.A + ac); val.x *= sx; val.y *= sx; val.z *= sx; val.w *= sx; }
                 }
-                float4 h, l;
-                split_tf32(val.x, h.x, l.x); split_tf32(val.y, h.y, l.y); split_tf32(val.z, h.z, l.z); split_tf32(val.w, h.w, l.w);
-                *reinterpret_cast<float4*>(sb + c * LBO_B + r * 16) = h;
-                *reinterpret_cast<float4*>(sb + X_HALF + c * LBO_B + r * 16) = l;
+                r.x[k] = val;
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR_X_FULL(slot));
-            ++xc;
-        };
-        auto fill_g_row = [&](const Unit& u, int i) {
-            const int y = u.r0 + i;
-            const uint32_t slot = gc % GS;
-            mbar_wait(BAR_G_EMPTY(slot), ((gc / GS) & 1) ^ 1);
-            uint8_t* sb = gbase + OFF_G + slot * G_SLOT;
+            const int i = t.j - (K - 1);
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const int id = ct + t * WG_CONS_THREADS;                       // 512 items: (row m, chunk c)
+            for (int k = 0; k < 2; ++k) {
+                const int id = ct + k * WG_CONS_THREADS;                       // 512 items: (row m, chunk c)
                 const int c = id & 3, m = id >> 2;
                 const int s = m >> p.rb_shift, bc = u.b0 + (m & (p.RB - 1));
                 const int x0 = u.u0 + 4 * c - (u.kx0 + s - p.pad_x);           // G column of the chunk's first pixel
                 float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (s < u.ns && bc < p.B && x0 + 3 >= 0 && x0 < p.WB) {
-                    const float* src = p.G + (((size_t)u.n * p.B + bc) * p.HB + y) * p.WB;
+                if (i >= 0 && s < u.ns && bc < p.B && x0 + 3 >= 0 && x0 < p.WB) {
+                    const float* src = p.G + (((size_t)u.n * p.B + bc) * p.HB + (u.r0 + i)) * p.WB;
                     if (p.vecG && (x0 & 3) == 0 && x0 >= 0 && x0 + 3 < p.WB) {
                         val = __ldg(reinterpret_cast<const float4*>(src + x0));
                     } else {
@@ -224,27 +227,60 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
                     }
                     if (p.gs) { const float sg = __ldg(p.gs + (size_t)u.n * p.B + bc); val.x *= sg; val.y *= sg; val.z *= sg; val.w *= sg; }
                 }
-                float4 h, l;
-                split_tf32(val.x, h.x, l.x); split_tf32(val.y, h.y, l.y); split_tf32(val.z, h.z, l.z); split_tf32(val.w, h.w, l.w);
-                *reinterpret_cast<float4*>(sb + c * LBO_A + m * 16) = h;
-                *reinterpret_cast<float4*>(sb + G_HALF + c * LBO_A + m * 16) = l;
+                r.g[k] = val;
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR_G_FULL(slot));
-            ++gc;
         };
+        auto store_split = [&](uint8_t* hi_addr, uint32_t half_bytes, const float4& val) {
+            float4 h, l;
+            split_tf32(val.x, h.x, l.x); split_tf32(val.y, h.y, l.y); split_tf32(val.z, h.z, l.z); split_tf32(val.w, h.w, l.w);
+            *reinterpret_cast<float4*>(hi_addr) = h;
+            *reinterpret_cast<float4*>(hi_addr + half_bytes) = l;
+        };
+        auto store_task = [&](const Task& t, const Regs& r) {
+            {
+                const uint32_t slot = xc % XS;
+                mbar_wait(BAR_X_EMPTY(slot), ((xc / XS) & 1) ^ 1);
+                uint8_t* sb = gbase + OFF_X + slot * X_SLOT;
+#pragma unroll
+                for (int k = 0; k < XI; ++k) {
+                    const int id = ct + k * WG_CONS_THREADS;
+                    if (id < NTA * 4) store_split(sb + (id & 3) * LBO_B + (id >> 2) * 16, X_HALF, r.x[k]);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR_X_FULL(slot));
+                ++xc;
+            }
+            if (t.j >= K - 1) {
+                const uint32_t slot = gc % GS;
+                mbar_wait(BAR_G_EMPTY(slot), ((gc / GS) & 1) ^ 1);
+                uint8_t* sb = gbase + OFF_G + slot * G_SLOT;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int id = ct + k * WG_CONS_THREADS;
+                    store_split(sb + (id & 3) * LBO_A + (id >> 2) * 16, G_HALF, r.g[k]);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR_G_FULL(slot));
+                ++gc;
+            }
+        };
+        // Accumulator ownership: this thread holds, for every ky, input channels [half*HN, half*HN + HN) of TMEM lane q*32+lane.
         auto drain = [&](uint32_t k) {                  // TMEM accumulator set of strip k -> registers (RN adds)
             const uint32_t buf = k & 1;
             mbar_wait(BAR_ACC_FULL(buf), (k >> 1) & 1);
             tc_fence_after();
 #pragma unroll
-            for (int cb = 0; cb < HC; cb += 16) {
-                if (cb < hcols) {
-                    uint32_t v[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_STRIDE + (uint32_t)(half * hcols + cb), v);
+            for (int ky = 0; ky < 3; ++ky) {
+                if (ky < K) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[cb + j] += __uint_as_float(v[j]);
+                    for (int cb = 0; cb < HN; cb += 16) {
+                        uint32_t v[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_STRIDE + (uint32_t)(ky * NTA + half * HN + cb), v);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[ky * HN + cb + j] += __uint_as_float(v[j]);
+                    }
                 }
             }
             tc_fence_before();
@@ -257,36 +293,48 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
             const bool row_ok = s < u.ns && bc < p.B;
             int kx = u.kx0 + s;
             if (p.flip_w) kx = K - 1 - kx;
+            const int ac0 = u.a0 + half * HN;
+            const int nvalid = row_ok ? min(HN, p.A - ac0) : 0;
+            const size_t astep = p.out_layout ? (size_t)p.B * K * K : (size_t)K * K;     // dw stride of one input channel
 #pragma unroll
-            for (int j = 0; j < HC; ++j) {
-                if (j < hcols) {
-                    const int col = half * hcols + j;
-                    int ky = col / NTA;
-                    const int ac = u.a0 + (col - ky * NTA);
-                    if (p.flip_w) ky = K - 1 - ky;
-                    if (row_ok && ac < p.A) {
-                        const size_t idx = p.out_layout ? ((((size_t)ac * p.B + bc) * K + ky) * K + kx)
-                                                        : ((((size_t)bc * p.A + ac) * K + ky) * K + kx);
-                        atomicAdd(p.dw + idx, acc[j]);
-                    }
+            for (int ky = 0; ky < 3; ++ky) {
+                const int kyo = p.flip_w ? K - 1 - ky : ky;
+                float* dst = p.dw + (p.out_layout ? ((((size_t)ac0 * p.B + bc) * K + kyo) * K + kx)
+                                                  : ((((size_t)bc * p.A + ac0) * K + kyo) * K + kx));
+#pragma unroll
+                for (int j = 0; j < HN; ++j) {
+                    if (ky < K && j < nvalid) atomicAdd(dst, acc[ky * HN + j]);
+                    dst += astep;
+                    acc[ky * HN + j] = 0.f;
                 }
-                acc[j] = 0.f;
             }
         };
-
-        for (int unit = unit_beg; unit < unit_end; ++unit) {
-            const Unit u = decode_unit(unit, p, NTA);
-            for (int j = 0; j < K - 1; ++j) fill_x_row(u, j);
-            for (int i = 0; i < u.rows; ++i) {
-                fill_x_row(u, i + K - 1);
-                fill_g_row(u, i);
-            }
+        auto finish_task = [&](const Task& t) {         // after the last row of a unit: drain the PREVIOUS strip (its MMAs are done)
+            if (t.j != t.u.rows + K - 2) return;
             if (pend) {
                 drain(pend_sc);
-                if (pu.tile != u.tile) flush(pu);
+                if (pu.tile != t.u.tile) flush(pu);
             }
-            pend = true; pu = u; pend_sc = sc;
+            pend = true; pu = t.u; pend_sc = sc;
             ++sc;
+        };
+        // two cursors: L runs three tasks ahead issuing the global loads, S converts / stores / drains
+        Task L, S;
+        task_begin(L, unit_beg);
+        task_begin(S, unit_beg);
+        Regs r0, r1, r2;
+        if (L.valid) { load_task(L, r0); task_advance(L); }
+        if (L.valid) { load_task(L, r1); task_advance(L); }
+        if (L.valid) { load_task(L, r2); task_advance(L); }
+        while (S.valid) {
+            store_task(S, r0); finish_task(S); task_advance(S);
+            if (L.valid) { load_task(L, r0); task_advance(L); }
+            if (!S.valid) break;
+            store_task(S, r1); finish_task(S); task_advance(S);
+            if (L.valid) { load_task(L, r1); task_advance(L); }
+            if (!S.valid) break;
+            store_task(S, r2); finish_task(S); task_advance(S);
+            if (L.valid) { load_task(L, r2); task_advance(L); }
         }
         if (pend) { drain(pend_sc); flush(pu); }
         tc_fence_before();
@@ -338,7 +386,7 @@ int wgrad_tc(const float* a, const float* b, float* dw, int N, int A, int HA, in
     const int NTA = A > 32 ? 64 : 32;
     p.btiles = (B + p.RB - 1) / p.RB;
     p.atiles = (A + NTA - 1) / NTA;
-    p.RR = HB < 32 ? HB : 32;
+    p.RR = HB < 16 ? HB : 16;   // rows per strip = TMEM chain length / 6 (96 truncating accumulates at most)
     p.ustrips = (WA + UW - 1) / UW;
     p.rstrips = (HB + p.RR - 1) / p.RR;
     const int64_t S = (int64_t)N * p.ustrips * p.rstrips;

@@ -187,6 +187,9 @@ def _conv_oracle(x, w, stride, pad, transposed, outpad=0):
     # 2x2 kernels (the phase-major form of the stride-2 layers), ragged channel counts, many tiles per persistent CTA
     (2, 64, 32, 20, 20, 2, 1, 0, False), (2, 32, 64, 16, 16, 2, 1, 1, False), (1, 512, 130, 16, 16, 3, 1, 1, False),
     (3, 48, 48, 40, 40, 3, 1, 1, True), (5, 32, 32, 72, 72, 3, 1, 1, False), (2, 256, 48, 12, 12, 2, 1, 1, True),
+    # weight-gradient tilings: 2 kx groups (64 grad channels), 1 kx per group (>=128), ragged widths, 2x2 kernels
+    (2, 64, 200, 40, 40, 3, 1, 1, False), (1, 160, 96, 24, 20, 2, 1, 0, False), (2, 96, 40, 33, 17, 3, 1, 1, True),
+    (1, 20, 24, 70, 50, 3, 1, 1, False),
 ])
 def test_conv2d_fwd_dgrad_wgrad_vs_oracle(ops, device, case, prec):
     N, I, O, H, W, k, stride, pad, transposed = case
@@ -227,6 +230,47 @@ def test_conv2d_tc_is_fp32_faithful(ops, device):
     rms = float((y - ref).square().mean().sqrt() / ref.abs().mean())
     print(f'tf32x3 512ch: mean signed rel err {bias:+.2e}, rms {rms:.2e}')
     assert abs(bias) < 2e-6 and rms < 4e-6
+
+
+def test_conv2d_wgrad_tc_is_fp32_faithful_and_scaled(ops, device):
+    # long reductions (64k pixels) with same-sign products: the per-strip register accumulation must keep the tensor
+    # core's truncation bias out; per-sample scales on both operands (the modulated_conv2d factors)
+    g = torch.Generator().manual_seed(8)
+    plugin = ops.custom_ops.get_plugin('conv2d_plugin')
+    x = torch.randn(4, 32, 128, 128, generator=g).abs(); dy = torch.randn(4, 64, 128, 128, generator=g).abs()
+    a = torch.rand(4, 32, generator=g) + 0.5; b = torch.rand(4, 64, generator=g) + 0.5
+    xd = (x * a[:, :, None, None]).double().requires_grad_(False); dyd = (dy * b[:, :, None, None]).double()
+    w = torch.zeros(64, 32, 3, 3, dtype=torch.float64, requires_grad=True)
+    ref, = torch.autograd.grad(torch.nn.functional.conv2d(xd, w, padding=1), w, dyd)
+    got = plugin.conv2d_wgrad(x.to(device), dy.to(device), (3, 3), padding=(1, 1), a_scale=a.to(device), b_scale=b.to(device),
+                              prec=ops.custom_ops.PREC_TF32X3).double().cpu()
+    assert plugin.last_wgrad_prec == 3
+    bias = float(((got - ref) / ref).mean()); worst = float(((got - ref) / ref).abs().max())
+    print(f'wgrad tf32x3 64k pixels: mean signed rel err {bias:+.2e}, worst {worst:.2e}')
+    assert abs(bias) < 4e-6 and worst < 1e-5      # un-chunked this would be ~4e-4
+
+
+@pytest.mark.parametrize('case', [(2, 32, 3, 64, 64), (2, 3, 32, 64, 64), (3, 512, 3, 8, 8), (1, 3, 64, 32, 48), (2, 4, 4, 16, 16)])
+def test_conv1x1_thin_channels_fwd_dgrad_wgrad_scaled(ops, device, case):
+    # ToRGB (C -> 3, modulated) / fromRGB (3 -> C): the HBM-streaming 1x1 kernels, with per-sample scales on both sides
+    N, I, O, H, W = case
+    g = torch.Generator().manual_seed(I * 7 + O)
+    plugin = ops.custom_ops.get_plugin('conv2d_plugin')
+    x = torch.randn(N, I, H, W, generator=g); w = torch.randn(O, I, 1, 1, generator=g)
+    a = torch.randn(N, I, generator=g); b = torch.randn(N, O, generator=g); dy = torch.randn(N, O, H, W, generator=g)
+    want = torch.nn.functional.conv2d(x * a[:, :, None, None], w) * b[:, :, None, None]
+    got = plugin.conv2d(x.to(device), w.to(device), in_scale=a.to(device), out_scale=b.to(device))
+    assert plugin.last_conv_prec == 0
+    assert_close(got, want, 2e-6, 'fwd')
+    wt = w.transpose(0, 1).contiguous()                                     # [I,O,1,1] read through the transposed layout
+    got_t = plugin.conv2d(x.to(device), wt.to(device), transposed=True, in_scale=a.to(device), out_scale=b.to(device))
+    assert_close(got_t, want, 2e-6, 'fwd(transposed layout)')
+    wdw = torch.einsum('nohw,nihw->oi', dy * b[:, :, None, None], x * a[:, :, None, None])[:, :, None, None]
+    gdw = plugin.conv2d_wgrad(x.to(device), dy.to(device), (1, 1), a_scale=a.to(device), b_scale=b.to(device))
+    assert plugin.last_wgrad_prec == 0
+    assert_close(gdw, wdw, 2e-5, 'wgrad')
+    gdw_t = plugin.conv2d_wgrad(x.to(device), dy.to(device), (1, 1), a_scale=a.to(device), b_scale=b.to(device), out_layout=1)
+    assert_close(gdw_t, wdw.transpose(0, 1), 2e-5, 'wgrad [A,B] layout')
 
 
 def test_conv2d_tc_zero_block_skipping(ops, device):

@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Where does one training iteration spend its GPU time?  torch.profiler (CUPTI) kernel table of one bench.py step
+(config-f, --res, batch/batch_gpu as given), grouped by kernel name.  Development tool; the judged numbers come from
+bench.py and the ncu captures under profiles/.
+
+    python tools/profile_step.py [--res 1024] [--batch 8] [--batch-gpu 4] [--out gpurun_out/step_profile.txt]
+"""
+import os
+import sys
+import argparse
+import collections
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, 'ga-gan_b200')):
+    sys.path.insert(0, p)
+
+import torch  # noqa: E402
+from torch.profiler import profile, ProfilerActivity  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--res', type=int, default=1024)
+    ap.add_argument('--cfg', default='stylegan2')
+    ap.add_argument('--batch', type=int, default=8)
+    ap.add_argument('--batch-gpu', type=int, default=4)
+    ap.add_argument('--out', default='')
+    args = ap.parse_args()
+    from torch_utils import custom_ops
+    from training import training_loop
+    dev = torch.device('cuda:0')
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    custom_ops.verbosity = 'none'
+    spec = training_loop.CONFIGS[args.cfg]
+    torch.manual_seed(0)
+    G, D = training_loop.build_networks(args.res, args.cfg, device=dev)
+    step = training_loop.TrainingStep(G, D, batch_size=args.batch, batch_gpu=min(args.batch_gpu, args.batch), device=dev,
+                                      lrate=spec['lrate'], r1_gamma=spec['gamma'], ema_kimg=spec['ema'])
+    real = torch.rand(args.batch, 3, args.res, args.res, device=dev) * 2 - 1
+    for _ in range(2):
+        step.cur_it = 0
+        step.run(real)
+    torch.cuda.synchronize()
+    step.cur_it = 0                      # all four phases fire
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step.run(real)
+        torch.cuda.synchronize()
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for ev in prof.events():
+        if ev.device_type == torch.autograd.DeviceType.CUDA:
+            name = ev.name
+            for cut in ('<', '('):
+                if cut in name and not name.startswith('void '):
+                    name = name.split(cut)[0]
+            agg[name[:110]][0] += 1
+            agg[name[:110]][1] += ev.device_time if hasattr(ev, 'device_time') else ev.cuda_time
+    total = sum(v[1] for v in agg.values())
+    lines = [f'one iteration with all four phases, res {args.res}, batch {args.batch} in rounds of {args.batch_gpu}: '
+             f'{total / 1000:.1f} ms of kernel time in {sum(v[0] for v in agg.values())} launches']
+    for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+        lines.append(f'{us / 1000:10.2f} ms {100 * us / total:5.1f}%  {n:6d}x  {name}')
+    text = '\n'.join(lines)
+    print(text)
+    if args.out:
+        os.makedirs(os.path.dirname(args.out) or '.', exist_ok=True)
+        open(args.out, 'w').write(text + '\n')
+
+
+if __name__ == '__main__':
+    main()
