@@ -87,6 +87,7 @@ __global__ void pack_weights_kernel(PackP p) {
 // ------------------------------------------------------------------------------------------------ the conv kernel
 constexpr int TILE_W = 16, TILE_H = 16;   // output pixels per tile: two 8x16 UMMA M-tiles side by side
 constexpr int W_STAGES = 4;
+constexpr int CHUNK_TAPS = 3;   // live taps accumulated in TMEM before the partial sum is drained (18 truncating accumulates)
 constexpr int CONS_WARPS = 8;
 constexpr int CONS_THREADS = CONS_WARPS * 32;
 constexpr int PROD_WARPS = 4;           // one warpgroup: TMA(x), TMA(weights), MMA, idle -- so that setmaxnreg can shift registers
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         // ===== MMA issuer (one thread).  Descriptors are 64-bit adds on per-K-block bases: the issue loop has to stay well
         // under the 64-cycle tensor-core time of one M=128 x N=128 x K=8 instruction.
         if (lane == 0) {
-            uint32_t kbc = 0, ws = 0, wph = 0;
+            uint32_t kbc = 0, ws = 0, wph = 0, ac = 0;          // K-block, weight-stage and accumulator-chunk counters
             const uint32_t idesc = umma_idesc_tf32(128, NT, 0, 0);
             // descriptor: bits [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, bit 46 = version 1
             //   A: LBO = npix*16 B (between 4-channel chunks), SBO = boxW*16 B (next pixel row = next 8-row group)
@@ -272,15 +273,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     if (m == 0u) continue;
                     const uint32_t cs = kbc & 1, cph = (kbc >> 1) & 1;
                     mbar_wait(BAR_CVT_FULL(cs), cph);
-                    mbar_wait(BAR_ACC_EMPTY(cs), cph ^ 1);             // accumulator set cs was drained (two K-blocks ago)
                     tc_fence_after();
                     const uint64_t a_hi0 = a_word + ((base + L.cvt(cs, 0)) >> 4), a_lo0 = a_word + ((base + L.cvt(cs, 1)) >> 4);
-                    const uint32_t d0 = tmem_base + cs * 2u * NT, d1 = d0 + NT;
-                    uint32_t accf = 0u;                               // first MMA of the K-block overwrites the accumulator
+                    uint32_t d0 = 0, d1 = 0;
+                    uint32_t accf = 0u;                               // first MMA of a chunk overwrites the accumulator
                     uint32_t tap = 0;
+                    int in_chunk = 0, left = __popc(m);
                     for (int ky = 0; ky < p.K; ++ky) {
                         for (int kx = 0; kx < p.K; ++kx, ++tap) {
                             if (!((m >> tap) & 1u)) continue;
+                            if (in_chunk == 0) {                      // open a chunk: TMEM accumulator set ac & 1, drained two chunks ago
+                                const uint32_t as = ac & 1;
+                                mbar_wait(BAR_ACC_EMPTY(as), ((ac >> 1) & 1) ^ 1);
+                                d0 = tmem_base + as * 2u * NT; d1 = d0 + NT;
+                                accf = 0u;
+                            }
                             mbar_wait(BAR_W_FULL(ws), wph);
                             tc_fence_after();
                             const uint32_t toff = (uint32_t)(ky * p.boxW + kx);
@@ -309,10 +316,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             umma_commit(BAR_W_EMPTY(ws));          // frees the weight stage when these MMAs have read it
                             if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
                             accf = 1u;
+                            --left;
+                            if (++in_chunk == CHUNK_TAPS || left == 0) {   // close the chunk: its partial sums are complete in TMEM
+                                umma_commit(BAR_ACC_FULL(ac & 1));
+                                ++ac; in_chunk = 0;
+                            }
                         }
                     }
                     umma_commit(BAR_CVT_EMPTY(cs));                // frees the converted tile
-                    umma_commit(BAR_ACC_FULL(cs));                 // this K-block's partial sums are complete in TMEM set cs
                     ++kbc;
                 }
             }
@@ -336,7 +347,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         KbMasks M; int cur_nt = -1, cur_img = -1;
         uint32_t kbc = 0;
         bool pend = false, pend_last = false;
-        uint32_t pend_kbc = 0;
+        uint32_t ac = 0, pend_ac = 0;                   // accumulator-chunk counter (same sequence as the MMA issuer's)
+        int pend_live = 0;                              // live taps of the pending K-block
         TileCoord pend_tc{0, 0, 0, 0};
         const size_t plane = (size_t)p.OH * p.OW;
 
@@ -364,7 +376,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 }
             }
         };
-        auto drain = [&](uint32_t k) {
+        auto drain_chunk = [&](uint32_t k, float kc) {
             const int s = k & 1;
             mbar_wait(BAR_ACC_FULL(s), (k >> 1) & 1);
             tc_fence_after();
@@ -375,7 +387,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     uint32_t v[16];
                     tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 2 * NT + sub * NT + hcol * HN + cb), v);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[sub][cb + j] += __uint_as_float(v[j]);
+                    for (int j = 0; j < 16; ++j) acc[sub][cb + j] = fmaf(__uint_as_float(v[j]), kc, acc[sub][cb + j]);
                 }
             }
             tc_fence_before();
@@ -383,11 +395,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             if (lane == 0) mbar_arrive(BAR_ACC_EMPTY(s));
         };
 
+        auto drain = [&](uint32_t first_chunk, int live) {   // all chunks of one K-block, with the truncation compensation
+            for (int c = 0; live > 0; ++c, live -= CHUNK_TAPS)
+                drain_chunk(first_chunk + c, rz_compensation(2 * min(live, CHUNK_TAPS), p.nprod));
+        };
+
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             const TileCoord tc = decode_tile(t, p);
             if (tc.nt != cur_nt) { M.load(p, tc.nt, lane); cur_nt = tc.nt; }
             if (M.last_kb < 0) {                        // the whole n-tile of weights is zero: the output tile is zero
-                if (pend) { drain(pend_kbc); if (pend_last) store_tile(pend_tc); pend = false; }
+                if (pend) { drain(pend_ac, pend_live); if (pend_last) store_tile(pend_tc); pend = false; }
                 store_tile(tc);
                 continue;
             }
@@ -412,7 +429,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                                                                                                : (chunk < 4 ? -1 : -2);
             }
             for (int kb = 0; kb < p.num_kb; ++kb) {
-                if (M.get(kb) == 0u) continue;
+                const uint32_t live = M.get(kb);
+                if (live == 0u) continue;
                 const int s = kbc & 1;
                 mbar_wait(BAR_RAW_FULL(s), (kbc >> 1) & 1);
                 mbar_wait(BAR_CVT_EMPTY(s), ((kbc >> 1) & 1) ^ 1);
@@ -442,12 +460,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(BAR_CVT_FULL(s)); mbar_arrive(BAR_RAW_EMPTY(s)); }
-                if (pend) { drain(pend_kbc); if (pend_last) store_tile(pend_tc); }
-                pend = true; pend_kbc = kbc; pend_last = (kb == M.last_kb); pend_tc = tc;
+                if (pend) { drain(pend_ac, pend_live); if (pend_last) store_tile(pend_tc); }
+                pend = true; pend_last = (kb == M.last_kb); pend_tc = tc;
+                pend_ac = ac; pend_live = __popc(live);
+                ac += (pend_live + CHUNK_TAPS - 1) / CHUNK_TAPS;
                 ++kbc;
             }
         }
-        if (pend) { drain(pend_kbc); if (pend_last) store_tile(pend_tc); }
+        if (pend) { drain(pend_ac, pend_live); if (pend_last) store_tile(pend_tc); }
         tc_fence_before();
     }
     __syncthreads();
@@ -516,7 +536,10 @@ bool conv2d_tc_eligible(int N, int I, int H, int W, int O, int KH, int KW, int O
     if (N < 1 || I < 16 || O < 16) return false;       // 3-channel fromRGB / ToRGB stay on the FFMA path (HBM-bound, AI ~ 1.4)
     if (I > MAX_KB * KB_CH) return false;
     if (W % 4 != 0) return false;                      // TMA global strides must be multiples of 16 bytes
-    if (OW < 8 || OH < 8) return false;                // 4x4 maps: < 0.1 % of the FLOPs, served by the FFMA kernel
+    // small maps (4x4, 5x8 ...) also run here: one mostly empty 16x16 tile per image and n-tile still beats an FFMA kernel that
+    // can only spread N*OH*OW <= 128 output pixels over a handful of CTAs while walking K = 9*512 sequentially.
+    static const int min_hw = [] { const char* e = getenv("GG_TC_MIN_HW"); return e ? atoi(e) : 1; }();   // debug: force small maps to FFMA
+    if (OW < min_hw || OH < min_hw) return false;
     (void)H; (void)transposed;
     return true;
 }

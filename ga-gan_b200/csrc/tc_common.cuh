@@ -88,4 +88,15 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
 }
 
 
+// Expected-value compensation of the tensor core's truncating fp32 accumulator.  Every accumulate step chops the running
+// sum P toward zero by 0.5 ulp(P) on average.  Because sign(P)*|P| = P the CONDITIONAL MEAN of the accumulated loss, given
+// the final chunk sum S, is -beta * S * sum_j(P_j / S) whatever the signs of the data (a bridge from 0 to S has E[P_j] =
+// S*j/m).  With nprod accumulates per hi*hi product and m hi*hi products per accumulator and chunk, sum_j P_j / S =
+// nprod*(m+1)/2.  beta = 0.5 * E[ulp(P)/|P|] ~ 0.5 * 2^-23 * 0.72, calibrated on B200 (tools/tc_rounding.py: -1.37e-6 at
+// m = 18, nprod = 3; wgrad -5.3e-6 at m = 64) to 5.0e-8.  The drained chunk sum is multiplied by 1 + kappa; what is left of
+// the truncation is zero-mean noise of ~1e-7 (profiles/r1_tc_rounding.txt).
+__device__ __forceinline__ float rz_compensation(int m, int nprod) {
+    return 1.0f + 5.0e-8f * (float)nprod * 0.5f * (float)(m + 1);
+}
+
 }  // namespace ggtc

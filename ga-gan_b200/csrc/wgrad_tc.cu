@@ -267,7 +267,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
             }
         };
         // Accumulator ownership: this thread holds, for every ky, input channels [half*HN, half*HN + HN) of TMEM lane q*32+lane.
-        auto drain = [&](uint32_t k) {                  // TMEM accumulator set of strip k -> registers (RN adds)
+        auto drain = [&](uint32_t k, int rows) {        // TMEM accumulator set of strip k -> registers (RN adds)
+            const float kc = rz_compensation(2 * rows, p.nprod);
             const uint32_t buf = k & 1;
             mbar_wait(BAR_ACC_FULL(buf), (k >> 1) & 1);
             tc_fence_after();
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
                         uint32_t v[16];
                         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_STRIDE + (uint32_t)(ky * NTA + half * HN + cb), v);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[ky * HN + cb + j] += __uint_as_float(v[j]);
+                        for (int j = 0; j < 16; ++j) acc[ky * HN + cb + j] = fmaf(__uint_as_float(v[j]), kc, acc[ky * HN + cb + j]);
                     }
                 }
             }
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
         auto finish_task = [&](const Task& t) {         // after the last row of a unit: drain the PREVIOUS strip (its MMAs are done)
             if (t.j != t.u.rows + K - 2) return;
             if (pend) {
-                drain(pend_sc);
+                drain(pend_sc, pu.rows);
                 if (pu.tile != t.u.tile) flush(pu);
             }
             pend = true; pu = t.u; pend_sc = sc;
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
             store_task(S, r2); finish_task(S); task_advance(S);
             if (L.valid) { load_task(L, r2); task_advance(L); }
         }
-        if (pend) { drain(pend_sc); flush(pu); }
+        if (pend) { drain(pend_sc, pu.rows); flush(pu); }
         tc_fence_before();
     }
     __syncthreads();

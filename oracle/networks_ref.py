@@ -75,7 +75,7 @@ def normalize_2nd_moment(x, dim=1, eps=1e-8):
 
 def mapping(P, z, num_ws, num_layers=8, prefix='mapping', truncation_psi=1, truncation_cutoff=None):
     """networks.py:807-842 (c_dim=0; the w_avg EMA update is a side effect handled by the caller)."""
-    x = normalize_2nd_moment(z.to(torch.float32))
+    x = normalize_2nd_moment(z.to(P[f'{prefix}.fc0.weight'].dtype))   # float32 in the reference (:815); the parameter dtype lets tests run an fp64 truth
     for i in range(num_layers):
         x = fully_connected(P, f'{prefix}.fc{i}', x, activation='lrelu', lr_multiplier=0.01)
     x = x.unsqueeze(1).repeat([1, num_ws, 1])
@@ -118,7 +118,7 @@ def synthesis(P, ws, img_resolution, noise_mode='random', fused_modconv=False, p
     log2 = int(np.log2(img_resolution))
     x = img = None
     w_idx = 0
-    ws = ws.to(torch.float32)
+    ws = ws.to(P[f'{prefix}.b4.const'].dtype)                          # float32 in the reference (:1119)
     for res in [2 ** i for i in range(2, log2 + 1)]:
         b = f'{prefix}.b{res}'
         if res == 4:

@@ -48,14 +48,18 @@ def run(phase, tag):
         errs.append((max_rel_err(p.grad, want), k))
     errs.sort(reverse=True)
     print(f'[{tag}] {phase}: ' + '  '.join(f'{k}={e:.2e}' for e, k in errs[:4]), flush=True)
+    return {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
 
 
 phases = sys.argv[1:] or ['Dreg']
 for ph in phases:
-    run(ph, 'default')
+    ga = run(ph, 'default')
     custom_ops.conv_precision = custom_ops.PREC_FP32_SIMT
-    run(ph, 'conv=fp32_simt')
+    gb = run(ph, 'conv=fp32_simt')
     custom_ops.conv_precision = custom_ops.PREC_AUTO
+    key = os.environ.get('GG_DEBUG_PARAM', '')
+    if key and key in ga:
+        print(f'   {key}: default {ga[key].flatten()[:4].tolist()}  simt {gb[key].flatten()[:4].tolist()}  golden {g[ph + ".grad." + key].flatten()[:4].tolist()}')
 
     orig_ba = plugin.bias_act.__func__
 

@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, 'ga-gan_b200')):
     sys.path.insert(0, p)
 
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 from torch.profiler import profile, ProfilerActivity  # noqa: E402
 
@@ -42,6 +43,31 @@ def main():
         step.cur_it = 0
         step.run(real)
     torch.cuda.synchronize()
+    # which conv shapes miss the tensor-core path?
+    plugin = custom_ops.get_plugin('conv2d_plugin')
+    shapes = collections.Counter()
+    orig_conv, orig_wgrad = plugin.conv2d, plugin.conv2d_wgrad
+
+    def conv2d(x, w, **kw):
+        y = orig_conv(x, w, **kw)
+        shapes[('conv', tuple(x.shape), tuple(w.shape), kw.get('stride', 1), tuple(kw.get('padding', (0, 0))), bool(kw.get('transposed', False)),
+                tuple(y.shape[2:]), plugin.last_conv_prec)] += 1
+        return y
+
+    def conv2d_wgrad(a, b, ks, **kw):
+        y = orig_wgrad(a, b, ks, **kw)
+        shapes[('wgrad', tuple(a.shape), tuple(b.shape), kw.get('stride', 1), tuple(kw.get('padding', (0, 0))), False, tuple(ks),
+                plugin.last_wgrad_prec)] += 1
+        return y
+    plugin.conv2d, plugin.conv2d_wgrad = conv2d, conv2d_wgrad
+    step.cur_it = 0
+    step.run(real)
+    plugin.conv2d, plugin.conv2d_wgrad = orig_conv, orig_wgrad
+    print('conv shapes NOT on the tcgen05 path (kind, x, w, stride, pad, transposed, out/k, prec) x count:')
+    for k, n in sorted(shapes.items(), key=lambda kv: -int(np.prod(kv[0][1])) * kv[1]):
+        if k[-1] == 0:
+            print('   ', k, 'x', n)
+    torch.cuda.synchronize()
     step.cur_it = 0                      # all four phases fire
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         step.run(real)
@@ -49,10 +75,7 @@ def main():
     agg = collections.defaultdict(lambda: [0, 0.0])
     for ev in prof.events():
         if ev.device_type == torch.autograd.DeviceType.CUDA:
-            name = ev.name
-            for cut in ('<', '('):
-                if cut in name and not name.startswith('void '):
-                    name = name.split(cut)[0]
+            name = ev.name.replace('(anonymous namespace)::', '').replace('void ', '')
             agg[name[:110]][0] += 1
             agg[name[:110]][1] += ev.device_time if hasattr(ev, 'device_time') else ev.cuda_time
     total = sum(v[1] for v in agg.values())
