@@ -1,0 +1,98 @@
+"""GA population fitness evaluation over StyleSpace directions, sharded by individual (BASELINE configs[3]).
+
+The reference has no working GA evaluator: `GA/` is un-importable (GA/__init__.py:5 names a function that does not exist)
+and the hooks in DissimilarDomains/training/training_loop.py:392-434 call undefined helpers.  The workload is defined
+from its pieces (SURVEY.md section 8(d) cfg 4):
+
+    individual   = one additive StyleSpace offset `offset[1, C_l]` for every conv / ToRGB layer of a generator built with
+                   use_domain_modulation=True, domain_modulation_parametrization='additive'
+                   (networks.py:140-160, 515-523); initialised 0.1 * randn (the mutation scale of
+                   GA/crossover_mutation.py:17-20)
+    fitness_i    = mean over a fixed latent batch of D(G.synthesis(ws; offset_i)) logits -- the quantity
+                   apply_genetic_algorithm thresholds on (training_loop.py:412-434); G in eval mode, noise_mode='const'
+    sharding     = individual i -> rank i % world (individuals are independent); every rank holds a full G/D replica and
+                   the shared latent batch; ONE all_gather of the per-rank fitness slices, nothing else crosses ranks.
+
+Selection / crossover / mutation on the gathered [P] vector is host-side work outside the hot path.
+"""
+import torch
+import torch.distributed as dist
+
+
+def offset_layers(G):
+    """[(name, module)] of every synthesis layer that carries a StyleSpace `offset` parameter, in network order."""
+    return [(name, m) for name, m in G.synthesis.named_modules() if isinstance(getattr(m, 'offset', None), torch.nn.Parameter)]
+
+
+def genome_size(G):
+    return sum(m.offset.numel() for _, m in offset_layers(G))
+
+
+def init_population(G, size, scale=0.1, seed=0):
+    """[size, genome] fp32 on the CPU; identical on every rank for a given seed."""
+    gen = torch.Generator().manual_seed(seed)
+    return torch.randn(size, genome_size(G), generator=gen) * scale
+
+
+@torch.no_grad()
+def load_individual(G, genome):
+    """Write one genome [genome_size] into the per-layer offsets of G."""
+    pos = 0
+    for _, m in offset_layers(G):
+        n = m.offset.numel()
+        m.offset.copy_(genome[pos:pos + n].reshape(m.offset.shape).to(m.offset.device))
+        pos += n
+    assert pos == genome.numel(), 'genome length does not match the generator'
+
+
+def shard_indices(population_size, rank, world):
+    """Individuals of this rank: i % world == rank."""
+    return list(range(rank, population_size, world))
+
+
+def gather_fitness(local, population_size, rank, world, device):
+    """Per-rank fitness slices -> the full [P] vector on every rank: ONE all_gather (padded to equal length)."""
+    per = (population_size + world - 1) // world
+    buf = torch.full([per], float('nan'), device=device)
+    if len(local):
+        buf[:len(local)] = torch.stack([torch.as_tensor(v, dtype=torch.float32, device=device).reshape([]) for v in local])
+    if world == 1:
+        parts = [buf]
+    else:
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf)
+    out = torch.empty([population_size], device=device)
+    for r in range(world):
+        idx = shard_indices(population_size, r, world)
+        out[idx] = parts[r][:len(idx)]
+    return out
+
+
+@torch.no_grad()
+def default_fitness(G, D, ws, c):
+    """mean_b D(G.synthesis(ws_b; current offsets))."""
+    img = G.synthesis(ws, noise_mode='const')
+    return D(img, c).mean()
+
+
+@torch.no_grad()
+def evaluate_population(G, D, population, z, c=None, rank=0, world=1, fitness_fn=None):
+    """Fitness [P] of every individual, identical on all ranks.
+
+    G, D: this rank's replicas (G built with additive domain modulation); population: [P, genome] (same on every rank);
+    z: the shared latent batch [B, z_dim] on this rank's device.  `fitness_fn(G, D, ws, c)` defaults to the mean logit.
+    """
+    fitness_fn = fitness_fn or default_fitness
+    device = z.device
+    if c is None:
+        c = torch.zeros([z.shape[0], 0], device=device)
+    was_training = (G.training, D.training)
+    G.eval(); D.eval()
+    ws = G.mapping(z, c)                                  # shared by all individuals: offsets live in the synthesis layers only
+    local = []
+    for i in shard_indices(population.shape[0], rank, world):
+        load_individual(G, population[i])
+        local.append(fitness_fn(G, D, ws, c))
+    out = gather_fitness(local, population.shape[0], rank, world, device)
+    G.train(was_training[0]); D.train(was_training[1])
+    return out

@@ -76,3 +76,27 @@ def test_loss_phase_parameter_gradients(nets, device, phase):
     if phase == 'Greg':
         assert_close(loss.pl_mean, g['Greg.pl_mean'], TOL, 'pl_mean')
     print(f'{phase}: worst max-rel-err {worst[1]:.2e} at {worst[0]}')
+
+
+def test_ga_population_fitness_eval_on_the_device(device):
+    """BASELINE configs[3] at toy size: fitness of StyleSpace-offset individuals through the CUDA G/D (world = 1)."""
+    from training import networks, ga_eval
+    torch.manual_seed(3)
+    G = networks.Generator(z_dim=32, c_dim=0, w_dim=32, img_resolution=32, img_channels=3, mapping_kwargs=dict(num_layers=2),
+                           synthesis_kwargs=dict(channel_base=512, channel_max=32, use_domain_modulation=True,
+                                                 domain_modulation_parametrization='additive')).to(device)
+    D = networks.Discriminator(c_dim=0, img_resolution=32, img_channels=3, channel_base=512, channel_max=32).to(device)
+    n_layers = len(ga_eval.offset_layers(G))
+    assert n_layers == 4 * 2 + 4 - 1 and ga_eval.genome_size(G) == 32 * n_layers     # conv0/conv1/torgb per block, no conv0 in b4
+    pop = ga_eval.init_population(G, size=5, scale=0.1, seed=1)
+    pop[2].zero_()                                                          # individual 2 = the unmodified generator
+    z = torch.randn(4, 32, device=device)
+    fit = ga_eval.evaluate_population(G, D, pop, z)
+    assert fit.shape == (5,) and torch.isfinite(fit).all()
+    G.eval(); D.eval()
+    with torch.no_grad():
+        ga_eval.load_individual(G, torch.zeros(ga_eval.genome_size(G)))
+        c = torch.zeros(4, 0, device=device)
+        base = D(G.synthesis(G.mapping(z, c), noise_mode='const'), c).mean()
+    assert abs(float(fit[2] - base)) <= 1e-5 * max(1.0, abs(float(base)))
+    assert len({round(float(v), 5) for v in fit}) == 5                      # different offsets, different fitness

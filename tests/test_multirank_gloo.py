@@ -1,0 +1,174 @@
+"""world_size-2 `gloo` tests (CPU) of the multi-GPU host logic:
+
+  * the G+D training step shards by minibatch: `TrainingStep` wraps the modules in DistributedDataParallel exactly where
+    the reference does (training_loop.py:270-285) and all-reduces the phase's gradients once, on its last accumulation
+    round -- two ranks with half the batch each must end with the SAME parameters as one process with the whole batch;
+  * GA population evaluation shards by individual (i % world) with ONE all_gather of the fitness slices.
+
+The CUDA ops have no CPU path, so the ranks run stand-in networks with the same module interface (mapping / synthesis /
+D(img, c)); what is under test is the partitioning, the sync flags and the collectives, not the kernels.
+"""
+import os
+import socket
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import tests.util  # noqa: F401  (sys.path)
+
+
+class _Mapping(torch.nn.Module):
+    def __init__(self, z_dim, w_dim, num_ws):
+        super().__init__()
+        self.fc = torch.nn.Linear(z_dim, w_dim)
+        self.num_ws = num_ws
+
+    def forward(self, z, c, skip_w_avg_update=False, **_):
+        return torch.tanh(self.fc(z)).unsqueeze(1).repeat(1, self.num_ws, 1)
+
+
+class _Layer(torch.nn.Module):
+    def __init__(self, ch):
+        super().__init__()
+        self.offset = torch.nn.Parameter(torch.zeros([1, ch]))
+
+
+class _Synthesis(torch.nn.Module):
+    def __init__(self, w_dim, res):
+        super().__init__()
+        self.res = res
+        self.l0 = _Layer(w_dim)
+        self.l1 = _Layer(w_dim)
+        self.fc = torch.nn.Linear(w_dim, 3 * res * res)
+
+    def forward(self, ws, noise_mode='random', **_):
+        s = ws[:, 0] + self.l0.offset + 2.0 * self.l1.offset
+        return torch.tanh(self.fc(s)).reshape(-1, 3, self.res, self.res)
+
+
+class _G(torch.nn.Module):
+    def __init__(self, z_dim=8, w_dim=8, res=4):
+        super().__init__()
+        self.z_dim, self.w_dim = z_dim, w_dim
+        self.mapping = _Mapping(z_dim, w_dim, 2)
+        self.synthesis = _Synthesis(w_dim, res)
+
+    def forward(self, z, c, **kw):
+        return self.synthesis(self.mapping(z, c), **kw)
+
+
+class _D(torch.nn.Module):
+    def __init__(self, res=4):
+        super().__init__()
+        self.fc0 = torch.nn.Linear(3 * res * res, 16)
+        self.fc1 = torch.nn.Linear(16, 1)
+
+    def forward(self, img, c, **_):
+        return self.fc1(torch.nn.functional.softplus(self.fc0(img.flatten(1))))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _run_step(rank, world, port, out_dir):
+    from training.training_loop import TrainingStep
+    if world > 1:
+        os.environ['MASTER_ADDR'] = '127.0.0.1'
+        os.environ['MASTER_PORT'] = str(port)
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)                                   # identical initial weights on every rank
+    G, D = _G(), _D()
+    gen = torch.Generator().manual_seed(123)
+    batch = 8
+    real = torch.rand(batch, 3, 4, 4, generator=gen) * 2 - 1
+    step = TrainingStep(G, D, batch_size=batch, batch_gpu=2, device='cpu', lrate=0.01, r1_gamma=0.0, pl_weight=0.0,
+                        style_mixing_prob=0.0, rank=rank, num_gpus=world)
+    zs = torch.randn(len(step.phases), batch, 8, generator=gen)
+    per = batch // world
+    sl = slice(rank * per, (rank + 1) * per)
+    # count gradient all-reduces: DDP must sync once per phase with a backward pass (last accumulation round only)
+    syncs = []
+    orig = step.loss.accumulate_gradients
+
+    def counted(phase, real_img, real_c, gen_z, gen_c, sync, gain):
+        syncs.append((phase, bool(sync)))
+        return orig(phase=phase, real_img=real_img, real_c=real_c, gen_z=gen_z, gen_c=gen_c, sync=sync, gain=gain)
+    step.loss.accumulate_gradients = counted
+    for _ in range(2):
+        step.run(real[sl], zs[:, sl])
+    params = {('G.' + k): v.detach().clone() for k, v in G.state_dict().items()}
+    params.update({('D.' + k): v.detach().clone() for k, v in D.state_dict().items()})
+    params.update({('Gema.' + k): v.detach().clone() for k, v in step.G_ema.state_dict().items()})
+    torch.save(dict(params=params, syncs=syncs), os.path.join(out_dir, f'step_w{world}_r{rank}.pt'))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_training_step_shards_by_minibatch_and_allreduces_once_per_phase():
+    with tempfile.TemporaryDirectory() as d:
+        _run_step(0, 1, 0, d)
+        mp.spawn(_run_step, args=(2, _free_port(), d), nprocs=2, join=True)
+        one = torch.load(os.path.join(d, 'step_w1_r0.pt'))
+        r0 = torch.load(os.path.join(d, 'step_w2_r0.pt'))
+        r1 = torch.load(os.path.join(d, 'step_w2_r1.pt'))
+    for k, v in one['params'].items():
+        assert torch.allclose(r0['params'][k], r1['params'][k], rtol=0, atol=0), f'ranks diverged on {k}'
+        # DDP averages over ranks what one process sums over twice as many rounds (factor 2 on the gradients, exactly as in
+        # the reference loop); Adam is scale-invariant up to its eps, hence the small absolute tolerance
+        assert torch.allclose(r0['params'][k], v, rtol=1e-4, atol=2e-5), f'2-rank result differs from 1 process on {k}'
+    # 8 images / (2 per round * 2 ranks) = 2 rounds per phase: sync only on the last one (training_loop.py:498)
+    by_phase = {}
+    for phase, sync in r0['syncs']:
+        by_phase.setdefault(phase, []).append(sync)
+    for phase, flags in by_phase.items():
+        assert flags == [False, True] * (len(flags) // 2), (phase, flags)
+    # the single process runs 4 rounds per phase
+    assert len(one['syncs']) == 2 * len(r0['syncs'])
+
+
+def _run_ga(rank, world, port, out_dir):
+    from training import ga_eval
+    if world > 1:
+        os.environ['MASTER_ADDR'] = '127.0.0.1'
+        os.environ['MASTER_PORT'] = str(port)
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    G, D = _G(), _D()
+    pop = ga_eval.init_population(G, size=7, scale=0.1, seed=5)         # 7 individuals: ragged over 2 ranks (4 + 3)
+    assert pop.shape == (7, ga_eval.genome_size(G)) and ga_eval.genome_size(G) == 16
+    z = torch.randn(4, 8, generator=torch.Generator().manual_seed(9))
+    seen = []
+
+    def fitness(G_, D_, ws, c):
+        seen.append(float(G_.synthesis.l0.offset.sum() + G_.synthesis.l1.offset.sum()))
+        return ga_eval.default_fitness(G_, D_, ws, c)
+    fit = ga_eval.evaluate_population(G, D, pop, z, rank=rank, world=world, fitness_fn=fitness)
+    torch.save(dict(fit=fit, seen=seen, idx=ga_eval.shard_indices(7, rank, world)), os.path.join(out_dir, f'ga_w{world}_r{rank}.pt'))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_ga_population_eval_shards_by_individual_with_one_all_gather():
+    with tempfile.TemporaryDirectory() as d:
+        _run_ga(0, 1, 0, d)
+        mp.spawn(_run_ga, args=(2, _free_port(), d), nprocs=2, join=True)
+        one = torch.load(os.path.join(d, 'ga_w1_r0.pt'))
+        r0 = torch.load(os.path.join(d, 'ga_w2_r0.pt'))
+        r1 = torch.load(os.path.join(d, 'ga_w2_r1.pt'))
+    assert r0['idx'] == [0, 2, 4, 6] and r1['idx'] == [1, 3, 5]
+    assert len(r0['seen']) == 4 and len(r1['seen']) == 3                  # each rank evaluated only its own individuals
+    assert torch.equal(r0['fit'], r1['fit'])                              # every rank holds the full fitness vector
+    assert torch.allclose(r0['fit'], one['fit'], rtol=1e-6, atol=1e-7)
+    assert not torch.isnan(r0['fit']).any()
+    assert len(set(np.round(one['fit'].numpy(), 6))) > 1                  # the offsets do change the fitness
