@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         // zero-filled by the TMA unit (= the conv padding).  The innermost start coordinate must land on a 16-byte boundary
         // (an unaligned or negative one faults with "illegal instruction"), so the box starts at the aligned, clamped
         // (cx, cy) and the converter shifts it back and re-creates the left / top padding (see cvt_src below).
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t kbc = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(t, p);
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
     } else if (warp == 1) {
         // ===== weight producer (one thread): one bulk copy (hi+lo image of one live tap) per ring stage
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t ws = 0, wph = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(t, p);
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     } else if (warp == 2) {
         // ===== MMA issuer (one thread).  Descriptors are 64-bit adds on per-K-block bases: the issue loop has to stay well
         // under the 64-cycle tensor-core time of one M=128 x N=128 x K=8 instruction.
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t kbc = 0, ws = 0, wph = 0, ac = 0;          // K-block, weight-stage and accumulator-chunk counters
             const uint32_t idesc = umma_idesc_tf32(128, NT, 0, 0);
             // descriptor: bits [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, bit 46 = version 1

@@ -35,7 +35,12 @@ constexpr int WG_THREADS = (WG_PROD_WARPS + WG_CONS_WARPS) * 32;   // w4..w11 = 
 constexpr int UW = 16;                                   // image columns per strip (two K=8 steps)
 constexpr int GS = 3;                                    // G-row ring slots
 constexpr int XS = 5;                                    // X-row ring slots (k live rows + rows in flight)
-constexpr uint32_t LBO_A = 128 * 16 + 32;                // chunk pitch of the G image (+32 B: conflict-free 128-bit stores)
+constexpr uint32_t LBO_A = 128 * 16;                     // chunk pitch of the G image: every 8-row core matrix stays 128-byte aligned
+// Item -> (row, chunk) mapping of the converter threads: 8 consecutive lanes write 8 consecutive rows of ONE chunk (a 128-byte
+// conflict-free quarter-warp store), the four quarter-warps take the four chunks; in global memory the same warp reads 8
+// channels x 64 contiguous bytes.
+__device__ __forceinline__ int item_chunk(int id) { return (id >> 3) & 3; }
+__device__ __forceinline__ int item_row(int id) { return (id & 7) | ((id >> 5) << 3); }
 
 struct WgP {
     const float* X; const float* G; float* dw; const float* xs; const float* gs;
@@ -74,7 +79,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    constexpr uint32_t LBO_B = NTA * 16 + 32;
+    constexpr uint32_t LBO_B = NTA * 16;
     constexpr uint32_t G_HALF = 4 * LBO_A, G_SLOT = 2 * G_HALF;          // hi image, lo image
     constexpr uint32_t X_HALF = 4 * LBO_B, X_SLOT = 2 * X_HALF;
     constexpr uint32_t OFF_G = 0, OFF_X = OFF_G + GS * G_SLOT, OFF_BAR = OFF_X + XS * X_SLOT, OFF_SLOT = OFF_BAR + 256;
@@ -101,14 +106,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + OFF_SLOT);
 
-    const int unit_beg = blockIdx.x * p.units_per_cta;
-    const int unit_end = min(p.total_units, unit_beg + p.units_per_cta);
+    // CTA -> (tile, strip partition): consecutive CTAs take DIFFERENT tiles of the SAME partition and walk its strips in the same
+    // order, so the CTAs that are resident together read the same X / G rows at about the same time (L2 hits instead of
+    // DRAM re-reads: every strip is needed by btiles*zgroups + atiles tiles).
+    const int ntiles = p.btiles * p.atiles * p.zgroups;
+    const int my_tile = blockIdx.x % ntiles, my_part = blockIdx.x / ntiles;
+    const int unit_beg = my_tile * p.S + min(p.S, my_part * p.units_per_cta);
+    const int unit_end = my_tile * p.S + min(p.S, (my_part + 1) * p.units_per_cta);
     const int K = p.K;
 
     if (warp < WG_PROD_WARPS) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         // ===== MMA issuer (one thread)
-        if (warp == 0 && lane == 0) {
+        if (warp == 0 && elect_one()) {
             const uint32_t idesc = umma_idesc_tf32(128, NTA, 0, 0);
             const uint64_t a_word = ((uint64_t)(8u | (1u << 14)) << 32) | ((uint64_t)(LBO_A >> 4) << 16);   // SBO 128 B, LBO
             const uint64_t b_word = ((uint64_t)(8u | (1u << 14)) << 32) | ((uint64_t)(LBO_B >> 4) << 16);
@@ -169,83 +179,106 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
         for (int j = 0; j < HC; ++j) acc[j] = 0.f;
         uint32_t gc = 0, xc = 0, sc = 0;
         bool pend = false;
-        Unit pu{};
+        int pend_unit = 0, pend_rows = 0, pend_tile = -1;
         uint32_t pend_sc = 0;
 
         // One converter task = local X row j of a unit (image row r0 - pad_y + j) plus, for j >= K-1, G row j-(K-1).
         // Loads are issued THREE tasks ahead of their conversion (global/L2 latency is ~1-2 us, a task ~0.3 us).
-        constexpr int XI = (NTA * 4 + WG_CONS_THREADS - 1) / WG_CONS_THREADS;     // X items per thread (1)
-        struct Task { Unit u; int unit, j; bool valid; };   // a cursor into the CTA's task sequence
-        struct Regs { float4 x[XI]; float4 g[2]; };
-        auto task_begin = [&](Task& t, int unit) {
+        // Everything that does not change within a unit (this thread's source pointers, scales, validity) is worked out
+        // once per unit, so that a task costs a handful of address adds and three 128-bit loads per thread.
+        static_assert(NTA * 4 <= WG_CONS_THREADS, "one X item per converter thread");
+        struct Regs { float4 x; float4 g[2]; float xs, gs[2]; };   // raw loads + the scales to apply when they are converted
+        struct LoadCursor {                              // runs three tasks ahead
+            int unit, j, ntask; bool valid;
+            const float* xp; const float* gp[2];         // X[n,ac,0,col] and G[n,bc,0,x0] of this thread's items
+            float xs, gs[2];
+            int xmode, gmode[2];                         // 0 = zero item, 1 = aligned 128-bit load, 2 = bounds-checked scalar loads
+            int gx0[2], v0, y0;                          // first G column of the item; image rows of task 0
+        };
+        struct StoreCursor { int unit, j, ntask, tile; bool valid; };
+        const int x_c = item_chunk(ct), x_row = item_row(ct);   // this thread's X item: chunk, channel row
+        auto load_begin = [&](LoadCursor& t, int unit) {
             t.unit = unit; t.j = 0; t.valid = unit < unit_end;
-            if (t.valid) t.u = decode_unit(unit, p, NTA);
-        };
-        auto task_advance = [&](Task& t) {
-            if (t.valid && ++t.j == t.u.rows + K - 1) task_begin(t, t.unit + 1);
-        };
-        auto load_task = [&](const Task& t, Regs& r) {
-            const Unit& u = t.u;
-            const int v = u.r0 - p.pad_y + t.j;
-#pragma unroll
-            for (int k = 0; k < XI; ++k) {
-                const int id = ct + k * WG_CONS_THREADS;
-                const int c = id & 3, row = id >> 2;
-                const int ac = u.a0 + row, col = u.u0 + 4 * c;
-                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row < NTA && v >= 0 && v < p.HA && ac < p.A && col < p.WA) {
-                    const float* src = p.X + (((size_t)u.n * p.A + ac) * p.HA + v) * p.WA + col;
-                    if (p.vecX && col + 3 < p.WA) {
-                        val = __ldg(reinterpret_cast<const float4*>(src));
-                    } else {
-                        val.x = __ldg(src);
-                        if (col + 1 < p.WA) val.y = __ldg(src + 1);
-                        if (col + 2 < p.WA) val.z = __ldg(src + 2);
-                        if (col + 3 < p.WA) val.w = __ldg(src + 3);
-                    }
-                    if (p.xs) { const float sx = __ldg(p.xs + (size_t)u.n * p.A + ac); val.x *= sx; val.y *= sx; val.z *= sx; val.w *= sx; }
-                }
-                r.x[k] = val;
+            if (!t.valid) return;
+            const Unit u = decode_unit(unit, p, NTA);
+            t.ntask = u.rows + K - 1; t.v0 = u.r0 - p.pad_y; t.y0 = u.r0 - (K - 1);
+            {
+                const int ac = u.a0 + x_row, col = u.u0 + 4 * x_c;
+                t.xmode = (x_row < NTA && ac < p.A && col < p.WA) ? ((p.vecX && col + 3 < p.WA) ? 1 : 2) : 0;
+                t.xp = p.X + ((size_t)u.n * p.A + (t.xmode ? ac : 0)) * p.HA * p.WA + col;
+                t.xs = (t.xmode && p.xs) ? __ldg(p.xs + (size_t)u.n * p.A + ac) : 1.f;
             }
-            const int i = t.j - (K - 1);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const int id = ct + k * WG_CONS_THREADS;                       // 512 items: (row m, chunk c)
-                const int c = id & 3, m = id >> 2;
-                const int s = m >> p.rb_shift, bc = u.b0 + (m & (p.RB - 1));
-                const int x0 = u.u0 + 4 * c - (u.kx0 + s - p.pad_x);           // G column of the chunk's first pixel
-                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i >= 0 && s < u.ns && bc < p.B && x0 + 3 >= 0 && x0 < p.WB) {
-                    const float* src = p.G + (((size_t)u.n * p.B + bc) * p.HB + (u.r0 + i)) * p.WB;
-                    if (p.vecG && (x0 & 3) == 0 && x0 >= 0 && x0 + 3 < p.WB) {
-                        val = __ldg(reinterpret_cast<const float4*>(src + x0));
-                    } else {
-                        if (x0 >= 0) val.x = __ldg(src + x0);
-                        if (x0 + 1 >= 0 && x0 + 1 < p.WB) val.y = __ldg(src + x0 + 1);
-                        if (x0 + 2 >= 0 && x0 + 2 < p.WB) val.z = __ldg(src + x0 + 2);
-                        if (x0 + 3 < p.WB) val.w = __ldg(src + x0 + 3);
-                    }
-                    if (p.gs) { const float sg = __ldg(p.gs + (size_t)u.n * p.B + bc); val.x *= sg; val.y *= sg; val.z *= sg; val.w *= sg; }
-                }
-                r.g[k] = val;
+                const int c = item_chunk(id), m = item_row(id);
+                const int sft = m >> p.rb_shift, bc = u.b0 + (m & (p.RB - 1));
+                const int x0 = u.u0 + 4 * c - (u.kx0 + sft - p.pad_x);         // G column of the chunk's first pixel
+                const bool ok = sft < u.ns && bc < p.B && x0 + 3 >= 0 && x0 < p.WB;
+                t.gmode[k] = ok ? ((p.vecG && (x0 & 3) == 0 && x0 >= 0 && x0 + 3 < p.WB) ? 1 : 2) : 0;
+                t.gx0[k] = x0;
+                t.gp[k] = p.G + ((size_t)u.n * p.B + (ok ? bc : 0)) * p.HB * p.WB;
+                t.gs[k] = (ok && p.gs) ? __ldg(p.gs + (size_t)u.n * p.B + bc) : 1.f;
             }
         };
-        auto store_split = [&](uint8_t* hi_addr, uint32_t half_bytes, const float4& val) {
+        auto load_advance = [&](LoadCursor& t) {
+            if (t.valid && ++t.j == t.ntask) load_begin(t, t.unit + 1);
+        };
+        auto store_begin = [&](StoreCursor& t, int unit) {
+            t.unit = unit; t.j = 0; t.valid = unit < unit_end;
+            if (!t.valid) return;
+            const Unit u = decode_unit(unit, p, NTA);
+            t.ntask = u.rows + K - 1; t.tile = u.tile;
+        };
+        auto store_advance = [&](StoreCursor& t) {
+            if (t.valid && ++t.j == t.ntask) store_begin(t, t.unit + 1);
+        };
+        auto load_task = [&](const LoadCursor& t, Regs& r) {
+            const int v = t.v0 + t.j, y = t.y0 + t.j;
+            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t.xmode != 0 && v >= 0 && v < p.HA) {
+                const float* src = t.xp + (size_t)v * p.WA;
+                if (t.xmode == 1) {
+                    val = __ldg(reinterpret_cast<const float4*>(src));
+                } else {
+                    const int col = (int)((t.xp - p.X) % p.WA);
+                    val.x = __ldg(src);
+                    if (col + 1 < p.WA) val.y = __ldg(src + 1);
+                    if (col + 2 < p.WA) val.z = __ldg(src + 2);
+                    if (col + 3 < p.WA) val.w = __ldg(src + 3);
+                }
+            }
+            r.x = val; r.xs = t.xs;                     // NOT multiplied here: that would wait for the load right away
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t.gmode[k] != 0 && y >= t.y0 + (K - 1)) {
+                    const float* src = t.gp[k] + (size_t)y * p.WB;
+                    const int x0 = t.gx0[k];
+                    if (t.gmode[k] == 1) {
+                        g4 = __ldg(reinterpret_cast<const float4*>(src + x0));
+                    } else {
+                        if (x0 >= 0) g4.x = __ldg(src + x0);
+                        if (x0 + 1 >= 0 && x0 + 1 < p.WB) g4.y = __ldg(src + x0 + 1);
+                        if (x0 + 2 >= 0 && x0 + 2 < p.WB) g4.z = __ldg(src + x0 + 2);
+                        if (x0 + 3 < p.WB) g4.w = __ldg(src + x0 + 3);
+                    }
+                }
+                r.g[k] = g4; r.gs[k] = t.gs[k];
+            }
+        };
+        auto store_split = [&](uint8_t* hi_addr, uint32_t half_bytes, const float4& val, float sc) {
             float4 h, l;
-            split_tf32(val.x, h.x, l.x); split_tf32(val.y, h.y, l.y); split_tf32(val.z, h.z, l.z); split_tf32(val.w, h.w, l.w);
+            split_tf32(val.x * sc, h.x, l.x); split_tf32(val.y * sc, h.y, l.y); split_tf32(val.z * sc, h.z, l.z); split_tf32(val.w * sc, h.w, l.w);
             *reinterpret_cast<float4*>(hi_addr) = h;
             *reinterpret_cast<float4*>(hi_addr + half_bytes) = l;
         };
-        auto store_task = [&](const Task& t, const Regs& r) {
+        auto store_task = [&](const StoreCursor& t, const Regs& r) {
             {
                 const uint32_t slot = xc % XS;
                 mbar_wait(BAR_X_EMPTY(slot), ((xc / XS) & 1) ^ 1);
                 uint8_t* sb = gbase + OFF_X + slot * X_SLOT;
-#pragma unroll
-                for (int k = 0; k < XI; ++k) {
-                    const int id = ct + k * WG_CONS_THREADS;
-                    if (id < NTA * 4) store_split(sb + (id & 3) * LBO_B + (id >> 2) * 16, X_HALF, r.x[k]);
-                }
+                if (x_row < NTA) store_split(sb + x_c * LBO_B + x_row * 16, X_HALF, r.x, r.xs);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR_X_FULL(slot));
@@ -258,7 +291,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     const int id = ct + k * WG_CONS_THREADS;
-                    store_split(sb + (id & 3) * LBO_A + (id >> 2) * 16, G_HALF, r.g[k]);
+                    store_split(sb + item_chunk(id) * LBO_A + item_row(id) * 16, G_HALF, r.g[k], r.gs[k]);
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -310,34 +343,35 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
                 }
             }
         };
-        auto finish_task = [&](const Task& t) {         // after the last row of a unit: drain the PREVIOUS strip (its MMAs are done)
-            if (t.j != t.u.rows + K - 2) return;
+        auto finish_task = [&](const StoreCursor& t) {  // after the last row of a unit: drain the PREVIOUS strip (its MMAs are done)
+            if (t.j != t.ntask - 1) return;
             if (pend) {
-                drain(pend_sc, pu.rows);
-                if (pu.tile != t.u.tile) flush(pu);
+                drain(pend_sc, pend_rows);
+                if (pend_tile != t.tile) flush(decode_unit(pend_unit, p, NTA));
             }
-            pend = true; pu = t.u; pend_sc = sc;
+            pend = true; pend_unit = t.unit; pend_rows = t.ntask - (K - 1); pend_tile = t.tile; pend_sc = sc;
             ++sc;
         };
         // two cursors: L runs three tasks ahead issuing the global loads, S converts / stores / drains
-        Task L, S;
-        task_begin(L, unit_beg);
-        task_begin(S, unit_beg);
+        LoadCursor L;
+        StoreCursor S;
+        load_begin(L, unit_beg);
+        store_begin(S, unit_beg);
         Regs r0, r1, r2;
-        if (L.valid) { load_task(L, r0); task_advance(L); }
-        if (L.valid) { load_task(L, r1); task_advance(L); }
-        if (L.valid) { load_task(L, r2); task_advance(L); }
+        if (L.valid) { load_task(L, r0); load_advance(L); }
+        if (L.valid) { load_task(L, r1); load_advance(L); }
+        if (L.valid) { load_task(L, r2); load_advance(L); }
         while (S.valid) {
-            store_task(S, r0); finish_task(S); task_advance(S);
-            if (L.valid) { load_task(L, r0); task_advance(L); }
+            store_task(S, r0); finish_task(S); store_advance(S);
+            if (L.valid) { load_task(L, r0); load_advance(L); }
             if (!S.valid) break;
-            store_task(S, r1); finish_task(S); task_advance(S);
-            if (L.valid) { load_task(L, r1); task_advance(L); }
+            store_task(S, r1); finish_task(S); store_advance(S);
+            if (L.valid) { load_task(L, r1); load_advance(L); }
             if (!S.valid) break;
-            store_task(S, r2); finish_task(S); task_advance(S);
-            if (L.valid) { load_task(L, r2); task_advance(L); }
+            store_task(S, r2); finish_task(S); store_advance(S);
+            if (L.valid) { load_task(L, r2); load_advance(L); }
         }
-        if (pend) { drain(pend_sc, pu.rows); flush(pu); }
+        if (pend) { drain(pend_sc, pend_rows); flush(decode_unit(pend_unit, p, NTA)); }
         tc_fence_before();
     }
     __syncthreads();
@@ -349,7 +383,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
 
 template <int NTA>
 int launch_wgrad(const WgP& p, int grid, cudaStream_t st) {
-    constexpr uint32_t LBO_B = NTA * 16 + 32;
+    constexpr uint32_t LBO_B = NTA * 16;
     const size_t smem = GS * 2 * 4 * LBO_A + XS * 2 * 4 * LBO_B + 256 + 16 + 128;
     static std::atomic<int> attr_set{0};
     if (!attr_set.load()) {
@@ -394,9 +428,13 @@ int wgrad_tc(const float* a, const float* b, float* dw, int N, int A, int HA, in
     const int64_t total = S * p.btiles * p.atiles * p.zgroups;
     if (total > 0x7fffffffLL) { set_error("conv2d_wgrad(tc): too many work units"); return GG_EINVAL; }
     p.S = (int)S; p.total_units = (int)total;
-    int grid = total < GG_NUM_SMS ? (int)total : GG_NUM_SMS;
-    p.units_per_cta = (int)((total + grid - 1) / grid);
-    grid = (int)((total + p.units_per_cta - 1) / p.units_per_cta);
+    const int ntiles = p.btiles * p.atiles * p.zgroups;
+    int64_t parts = (4LL * GG_NUM_SMS + ntiles - 1) / ntiles;          // ~4 waves of CTAs; one atomic flush per CTA
+    if (parts > S) parts = S;
+    if (parts < 1) parts = 1;
+    p.units_per_cta = (int)((S + parts - 1) / parts);                  // strips per CTA
+    parts = (S + p.units_per_cta - 1) / p.units_per_cta;
+    const int grid = (int)(parts * ntiles);
     p.nprod = (nprod == GG_PREC_TF32X1) ? 1 : 3;
     p.vecX = ((reinterpret_cast<uintptr_t>(a) & 15) == 0 && WA % 4 == 0) ? 1 : 0;
     p.vecG = ((reinterpret_cast<uintptr_t>(b) & 15) == 0 && WB % 4 == 0) ? 1 : 0;
