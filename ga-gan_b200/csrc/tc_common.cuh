@@ -86,12 +86,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_ma
 // 3xTF32 operand split.  Both parts are rounded to nearest tf32 (cvt.rna) rather than left to the tensor core's
 // truncation: |lo| <= 2^-12 |v| and lo itself carries a 2^-12 relative rounding error, so hi*hi + hi*lo + lo*hi
 // reproduces the fp32 product to ~2^-22 (the dropped lo*lo term is 2^-24).
+__device__ __forceinline__ float round_tf32(float v) {
+    // round-to-nearest (ties away from zero) to 10 explicit mantissa bits in the integer domain: 2 instructions.
+    // (cvt.rna.tf32.f32 expands to a ~12-instruction sequence on sm_100a and dominated the operand converters.)
+    return __uint_as_float((__float_as_uint(v) + 0x00001000u) & 0xFFFFE000u);
+}
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-    uint32_t h, l;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-    hi = __uint_as_float(h);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
-    lo = __uint_as_float(l);
+    hi = round_tf32(v);
+    lo = round_tf32(v - hi);          // v - hi is exact in fp32
 }
 
 

@@ -87,7 +87,8 @@ def test_ga_population_fitness_eval_on_the_device(device):
                                                  domain_modulation_parametrization='additive')).to(device)
     D = networks.Discriminator(c_dim=0, img_resolution=32, img_channels=3, channel_base=512, channel_max=32).to(device)
     n_layers = len(ga_eval.offset_layers(G))
-    assert n_layers == 4 * 2 + 4 - 1 and ga_eval.genome_size(G) == 32 * n_layers     # conv0/conv1/torgb per block, no conv0 in b4
+    assert n_layers == 4 * 2 + 4 - 1                                       # conv0/conv1/torgb per block, no conv0 in b4
+    assert ga_eval.genome_size(G) == sum(m.weight.shape[1] for _, m in ga_eval.offset_layers(G))   # one offset per input channel
     pop = ga_eval.init_population(G, size=5, scale=0.1, seed=1)
     pop[2].zero_()                                                          # individual 2 = the unmodified generator
     z = torch.randn(4, 32, device=device)
