@@ -99,8 +99,10 @@ struct ThinWgP {
     int chunks;                  // pixel chunks per image (grid.x)
 };
 
+constexpr int WCH = 16;          // wide channels per pass: THIN x WCH partial sums live in registers
+
 __global__ void __launch_bounds__(256) wgrad1x1_thin(ThinWgP p) {
-    __shared__ float red[8][THIN];
+    __shared__ float red[8][WCH][THIN];
     const int n = blockIdx.y;
     const int64_t P4 = p.P >> 2;
     const int64_t per = (P4 + p.chunks - 1) / p.chunks;
@@ -108,36 +110,48 @@ __global__ void __launch_bounds__(256) wgrad1x1_thin(ThinWgP p) {
     const float4* tn = reinterpret_cast<const float4*>(p.T + (int64_t)n * p.CT * p.P);
     const float4* wn = reinterpret_cast<const float4*>(p.Wd + (int64_t)n * p.CW * p.P);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // wide channels are walked in the outer loop so that the thin planes (re-read per wide channel) stay in L1/L2
-    for (int c = 0; c < p.CW; ++c) {
-        float acc[THIN] = {0.f, 0.f, 0.f, 0.f};
-        for (int64_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
-            const float4 g = __ldg(wn + (int64_t)c * P4 + q);
+    // Every element is read ONCE per pass of WCH wide channels: the thin planes of a pixel stay in registers while the
+    // wide channels stream by (the thin planes are re-read CW/WCH times, from L2).
+    for (int c0 = 0; c0 < p.CW; c0 += WCH) {
+        float acc[WCH][THIN];
 #pragma unroll
-            for (int t = 0; t < THIN; ++t) {
-                if (t < p.CT) {
-                    const float4 v = __ldg(tn + (int64_t)t * P4 + q);
-                    acc[t] = fmaf(g.x, v.x, fmaf(g.y, v.y, fmaf(g.z, v.z, fmaf(g.w, v.w, acc[t]))));
+        for (int c = 0; c < WCH; ++c)
+#pragma unroll
+            for (int t = 0; t < THIN; ++t) acc[c][t] = 0.f;
+        for (int64_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+            float4 v[THIN];
+#pragma unroll
+            for (int t = 0; t < THIN; ++t) v[t] = (t < p.CT) ? __ldg(tn + (int64_t)t * P4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < WCH; ++c) {
+                if (c0 + c < p.CW) {
+                    const float4 g = __ldg(wn + (int64_t)(c0 + c) * P4 + q);
+#pragma unroll
+                    for (int t = 0; t < THIN; ++t)
+                        acc[c][t] = fmaf(g.x, v[t].x, fmaf(g.y, v[t].y, fmaf(g.z, v[t].z, fmaf(g.w, v[t].w, acc[c][t]))));
                 }
             }
         }
 #pragma unroll
-        for (int t = 0; t < THIN; ++t) acc[t] = gg::warp_sum(acc[t]);
-        if (lane == 0) {
+        for (int c = 0; c < WCH; ++c)
 #pragma unroll
-            for (int t = 0; t < THIN; ++t) red[warp][t] = acc[t];
-        }
+            for (int t = 0; t < THIN; ++t) {
+                const float s = gg::warp_sum(acc[c][t]);
+                if (lane == 0) red[warp][c][t] = s;
+            }
         __syncthreads();
-        if (threadIdx.x < p.CT) {
-            const int t = threadIdx.x;
-            float s = 0.f;
-            for (int w8 = 0; w8 < 8; ++w8) s += red[w8][t];
-            if (p.ws) s *= __ldg(p.ws + (int64_t)n * p.CW + c);
-            if (p.ts) s *= __ldg(p.ts + (int64_t)n * p.CT + t);
-            // dw is [B,A] (out_layout 0) or [A,B] (1); a = conv input channel, b = gradient channel
-            const int a = p.thin_is_a ? t : c, b = p.thin_is_a ? c : t;
-            const int A = p.thin_is_a ? p.CT : p.CW, B = p.thin_is_a ? p.CW : p.CT;
-            atomicAdd(p.dw + (p.out_layout ? (int64_t)a * B + b : (int64_t)b * A + a), s);
+        if (threadIdx.x < WCH * THIN) {
+            const int c = threadIdx.x / THIN, t = threadIdx.x - c * THIN;
+            if (c0 + c < p.CW && t < p.CT) {
+                float s = 0.f;
+                for (int w8 = 0; w8 < 8; ++w8) s += red[w8][c][t];
+                if (p.ws) s *= __ldg(p.ws + (int64_t)n * p.CW + c0 + c);
+                if (p.ts) s *= __ldg(p.ts + (int64_t)n * p.CT + t);
+                // dw is [B,A] (out_layout 0) or [A,B] (1); a = conv input channel, b = gradient channel
+                const int a = p.thin_is_a ? t : c0 + c, b = p.thin_is_a ? c0 + c : t;
+                const int A = p.thin_is_a ? p.CT : p.CW, B = p.thin_is_a ? p.CW : p.CT;
+                atomicAdd(p.dw + (p.out_layout ? (int64_t)a * B + b : (int64_t)b * A + a), s);
+            }
         }
         __syncthreads();
     }
@@ -183,8 +197,8 @@ int wgrad1x1_thin(const float* a, const float* b, float* dw, int N, int A, int H
     ThinWgP p{thin_is_a ? a : b, thin_is_a ? b : a, dw, thin_is_a ? a_scale : b_scale, thin_is_a ? b_scale : a_scale,
               N, thin_is_a ? A : B, thin_is_a ? B : A, thin_is_a ? 1 : 0, out_layout, (int64_t)HA * WA, 1};
     const int64_t P4 = p.P >> 2;
-    int chunks = (int)((P4 + 2047) / 2048);              // >= 8 float4 per thread and wide channel
-    const int cap = (GG_NUM_SMS * 4 + N - 1) / N;
+    int chunks = (int)((P4 + 4095) / 4096);              // >= 16 float4 per thread and pass
+    const int cap = (GG_NUM_SMS * 8 + N - 1) / N;
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;
     p.chunks = chunks;

@@ -186,6 +186,125 @@ int launch_tile(const Params& p, cudaStream_t st) {
     return gg::check_launch("upfirdn2d(fir4_tile)");
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// fir_stream<IN_PM, OUT_PM>: 4x4 FIR at unit rate (up = down = 1) that streams rows through registers and reads / writes
+// the PHASE-MAJOR layout of conv2d_resample.py on the fly, so that the space-to-depth / depth-to-space passes around the
+// tensor-core convolutions of the stride-2 layers cost no extra HBM traffic:
+//
+//   phase-major tensor  t_pm[n, (py,px,c), Y, X]  <->  logical image  t[n, c, 2Y+py, 2X+px]
+//
+//   IN_PM : the input is phase-major [N,4C,pmH,pmW]; logical pixels outside (validH, validW) count as zero
+//   OUT_PM: the output is phase-major [N,4C,pmH,pmW]; logical pixels outside (outH, outW) are written as zero
+//
+// One thread produces OXT consecutive output columns of RY consecutive rows: every input row is loaded once (scalar,
+// coalesced across the warp; the 3-column overlap between neighbouring threads is an L1 hit) and feeds the up-to-4 output
+// rows it contributes to.  Stores are 128-bit.
+struct StreamP {
+    const float* x; const float* f; float* y;
+    int N, C, inH, inW, padx0, pady0, flip;     // logical input extent (IN_PM: the valid extent)
+    float gain;
+    int outH, outW;                             // logical (valid) output extent
+    int ipH, ipW, opH, opW;                     // phase-major plane sizes (IN_PM / OUT_PM)
+};
+
+template <bool IN_PM, bool OUT_PM>
+__global__ void __launch_bounds__(256) fir_stream(StreamP p) {
+    constexpr int OXT = OUT_PM ? 8 : 4;         // OUT_PM: 8 logical columns = one float4 per column phase
+    constexpr int RY = OUT_PM ? 4 : 8;
+    __shared__ float sK[16];
+    if (threadIdx.x < 16) {
+        int ky = threadIdx.x >> 2, kx = threadIdx.x & 3;
+        int sy = p.flip ? ky : 3 - ky, sx = p.flip ? kx : 3 - kx;
+        sK[threadIdx.x] = p.gain * __ldg(p.f + sy * 4 + sx);
+    }
+    __syncthreads();
+    float K[4][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) K[i >> 2][i & 3] = sK[i];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = (blockIdx.x * 32 + lane) * OXT;
+    const int y0 = (blockIdx.y * 8 + warp) * RY;
+    const int fullW = OUT_PM ? 2 * p.opW : p.outW, fullH = OUT_PM ? 2 * p.opH : p.outH;
+    if (x0 >= fullW || y0 >= fullH) return;
+    for (int nc = blockIdx.z; nc < p.N * p.C; nc += gridDim.z) {
+    const int n = nc / p.C, c = nc - n * p.C;
+
+    const size_t iplane = IN_PM ? (size_t)p.ipH * p.ipW : (size_t)p.inH * p.inW;
+    const float* xin = p.x + (IN_PM ? (size_t)n * 4 * p.C * iplane : (size_t)nc * iplane);
+
+    float acc[RY][OXT];
+#pragma unroll
+    for (int r = 0; r < RY; ++r)
+#pragma unroll
+        for (int t = 0; t < OXT; ++t) acc[r][t] = 0.f;
+
+#pragma unroll
+    for (int rr = 0; rr < RY + 3; ++rr) {
+        const int r = y0 + rr - p.pady0;                        // logical input row
+        float in[OXT + 3];
+        const bool row_ok = r >= 0 && r < p.inH;
+        const float* rowp;
+        if (IN_PM) rowp = xin + ((size_t)((r & 1) * 2) * p.C + c) * iplane + (size_t)(r >> 1) * p.ipW;   // px = 0 plane; px = 1 is C planes further
+        else       rowp = xin + (size_t)r * p.inW;
+#pragma unroll
+        for (int j = 0; j < OXT + 3; ++j) {
+            const int col = x0 + j - p.padx0;
+            float v = 0.f;
+            if (row_ok && col >= 0 && col < p.inW) {
+                if (IN_PM) v = __ldg(rowp + (size_t)(col & 1) * p.C * iplane + (col >> 1));
+                else       v = __ldg(rowp + col);
+            }
+            in[j] = v;
+        }
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+            const int yy = rr - ky;                              // output row (relative) fed through filter row ky
+            if (yy < 0 || yy >= RY) continue;                    // compile-time after unrolling
+#pragma unroll
+            for (int t = 0; t < OXT; ++t)
+#pragma unroll
+                for (int kx = 0; kx < 4; ++kx) acc[yy][t] = fmaf(K[ky][kx], in[t + kx], acc[yy][t]);
+        }
+    }
+
+#pragma unroll
+    for (int r = 0; r < RY; ++r) {
+        const int y = y0 + r;
+        if (y >= fullH) continue;
+        if (OUT_PM) {
+            // logical (y, x0 + 2X' + px) -> plane (y&1, px, c), row y>>1, columns x0/2 + X'
+            float v[OXT];
+#pragma unroll
+            for (int t = 0; t < OXT; ++t) v[t] = (y < p.outH && x0 + t < p.outW) ? acc[r][t] : 0.f;
+            const size_t oplane = (size_t)p.opH * p.opW;
+            float* base = p.y + ((size_t)n * 4 * p.C + (size_t)((y & 1) * 2) * p.C + c) * oplane + (size_t)(y >> 1) * p.opW + (x0 >> 1);
+            *reinterpret_cast<float4*>(base) = make_float4(v[0], v[2], v[4], v[6]);
+            *reinterpret_cast<float4*>(base + (size_t)p.C * oplane) = make_float4(v[1], v[3], v[5], v[7]);
+        } else {
+            float* dst = p.y + (size_t)nc * p.outH * p.outW + (size_t)y * p.outW + x0;
+            if ((p.outW & 3) == 0 && x0 + 3 < p.outW) {
+                *reinterpret_cast<float4*>(dst) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+            } else {
+#pragma unroll
+                for (int t = 0; t < OXT; ++t)
+                    if (x0 + t < p.outW) dst[t] = acc[r][t];
+            }
+        }
+    }
+    }
+}
+
+template <bool IN_PM, bool OUT_PM>
+int launch_stream(const StreamP& p, cudaStream_t st) {
+    constexpr int OXT = OUT_PM ? 8 : 4, RY = OUT_PM ? 4 : 8;
+    const int fullW = OUT_PM ? 2 * p.opW : p.outW, fullH = OUT_PM ? 2 * p.opH : p.outH;
+    dim3 grid((unsigned)((fullW + 32 * OXT - 1) / (32 * OXT)), (unsigned)((fullH + 8 * RY - 1) / (8 * RY)), (unsigned)(p.N * p.C < 65535 ? p.N * p.C : 65535));
+    fir_stream<IN_PM, OUT_PM><<<grid, 256, 0, st>>>(p);
+    return gg::check_launch("upfirdn2d(fir_stream)");
+}
+
 }  // namespace
 
 extern "C" GG_API int gg_upfirdn2d_f32(const float* x, const float* f, float* y, int N, int C, int inH, int inW, int fH, int fW,
@@ -207,7 +326,10 @@ extern "C" GG_API int gg_upfirdn2d_f32(const float* x, const float* f, float* y,
     cudaStream_t st = (cudaStream_t)stream;
 
     const bool f4 = (fH == 4 && fW == 4) && upx == upy && downx == downy && outW >= 48;
-    if (f4 && upx == 1 && downx == 1) return launch_tile<1, 1, 0, 4, 4>(p, st);
+    if (f4 && upx == 1 && downx == 1) {   // unit rate: the register-streaming kernel (also serves the phase-major layouts)
+        StreamP sp{x, f, y, N, C, inH, inW, padx0, pady0, flip, gain, outH, outW, 0, 0, 0, 0};
+        return launch_stream<false, false>(sp, st);
+    }
     if (f4 && upx == 1 && downx == 2) return launch_tile<1, 2, 0, 2, 2>(p, st);
     if (f4 && upx == 2 && downx == 1) {
         // PEX = parity of (ox0 - padx0) for the first column of any thread (ox0 is a multiple of 4)
@@ -219,4 +341,24 @@ extern "C" GG_API int gg_upfirdn2d_f32(const float* x, const float* f, float* y,
     if (grid > GG_NUM_SMS * 32) grid = GG_NUM_SMS * 32;
     upfirdn2d_generic<<<(unsigned)grid, 256, (size_t)fH * fW * sizeof(float), st>>>(p);
     return gg::check_launch("upfirdn2d(generic)");
+}
+
+
+extern "C" GG_API int gg_fir4_pm_f32(const float* x, const float* f, float* y, int N, int C, int inH, int inW, int padx0, int pady0,
+                              int flip, float gain, int outH, int outW, int in_pm, int in_pmH, int in_pmW, int out_pm, int out_pmH,
+                              int out_pmW, gg_stream_t stream) {
+    GG_REQUIRE(x && f && y, "fir4_pm: null pointer");
+    GG_REQUIRE(N >= 0 && C >= 1 && inH >= 1 && inW >= 1 && outH >= 1 && outW >= 1, "fir4_pm: bad shape");
+    GG_REQUIRE(!(in_pm && out_pm), "fir4_pm: at most one side may be phase-major");
+    GG_REQUIRE(!in_pm || (in_pmH >= 1 && in_pmW >= 1 && inH <= 2 * in_pmH && inW <= 2 * in_pmW), "fir4_pm: phase-major input planes are smaller than the valid extent");
+    GG_REQUIRE(!out_pm || (out_pmH >= 1 && out_pmW >= 1 && out_pmW % 4 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0),
+               "fir4_pm: phase-major output planes must be 16-byte aligned with a width that is a multiple of 4");
+    GG_REQUIRE((int64_t)N * C * (in_pm ? 4LL * in_pmH * in_pmW : (int64_t)inH * inW) <= 0x7fffffffLL &&
+               (int64_t)N * C * (out_pm ? 4LL * out_pmH * out_pmW : (int64_t)outH * outW) <= 0x7fffffffLL, "fir4_pm: tensor is too large");
+    if (N == 0) return GG_OK;
+    StreamP p{x, f, y, N, C, inH, inW, padx0, pady0, flip, gain, outH, outW, in_pmH, in_pmW, out_pmH, out_pmW};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (in_pm) return launch_stream<true, false>(p, st);
+    if (out_pm) return launch_stream<false, true>(p, st);
+    return launch_stream<false, false>(p, st);
 }

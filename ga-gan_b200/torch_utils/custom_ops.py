@@ -69,6 +69,7 @@ _SIGNATURES = {
                                                           ctypes.c_void_p]),
     'gg_upfirdn2d_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 15 + [ctypes.c_float, ctypes.c_int, ctypes.c_int,
                                                            ctypes.c_void_p]),
+    'gg_fir4_pm_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 7 + [ctypes.c_float] + [ctypes.c_int] * 8 + [ctypes.c_void_p]),
     'gg_conv2d_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 14 + [_c_float_p, _c_float_p, ctypes.c_int,
                                                         ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
     'gg_conv2d_wgrad_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 14 + [_c_float_p, _c_float_p, ctypes.c_int,
@@ -216,6 +217,31 @@ class _Plugin:
             _check(self._lib.gg_upfirdn2d_f32(_ptr(x), _ptr(f), _ptr(y), N, C, H, W, f.shape[0], f.shape[1], int(upx), int(upy),
                                              int(downx), int(downy), int(padx0), int(padx1), int(pady0), int(pady1),
                                              1 if flip else 0, float(gain), out_h, out_w, _stream(x)), 'upfirdn2d')
+        return y
+
+    # 4x4 FIR at unit rate with a phase-major side (include/gagan_b200.h: gg_fir4_pm_f32)
+    def fir4_pm(self, x, f, padx0, pady0, flip, gain, in_hw, out_hw, in_pm=None, out_pm=None):
+        """x: plain [N,C,H,W] or, with in_pm=(pmH,pmW), phase-major [N,4C,pmH,pmW] whose valid logical extent is in_hw.
+        Returns plain [N,C,*out_hw] or, with out_pm=(pmH,pmW), phase-major [N,4C,pmH,pmW] (zero outside out_hw)."""
+        _require_cuda(x, 'x')
+        _check_device(x)
+        if f.shape != (4, 4) or f.dtype != torch.float32 or f.device != x.device:
+            raise RuntimeError('fir4_pm: f must be a 4x4 float32 filter on the device of x')
+        x = x.contiguous(); f = f.contiguous()
+        N = x.shape[0]
+        C = x.shape[1] // 4 if in_pm is not None else x.shape[1]
+        if in_pm is not None and tuple(x.shape[1:]) != (4 * C, in_pm[0], in_pm[1]):
+            raise RuntimeError('fir4_pm: phase-major input has the wrong shape')
+        if in_pm is None and tuple(x.shape[2:]) != tuple(in_hw):
+            raise RuntimeError('fir4_pm: in_hw does not match x')
+        shape = [N, 4 * C, out_pm[0], out_pm[1]] if out_pm is not None else [N, C, out_hw[0], out_hw[1]]
+        y = torch.empty(shape, dtype=x.dtype, device=x.device)
+        ip, op = (in_pm or (0, 0)), (out_pm or (0, 0))
+        with torch.cuda.device(x.device):
+            _check(self._lib.gg_fir4_pm_f32(_ptr(x), _ptr(f), _ptr(y), N, C, int(in_hw[0]), int(in_hw[1]), int(padx0), int(pady0),
+                                           1 if flip else 0, float(gain), int(out_hw[0]), int(out_hw[1]),
+                                           1 if in_pm is not None else 0, int(ip[0]), int(ip[1]),
+                                           1 if out_pm is not None else 0, int(op[0]), int(op[1]), _stream(x)), 'fir4_pm')
         return y
 
     # replaces torch.nn.functional.conv2d / conv_transpose2d (conv2d_gradfix.py:141-146), groups == 1

@@ -74,28 +74,30 @@ def _round_up(v, m):
     return (v + m - 1) // m * m
 
 
-def down2_phase_major(x, w, f, fir_pad, flip_weight, flip_filter, conv_s1, fir):
+def down2_phase_major(x, w, f, fir_pad, flip_weight, flip_filter, conv_s1, fir_to_pm):
     """conv2d_resample.py:119-122 (FIR, then stride-2 conv) with the conv in phase-major form.
-    `conv_s1(x, w, padding, out_hw, live)` and `fir(x, f, padding, flip_filter)` are injected (tests pass torch stand-ins)."""
+    `conv_s1(x, w, padding, out_hw, live)` and `fir_to_pm(x, f, padding, flip_filter, gain, ys, xs)` are injected (the CPU
+    algebra test passes torch stand-ins); on the device the FIR writes the phase-major tensor directly."""
     kh, kw = int(w.shape[2]), int(w.shape[3])
-    x = fir(x, f, fir_pad, flip_filter)
-    oh, ow = (x.shape[2] - kh) // 2 + 1, (x.shape[3] - kw) // 2 + 1
+    fw, fh = _get_filter_size(f)
+    px0, px1, py0, py1 = fir_pad
+    fir_h, fir_w = x.shape[2] + py0 + py1 - fh + 1, x.shape[3] + px0 + px1 - fw + 1
+    oh, ow = (fir_h - kh) // 2 + 1, (fir_w - kw) // 2 + 1
     if not flip_weight:
         w = w.flip([2, 3])
-    xs = space_to_depth(x, oh + 1, _round_up(ow + 1, 4))     # width multiple of 4: TMA row pitch must be 16-byte aligned
+    xs = fir_to_pm(x, f, fir_pad, flip_filter, 1, oh + 1, _round_up(ow + 1, 4))   # width % 4: TMA row pitch must be 16-byte aligned
     return conv_s1(xs, phase_major_weight_down(w), (0, 0), (oh, ow), _PM_LIVE)
 
 
-def up2_phase_major(x, w, f, fir_pad, flip_weight, flip_filter, conv_s1, fir):
-    """conv2d_resample.py:125-139 (stride-2 transposed conv with pad 0, then FIR with gain 4) in phase-major form."""
+def up2_phase_major(x, w, f, fir_pad, flip_weight, flip_filter, conv_s1, fir_from_pm):
+    """conv2d_resample.py:125-139 (stride-2 transposed conv with pad 0, then FIR with gain 4) in phase-major form;
+    `fir_from_pm(z, f, padding, flip_filter, gain, valid_hw)` reads the phase-major conv output directly."""
     N, I, H, W = x.shape
     if flip_weight:                      # the reference hands `not flip_weight` to the transposed conv (:138)
         w = w.flip([2, 3])
     xs_w = _round_up(W + 1, 4)           # the gradient of this tensor is a TMA source in backward: keep the width aligned
-    z = conv_s1(x, phase_major_weight_up(w), (1, 1), (H + 1, xs_w), _PM_LIVE)
-    z = depth_to_space(z)                # [N,O,2H+2,2xs_w]; rows/cols beyond 2H+1 / 2W+1 are exact zeros
-    px0, px1, py0, py1 = fir_pad
-    return fir(z, f, [px0, px1 - (2 * xs_w - (2 * W + 1)), py0, py1 - 1], flip_filter, 4)
+    z = conv_s1(x, phase_major_weight_up(w), (1, 1), (H + 1, xs_w), _PM_LIVE)    # [N,4O,H+1,xs_w]; valid logical extent 2H+1 x 2W+1
+    return fir_from_pm(z, f, fir_pad, flip_filter, 4, (2 * H + 1, 2 * W + 1))
 
 
 def plan(w_shape, f, up, down, padding):
@@ -130,8 +132,19 @@ def _conv_s1(x, w, padding, out_hw, live):
     return conv2d_gradfix.conv2d_s1(x, w, padding=padding, out_hw=out_hw, live=live)
 
 
-def _fir(x, f, padding, flip_filter, gain=1):
-    return upfirdn2d.upfirdn2d(x=x, f=f, padding=padding, flip_filter=flip_filter, gain=gain)
+def _fir_to_pm(x, f, padding, flip_filter, gain, ys, xs):
+    if f is not None and f.ndim == 2 and tuple(f.shape) == (4, 4):
+        return upfirdn2d.fir_to_pm(x, f, padding, flip_filter, gain, ys, xs)           # one fused kernel
+    return space_to_depth(upfirdn2d.upfirdn2d(x=x, f=f, padding=padding, flip_filter=flip_filter, gain=gain), ys, xs)
+
+
+def _fir_from_pm(z, f, padding, flip_filter, gain, valid_hw):
+    if f is not None and f.ndim == 2 and tuple(f.shape) == (4, 4):
+        return upfirdn2d.fir_from_pm(z, f, padding, flip_filter, gain, valid_hw)       # one fused kernel
+    full = depth_to_space(z)
+    px0, px1, py0, py1 = padding
+    pad = [px0, px1 - (full.shape[3] - valid_hw[1]), py0, py1 - (full.shape[2] - valid_hw[0])]
+    return upfirdn2d.upfirdn2d(x=full, f=f, padding=pad, flip_filter=flip_filter, gain=gain)
 
 
 @misc.profiled_function
@@ -161,13 +174,13 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
 
     if branch == 'down':          # FIR at full resolution, then a strided conv
         if down == 2 and groups == 1 and kh <= 4 and kw <= 4:
-            return down2_phase_major(x, w, f, pl['fir_pad'], flip_weight, flip_filter, _conv_s1, _fir)
+            return down2_phase_major(x, w, f, pl['fir_pad'], flip_weight, flip_filter, _conv_s1, _fir_to_pm)
         x = upfirdn2d.upfirdn2d(x=x, f=f, padding=pl['fir_pad'], flip_filter=flip_filter)
         return _conv2d_wrapper(x=x, w=w, stride=down, groups=groups, flip_weight=flip_weight)
 
     if branch == 'up':            # transposed strided conv, then FIR (then optional decimation)
         if up == 2 and down == 1 and groups == 1 and kh <= 4 and kw <= 4 and pl['conv_pad'] == [0, 0]:
-            return up2_phase_major(x, w, f, pl['fir_pad'], flip_weight, flip_filter, _conv_s1, _fir)
+            return up2_phase_major(x, w, f, pl['fir_pad'], flip_weight, flip_filter, _conv_s1, _fir_from_pm)
         if groups == 1:
             w = w.transpose(0, 1)
         else:

@@ -168,6 +168,66 @@ def _upfirdn2d_cuda(up=1, down=1, padding=0, flip_filter=False, gain=1):
 
 
 # ----------------------------------------------------------------------------
+# Unit-rate FIR fused with the phase-major re-layout of conv2d_resample's stride-2 paths.
+#
+#   t_pm[n, (py,px,c), Y, X]  <->  t[n, c, 2Y+py, 2X+px]
+#
+# fir_to_pm   : plain x -> upfirdn2d(x, f, padding) -> phase-major [N,4C,ys,xs] (zero outside the FIR output)
+# fir_from_pm : phase-major z (valid logical extent `valid_hw`) -> upfirdn2d(..., padding) -> plain
+# Each is the other's gradient (same rule as upfirdn2d.py:264-283: flipped filter, padding p), so gradients of any order
+# exist.  Only 4x4 filters; other filters take the unfused route in conv2d_resample.
+
+_fir_pm_cache = dict()
+
+
+def fir_to_pm(x, f, padding, flip_filter, gain, ys, xs):
+    _init()
+    px0, px1, py0, py1 = _parse_padding(padding)
+    oh, ow = x.shape[2] + py0 + py1 - 3, x.shape[3] + px0 + px1 - 3
+    return _fir_pm(True, px0, py0, bool(flip_filter), float(gain), (int(x.shape[2]), int(x.shape[3])), (oh, ow), (int(ys), int(xs))).apply(x, f)
+
+
+def fir_from_pm(z, f, padding, flip_filter, gain, valid_hw):
+    _init()
+    px0, px1, py0, py1 = _parse_padding(padding)
+    vh, vw = int(valid_hw[0]), int(valid_hw[1])
+    oh, ow = vh + py0 + py1 - 3, vw + px0 + px1 - 3
+    return _fir_pm(False, px0, py0, bool(flip_filter), float(gain), (vh, vw), (oh, ow), (int(z.shape[2]), int(z.shape[3]))).apply(z, f)
+
+
+def _fir_pm(to_pm, px0, py0, flip, gain, in_hw, out_hw, pm_hw):
+    """to_pm: plain [N,C,*in_hw] -> phase-major [N,4C,*pm_hw] with valid extent out_hw;
+    else: phase-major [N,4C,*pm_hw] with valid extent in_hw -> plain [N,C,*out_hw]."""
+    key = (to_pm, px0, py0, flip, gain, in_hw, out_hw, pm_hw)
+    if key in _fir_pm_cache:
+        return _fir_pm_cache[key]
+    assert out_hw[0] >= 1 and out_hw[1] >= 1
+
+    class FirPM(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, f):
+            if x.dtype != torch.float32:
+                raise RuntimeError('upfirdn2d: this build serves fp32 only')
+            ctx.save_for_backward(f)
+            if to_pm:
+                return _plugin.fir4_pm(x, f, px0, py0, flip, gain, in_hw, out_hw, out_pm=pm_hw)
+            return _plugin.fir4_pm(x, f, px0, py0, flip, gain, in_hw, out_hw, in_pm=pm_hw)
+
+        @staticmethod
+        def backward(ctx, dy):
+            f, = ctx.saved_tensors
+            dx = None
+            if ctx.needs_input_grad[0]:
+                # adjoint of a unit-rate FIR: the same FIR with the filter flipped and padding (3 - p0) on the leading side;
+                # its input extent is this op's output extent and vice versa (upfirdn2d.py:270-275 with up = down = 1)
+                dx = _fir_pm(not to_pm, 3 - px0, 3 - py0, not flip, gain, out_hw, in_hw, pm_hw).apply(dy, f)
+            return dx, None
+
+    _fir_pm_cache[key] = FirPM
+    return FirPM
+
+
+# ----------------------------------------------------------------------------
 
 def filter2d(x, f, padding=0, flip_filter=False, gain=1, impl='cuda'):
     r"""Filter a batch of 2D images; output shape == input shape (upfirdn2d.py:292-324)."""

@@ -89,6 +89,23 @@ GG_API int gg_upfirdn2d_f32(const float* x, const float* f, float* y, int N, int
                      int upx, int upy, int downx, int downy, int padx0, int padx1, int pady0, int pady1,
                      int flip, float gain, int outH, int outW, gg_stream_t stream);
 
+/* 4x4 FIR at unit rate (up = down = 1) with an optional PHASE-MAJOR side -- the filter passes of the stride-2 layers
+ * (conv2d_resample.py:119-122 FIR before the stride-2 conv, :139 FIR after the stride-2 transposed conv) fused with the
+ * space-to-depth / depth-to-space re-layout that lets those convolutions run as stride-1 tensor-core GEMMs:
+ *
+ *   t_pm[n, (py,px,c), Y, X]  <->  t[n, c, 2Y+py, 2X+px]
+ *
+ *   y[n,c,oy,ox] = gain * sum_{ky,kx} F[ky][kx] * x[n,c, oy+ky-pady0, ox+kx-padx0]      (x == 0 outside inH x inW)
+ *   F = f (flip=1) or f flipped in both axes (flip=0), exactly as gg_upfirdn2d_f32.
+ *
+ * in_pm=1 : x is [N,4C,in_pmH,in_pmW] phase-major, (inH,inW) is the valid logical extent (<= 2*in_pmH x 2*in_pmW).
+ * out_pm=1: y is [N,4C,out_pmH,out_pmW] phase-major; logical positions outside (outH,outW) are written as zero.
+ * Otherwise the side is plain [N,C,H,W].  At most one side is phase-major.
+ */
+GG_API int gg_fir4_pm_f32(const float* x, const float* f, float* y, int N, int C, int inH, int inW, int padx0, int pady0,
+                   int flip, float gain, int outH, int outW, int in_pm, int in_pmH, int in_pmW, int out_pm, int out_pmH,
+                   int out_pmW, gg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * conv2d -- replaces the ATen/cuDNN calls behind `conv2d_gradfix.conv2d / conv_transpose2d`
  * (torch_utils/ops/conv2d_gradfix.py:37-58,138-148) and, with the optional per-sample scales, the

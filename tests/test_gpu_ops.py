@@ -83,6 +83,40 @@ def test_upfirdn2d_double_backward(ops, device):
     assert_close(ddy, ops.upfirdn2d.upsample2d(v, f), 1e-5)
 
 
+@pytest.mark.parametrize('case', [(2, 5, 16, 16, [2, 2, 2, 2]), (1, 3, 33, 21, [2, 2, 2, 2]), (2, 4, 64, 300, [1, 1, 1, 1]), (1, 2, 7, 9, [2, 1, 2, 1])])
+def test_fir_phase_major_fused_layouts(ops, device, case):
+    # unit-rate 4x4 FIR fused with space-to-depth (fir_to_pm) / depth-to-space (fir_from_pm), forward and gradient,
+    # against the oracle's upfirdn2d composed with the host re-layout helpers
+    N, C, H, W, pad = case
+    cr = ops.conv2d_resample
+    g = torch.Generator().manual_seed(H * 100 + W)
+    f = R.setup_filter([1, 3, 3, 1])
+    x = torch.randn(N, C, H, W, generator=g)
+    oh, ow = H + pad[2] + pad[3] - 3, W + pad[0] + pad[1] - 3
+    ys, xs = (oh + 1) // 2 + 1, ((ow + 1) // 2 + 4) // 4 * 4
+    xc = x.clone().requires_grad_(True)
+    want = cr.space_to_depth(R.upfirdn2d(xc, f, padding=pad, gain=2.0), ys, xs)
+    dy = torch.randn(want.shape, generator=g)
+    wdx, = torch.autograd.grad(want, xc, dy)
+    xg = x.to(device).requires_grad_(True)
+    got = ops.upfirdn2d.fir_to_pm(xg, f.to(device), pad, False, 2.0, ys, xs)
+    assert_close(got, want, 1e-6, 'fir_to_pm')
+    gdx, = torch.autograd.grad(got, xg, dy.to(device))
+    assert_close(gdx, wdx, 1e-6, 'fir_to_pm.dx')
+    # the other direction: a phase-major tensor with a valid extent smaller than its planes
+    z = torch.randn(N, 4 * C, ys, xs, generator=g)
+    vh, vw = 2 * ys - 1, 2 * xs - 3
+    zc = z.clone().requires_grad_(True)
+    want2 = R.upfirdn2d(cr.depth_to_space(zc)[:, :, :vh, :vw], f, padding=pad, flip_filter=True, gain=4.0)
+    dy2 = torch.randn(want2.shape, generator=g)
+    wdz, = torch.autograd.grad(want2, zc, dy2)
+    zg = z.to(device).requires_grad_(True)
+    got2 = ops.upfirdn2d.fir_from_pm(zg, f.to(device), pad, True, 4.0, (vh, vw))
+    assert_close(got2, want2, 1e-6, 'fir_from_pm')
+    gdz, = torch.autograd.grad(got2, zg, dy2.to(device))
+    assert_close(gdz, wdz, 1e-6, 'fir_from_pm.dz')
+
+
 def test_upfirdn2d_errors(ops, device):
     x = torch.randn(1, 1, 2, 2, device=device)
     f = R.setup_filter([1, 3, 3, 1]).to(device)

@@ -138,8 +138,12 @@ def test_phase_major_forms_of_the_stride2_layers_match_the_oracle():
         xp = F.pad(x, (px, max(need_w - W - px, 0), py, max(need_h - H - py, 0)))[:, :, :need_h, :need_w]
         return F.conv2d(xp, w)
 
-    def fir(x, f, padding, flip_filter, gain=1):
-        return R.upfirdn2d(x, f, padding=padding, flip_filter=flip_filter, gain=gain)
+    def fir_to_pm(x, f, padding, flip_filter, gain, ys, xs):
+        return cr.space_to_depth(R.upfirdn2d(x, f, padding=padding, flip_filter=flip_filter, gain=gain), ys, xs)
+
+    def fir_from_pm(z, f, padding, flip_filter, gain, valid_hw):
+        full = cr.depth_to_space(z)[:, :, :valid_hw[0], :valid_hw[1]]
+        return R.upfirdn2d(full, f, padding=padding, flip_filter=flip_filter, gain=gain)
 
     g = torch.Generator().manual_seed(11)
     f = R.setup_filter([1, 3, 3, 1])
@@ -149,8 +153,10 @@ def test_phase_major_forms_of_the_stride2_layers_match_the_oracle():
         for up, down in [(2, 1), (1, 2)]:
             want = R.conv2d_resample(x, w, f=f, up=up, down=down, padding=1, flip_weight=flip_weight)
             pl = cr.plan(w.shape, f, up, down, 1)
-            fn = cr.up2_phase_major if up == 2 else cr.down2_phase_major
-            got = fn(x, w, f, pl['fir_pad'], flip_weight, False, conv_s1, fir)
+            if up == 2:
+                got = cr.up2_phase_major(x, w, f, pl['fir_pad'], flip_weight, False, conv_s1, fir_from_pm)
+            else:
+                got = cr.down2_phase_major(x, w, f, pl['fir_pad'], flip_weight, False, conv_s1, fir_to_pm)
             assert got.shape == want.shape, (got.shape, want.shape)
             assert float((got - want).abs().max()) < 1e-12, (up, down, flip_weight)
     # 7 of the 16 (phase, tap) blocks of the phase-major weights are structurally zero
