@@ -204,6 +204,7 @@ extern "C" GG_API int gg_bias_act_f32(const float* x, const float* b, const floa
     GG_REQUIRE(b == nullptr || (sizeB >= 1 && stepB >= 1), "bias_act: b has wrong number of elements");
     GG_REQUIRE(dbias == nullptr || (sizeB >= 1 && stepB >= 1), "bias_act: dbias needs sizeB/stepB");
     if (sizeX == 0) return GG_OK;
+    if (b == nullptr && dbias == nullptr) { sizeB = 1; stepB = (int64_t)1 << 30; }   // no per-channel work: any layout vectorises
     Params p{x, b, xref, yref, dy, y, dbias, alpha, gain, clamp, sizeX, sizeB < 1 ? 1 : sizeB, stepB < 1 ? 1 : stepB};
     cudaStream_t st = (cudaStream_t)stream;
     switch (act) {

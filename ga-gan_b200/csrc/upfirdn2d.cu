@@ -208,10 +208,15 @@ struct StreamP {
     int ipH, ipW, opH, opW;                     // phase-major plane sizes (IN_PM / OUT_PM)
 };
 
-template <bool IN_PM, bool OUT_PM>
+// LAYOUT 0: plain -> plain, 1: phase-major in -> plain out, 2: plain in -> phase-major out.  PX0 = padx0 (0..3) is a template
+// parameter so that the position of every needed input column inside the aligned 128-bit blocks is known at compile time.
+// One thread = 8 output columns x 8 output rows; per input row it issues 4 (plain) or 6 (phase-major: 3 per column phase)
+// aligned 128-bit loads; rows and column blocks that stick out of the image take a guarded scalar path.
+template <int LAYOUT, int PX0>
 __global__ void __launch_bounds__(256) fir_stream(StreamP p) {
-    constexpr int OXT = OUT_PM ? 8 : 4;         // OUT_PM: 8 logical columns = one float4 per column phase
-    constexpr int RY = OUT_PM ? 4 : 8;
+    constexpr bool IN_PM = LAYOUT == 1, OUT_PM = LAYOUT == 2;
+    constexpr int OXT = 8, RY = 8;
+    constexpr int NB = IN_PM ? 3 : 4;                 // 128-bit blocks per row (and per column phase for IN_PM)
     __shared__ float sK[16];
     if (threadIdx.x < 16) {
         int ky = threadIdx.x >> 2, kx = threadIdx.x & 3;
@@ -228,81 +233,136 @@ __global__ void __launch_bounds__(256) fir_stream(StreamP p) {
     const int y0 = (blockIdx.y * 8 + warp) * RY;
     const int fullW = OUT_PM ? 2 * p.opW : p.outW, fullH = OUT_PM ? 2 * p.opH : p.outH;
     if (x0 >= fullW || y0 >= fullH) return;
-    for (int nc = blockIdx.z; nc < p.N * p.C; nc += gridDim.z) {
-    const int n = nc / p.C, c = nc - n * p.C;
-
+    const int pitch = IN_PM ? p.ipW : p.inW;          // floats per stored input row
     const size_t iplane = IN_PM ? (size_t)p.ipH * p.ipW : (size_t)p.inH * p.inW;
-    const float* xin = p.x + (IN_PM ? (size_t)n * 4 * p.C * iplane : (size_t)nc * iplane);
+    // first column of block 0 in the stored row: logical x0-4 (plain) or phase-major column x0/2-4
+    const int cb0 = IN_PM ? (x0 >> 1) - 4 : x0 - 4;
+    const int climit = IN_PM ? p.ipW : p.inW;         // stored columns
+    // the valid extent may end inside the stored row (IN_PM): logical col < inW  <=>  2X+px < inW
+    for (int nc = blockIdx.z; nc < p.N * p.C; nc += gridDim.z) {
+        const int n = nc / p.C, c = nc - n * p.C;
+        const float* xin = p.x + (IN_PM ? ((size_t)n * 4 * p.C + c) * iplane : (size_t)nc * iplane);
 
-    float acc[RY][OXT];
+        float acc[RY][OXT];
 #pragma unroll
-    for (int r = 0; r < RY; ++r)
+        for (int r = 0; r < RY; ++r)
 #pragma unroll
-        for (int t = 0; t < OXT; ++t) acc[r][t] = 0.f;
-
-#pragma unroll
-    for (int rr = 0; rr < RY + 3; ++rr) {
-        const int r = y0 + rr - p.pady0;                        // logical input row
-        float in[OXT + 3];
-        const bool row_ok = r >= 0 && r < p.inH;
-        const float* rowp;
-        if (IN_PM) rowp = xin + ((size_t)((r & 1) * 2) * p.C + c) * iplane + (size_t)(r >> 1) * p.ipW;   // px = 0 plane; px = 1 is C planes further
-        else       rowp = xin + (size_t)r * p.inW;
-#pragma unroll
-        for (int j = 0; j < OXT + 3; ++j) {
-            const int col = x0 + j - p.padx0;
-            float v = 0.f;
-            if (row_ok && col >= 0 && col < p.inW) {
-                if (IN_PM) v = __ldg(rowp + (size_t)(col & 1) * p.C * iplane + (col >> 1));
-                else       v = __ldg(rowp + col);
-            }
-            in[j] = v;
-        }
-#pragma unroll
-        for (int ky = 0; ky < 4; ++ky) {
-            const int yy = rr - ky;                              // output row (relative) fed through filter row ky
-            if (yy < 0 || yy >= RY) continue;                    // compile-time after unrolling
-#pragma unroll
-            for (int t = 0; t < OXT; ++t)
-#pragma unroll
-                for (int kx = 0; kx < 4; ++kx) acc[yy][t] = fmaf(K[ky][kx], in[t + kx], acc[yy][t]);
-        }
-    }
+            for (int t = 0; t < OXT; ++t) acc[r][t] = 0.f;
 
 #pragma unroll
-    for (int r = 0; r < RY; ++r) {
-        const int y = y0 + r;
-        if (y >= fullH) continue;
-        if (OUT_PM) {
-            // logical (y, x0 + 2X' + px) -> plane (y&1, px, c), row y>>1, columns x0/2 + X'
-            float v[OXT];
+        for (int rr = 0; rr < RY + 3; ++rr) {
+            const int r = y0 + rr - p.pady0;                    // logical input row
+            const bool row_ok = r >= 0 && r < p.inH;
+            float in[OXT + 3];
+            if (!IN_PM) {
+                float buf[4 * NB];
+                const float* rowp = xin + (size_t)(row_ok ? r : 0) * pitch;
 #pragma unroll
-            for (int t = 0; t < OXT; ++t) v[t] = (y < p.outH && x0 + t < p.outW) ? acc[r][t] : 0.f;
-            const size_t oplane = (size_t)p.opH * p.opW;
-            float* base = p.y + ((size_t)n * 4 * p.C + (size_t)((y & 1) * 2) * p.C + c) * oplane + (size_t)(y >> 1) * p.opW + (x0 >> 1);
-            *reinterpret_cast<float4*>(base) = make_float4(v[0], v[2], v[4], v[6]);
-            *reinterpret_cast<float4*>(base + (size_t)p.C * oplane) = make_float4(v[1], v[3], v[5], v[7]);
-        } else {
-            float* dst = p.y + (size_t)nc * p.outH * p.outW + (size_t)y * p.outW + x0;
-            if ((p.outW & 3) == 0 && x0 + 3 < p.outW) {
-                *reinterpret_cast<float4*>(dst) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                for (int b = 0; b < NB; ++b) {
+                    const int cb = cb0 + 4 * b;
+                    if (row_ok && cb >= 0 && cb + 3 < climit) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(rowp + cb));
+                        buf[4 * b] = v.x; buf[4 * b + 1] = v.y; buf[4 * b + 2] = v.z; buf[4 * b + 3] = v.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            buf[4 * b + e] = (row_ok && cb + e >= 0 && cb + e < climit) ? __ldg(rowp + cb + e) : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < OXT + 3; ++j) in[j] = buf[4 - PX0 + j];
             } else {
+                // logical column x0 - PX0 + j lives in column phase ph = (j - PX0) & 1 at phase-major column x0/2 + (j - PX0 - ph)/2
+                float buf[2][4 * NB];
+                const int py = r & 1;
+#pragma unroll
+                for (int ph = 0; ph < 2; ++ph) {
+                    const float* rowp = xin + (size_t)((py * 2 + ph) * p.C) * iplane + (size_t)(row_ok ? (r >> 1) : 0) * pitch;
+                    const int vcols = (p.inW - ph + 1) >> 1;    // valid phase-major columns of this phase
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        const int cb = cb0 + 4 * b;
+                        if (row_ok && cb >= 0 && cb + 3 < vcols) {
+                            const float4 v = __ldg(reinterpret_cast<const float4*>(rowp + cb));
+                            buf[ph][4 * b] = v.x; buf[ph][4 * b + 1] = v.y; buf[ph][4 * b + 2] = v.z; buf[ph][4 * b + 3] = v.w;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                buf[ph][4 * b + e] = (row_ok && cb + e >= 0 && cb + e < vcols) ? __ldg(rowp + cb + e) : 0.f;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < OXT + 3; ++j) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const int d = j - PX0;                       // compile-time after unrolling
+                    const int ph = d & 1;
+                    in[j] = buf[ph][4 + (d - ph) / 2];
+                }
+            }
+#pragma unroll
+            for (int ky = 0; ky < 4; ++ky) {
+                const int yy = rr - ky;                          // output row (relative) fed through filter row ky
+                if (yy < 0 || yy >= RY) continue;                // compile-time after unrolling
 #pragma unroll
                 for (int t = 0; t < OXT; ++t)
-                    if (x0 + t < p.outW) dst[t] = acc[r][t];
+#pragma unroll
+                    for (int kx = 0; kx < 4; ++kx) acc[yy][t] = fmaf(K[ky][kx], in[t + kx], acc[yy][t]);
             }
         }
-    }
+
+#pragma unroll
+        for (int r = 0; r < RY; ++r) {
+            const int y = y0 + r;
+            if (y >= fullH) continue;
+            if (OUT_PM) {
+                // logical (y, x0 + 2X' + px) -> plane (y&1, px, c), row y>>1, columns x0/2 + X'
+                float v[OXT];
+#pragma unroll
+                for (int t = 0; t < OXT; ++t) v[t] = (y < p.outH && x0 + t < p.outW) ? acc[r][t] : 0.f;
+                const size_t oplane = (size_t)p.opH * p.opW;
+                float* base = p.y + ((size_t)n * 4 * p.C + (size_t)((y & 1) * 2) * p.C + c) * oplane + (size_t)(y >> 1) * p.opW + (x0 >> 1);
+                *reinterpret_cast<float4*>(base) = make_float4(v[0], v[2], v[4], v[6]);
+                *reinterpret_cast<float4*>(base + (size_t)p.C * oplane) = make_float4(v[1], v[3], v[5], v[7]);
+            } else {
+                float* dst = p.y + (size_t)nc * p.outH * p.outW + (size_t)y * p.outW + x0;
+                if ((p.outW & 3) == 0 && x0 + 7 < p.outW) {
+                    *reinterpret_cast<float4*>(dst) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < OXT; ++t)
+                        if (x0 + t < p.outW) dst[t] = acc[r][t];
+                }
+            }
+        }
     }
 }
 
-template <bool IN_PM, bool OUT_PM>
-int launch_stream(const StreamP& p, cudaStream_t st) {
-    constexpr int OXT = OUT_PM ? 8 : 4, RY = OUT_PM ? 4 : 8;
-    const int fullW = OUT_PM ? 2 * p.opW : p.outW, fullH = OUT_PM ? 2 * p.opH : p.outH;
-    dim3 grid((unsigned)((fullW + 32 * OXT - 1) / (32 * OXT)), (unsigned)((fullH + 8 * RY - 1) / (8 * RY)), (unsigned)(p.N * p.C < 65535 ? p.N * p.C : 65535));
-    fir_stream<IN_PM, OUT_PM><<<grid, 256, 0, st>>>(p);
+template <int LAYOUT, int PX0>
+int launch_stream2(const StreamP& p, cudaStream_t st) {
+    constexpr int OXT = 8, RY = 8;
+    const int fullW = LAYOUT == 2 ? 2 * p.opW : p.outW, fullH = LAYOUT == 2 ? 2 * p.opH : p.outH;
+    dim3 grid((unsigned)((fullW + 32 * OXT - 1) / (32 * OXT)), (unsigned)((fullH + 8 * RY - 1) / (8 * RY)),
+              (unsigned)(p.N * p.C < 65535 ? p.N * p.C : 65535));
+    fir_stream<LAYOUT, PX0><<<grid, 256, 0, st>>>(p);
     return gg::check_launch("upfirdn2d(fir_stream)");
+}
+
+template <int LAYOUT>
+int launch_stream(const StreamP& p, cudaStream_t st) {
+    switch (p.padx0) {
+        case 0: return launch_stream2<LAYOUT, 0>(p, st);
+        case 1: return launch_stream2<LAYOUT, 1>(p, st);
+        case 2: return launch_stream2<LAYOUT, 2>(p, st);
+        default: return launch_stream2<LAYOUT, 3>(p, st);
+    }
+}
+
+// 128-bit row loads need 16-byte aligned rows; padx0 must be one of the four instantiations
+bool stream_ok(const StreamP& p, bool in_pm) {
+    const int pitch = in_pm ? p.ipW : p.inW;
+    return p.padx0 >= 0 && p.padx0 <= 3 && pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0;
 }
 
 }  // namespace
@@ -328,7 +388,8 @@ extern "C" GG_API int gg_upfirdn2d_f32(const float* x, const float* f, float* y,
     const bool f4 = (fH == 4 && fW == 4) && upx == upy && downx == downy && outW >= 48;
     if (f4 && upx == 1 && downx == 1) {   // unit rate: the register-streaming kernel (also serves the phase-major layouts)
         StreamP sp{x, f, y, N, C, inH, inW, padx0, pady0, flip, gain, outH, outW, 0, 0, 0, 0};
-        return launch_stream<false, false>(sp, st);
+        if (stream_ok(sp, false)) return launch_stream<0>(sp, st);
+        return launch_tile<1, 1, 0, 4, 4>(p, st);
     }
     if (f4 && upx == 1 && downx == 2) return launch_tile<1, 2, 0, 2, 2>(p, st);
     if (f4 && upx == 2 && downx == 1) {
@@ -358,7 +419,8 @@ extern "C" GG_API int gg_fir4_pm_f32(const float* x, const float* f, float* y, i
     if (N == 0) return GG_OK;
     StreamP p{x, f, y, N, C, inH, inW, padx0, pady0, flip, gain, outH, outW, in_pmH, in_pmW, out_pmH, out_pmW};
     cudaStream_t st = (cudaStream_t)stream;
-    if (in_pm) return launch_stream<true, false>(p, st);
-    if (out_pm) return launch_stream<false, true>(p, st);
-    return launch_stream<false, false>(p, st);
+    GG_REQUIRE(stream_ok(p, in_pm != 0), "fir4_pm: needs 0 <= padx0 <= 3 and 16-byte aligned input rows (width %% 4 == 0)");
+    if (in_pm) return launch_stream<1>(p, st);
+    if (out_pm) return launch_stream<2>(p, st);
+    return launch_stream<0>(p, st);
 }

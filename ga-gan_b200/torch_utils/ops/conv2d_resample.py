@@ -57,17 +57,8 @@ def phase_major_weight_up(w):
     return wp.permute(3, 5, 0, 1, 2, 4).reshape(4 * O, I, 2, 2)
 
 
-def space_to_depth(x, ys, xs):
-    """[N,C,H,W] -> [N,4C,ys,xs] phase-major, zero-padded (or cropped) to 2ys x 2xs first."""
-    N, C, H, W = x.shape
-    x = torch.nn.functional.pad(x, (0, 2 * xs - W, 0, 2 * ys - H))
-    return x.reshape(N, C, ys, 2, xs, 2).permute(0, 3, 5, 1, 2, 4).reshape(N, 4 * C, ys, xs)
-
-
-def depth_to_space(z):
-    """[N,4O,ys,xs] phase-major -> [N,O,2ys,2xs]."""
-    N, C4, ys, xs = z.shape
-    return z.reshape(N, 2, 2, C4 // 4, ys, xs).permute(0, 3, 4, 1, 5, 2).reshape(N, C4 // 4, 2 * ys, 2 * xs)
+space_to_depth = upfirdn2d.space_to_depth
+depth_to_space = upfirdn2d.depth_to_space
 
 
 def _round_up(v, m):
@@ -133,18 +124,11 @@ def _conv_s1(x, w, padding, out_hw, live):
 
 
 def _fir_to_pm(x, f, padding, flip_filter, gain, ys, xs):
-    if f is not None and f.ndim == 2 and tuple(f.shape) == (4, 4):
-        return upfirdn2d.fir_to_pm(x, f, padding, flip_filter, gain, ys, xs)           # one fused kernel
-    return space_to_depth(upfirdn2d.upfirdn2d(x=x, f=f, padding=padding, flip_filter=flip_filter, gain=gain), ys, xs)
+    return upfirdn2d.fir_to_pm(x, f, padding, flip_filter, gain, ys, xs)
 
 
 def _fir_from_pm(z, f, padding, flip_filter, gain, valid_hw):
-    if f is not None and f.ndim == 2 and tuple(f.shape) == (4, 4):
-        return upfirdn2d.fir_from_pm(z, f, padding, flip_filter, gain, valid_hw)       # one fused kernel
-    full = depth_to_space(z)
-    px0, px1, py0, py1 = padding
-    pad = [px0, px1 - (full.shape[3] - valid_hw[1]), py0, py1 - (full.shape[2] - valid_hw[0])]
-    return upfirdn2d.upfirdn2d(x=full, f=f, padding=pad, flip_filter=flip_filter, gain=gain)
+    return upfirdn2d.fir_from_pm(z, f, padding, flip_filter, gain, valid_hw)
 
 
 @misc.profiled_function

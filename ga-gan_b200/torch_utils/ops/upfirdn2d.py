@@ -180,9 +180,30 @@ def _upfirdn2d_cuda(up=1, down=1, padding=0, flip_filter=False, gain=1):
 _fir_pm_cache = dict()
 
 
+def space_to_depth(x, ys, xs):
+    """[N,C,H,W] -> [N,4C,ys,xs] phase-major, zero-padded (or cropped) to 2ys x 2xs first."""
+    N, C, H, W = x.shape
+    x = torch.nn.functional.pad(x, (0, 2 * xs - W, 0, 2 * ys - H))
+    return x.reshape(N, C, ys, 2, xs, 2).permute(0, 3, 5, 1, 2, 4).reshape(N, 4 * C, ys, xs)
+
+
+def depth_to_space(z):
+    """[N,4O,ys,xs] phase-major -> [N,O,2ys,2xs]."""
+    N, C4, ys, xs = z.shape
+    return z.reshape(N, 2, 2, C4 // 4, ys, xs).permute(0, 3, 4, 1, 5, 2).reshape(N, C4 // 4, 2 * ys, 2 * xs)
+
+
+def _fused_fir_ok(f, px0, plain_w, pm_w):
+    # the fused kernel wants a 2-D 4x4 filter, 0 <= padx0 <= 3 (also for its gradient, whose padx0 is 3 - padx0) and
+    # 16-byte aligned rows on both sides (128-bit loads / stores)
+    return f is not None and f.ndim == 2 and tuple(f.shape) == (4, 4) and 0 <= px0 <= 3 and plain_w % 4 == 0 and pm_w % 4 == 0
+
+
 def fir_to_pm(x, f, padding, flip_filter, gain, ys, xs):
     _init()
     px0, px1, py0, py1 = _parse_padding(padding)
+    if not _fused_fir_ok(f, px0, int(x.shape[3]), int(xs)):      # odd widths / other filters: the same result from the unfused ops
+        return space_to_depth(upfirdn2d(x, f, padding=padding, flip_filter=flip_filter, gain=gain), ys, xs)
     oh, ow = x.shape[2] + py0 + py1 - 3, x.shape[3] + px0 + px1 - 3
     return _fir_pm(True, px0, py0, bool(flip_filter), float(gain), (int(x.shape[2]), int(x.shape[3])), (oh, ow), (int(ys), int(xs))).apply(x, f)
 
@@ -191,7 +212,11 @@ def fir_from_pm(z, f, padding, flip_filter, gain, valid_hw):
     _init()
     px0, px1, py0, py1 = _parse_padding(padding)
     vh, vw = int(valid_hw[0]), int(valid_hw[1])
-    oh, ow = vh + py0 + py1 - 3, vw + px0 + px1 - 3
+    fw, fh = _get_filter_size(f)
+    oh, ow = vh + py0 + py1 - fh + 1, vw + px0 + px1 - fw + 1
+    if not _fused_fir_ok(f, px0, ow, int(z.shape[3])):
+        full = depth_to_space(z)[:, :, :vh, :vw]
+        return upfirdn2d(full, f, padding=padding, flip_filter=flip_filter, gain=gain)
     return _fir_pm(False, px0, py0, bool(flip_filter), float(gain), (vh, vw), (oh, ow), (int(z.shape[2]), int(z.shape[3]))).apply(z, f)
 
 

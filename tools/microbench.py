@@ -97,6 +97,21 @@ def main():
             ms = timeit(lambda: upfirdn2d.upfirdn2d(x, f, up=2, padding=[2, 1, 2, 1], gain=4))
             report('upfirdn2d', f'up2 [{N},{chan[2*r]},{r},{r}] (bwd of D skip)', ms, nbytes=4 * (x.numel() + 4 * x.numel()))
 
+    if args.only in ('', 'upfirdn2d', 'fir_pm'):
+        # the unit-rate FIRs of the stride-2 layers as the networks run them now: fused with the phase-major re-layout
+        for r in ([128, 512] if args.quick else [32, 128, 256, 512]):
+            C = chan[2 * r]
+            xs_w = (r + 1 + 3) // 4 * 4
+            z = torch.randn(N, 4 * C, r + 1, xs_w, device=dev)
+            ms = timeit(lambda: upfirdn2d.fir_from_pm(z, f, [1, 1, 1, 1], False, 4, (2 * r + 1, 2 * r + 1)))
+            report('upfirdn2d', f'fir_from_pm [{N},4x{C},{r+1},{xs_w}] -> [{N},{C},{2*r},{2*r}] (G up-conv)', ms,
+                   nbytes=4 * (N * C * (2 * r + 1) ** 2 + N * C * 4 * r * r))
+            x = torch.randn(N, C, 2 * r, 2 * r, device=dev)
+            ys, xs = r + 1, (r + 1 + 3) // 4 * 4
+            ms = timeit(lambda: upfirdn2d.fir_to_pm(x, f, [2, 2, 2, 2], False, 1, ys, xs))
+            report('upfirdn2d', f'fir_to_pm [{N},{C},{2*r},{2*r}] -> [{N},4x{C},{ys},{xs}] (D conv1)', ms,
+                   nbytes=4 * (x.numel() + N * C * (2 * r + 1) ** 2))
+
     if args.only in ('', 'conv'):
         precs = [('auto', custom_ops.PREC_AUTO), ('simt', custom_ops.PREC_FP32_SIMT)]
         shapes = [(64, 512, 512, 3), (256, 128, 128, 3), (1024, 32, 32, 3)] if args.quick else \
