@@ -110,9 +110,10 @@ __global__ void __launch_bounds__(256) wgrad1x1_thin(ThinWgP p) {
     const float4* tn = reinterpret_cast<const float4*>(p.T + (int64_t)n * p.CT * p.P);
     const float4* wn = reinterpret_cast<const float4*>(p.Wd + (int64_t)n * p.CW * p.P);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // Every element is read ONCE per pass of WCH wide channels: the thin planes of a pixel stay in registers while the
-    // wide channels stream by (the thin planes are re-read CW/WCH times, from L2).
-    for (int c0 = 0; c0 < p.CW; c0 += WCH) {
+    // The thin planes of a pixel stay in registers while WCH wide channels stream by; the wide tensor is read exactly once,
+    // the thin planes CW/WCH times (from L2).
+    {
+        const int c0 = blockIdx.z * WCH;             // one pass of WCH wide channels per CTA (grid.z)
         float acc[WCH][THIN];
 #pragma unroll
         for (int c = 0; c < WCH; ++c)
@@ -153,7 +154,6 @@ __global__ void __launch_bounds__(256) wgrad1x1_thin(ThinWgP p) {
                 atomicAdd(p.dw + (p.out_layout ? (int64_t)a * B + b : (int64_t)b * A + a), s);
             }
         }
-        __syncthreads();
     }
 }
 
@@ -203,7 +203,7 @@ int wgrad1x1_thin(const float* a, const float* b, float* dw, int N, int A, int H
     if (chunks < 1) chunks = 1;
     p.chunks = chunks;
     GG_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)A * B, st));
-    dim3 grid(chunks, N);
+    dim3 grid(chunks, N, (p.CW + WCH - 1) / WCH);
     wgrad1x1_thin<<<grid, 256, 0, st>>>(p);
     return check_launch("conv2d_wgrad(1x1 thin)");
 }

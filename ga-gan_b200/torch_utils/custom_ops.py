@@ -70,6 +70,7 @@ _SIGNATURES = {
     'gg_upfirdn2d_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 15 + [ctypes.c_float, ctypes.c_int, ctypes.c_int,
                                                            ctypes.c_void_p]),
     'gg_fir4_pm_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 7 + [ctypes.c_float] + [ctypes.c_int] * 8 + [ctypes.c_void_p]),
+    'gg_chan_dot_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
     'gg_conv2d_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 14 + [_c_float_p, _c_float_p, ctypes.c_int,
                                                         ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
     'gg_conv2d_wgrad_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 14 + [_c_float_p, _c_float_p, ctypes.c_int,
@@ -218,6 +219,20 @@ class _Plugin:
                                              int(downx), int(downy), int(padx0), int(padx1), int(pady0), int(pady1),
                                              1 if flip else 0, float(gain), out_h, out_w, _stream(x)), 'upfirdn2d')
         return y
+
+    # out[n,c] = sum over pixels of a*b (include/gagan_b200.h: gg_chan_dot_f32)
+    def chan_dot(self, a, b):
+        _require_cuda(a, 'a')
+        _require_cuda(b, 'b')
+        _check_device(a)
+        if a.shape != b.shape or a.dim() < 2:
+            raise RuntimeError('chan_dot: a and b must have the same [N,C,...] shape')
+        a = a.contiguous(); b = b.contiguous()
+        rows = a.shape[0] * a.shape[1]
+        out = torch.empty([a.shape[0], a.shape[1]], dtype=a.dtype, device=a.device)
+        with torch.cuda.device(a.device):
+            _check(self._lib.gg_chan_dot_f32(_ptr(a), _ptr(b), _ptr(out), rows, a.numel() // max(rows, 1), _stream(a)), 'chan_dot')
+        return out
 
     # 4x4 FIR at unit rate with a phase-major side (include/gagan_b200.h: gg_fir4_pm_f32)
     def fir4_pm(self, x, f, padx0, pady0, flip, gain, in_hw, out_hw, in_pm=None, out_pm=None):

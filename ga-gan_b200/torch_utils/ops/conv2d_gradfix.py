@@ -125,13 +125,97 @@ def _run_wgrad(grad_output, input, weight_shape, transpose, stride, padding, gro
 _conv2d_s1_cache = dict()
 
 
-def conv2d_s1(x, w, padding=(0, 0), out_hw=None, io=False, flip=False, live=1.0):
+def conv2d_s1(x, w, padding=(0, 0), out_hw=None, io=False, flip=False, live=1.0, in_scale=None, out_scale=None):
+    """`in_scale [N,I]` / `out_scale [N,O]`: per-sample channel scales folded into the kernel's operand conversion and
+    epilogue -- y = out_scale * conv(in_scale * x, w) -- i.e. the style modulation / demodulation of modulated_conv2d
+    (networks.py:642,648-651) without their full-tensor multiply passes."""
     _check_input(x)
     kh, kw = int(w.shape[2]), int(w.shape[3])
     padding = _tuple_of_ints(padding, 2)
     if out_hw is None:
         out_hw = (x.shape[2] + 2 * padding[0] - kh + 1, x.shape[3] + 2 * padding[1] - kw + 1)
-    return _conv2d_s1(tuple(w.shape), padding, (int(out_hw[0]), int(out_hw[1])), bool(io), bool(flip), float(live)).apply(x, w)
+    key = (tuple(w.shape), padding, (int(out_hw[0]), int(out_hw[1])), bool(io), bool(flip), float(live))
+    if in_scale is None and out_scale is None:
+        return _conv2d_s1(*key).apply(x, w)
+    if fuse_scales is False:            # debug switch: explicit multiply passes around the unscaled kernel
+        y = _conv2d_s1(*key).apply(x * in_scale[:, :, None, None] if in_scale is not None else x, w)
+        return y * out_scale[:, :, None, None] if out_scale is not None else y
+    return _scaled_conv2d_s1(*key, in_scale is not None, out_scale is not None).apply(x, w, in_scale, out_scale)
+
+
+fuse_scales = True
+_scaled_conv2d_s1_cache = dict()
+
+
+def _scaled_conv2d_s1(weight_shape, padding, out_hw, io, flip, live, has_a, has_b):
+    key = (weight_shape, padding, out_hw, io, flip, live, has_a, has_b)
+    if key in _scaled_conv2d_s1_cache:
+        return _scaled_conv2d_s1_cache[key]
+    kh, kw = weight_shape[2], weight_shape[3]
+    dpad = (kh - 1 - padding[0], kw - 1 - padding[1])
+
+    def kernel(x, w, a, b, pad, hw, io_, flip_):
+        if not io_:
+            return _plugin.conv2d(x, w, stride=1, padding=pad, transposed=False, flip_w=flip_, out_hw=hw, flop_scale=live,
+                                  in_scale=a, out_scale=b)
+        return _plugin.conv2d(x, w, stride=1, padding=(kh - 1 - pad[0], kw - 1 - pad[1]), transposed=True, flip_w=(not flip_),
+                              out_hw=hw, flop_scale=live, in_scale=a, out_scale=b)
+
+    class ScaledConvS1(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, w, a, b):
+            assert tuple(w.shape) == weight_shape
+            a_ = a.contiguous() if a is not None else None
+            b_ = b.contiguous() if b is not None else None
+            y = kernel(x, w, a_, b_, padding, out_hw, io, flip)
+            ctx.save_for_backward(x, w, a, b, y if b is not None else None)
+            return y
+
+        @staticmethod
+        def backward(ctx, dy):
+            x, w, a, b, y = ctx.saved_tensors
+            if torch.is_grad_enabled():
+                # A gradient of this gradient was requested (path-length / R1 regularisation): spell the four PARTIAL derivatives
+                # out with differentiable ops and the closed, unscaled primitives so that autograd can differentiate them again.
+                # (Re-running the forward and calling autograd.grad on it would be wrong: out_scale = dcoefs is itself a function
+                # of in_scale = styles, and the total derivative would count that path twice.)
+                conv = _conv2d_s1(weight_shape, padding, out_hw, io, flip, live)
+                conv_t = _conv2d_s1(weight_shape, dpad, (x.shape[2], x.shape[3]), not io, not flip, live)
+                xa = x * a[:, :, None, None] if a is not None else x
+                dyb = dy * b[:, :, None, None] if b is not None else dy
+                dx = dw = da = db = None
+                if ctx.needs_input_grad[0] or (a is not None and ctx.needs_input_grad[2]):
+                    u = conv_t.apply(dyb, w)
+                    if ctx.needs_input_grad[0]:
+                        dx = u * a[:, :, None, None] if a is not None else u
+                    if a is not None and ctx.needs_input_grad[2]:
+                        da = (x * u).sum([2, 3])
+                if ctx.needs_input_grad[1] and not weight_gradients_disabled:
+                    dw = conv.Wgrad.apply(dyb, xa)
+                if b is not None and ctx.needs_input_grad[3]:
+                    db = (dy * conv.apply(xa, w)).sum([2, 3])
+                return dx, dw, da, db
+            dx = dw = da = db = None
+            dy = dy.contiguous()
+            need_dx = ctx.needs_input_grad[0] or (a is not None and ctx.needs_input_grad[2])
+            if need_dx:
+                # d/dx = a * convT(b * dy): the same kernel with the scales swapped
+                dx = kernel(dy, w, b, a, dpad, (x.shape[2], x.shape[3]), not io, not flip)
+                if a is not None and ctx.needs_input_grad[2]:
+                    # d/da[n,i] = sum_p x * convT(b*dy) = sum_p x * dx / a      (a == 0 has measure zero; its gradient reads as 0)
+                    da = _plugin.chan_dot(x, dx) / torch.where(a == 0, torch.ones_like(a), a)
+                if not ctx.needs_input_grad[0]:
+                    dx = None
+            if ctx.needs_input_grad[1] and not weight_gradients_disabled:
+                dw = _plugin.conv2d_wgrad(x, dy, (kh, kw), stride=1, padding=padding, flip_w=flip, out_layout=(1 if io else 0),
+                                          flop_scale=live, a_scale=a, b_scale=b)
+            if b is not None and ctx.needs_input_grad[3]:
+                # d/db[n,o] = sum_p dy * conv(a*x, w) = sum_p dy * y / b
+                db = _plugin.chan_dot(dy, y) / torch.where(b == 0, torch.ones_like(b), b)
+            return dx, dw, da, db
+
+    _scaled_conv2d_s1_cache[key] = ScaledConvS1
+    return ScaledConvS1
 
 
 def _conv2d_s1(weight_shape, padding, out_hw, io, flip, live=1.0):
@@ -183,6 +267,7 @@ def _conv2d_s1(weight_shape, padding, out_hw, io, flip, live=1.0):
                 g_x = _conv2d_s1(weight_shape, dpad, (x.shape[2], x.shape[3]), not io, not flip, live).apply(dy, ggw)
             return g_dy, g_x
 
+    ConvS1.Wgrad = WgradS1
     _conv2d_s1_cache[key] = ConvS1
     return ConvS1
 

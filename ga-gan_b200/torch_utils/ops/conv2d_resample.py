@@ -80,14 +80,18 @@ def down2_phase_major(x, w, f, fir_pad, flip_weight, flip_filter, conv_s1, fir_t
     return conv_s1(xs, phase_major_weight_down(w), (0, 0), (oh, ow), _PM_LIVE)
 
 
-def up2_phase_major(x, w, f, fir_pad, flip_weight, flip_filter, conv_s1, fir_from_pm):
+def up2_phase_major(x, w, f, fir_pad, flip_weight, flip_filter, conv_s1, fir_from_pm, in_scale=None, out_scale=None):
     """conv2d_resample.py:125-139 (stride-2 transposed conv with pad 0, then FIR with gain 4) in phase-major form;
     `fir_from_pm(z, f, padding, flip_filter, gain, valid_hw)` reads the phase-major conv output directly."""
     N, I, H, W = x.shape
     if flip_weight:                      # the reference hands `not flip_weight` to the transposed conv (:138)
         w = w.flip([2, 3])
     xs_w = _round_up(W + 1, 4)           # the gradient of this tensor is a TMA source in backward: keep the width aligned
-    z = conv_s1(x, phase_major_weight_up(w), (1, 1), (H + 1, xs_w), _PM_LIVE)    # [N,4O,H+1,xs_w]; valid logical extent 2H+1 x 2W+1
+    if in_scale is not None or out_scale is not None:      # per-sample scales: the 4 output phases of channel o share out_scale[:, o]
+        z = conv_s1(x, phase_major_weight_up(w), (1, 1), (H + 1, xs_w), _PM_LIVE, in_scale=in_scale,
+                    out_scale=(out_scale.repeat(1, 4) if out_scale is not None else None))
+    else:
+        z = conv_s1(x, phase_major_weight_up(w), (1, 1), (H + 1, xs_w), _PM_LIVE)   # [N,4O,H+1,xs_w]; valid logical extent 2H+1 x 2W+1
     return fir_from_pm(z, f, fir_pad, flip_filter, 4, (2 * H + 1, 2 * W + 1))
 
 
@@ -119,8 +123,8 @@ def plan(w_shape, f, up, down, padding):
     return dict(branch='generic', fir_pad=[px0, px1, py0, py1])
 
 
-def _conv_s1(x, w, padding, out_hw, live):
-    return conv2d_gradfix.conv2d_s1(x, w, padding=padding, out_hw=out_hw, live=live)
+def _conv_s1(x, w, padding, out_hw, live, in_scale=None, out_scale=None):
+    return conv2d_gradfix.conv2d_s1(x, w, padding=padding, out_hw=out_hw, live=live, in_scale=in_scale, out_scale=out_scale)
 
 
 def _fir_to_pm(x, f, padding, flip_filter, gain, ys, xs):
@@ -132,7 +136,8 @@ def _fir_from_pm(z, f, padding, flip_filter, gain, valid_hw):
 
 
 @misc.profiled_function
-def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False):
+def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False, in_scale=None,
+                    out_scale=None):
     r"""2D convolution with optional up/downsampling; padding is applied once, up front.
 
     x `[N, I, H, W]`, w `[O, I//groups, kh, kw]`, f from `upfirdn2d.setup_filter()` or None.
@@ -147,6 +152,19 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
     out_channels, in_channels_per_group, kh, kw = _get_weight_shape(w)
     pl = plan(w.shape, f, up, down, padding)
     branch = pl['branch']
+
+    # `in_scale [N,I]` / `out_scale [N,O]` (an extension used by modulated_conv2d): y = out_scale * op(in_scale * x).  The
+    # stride-1 and the phase-major up path fold them into the tensor-core kernel; every other branch multiplies explicitly.
+    if in_scale is not None or out_scale is not None:
+        assert groups == 1
+        if branch == 'plain' and pl['conv_pad'][0] <= kh - 1 and pl['conv_pad'][1] <= kw - 1:
+            return conv2d_gradfix.conv2d_s1(x, w, padding=pl['conv_pad'], flip=(not flip_weight), in_scale=in_scale, out_scale=out_scale)
+        if branch == 'up' and up == 2 and down == 1 and kh <= 4 and kw <= 4 and pl['conv_pad'] == [0, 0]:
+            return up2_phase_major(x, w, f, pl['fir_pad'], flip_weight, flip_filter, _conv_s1, _fir_from_pm, in_scale, out_scale)
+        if in_scale is not None:
+            x = x * in_scale[:, :, None, None]
+        y = conv2d_resample(x, w, f=f, up=up, down=down, padding=padding, groups=groups, flip_weight=flip_weight, flip_filter=flip_filter)
+        return y * out_scale[:, :, None, None] if out_scale is not None else y
 
     if branch == 'down_1x1':      # FIR-decimate first, then the 1x1 conv on the small image
         x = upfirdn2d.upfirdn2d(x=x, f=f, down=down, padding=pl['fir_pad'], flip_filter=flip_filter)

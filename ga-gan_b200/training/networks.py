@@ -70,15 +70,11 @@ def modulated_conv2d(
         wsq = weight.square().sum(dim=[2, 3])                                  # [O, I]
         dcoefs = (styles.square() @ wsq.t() + 1e-8).rsqrt()                    # [N, O]
 
-    x = x * styles.to(x.dtype).reshape(batch_size, -1, 1, 1)
+    # styles and demodulation coefficients ride inside the convolution kernel (operand conversion / epilogue)
     x = conv2d_resample.conv2d_resample(x=x, w=weight.to(x.dtype), f=resample_filter, up=up, down=down, padding=padding,
-                                        flip_weight=flip_weight)
-    if demodulate and noise is not None:
-        x = fma.fma(x, dcoefs.to(x.dtype).reshape(batch_size, -1, 1, 1), noise.to(x.dtype))
-    elif demodulate:
-        x = x * dcoefs.to(x.dtype).reshape(batch_size, -1, 1, 1)
-    elif noise is not None:
-        x = x.add_(noise.to(x.dtype))
+                                        flip_weight=flip_weight, in_scale=styles.to(x.dtype), out_scale=dcoefs)
+    if noise is not None:
+        x = x + noise.to(x.dtype)
     return x
 
 

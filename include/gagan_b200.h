@@ -140,6 +140,11 @@ GG_API int gg_conv2d_wgrad_f32(const float* a, const float* b, float* dw, int N,
                         int KH, int KW, int stride, int pad_y, int pad_x, int flip_w, int out_layout,
                         const float* a_scale, const float* b_scale, int prec, int* used_prec, gg_stream_t stream);
 
+/* out[r] = sum_p a[r,p] * b[r,p] for `rows` rows of P contiguous floats (row = one (sample, channel) plane): the style and
+ * demodulation-coefficient gradients of modulated_conv2d once the per-sample scales live inside the conv kernels
+ * (training/networks.py:642,648-651 and their autograd reductions).  out is overwritten. */
+GG_API int gg_chan_dot_f32(const float* a, const float* b, float* out, int64_t rows, int64_t P, gg_stream_t stream);
+
 /* Number of kernels this library has launched since load (all streams); bench.py reports the delta. */
 GG_API int64_t gg_launch_count(void);
 

@@ -337,6 +337,41 @@ def test_conv2d_scales_fused(ops, device):
         assert_close(got, want, 1e-4)
 
 
+@pytest.mark.parametrize('k,pad', [(3, 1), (1, 0), (2, 1)])
+def test_scaled_conv_first_and_second_order_gradients(ops, device, k, pad):
+    # y = out_scale * conv(in_scale * x, w) with the scales inside the kernel: gradients w.r.t. x, w and both scales, and
+    # the path-length-style second-order gradient (gradient of a squared first-order gradient), against torch on the CPU
+    g = torch.Generator().manual_seed(20 + k)
+    N, I, O, H = 2, 24, 20, 12
+    x = torch.randn(N, I, H, H, generator=g); w = torch.randn(O, I, k, k, generator=g) / np.sqrt(I * k * k)
+    a = torch.randn(N, I, generator=g) + 1.5; b = torch.rand(N, O, generator=g) + 0.5
+    r = torch.randn(N, O, H + 2 * pad - k + 1, H + 2 * pad - k + 1, generator=g)
+
+    def run(conv, x, w, a, b, r):
+        ts = [t_.clone().requires_grad_(True) for t_ in (x, w, a, b)]
+        y = conv(*ts)
+        first = torch.autograd.grad((y * r).sum(), ts, create_graph=True)
+        pen = first[2].square().sum() + first[0].square().mean()          # depends on d/da and d/dx
+        second = torch.autograd.grad(pen, ts, allow_unused=True)
+        return y, first, second
+
+    ref = run(lambda x_, w_, a_, b_: torch.nn.functional.conv2d(x_ * a_[:, :, None, None], w_, padding=pad) * b_[:, :, None, None],
+              x, w, a, b, r)
+    dev = [t_.to(device) for t_ in (x, w, a, b, r)]
+    got = run(lambda x_, w_, a_, b_: ops.conv2d_gradfix.conv2d_s1(x_, w_, padding=(pad, pad), in_scale=a_, out_scale=b_), *dev)
+    assert_close(got[0], ref[0], 2e-5, 'y')
+    for name, g1, r1 in zip('xwab', got[1], ref[1]):
+        assert_close(g1, r1, 5e-5, 'd' + name)
+    for name, g2, r2 in zip('xwab', got[2], ref[2]):
+        assert_close(g2, r2, 2e-4, 'second-order d' + name)
+    # plain first-order backward (no create_graph) takes the fused kernels
+    ts = [t_.clone().requires_grad_(True) for t_ in dev[:4]]
+    y = ops.conv2d_gradfix.conv2d_s1(ts[0], ts[1], padding=(pad, pad), in_scale=ts[2], out_scale=ts[3])
+    grads = torch.autograd.grad(y, ts, dev[4])
+    for name, g1, r1 in zip('xwab', grads, ref[1]):
+        assert_close(g1, r1, 5e-5, 'fused d' + name)
+
+
 def test_conv2d_double_backward_closure(ops, device):
     # R1-style: gradient of ||d y / d x||^2 w.r.t. the weight goes conv -> dgrad -> (wgrad of dgrad)
     g = torch.Generator().manual_seed(4)
@@ -375,3 +410,34 @@ def test_modulated_conv2d_golden(ops, device):
         grads = torch.autograd.grad(y, [x, w, s] + ([noise] if noise is not None else []), t(g[name + '.dy'], device))
         for gname, got in zip(['dx', 'dw', 'ds', 'dnoise'], grads):
             assert_close(got, g[f'{name}.{gname}'], TOL, f'{name}.{gname}')
+
+
+@pytest.mark.parametrize('up,k,demod', [(1, 3, True), (2, 3, True), (1, 1, False)])
+def test_modulated_conv2d_second_order_vs_oracle(ops, device, up, k, demod):
+    # path-length-style regulariser through one modulated conv: the gradient of a squared first-order gradient w.r.t. the
+    # styles, taken under no_weight_gradients() exactly like loss.py:98, must match the oracle (torch ops on the CPU)
+    g = torch.Generator().manual_seed(40 + up + k)
+    N, I, O, H = 2, 24, 16 if k == 3 else 3, 8
+    x = torch.randn(N, I, H, H, generator=g); w = torch.randn(O, I, k, k, generator=g)
+    s = torch.randn(N, I, generator=g) * 0.5 + 1.0
+    noise = torch.randn(N, 1, H * up, H * up, generator=g) * 0.1 if demod else None
+    f = R.setup_filter([1, 3, 3, 1])
+    r = torch.randn(N, O, H * up, H * up, generator=g)
+
+    def run(mc, ctx, x, w, s, noise, f, r):
+        ts = [t_.clone().requires_grad_(True) for t_ in (x, w, s)]
+        y = mc(x=ts[0], weight=ts[1], styles=ts[2], noise=noise, up=up, padding=k // 2, resample_filter=f, demodulate=demod,
+               flip_weight=(up == 1), fused_modconv=False)
+        with ctx():
+            gs, gx = torch.autograd.grad((y * r).sum(), [ts[2], ts[0]], create_graph=True)
+        pen = gs.square().sum() + gx.square().sum()
+        return y, gs, torch.autograd.grad(pen, ts)
+
+    import contextlib
+    ref = run(R.modulated_conv2d, contextlib.nullcontext, x, w, s, noise, f, r)
+    d = lambda t_: t_.to(device) if t_ is not None else None
+    got = run(ops.networks.modulated_conv2d, ops.conv2d_gradfix.no_weight_gradients, d(x), d(w), d(s), d(noise), d(f), d(r))
+    assert_close(got[0], ref[0], 2e-5, 'y')
+    assert_close(got[1], ref[1], 5e-5, 'd styles')
+    for name, a_, b_ in zip(['x', 'w', 'styles'], got[2], ref[2]):
+        assert_close(a_, b_, 2e-4, 'second-order d' + name)

@@ -61,6 +61,10 @@ for ph in phases:
     if key and key in ga:
         print(f'   {key}: default {ga[key].flatten()[:4].tolist()}  simt {gb[key].flatten()[:4].tolist()}  golden {g[ph + ".grad." + key].flatten()[:4].tolist()}')
 
+    conv2d_gradfix.fuse_scales = False
+    run(ph, 'scales unfused')
+    conv2d_gradfix.fuse_scales = True
+
     orig_ba = plugin.bias_act.__func__
 
     def ba_unfused(self, x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp, dbias=None):
