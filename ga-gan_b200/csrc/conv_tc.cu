@@ -437,30 +437,42 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 const float* raw = reinterpret_cast<const float*>(gbase + L.raw(s));
                 float4* hi = reinterpret_cast<float4*>(gbase + L.cvt(s, 0));
                 float4* lo = reinterpret_cast<float4*>(gbase + L.cvt(s, 1));
+                // The conversion of K-block j is interleaved with draining the chunks of K-block j-1: each chunk is read out of
+                // TMEM shortly after the tensor core finished it, so the issuer never waits for a free accumulator set.
+                int pend_left = pend ? pend_live : 0;
+                uint32_t pend_chunk = pend_ac;
 #pragma unroll
                 for (int it = 0; it < CVT_ITEMS; ++it) {
                     const int src = cvt_src[it];
-                    if (src == -2) continue;            // past the end of the tile
-                    const int idx = ct + it * CONS_THREADS;
-                    float4 h = make_float4(0.f, 0.f, 0.f, 0.f), l = h;
-                    if (src >= 0) {
-                        float v0 = raw[src], v1 = raw[src + rpix], v2 = raw[src + 2 * rpix], v3 = raw[src + 3 * rpix];
-                        if (p.in_scale) {
-                            const int chunk = idx / npix;
-                            const float4 sv = *reinterpret_cast<const float4*>(sc_s + kb * KB_CH + chunk * 4);
-                            v0 *= sv.x; v1 *= sv.y; v2 *= sv.z; v3 *= sv.w;
+                    if (src != -2) {                    // -2: past the end of the tile
+                        const int idx = ct + it * CONS_THREADS;
+                        float4 h = make_float4(0.f, 0.f, 0.f, 0.f), l = h;
+                        if (src >= 0) {
+                            float v0 = raw[src], v1 = raw[src + rpix], v2 = raw[src + 2 * rpix], v3 = raw[src + 3 * rpix];
+                            if (p.in_scale) {
+                                const int chunk = idx / npix;
+                                const float4 sv = *reinterpret_cast<const float4*>(sc_s + kb * KB_CH + chunk * 4);
+                                v0 *= sv.x; v1 *= sv.y; v2 *= sv.z; v3 *= sv.w;
+                            }
+                            split_tf32(v0, h.x, l.x); split_tf32(v1, h.y, l.y);
+                            split_tf32(v2, h.z, l.z); split_tf32(v3, h.w, l.w);
                         }
-                        split_tf32(v0, h.x, l.x); split_tf32(v1, h.y, l.y);
-                        split_tf32(v2, h.z, l.z); split_tf32(v3, h.w, l.w);
+                        hi[idx] = h;
+                        lo[idx] = l;
                     }
-                    hi[idx] = h;
-                    lo[idx] = l;
-                    if (NT == 128 && (it & 1)) asm volatile("" ::: "memory");   // bound the live range: 128 accumulators are resident
+                    if ((it & 1) && it + 1 < CVT_ITEMS && pend_left > 0) {     // after every second item: one finished chunk
+                        drain_chunk(pend_chunk++, rz_compensation(2 * min(pend_left, CHUNK_TAPS), p.nprod));
+                        pend_left -= CHUNK_TAPS;
+                    }
                 }
                 fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(BAR_CVT_FULL(s)); mbar_arrive(BAR_RAW_EMPTY(s)); }
-                if (pend) { drain(pend_ac, pend_live); if (pend_last) store_tile(pend_tc); }
+                if (pend) {
+                    for (; pend_left > 0; pend_left -= CHUNK_TAPS)
+                        drain_chunk(pend_chunk++, rz_compensation(2 * min(pend_left, CHUNK_TAPS), p.nprod));
+                    if (pend_last) store_tile(pend_tc);
+                }
                 pend = true; pend_last = (kb == M.last_kb); pend_tc = tc;
                 pend_ac = ac; pend_live = __popc(live);
                 ac += (pend_live + CHUNK_TAPS - 1) / CHUNK_TAPS;

@@ -23,6 +23,7 @@
 //               strip into fp32 REGISTERS (round-to-nearest).  A tile's partial sum leaves the CTA once, with fp32 atomics
 //               into the zero-initialised dw (a handful of partials per tile: one per CTA that worked on it).
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 using namespace ggtc;
 
@@ -30,11 +31,13 @@ namespace {
 
 constexpr int WG_CONS_WARPS = 8;
 constexpr int WG_CONS_THREADS = WG_CONS_WARPS * 32;
+constexpr int WG_GROUP_WARPS = 4;                        // the converter warps work as two groups that alternate tasks
+constexpr int WG_GROUP_THREADS = WG_GROUP_WARPS * 32;
 constexpr int WG_PROD_WARPS = 4;                         // one warpgroup (w0 = MMA issuer + TMEM owner, w1..w3 idle) so that setmaxnreg applies
 constexpr int WG_THREADS = (WG_PROD_WARPS + WG_CONS_WARPS) * 32;   // w4..w11 = convert + drain + flush
 constexpr int UW = 16;                                   // image columns per strip (two K=8 steps)
-constexpr int GS = 3;                                    // G-row ring slots
-constexpr int XS = 5;                                    // X-row ring slots (k live rows + rows in flight)
+constexpr int GS = 4;                                    // G-row ring slots (power of two: slot = counter & (GS-1))
+constexpr int XS = 8;                                    // X-row ring slots (k live rows + rows in flight; power of two)
 constexpr uint32_t LBO_A = 128 * 16;                     // chunk pitch of the G image: every 8-row core matrix stays 128-byte aligned
 // Item -> (row, chunk) mapping of the converter threads: 8 consecutive lanes write 8 consecutive rows of ONE chunk (a 128-byte
 // conflict-free quarter-warp store), the four quarter-warps take the four chunks; in global memory the same warp reads 8
@@ -48,6 +51,7 @@ struct WgP {
     int RB, rb_shift, nshift, zgroups, btiles, atiles;
     int RR, ustrips, rstrips, S;
     int total_units, units_per_cta, nprod, vecX, vecG;
+    int dbg;                    // GG_WG_DBG experiments (timing only, results are garbage): 1 = no MMAs, 2 = no global loads, 4 = no split / st.shared, 8 = no proxy fence
 };
 
 struct Unit { int n, r0, rows, u0, b0, a0, kx0, ns, tile; };
@@ -95,8 +99,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
     auto BAR_ACC_EMPTY = [&](int s) { return bar0 + 8u * (2 * GS + 2 * XS + 2 + s); };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < GS; ++s) { mbar_init(BAR_G_FULL(s), WG_CONS_WARPS); mbar_init(BAR_G_EMPTY(s), 1); }
-        for (int s = 0; s < XS; ++s) { mbar_init(BAR_X_FULL(s), WG_CONS_WARPS); mbar_init(BAR_X_EMPTY(s), 1); }
+        for (int s = 0; s < GS; ++s) { mbar_init(BAR_G_FULL(s), WG_GROUP_WARPS); mbar_init(BAR_G_EMPTY(s), 1); }
+        for (int s = 0; s < XS; ++s) { mbar_init(BAR_X_FULL(s), WG_GROUP_WARPS); mbar_init(BAR_X_EMPTY(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(BAR_ACC_FULL(s), 1); mbar_init(BAR_ACC_EMPTY(s), WG_CONS_WARPS); }
         fence_barrier_init();
     }
@@ -123,27 +127,31 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
             const uint64_t a_word = ((uint64_t)(8u | (1u << 14)) << 32) | ((uint64_t)(LBO_A >> 4) << 16);   // SBO 128 B, LBO
             const uint64_t b_word = ((uint64_t)(8u | (1u << 14)) << 32) | ((uint64_t)(LBO_B >> 4) << 16);
             constexpr uint32_t a_ks = 2 * (LBO_A >> 4), b_ks = 2 * (LBO_B >> 4);
-            uint32_t gc = 0, xc = 0, sc = 0;        // running G-row, X-row and strip counters (ring positions)
+            // The issue loop is scalar code of ONE thread: it is kept to a few dozen instructions per image row (ring positions
+            // are masks / shifts of running counters), otherwise it -- not the tensor core -- sets the pace.
+            uint32_t gq = 0, xq = 0, sc = 0;        // running G-row, X-row and strip counters (ring positions)
+            const uint32_t g0_16 = (base + OFF_G) >> 4, x0_16 = (base + OFF_X) >> 4;
+            const int per_tile_strips = p.ustrips;  // strip index -> row strip: (strip / ustrips) % rstrips
             for (int unit = unit_beg; unit < unit_end; ++unit) {
-                const Unit u = decode_unit(unit, p, NTA);
+                const int strip = unit - my_tile * p.S;
+                const int r0 = ((strip / per_tile_strips) % p.rstrips) * p.RR;
+                const int rows = min(p.RR, p.HB - r0);
                 const uint32_t buf = sc & 1;
                 mbar_wait(BAR_ACC_EMPTY(buf), ((sc >> 1) & 1) ^ 1);
-                tc_fence_after();
                 const uint32_t d0 = tmem_base + buf * ACC_STRIDE;
-                for (int i = 0; i < u.rows; ++i) {
-                    const uint32_t gslot = gc % GS;
-                    mbar_wait(BAR_G_FULL(gslot), (gc / GS) & 1);
-                    for (int j = (i == 0 ? 0 : K - 1); j < K; ++j) {           // X rows i .. i+K-1 must have landed
-                        const uint32_t c = xc + i + j;
-                        mbar_wait(BAR_X_FULL(c % XS), (c / XS) & 1);
-                    }
+                for (int j = 0; j < K - 1; ++j) mbar_wait(BAR_X_FULL((xq + j) & (XS - 1)), ((xq + j) / XS) & 1);
+                for (int i = 0; i < rows; ++i) {
+                    const uint32_t gslot = gq & (GS - 1), xlast = xq + K - 1;
+                    mbar_wait(BAR_G_FULL(gslot), (gq / GS) & 1);
+                    mbar_wait(BAR_X_FULL(xlast & (XS - 1)), (xlast / XS) & 1);          // X rows i .. i+K-2 were waited for earlier
                     tc_fence_after();
-                    const uint64_t g_hi = a_word + ((base + OFF_G + gslot * G_SLOT) >> 4), g_lo = g_hi + (G_HALF >> 4);
-                    for (int ky = 0; ky < K; ++ky) {
-                        const uint32_t xslot = (xc + i + ky) % XS;
-                        const uint64_t x_hi = b_word + ((base + OFF_X + xslot * X_SLOT) >> 4), x_lo = x_hi + (X_HALF >> 4);
+                    const uint64_t g_hi = a_word + (g0_16 + gslot * (G_SLOT >> 4)), g_lo = g_hi + (G_HALF >> 4);
+                    const uint32_t accf = i > 0 ? 1u : 0u;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        if (ky >= K || (p.dbg & 1)) continue;
+                        const uint64_t x_hi = b_word + (x0_16 + ((xq + ky) & (XS - 1)) * (X_SLOT >> 4)), x_lo = x_hi + (X_HALF >> 4);
                         const uint32_t d = d0 + (uint32_t)ky * NTA;
-                        const uint32_t accf = i > 0 ? 1u : 0u;
                         if (p.nprod == 3) {
                             umma_tf32(d, g_hi, x_hi, idesc, accf);
                             umma_tf32(d, g_hi, x_lo, idesc, 1u);
@@ -157,11 +165,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
                         }
                     }
                     umma_commit(BAR_G_EMPTY(gslot));
-                    umma_commit(BAR_X_EMPTY((xc + i) % XS));                 // X row i is not needed by later G rows
-                    ++gc;
+                    umma_commit(BAR_X_EMPTY(xq & (XS - 1)));                           // X row i is not needed by later G rows
+                    ++gq; ++xq;
                 }
-                for (int j = 0; j < K - 1; ++j) umma_commit(BAR_X_EMPTY((xc + u.rows + j) % XS));   // the strip's bottom halo rows
-                xc += u.rows + K - 1;
+                for (int j = 0; j < K - 1; ++j) umma_commit(BAR_X_EMPTY((xq + j) & (XS - 1)));   // the strip's bottom halo rows
+                xq += K - 1;
                 umma_commit(BAR_ACC_FULL(buf));
                 ++sc;
             }
@@ -171,46 +179,53 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
         // ===== converter warps: fill the rings for strip s, then drain strip s-1 from TMEM into registers
         const int ct = threadIdx.x - WG_PROD_WARPS * 32;   // 0..255
         const int q = warp & 3;                            // TMEM lane quarter
-        const int half = (warp - WG_PROD_WARPS) >> 2;      // which half of the accumulator columns this warp owns
+        const int half = (warp - WG_PROD_WARPS) >> 2;      // which half of the accumulator columns this warp owns (= its converter group)
         constexpr int HN = NTA / 2;                     // input channels per thread and ky
         constexpr int HC = 3 * HN;                      // accumulator registers per thread
         float acc[HC];
 #pragma unroll
         for (int j = 0; j < HC; ++j) acc[j] = 0.f;
-        uint32_t gc = 0, xc = 0, sc = 0;
+        uint32_t sc = 0;
         bool pend = false;
-        int pend_unit = 0, pend_rows = 0, pend_tile = -1;
+        int pend_unit = 0, pend_rows = 0;
         uint32_t pend_sc = 0;
 
         // One converter task = local X row j of a unit (image row r0 - pad_y + j) plus, for j >= K-1, G row j-(K-1).
-        // Loads are issued THREE tasks ahead of their conversion (global/L2 latency is ~1-2 us, a task ~0.3 us).
+        // The eight converter warps form TWO groups of four that take the tasks alternately.  A group's iteration is
+        //   wait for its loads -> split / st.shared -> fence.proxy.async -> arrive -> issue the loads of its next task
+        // i.e. the proxy fence (which also waits for the thread's outstanding global loads) always runs BEFORE new loads are
+        // issued, and the global/L2 latency of one group overlaps with the conversion work of the other.
         // Everything that does not change within a unit (this thread's source pointers, scales, validity) is worked out
-        // once per unit, so that a task costs a handful of address adds and three 128-bit loads per thread.
-        static_assert(NTA * 4 <= WG_CONS_THREADS, "one X item per converter thread");
-        struct Regs { float4 x; float4 g[2]; float xs, gs[2]; };   // raw loads + the scales to apply when they are converted
-        struct LoadCursor {                              // runs three tasks ahead
-            int unit, j, ntask; bool valid;
-            const float* xp; const float* gp[2];         // X[n,ac,0,col] and G[n,bc,0,x0] of this thread's items
-            float xs, gs[2];
-            int xmode, gmode[2];                         // 0 = zero item, 1 = aligned 128-bit load, 2 = bounds-checked scalar loads
-            int gx0[2], v0, y0;                          // first G column of the item; image rows of task 0
+        // once per unit, so that a task costs a handful of address adds and six 128-bit loads per thread.
+        constexpr int XI = NTA * 4 / WG_GROUP_THREADS;   // X items per thread (2 for NTA = 64, 1 for 32)
+        constexpr int GI = 512 / WG_GROUP_THREADS;       // G items per thread (4)
+        static_assert(XI >= 1 && NTA * 4 % WG_GROUP_THREADS == 0, "X items must tile the group");
+        const int grp = (warp - WG_PROD_WARPS) >> 2;     // 0 / 1: also the half of the accumulator columns this warp owns
+        const int gt = ct & (WG_GROUP_THREADS - 1);      // thread index inside the group
+        struct Regs { float4 x[XI]; float4 g[GI]; float xs[XI], gs[GI]; };
+        struct Cursor {                                  // position in the CTA's task sequence + this thread's load plan
+            int unit, j, ntask, tile; bool valid;
+            uint32_t xc, gc;                             // ring positions of this task's X row / G row
+            const float* xp[XI]; const float* gp[GI];
+            float xs[XI], gs[GI];
+            int xmode[XI], gmode[GI];                    // 0 = zero item, 1 = aligned 128-bit load, 2 = bounds-checked scalar loads
+            int gx0[GI], v0, y0;
         };
-        struct StoreCursor { int unit, j, ntask, tile; bool valid; };
-        const int x_c = item_chunk(ct), x_row = item_row(ct);   // this thread's X item: chunk, channel row
-        auto load_begin = [&](LoadCursor& t, int unit) {
-            t.unit = unit; t.j = 0; t.valid = unit < unit_end;
-            if (!t.valid) return;
-            const Unit u = decode_unit(unit, p, NTA);
-            t.ntask = u.rows + K - 1; t.v0 = u.r0 - p.pad_y; t.y0 = u.r0 - (K - 1);
-            {
-                const int ac = u.a0 + x_row, col = u.u0 + 4 * x_c;
-                t.xmode = (x_row < NTA && ac < p.A && col < p.WA) ? ((p.vecX && col + 3 < p.WA) ? 1 : 2) : 0;
-                t.xp = p.X + ((size_t)u.n * p.A + (t.xmode ? ac : 0)) * p.HA * p.WA + col;
-                t.xs = (t.xmode && p.xs) ? __ldg(p.xs + (size_t)u.n * p.A + ac) : 1.f;
+        auto plan_unit = [&](Cursor& t) {
+            const Unit u = decode_unit(t.unit, p, NTA);
+            t.ntask = u.rows + K - 1; t.tile = u.tile; t.v0 = u.r0 - p.pad_y; t.y0 = u.r0 - (K - 1);
+#pragma unroll
+            for (int k = 0; k < XI; ++k) {
+                const int id = gt + k * WG_GROUP_THREADS;
+                const int c = item_chunk(id), row = item_row(id);
+                const int ac = u.a0 + row, col = u.u0 + 4 * c;
+                t.xmode[k] = (ac < p.A && col < p.WA) ? ((p.vecX && col + 3 < p.WA) ? 1 : 2) : 0;
+                t.xp[k] = p.X + ((size_t)u.n * p.A + (t.xmode[k] ? ac : 0)) * p.HA * p.WA + col;
+                t.xs[k] = (t.xmode[k] && p.xs) ? __ldg(p.xs + (size_t)u.n * p.A + ac) : 1.f;
             }
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int id = ct + k * WG_CONS_THREADS;                       // 512 items: (row m, chunk c)
+            for (int k = 0; k < GI; ++k) {
+                const int id = gt + k * WG_GROUP_THREADS;                      // 512 items: (row m, chunk c)
                 const int c = item_chunk(id), m = item_row(id);
                 const int sft = m >> p.rb_shift, bc = u.b0 + (m & (p.RB - 1));
                 const int x0 = u.u0 + 4 * c - (u.kx0 + sft - p.pad_x);         // G column of the chunk's first pixel
@@ -221,38 +236,42 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
                 t.gs[k] = (ok && p.gs) ? __ldg(p.gs + (size_t)u.n * p.B + bc) : 1.f;
             }
         };
-        auto load_advance = [&](LoadCursor& t) {
-            if (t.valid && ++t.j == t.ntask) load_begin(t, t.unit + 1);
-        };
-        auto store_begin = [&](StoreCursor& t, int unit) {
-            t.unit = unit; t.j = 0; t.valid = unit < unit_end;
+        auto step_one = [&](Cursor& t, bool plan) {      // advance by ONE task, keeping the ring counters of both groups in step
             if (!t.valid) return;
-            const Unit u = decode_unit(unit, p, NTA);
-            t.ntask = u.rows + K - 1; t.tile = u.tile;
-        };
-        auto store_advance = [&](StoreCursor& t) {
-            if (t.valid && ++t.j == t.ntask) store_begin(t, t.unit + 1);
-        };
-        auto load_task = [&](const LoadCursor& t, Regs& r) {
-            const int v = t.v0 + t.j, y = t.y0 + t.j;
-            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t.xmode != 0 && v >= 0 && v < p.HA) {
-                const float* src = t.xp + (size_t)v * p.WA;
-                if (t.xmode == 1) {
-                    val = __ldg(reinterpret_cast<const float4*>(src));
-                } else {
-                    const int col = (int)((t.xp - p.X) % p.WA);
-                    val.x = __ldg(src);
-                    if (col + 1 < p.WA) val.y = __ldg(src + 1);
-                    if (col + 2 < p.WA) val.z = __ldg(src + 2);
-                    if (col + 3 < p.WA) val.w = __ldg(src + 3);
+            ++t.xc;
+            if (t.j >= K - 1) ++t.gc;
+            if (++t.j == t.ntask) {
+                t.j = 0; ++t.unit;
+                t.valid = t.unit < unit_end;
+                if (t.valid) {
+                    if (plan) plan_unit(t);
+                    else { const Unit u = decode_unit(t.unit, p, NTA); t.ntask = u.rows + K - 1; t.tile = u.tile; }
                 }
             }
-            r.x = val; r.xs = t.xs;                     // NOT multiplied here: that would wait for the load right away
+        };
+        auto load_task = [&](const Cursor& t, Regs& r) {
+            const int v = (p.dbg & 2) ? -1000000 : t.v0 + t.j, y = t.y0 + t.j;
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
+            for (int k = 0; k < XI; ++k) {
+                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t.xmode[k] != 0 && v >= 0 && v < p.HA) {
+                    const float* src = t.xp[k] + (size_t)v * p.WA;
+                    if (t.xmode[k] == 1) {
+                        val = __ldg(reinterpret_cast<const float4*>(src));
+                    } else {
+                        const int col = (int)((t.xp[k] - p.X) % p.WA);
+                        val.x = __ldg(src);
+                        if (col + 1 < p.WA) val.y = __ldg(src + 1);
+                        if (col + 2 < p.WA) val.z = __ldg(src + 2);
+                        if (col + 3 < p.WA) val.w = __ldg(src + 3);
+                    }
+                }
+                r.x[k] = val; r.xs[k] = t.xs[k];         // NOT multiplied here: that would wait for the load right away
+            }
+#pragma unroll
+            for (int k = 0; k < GI; ++k) {
                 float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t.gmode[k] != 0 && y >= t.y0 + (K - 1)) {
+                if (t.gmode[k] != 0 && t.j >= K - 1 && !(p.dbg & 2)) {
                     const float* src = t.gp[k] + (size_t)y * p.WB;
                     const int x0 = t.gx0[k];
                     if (t.gmode[k] == 1) {
@@ -267,36 +286,37 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
                 r.g[k] = g4; r.gs[k] = t.gs[k];
             }
         };
-        auto store_split = [&](uint8_t* hi_addr, uint32_t half_bytes, const float4& val, float sc) {
+        auto store_split = [&](uint8_t* hi_addr, uint32_t half_bytes, const float4& val, float sc_) {
             float4 h, l;
-            split_tf32(val.x * sc, h.x, l.x); split_tf32(val.y * sc, h.y, l.y); split_tf32(val.z * sc, h.z, l.z); split_tf32(val.w * sc, h.w, l.w);
+            split_tf32(val.x * sc_, h.x, l.x); split_tf32(val.y * sc_, h.y, l.y); split_tf32(val.z * sc_, h.z, l.z); split_tf32(val.w * sc_, h.w, l.w);
             *reinterpret_cast<float4*>(hi_addr) = h;
             *reinterpret_cast<float4*>(hi_addr + half_bytes) = l;
         };
-        auto store_task = [&](const StoreCursor& t, const Regs& r) {
-            {
-                const uint32_t slot = xc % XS;
-                mbar_wait(BAR_X_EMPTY(slot), ((xc / XS) & 1) ^ 1);
-                uint8_t* sb = gbase + OFF_X + slot * X_SLOT;
-                if (x_row < NTA) store_split(sb + x_c * LBO_B + x_row * 16, X_HALF, r.x, r.xs);
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR_X_FULL(slot));
-                ++xc;
-            }
-            if (t.j >= K - 1) {
-                const uint32_t slot = gc % GS;
-                mbar_wait(BAR_G_EMPTY(slot), ((gc / GS) & 1) ^ 1);
-                uint8_t* sb = gbase + OFF_G + slot * G_SLOT;
+        auto store_task = [&](const Cursor& t, const Regs& r) {
+            const uint32_t xslot = t.xc % XS, gslot = t.gc % GS;
+            const bool has_g = t.j >= K - 1;
+            mbar_wait(BAR_X_EMPTY(xslot), ((t.xc / XS) & 1) ^ 1);
+            if (has_g) mbar_wait(BAR_G_EMPTY(gslot), ((t.gc / GS) & 1) ^ 1);
+            uint8_t* xb = gbase + OFF_X + xslot * X_SLOT;
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int id = ct + k * WG_CONS_THREADS;
-                    store_split(sb + item_chunk(id) * LBO_A + item_row(id) * 16, G_HALF, r.g[k], r.gs[k]);
+            for (int k = 0; k < XI; ++k) {
+                if (p.dbg & 4) break;
+                const int id = gt + k * WG_GROUP_THREADS;
+                store_split(xb + item_chunk(id) * LBO_B + item_row(id) * 16, X_HALF, r.x[k], r.xs[k]);
+            }
+            if (has_g && !(p.dbg & 4)) {
+                uint8_t* gb = gbase + OFF_G + gslot * G_SLOT;
+#pragma unroll
+                for (int k = 0; k < GI; ++k) {
+                    const int id = gt + k * WG_GROUP_THREADS;
+                    store_split(gb + item_chunk(id) * LBO_A + item_row(id) * 16, G_HALF, r.g[k], r.gs[k]);
                 }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR_G_FULL(slot));
-                ++gc;
+            }
+            if (!(p.dbg & 8)) fence_proxy_async();       // one proxy fence per task, before any new global load is in flight
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(BAR_X_FULL(xslot));
+                if (has_g) mbar_arrive(BAR_G_FULL(gslot));
             }
         };
         // Accumulator ownership: this thread holds, for every ky, input channels [half*HN, half*HN + HN) of TMEM lane q*32+lane.
@@ -343,33 +363,37 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
                 }
             }
         };
-        auto finish_task = [&](const StoreCursor& t) {  // after the last row of a unit: drain the PREVIOUS strip (its MMAs are done)
-            if (t.j != t.ntask - 1) return;
-            if (pend) {
-                drain(pend_sc, pend_rows);
-                if (pend_tile != t.tile) flush(decode_unit(pend_unit, p, NTA));
-            }
-            pend = true; pend_unit = t.unit; pend_rows = t.ntask - (K - 1); pend_tile = t.tile; pend_sc = sc;
+        // Both groups drain their half of the accumulator columns at the end of every unit (strip): the unit that finished
+        // one strip earlier is complete in TMEM by then.  All units of a CTA belong to one tile, so there is one flush.
+        auto end_of_unit = [&](int unit, int rows) {
+            if (pend) drain(pend_sc, pend_rows);
+            pend = true; pend_unit = unit; pend_rows = rows; pend_sc = sc;
             ++sc;
         };
-        // two cursors: L runs three tasks ahead issuing the global loads, S converts / stores / drains
-        LoadCursor L;
-        StoreCursor S;
-        load_begin(L, unit_beg);
-        store_begin(S, unit_beg);
-        Regs r0, r1, r2;
-        if (L.valid) { load_task(L, r0); load_advance(L); }
-        if (L.valid) { load_task(L, r1); load_advance(L); }
-        if (L.valid) { load_task(L, r2); load_advance(L); }
-        while (S.valid) {
-            store_task(S, r0); finish_task(S); store_advance(S);
-            if (L.valid) { load_task(L, r0); load_advance(L); }
-            if (!S.valid) break;
-            store_task(S, r1); finish_task(S); store_advance(S);
-            if (L.valid) { load_task(L, r1); load_advance(L); }
-            if (!S.valid) break;
-            store_task(S, r2); finish_task(S); store_advance(S);
-            if (L.valid) { load_task(L, r2); load_advance(L); }
+        Cursor C;
+        C.unit = unit_beg; C.j = 0; C.xc = 0; C.gc = 0; C.valid = unit_beg < unit_end;
+        if (C.valid) plan_unit(C);
+        int planned_unit = C.unit;                       // the unit this thread's load plan belongs to
+        // advance by one task; when that task was the last one of its unit, both groups run end_of_unit (in the same order)
+        auto advance = [&]() {
+            if (!C.valid) return;
+            const int unit0 = C.unit, ntask0 = C.ntask;
+            const bool last = (C.j == ntask0 - 1);
+            step_one(C, false);
+            if (last) end_of_unit(unit0, ntask0 - (K - 1));
+        };
+        auto replan = [&]() {
+            if (C.valid && C.unit != planned_unit) { plan_unit(C); planned_unit = C.unit; }
+        };
+        if (grp == 1) { advance(); replan(); }           // group 1 starts at the second task
+        Regs R;
+        if (C.valid) load_task(C, R);
+        while (C.valid) {
+            store_task(C, R);
+            advance();                                   // past this group's task ...
+            advance();                                   // ... and past the other group's
+            replan();
+            if (C.valid) load_task(C, R);
         }
         if (pend) { drain(pend_sc, pend_rows); flush(decode_unit(pend_unit, p, NTA)); }
         tc_fence_before();
@@ -429,13 +453,14 @@ int wgrad_tc(const float* a, const float* b, float* dw, int N, int A, int HA, in
     if (total > 0x7fffffffLL) { set_error("conv2d_wgrad(tc): too many work units"); return GG_EINVAL; }
     p.S = (int)S; p.total_units = (int)total;
     const int ntiles = p.btiles * p.atiles * p.zgroups;
-    int64_t parts = (4LL * GG_NUM_SMS + ntiles - 1) / ntiles;          // ~4 waves of CTAs; one atomic flush per CTA
+    int64_t parts = (2LL * GG_NUM_SMS + ntiles - 1) / ntiles;          // ~2 waves of CTAs; one atomic flush per CTA
     if (parts > S) parts = S;
     if (parts < 1) parts = 1;
     p.units_per_cta = (int)((S + parts - 1) / parts);                  // strips per CTA
     parts = (S + p.units_per_cta - 1) / p.units_per_cta;
     const int grid = (int)(parts * ntiles);
     p.nprod = (nprod == GG_PREC_TF32X1) ? 1 : 3;
+    { const char* e = getenv("GG_WG_DBG"); p.dbg = e ? atoi(e) : 0; }
     p.vecX = ((reinterpret_cast<uintptr_t>(a) & 15) == 0 && WA % 4 == 0) ? 1 : 0;
     p.vecG = ((reinterpret_cast<uintptr_t>(b) & 15) == 0 && WB % 4 == 0) ? 1 : 0;
     GG_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)A * B * K * K, st));
