@@ -137,13 +137,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
                 const int r0 = ((strip / per_tile_strips) % p.rstrips) * p.RR;
                 const int rows = min(p.RR, p.HB - r0);
                 const uint32_t buf = sc & 1;
-                mbar_wait(BAR_ACC_EMPTY(buf), ((sc >> 1) & 1) ^ 1);
+                mbar_wait_spin(BAR_ACC_EMPTY(buf), ((sc >> 1) & 1) ^ 1);
                 const uint32_t d0 = tmem_base + buf * ACC_STRIDE;
-                for (int j = 0; j < K - 1; ++j) mbar_wait(BAR_X_FULL((xq + j) & (XS - 1)), ((xq + j) / XS) & 1);
+                for (int j = 0; j < K - 1; ++j) mbar_wait_spin(BAR_X_FULL((xq + j) & (XS - 1)), ((xq + j) / XS) & 1);
                 for (int i = 0; i < rows; ++i) {
                     const uint32_t gslot = gq & (GS - 1), xlast = xq + K - 1;
-                    mbar_wait(BAR_G_FULL(gslot), (gq / GS) & 1);
-                    mbar_wait(BAR_X_FULL(xlast & (XS - 1)), (xlast / XS) & 1);          // X rows i .. i+K-2 were waited for earlier
+                    mbar_wait_spin(BAR_G_FULL(gslot), (gq / GS) & 1);
+                    mbar_wait_spin(BAR_X_FULL(xlast & (XS - 1)), (xlast / XS) & 1);          // X rows i .. i+K-2 were waited for earlier
                     tc_fence_after();
                     const uint64_t g_hi = a_word + (g0_16 + gslot * (G_SLOT >> 4)), g_lo = g_hi + (G_HALF >> 4);
                     const uint32_t accf = i > 0 ? 1u : 0u;
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
         const int gt = ct & (WG_GROUP_THREADS - 1);      // thread index inside the group
         struct Regs { float4 x[XI]; float4 g[GI]; float xs[XI], gs[GI]; };
         struct Cursor {                                  // position in the CTA's task sequence + this thread's load plan
-            int unit, j, ntask, tile; bool valid;
+            int unit, j, ntask, tile;
             uint32_t xc, gc;                             // ring positions of this task's X row / G row
             const float* xp[XI]; const float* gp[GI];
             float xs[XI], gs[GI];
@@ -234,19 +234,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
                 t.gx0[k] = x0;
                 t.gp[k] = p.G + ((size_t)u.n * p.B + (ok ? bc : 0)) * p.HB * p.WB;
                 t.gs[k] = (ok && p.gs) ? __ldg(p.gs + (size_t)u.n * p.B + bc) : 1.f;
-            }
-        };
-        auto step_one = [&](Cursor& t, bool plan) {      // advance by ONE task, keeping the ring counters of both groups in step
-            if (!t.valid) return;
-            ++t.xc;
-            if (t.j >= K - 1) ++t.gc;
-            if (++t.j == t.ntask) {
-                t.j = 0; ++t.unit;
-                t.valid = t.unit < unit_end;
-                if (t.valid) {
-                    if (plan) plan_unit(t);
-                    else { const Unit u = decode_unit(t.unit, p, NTA); t.ntask = u.rows + K - 1; t.tile = u.tile; }
-                }
             }
         };
         auto load_task = [&](const Cursor& t, Regs& r) {
@@ -295,8 +282,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
         auto store_task = [&](const Cursor& t, const Regs& r) {
             const uint32_t xslot = t.xc % XS, gslot = t.gc % GS;
             const bool has_g = t.j >= K - 1;
-            mbar_wait(BAR_X_EMPTY(xslot), ((t.xc / XS) & 1) ^ 1);
-            if (has_g) mbar_wait(BAR_G_EMPTY(gslot), ((t.gc / GS) & 1) ^ 1);
+            mbar_wait_spin(BAR_X_EMPTY(xslot), ((t.xc / XS) & 1) ^ 1);
+            if (has_g) mbar_wait_spin(BAR_G_EMPTY(gslot), ((t.gc / GS) & 1) ^ 1);
             uint8_t* xb = gbase + OFF_X + xslot * X_SLOT;
 #pragma unroll
             for (int k = 0; k < XI; ++k) {
@@ -323,7 +310,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
         auto drain = [&](uint32_t k, int rows) {        // TMEM accumulator set of strip k -> registers (RN adds)
             const float kc = rz_compensation(2 * rows, p.nprod);
             const uint32_t buf = k & 1;
-            mbar_wait(BAR_ACC_FULL(buf), (k >> 1) & 1);
+            mbar_wait_spin(BAR_ACC_FULL(buf), (k >> 1) & 1);
             tc_fence_after();
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
@@ -370,30 +357,25 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
             pend = true; pend_unit = unit; pend_rows = rows; pend_sc = sc;
             ++sc;
         };
+        // Group g converts the local tasks j = g, g+2, ... of every unit; the ring positions follow from per-unit bases, so the
+        // per-task bookkeeping is three adds.  The loads of task j+2 are issued right after task j has been published.
         Cursor C;
-        C.unit = unit_beg; C.j = 0; C.xc = 0; C.gc = 0; C.valid = unit_beg < unit_end;
-        if (C.valid) plan_unit(C);
-        int planned_unit = C.unit;                       // the unit this thread's load plan belongs to
-        // advance by one task; when that task was the last one of its unit, both groups run end_of_unit (in the same order)
-        auto advance = [&]() {
-            if (!C.valid) return;
-            const int unit0 = C.unit, ntask0 = C.ntask;
-            const bool last = (C.j == ntask0 - 1);
-            step_one(C, false);
-            if (last) end_of_unit(unit0, ntask0 - (K - 1));
-        };
-        auto replan = [&]() {
-            if (C.valid && C.unit != planned_unit) { plan_unit(C); planned_unit = C.unit; }
-        };
-        if (grp == 1) { advance(); replan(); }           // group 1 starts at the second task
-        Regs R;
-        if (C.valid) load_task(C, R);
-        while (C.valid) {
-            store_task(C, R);
-            advance();                                   // past this group's task ...
-            advance();                                   // ... and past the other group's
-            replan();
-            if (C.valid) load_task(C, R);
+        uint32_t xbase = 0, gbase = 0;                   // ring positions of the unit's first X row / G row
+        for (int unit = unit_beg; unit < unit_end; ++unit) {
+            C.unit = unit;
+            plan_unit(C);
+            const int ntask = C.ntask;
+            Regs R;
+            C.j = grp;
+            if (C.j < ntask) load_task(C, R);
+            for (int j = grp; j < ntask; j += 2) {
+                C.j = j; C.xc = xbase + (uint32_t)j; C.gc = gbase + (uint32_t)(j - (K - 1));
+                store_task(C, R);
+                C.j = j + 2;
+                if (C.j < ntask) load_task(C, R);
+            }
+            end_of_unit(unit, ntask - (K - 1));
+            xbase += (uint32_t)ntask; gbase += (uint32_t)(ntask - (K - 1));
         }
         if (pend) { drain(pend_sc, pend_rows); flush(decode_unit(pend_unit, p, NTA)); }
         tc_fence_before();
