@@ -85,8 +85,11 @@ __global__ void pack_weights_kernel(PackP p) {
 }
 
 // ------------------------------------------------------------------------------------------------ the conv kernel
-constexpr int TILE_W = 16, TILE_H = 16;   // output pixels per tile: two 8x16 UMMA M-tiles side by side
-constexpr int W_STAGES = 4;
+constexpr int TILE_H = 16;                // a tile is SUBS 8x16-pixel UMMA M-tiles side by side: 16x16 (SUBS = 2) or 8x16 pixels
+constexpr int MAX_W_STAGES = 4;
+// Tile configurations <NT, SUBS>: <32|64|128, 2> and <256, 1>.  The operand fetch of an MMA reads 128 A rows whatever N is, and the
+// kernel is shared-memory-bandwidth bound, so layers with >= 256 output channels use N = 256 (half the A traffic per FLOP).
+__host__ __device__ constexpr int w_stages_for(int NT) { return NT == 256 ? 3 : 4; }
 constexpr int CHUNK_TAPS = 3;   // live taps accumulated in TMEM before the partial sum is drained (18 truncating accumulates)
 constexpr int CONS_WARPS = 8;
 constexpr int CONS_THREADS = CONS_WARPS * 32;
@@ -111,6 +114,7 @@ struct SmemLayout {   // byte offsets from the 128-byte aligned dynamic smem bas
 };
 
 __host__ __device__ inline SmemLayout make_layout(int boxW, int boxH, int rawW, int NT) {
+    const int W_STAGES = w_stages_for(NT);
     SmemLayout L;
     L.tile = ((uint32_t)(KB_CH * boxW * boxH * 4) + 127) & ~127u;
     L.rtile = ((uint32_t)(KB_CH * rawW * boxH * 4) + 127) & ~127u;
@@ -167,8 +171,10 @@ struct KbMasks {
     }
 };
 
-template <int NT>
+template <int NT, int SUBS>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, TcP p) {
+    constexpr int W_STAGES = w_stages_for(NT);
+    constexpr int TILE_W = 8 * SUBS;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -183,14 +189,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     auto BAR_ACC_FULL = [&](int s) { return bar0 + 8u * (8 + s); };
     auto BAR_ACC_EMPTY = [&](int s) { return bar0 + 8u * (10 + s); };
     auto BAR_W_FULL = [&](int s) { return bar0 + 8u * (12 + s); };
-    auto BAR_W_EMPTY = [&](int s) { return bar0 + 8u * (12 + W_STAGES + s); };
+    auto BAR_W_EMPTY = [&](int s) { return bar0 + 8u * (12 + MAX_W_STAGES + s); };
 
     const int KK = p.K * p.K;
     const int npix = p.boxW * p.boxH;
     const int rpix = p.rawW * p.boxH;
     const uint32_t raw_bytes = (uint32_t)(KB_CH * rpix * 4);
     constexpr uint32_t w_bytes = (uint32_t)(2 * 4 * NT * 16);
-    constexpr uint32_t TMEM_COLS = 4 * NT;      // 2 accumulator sets x 2 sub-tiles x NT columns
+    constexpr uint32_t SET_COLS = SUBS * NT;    // TMEM columns of one accumulator set
+    constexpr uint32_t TMEM_COLS = 2 * SET_COLS; // two sets ping-pong
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
@@ -285,7 +292,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             if (in_chunk == 0) {                      // open a chunk: TMEM accumulator set ac & 1, drained two chunks ago
                                 const uint32_t as = ac & 1;
                                 mbar_wait(BAR_ACC_EMPTY(as), ((ac >> 1) & 1) ^ 1);
-                                d0 = tmem_base + as * 2u * NT; d1 = d0 + NT;
+                                d0 = tmem_base + as * SET_COLS; d1 = d0 + NT;
                                 accf = 0u;
                             }
                             mbar_wait(BAR_W_FULL(ws), wph);
@@ -301,17 +308,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                                 umma_tf32(d0, ah0 + a_ks, b_hi0 + b_ks, idesc, 1u);
                                 umma_tf32(d0, ah0 + a_ks, b_lo0 + b_ks, idesc, 1u);
                                 umma_tf32(d0, al0 + a_ks, b_hi0 + b_ks, idesc, 1u);
-                                umma_tf32(d1, ah0 + 8u, b_hi0, idesc, accf);
-                                umma_tf32(d1, ah0 + 8u, b_lo0, idesc, 1u);
-                                umma_tf32(d1, al0 + 8u, b_hi0, idesc, 1u);
-                                umma_tf32(d1, ah0 + 8u + a_ks, b_hi0 + b_ks, idesc, 1u);
-                                umma_tf32(d1, ah0 + 8u + a_ks, b_lo0 + b_ks, idesc, 1u);
-                                umma_tf32(d1, al0 + 8u + a_ks, b_hi0 + b_ks, idesc, 1u);
+                                if (SUBS == 2) {
+                                    umma_tf32(d1, ah0 + 8u, b_hi0, idesc, accf);
+                                    umma_tf32(d1, ah0 + 8u, b_lo0, idesc, 1u);
+                                    umma_tf32(d1, al0 + 8u, b_hi0, idesc, 1u);
+                                    umma_tf32(d1, ah0 + 8u + a_ks, b_hi0 + b_ks, idesc, 1u);
+                                    umma_tf32(d1, ah0 + 8u + a_ks, b_lo0 + b_ks, idesc, 1u);
+                                    umma_tf32(d1, al0 + 8u + a_ks, b_hi0 + b_ks, idesc, 1u);
+                                }
                             } else {
                                 umma_tf32(d0, ah0, b_hi0, idesc, accf);
                                 umma_tf32(d0, ah0 + a_ks, b_hi0 + b_ks, idesc, 1u);
-                                umma_tf32(d1, ah0 + 8u, b_hi0, idesc, accf);
-                                umma_tf32(d1, ah0 + 8u + a_ks, b_hi0 + b_ks, idesc, 1u);
+                                if (SUBS == 2) {
+                                    umma_tf32(d1, ah0 + 8u, b_hi0, idesc, accf);
+                                    umma_tf32(d1, ah0 + 8u + a_ks, b_hi0 + b_ks, idesc, 1u);
+                                }
                             }
                             umma_commit(BAR_W_EMPTY(ws));          // frees the weight stage when these MMAs have read it
                             if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
@@ -338,9 +349,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const int q = warp & 3;                         // TMEM lane quarter this warp may access
         const int hcol = cw >> 2;                       // which half of the NT accumulator columns this warp owns
         constexpr int HN = NT / 2;
-        float acc[2][HN];
+        float acc[SUBS][HN];
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
+        for (int s = 0; s < SUBS; ++s)
 #pragma unroll
             for (int j = 0; j < HN; ++j) acc[s][j] = 0.f;
         float* sc_s = reinterpret_cast<float*>(gbase + L.scale);
@@ -358,7 +369,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             const int oy = tc.ty * TILE_H + r;
             const int n0 = tc.nt * NT + hcol * HN;
 #pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
+            for (int sub = 0; sub < SUBS; ++sub) {
                 const int ox = tc.tx * TILE_W + 8 * sub + c;
                 const bool pix_ok = (oy < p.OH) && (ox < p.OW);
                 float* yp = p.y + ((size_t)tc.img * p.O + n0) * plane + (size_t)oy * p.OW + ox;
@@ -381,11 +392,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             mbar_wait(BAR_ACC_FULL(s), (k >> 1) & 1);
             tc_fence_after();
 #pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
+            for (int sub = 0; sub < SUBS; ++sub) {
 #pragma unroll
                 for (int cb = 0; cb < HN; cb += 16) {
                     uint32_t v[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 2 * NT + sub * NT + hcol * HN + cb), v);
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * SET_COLS + sub * NT + hcol * HN + cb), v);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) acc[sub][cb + j] = fmaf(__uint_as_float(v[j]), kc, acc[sub][cb + j]);
                 }
@@ -522,18 +533,18 @@ void keep_pool_memory() {
     done.fetch_or(1ull << dev);
 }
 
-template <int NT>
+template <int NT, int SUBS>
 int launch_conv_tc(const CUtensorMap& xmap, const TcP& p, cudaStream_t st) {
     const SmemLayout L = make_layout(p.boxW, p.boxH, p.rawW, NT);
     const size_t smem = L.total + 128;
     if (smem > 227 * 1024) { gg::set_error("conv2d(tc): shared-memory layout of %zu bytes does not fit", smem); return GG_EUNSUPPORTED; }
     static std::atomic<int> attr_set{0};
     if (!attr_set.load()) {
-        GG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        GG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT, SUBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set.store(1);
     }
     const int grid = p.total_tiles < GG_NUM_SMS ? p.total_tiles : GG_NUM_SMS;
-    conv_tc_kernel<NT><<<grid, NUM_THREADS, smem, st>>>(xmap, p);
+    conv_tc_kernel<NT, SUBS><<<grid, NUM_THREADS, smem, st>>>(xmap, p);
     return gg::check_launch("conv2d(tc)");
 }
 
@@ -559,7 +570,8 @@ bool conv2d_tc_eligible(int N, int I, int H, int W, int O, int KH, int KW, int O
 int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int K, int /*KW*/, int OH, int OW, int pad_y,
               int pad_x, int flip_w, int w_is_IO, const float* in_scale, const float* out_scale, int nprod, cudaStream_t st) {
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) { set_error("conv2d(tc): x must be 16-byte aligned"); return GG_EINVAL; }
-    const int NT = O > 64 ? 128 : (O > 32 ? 64 : 32);
+    const int NT = O > 128 ? 256 : (O > 64 ? 128 : (O > 32 ? 64 : 32));
+    const int TILE_W = NT == 256 ? 8 : 16;
     const int n_tiles = (O + NT - 1) / NT;
     const int num_kb = (I + KB_CH - 1) / KB_CH;
     const int KK = K * K;
@@ -608,9 +620,10 @@ int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int
     p.total_tiles = (int)total;
     p.boxW = boxW; p.boxH = boxH; p.rawW = rawW;
     int rc;
-    if (NT == 128) rc = launch_conv_tc<128>(xmap, p, st);
-    else if (NT == 64) rc = launch_conv_tc<64>(xmap, p, st);
-    else rc = launch_conv_tc<32>(xmap, p, st);
+    if (NT == 256) rc = launch_conv_tc<256, 1>(xmap, p, st);
+    else if (NT == 128) rc = launch_conv_tc<128, 2>(xmap, p, st);
+    else if (NT == 64) rc = launch_conv_tc<64, 2>(xmap, p, st);
+    else rc = launch_conv_tc<32, 2>(xmap, p, st);
     cudaFreeAsync(wp, st);
     return rc;
 }
