@@ -441,3 +441,66 @@ def test_modulated_conv2d_second_order_vs_oracle(ops, device, up, k, demod):
     assert_close(got[1], ref[1], 5e-5, 'd styles')
     for name, a_, b_ in zip(['x', 'w', 'styles'], got[2], ref[2]):
         assert_close(a_, b_, 2e-4, 'second-order d' + name)
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+@pytest.mark.parametrize('case', [
+    # (N, I, O, R, up, down): config-f layer shapes at BASELINE.json's full size (1024^2 generator / discriminator)
+    (2, 32, 32, 1024, 1, 1), (2, 64, 32, 512, 2, 1), (2, 32, 64, 1024, 1, 2), (4, 512, 512, 64, 1, 1), (4, 512, 512, 32, 2, 1),
+    (2, 128, 256, 256, 1, 2),
+])
+def test_full_size_conv_layers_linearity_and_adjoints(ops, device, case):
+    """Size-independent properties at full layer sizes (too large for the CPU oracle): the conv2d_resample layers are linear in
+    x and in w, their data gradient is the adjoint map (<A x, y> == <x, A^T y>) and their weight gradient the adjoint in w
+    (<A_w x, y> == <w, dW(x, y)>).  Inner products are accumulated in fp64."""
+    N, I, O, R, up, down = case
+    g = torch.Generator(device=device).manual_seed(R + I)
+    f = R_setup = ops.upfirdn2d.setup_filter([1, 3, 3, 1]).to(device)
+    x1 = torch.randn(N, I, R, R, device=device, generator=g); x2 = torch.randn(N, I, R, R, device=device, generator=g)
+    w = torch.randn(O, I, 3, 3, device=device, generator=g) / np.sqrt(9 * I)
+    w2 = torch.randn(O, I, 3, 3, device=device, generator=g) / np.sqrt(9 * I)
+
+    def A(x, w_):
+        return ops.conv2d_resample.conv2d_resample(x, w_, f=f, up=up, down=down, padding=1, flip_weight=(up == 1))
+
+    def dot(a, b):
+        return float((a.detach().double() * b.detach().double()).sum())
+
+    xr = x1.clone().requires_grad_(True); wr = w.clone().requires_grad_(True)
+    y = A(xr, wr)
+    assert y.shape == (N, O, R * up // down, R * up // down)
+    yy = torch.randn(y.shape, device=device, generator=g)
+    dx, dw = torch.autograd.grad(y, [xr, wr], yy)
+    lhs = dot(y, yy)
+    assert abs(lhs - dot(x1, dx)) <= 1e-5 * max(abs(lhs), np.sqrt(y.numel())), 'data gradient is not the adjoint'
+    assert abs(lhs - dot(w, dw)) <= 1e-5 * max(abs(lhs), np.sqrt(y.numel())), 'weight gradient is not the adjoint'
+    with torch.no_grad():
+        y1 = y.detach(); y2 = A(x2, w)
+        lin = A(0.5 * x1 - 2.0 * x2, w)
+        assert_close(lin, 0.5 * y1 - 2.0 * y2, 2e-5, 'linearity in x')
+        linw = A(x1, 0.25 * w + 3.0 * w2)
+        assert_close(linw, 0.25 * y1 + 3.0 * A(x1, w2), 2e-5, 'linearity in w')
+
+
+def test_full_size_elementwise_properties(ops, device):
+    """bias_act / upfirdn2d at the largest config-f tensors: relu-type idempotence, exact clamp, FIR linearity and the
+    adjoint pair upsample2d / its gradient (upfirdn2d.py:264-283)."""
+    g = torch.Generator(device=device).manual_seed(5)
+    x = torch.randn(4, 32, 1024, 1024, device=device, generator=g); b = torch.randn(32, device=device, generator=g)
+    y = ops.bias_act.bias_act(x, b, act='relu', gain=1.0)
+    assert torch.equal(ops.bias_act.bias_act(y, None, act='relu', gain=1.0), y)                       # idempotent
+    assert float(ops.bias_act.bias_act(x, b, act='lrelu', clamp=0.5).abs().max()) <= 0.5                 # clamp is exact
+    lin = ops.bias_act.bias_act(x, b, act='linear', gain=2.0)
+    assert_close(lin, 2.0 * (x + b[None, :, None, None]), 1e-6, 'linear')
+    f = ops.upfirdn2d.setup_filter([1, 3, 3, 1]).to(device)
+    img = torch.randn(4, 3, 512, 512, device=device, generator=g).requires_grad_(True)
+    up = ops.upfirdn2d.upsample2d(img, f)
+    assert up.shape == (4, 3, 1024, 1024)
+    yy = torch.randn(up.shape, device=device, generator=g)
+    dimg, = torch.autograd.grad(up, img, yy)
+    lhs = float((up.double() * yy.double()).sum())
+    assert abs(lhs - float((img.double() * dimg.double()).sum())) <= 1e-6 * max(abs(lhs), 1e3)
+    # a constant image stays constant under the normalised up / down filters (DC gain 1)
+    ones = torch.ones(2, 8, 256, 256, device=device)
+    assert_close(ops.upfirdn2d.upsample2d(ones, f)[:, :, 4:-4, 4:-4], torch.ones(2, 8, 504, 504), 1e-6, 'up2 DC gain')
+    assert_close(ops.upfirdn2d.downsample2d(ones, f)[:, :, 2:-2, 2:-2], torch.ones(2, 8, 124, 124), 1e-6, 'down2 DC gain')
