@@ -26,6 +26,7 @@ def main():
     ap.add_argument('--batch', type=int, default=8)
     ap.add_argument('--batch-gpu', type=int, default=4)
     ap.add_argument('--out', default='')
+    ap.add_argument('--main-only', action='store_true', help='profile an iteration without the lazy regularisation phases')
     args = ap.parse_args()
     from torch_utils import custom_ops
     from training import training_loop
@@ -68,7 +69,12 @@ def main():
         if k[-1] == 0:
             print('   ', k, 'x', n)
     torch.cuda.synchronize()
-    step.cur_it = 0                      # all four phases fire
+    step.cur_it = 1 if args.main_only else 0      # 0: all four phases fire
+    import time
+    t0 = time.perf_counter()
+    step.run(real); torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1000
+    step.cur_it = 1 if args.main_only else 0
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         step.run(real)
         torch.cuda.synchronize()
@@ -79,8 +85,8 @@ def main():
             agg[name[:110]][0] += 1
             agg[name[:110]][1] += ev.device_time if hasattr(ev, 'device_time') else ev.cuda_time
     total = sum(v[1] for v in agg.values())
-    lines = [f'one iteration with all four phases, res {args.res}, batch {args.batch} in rounds of {args.batch_gpu}: '
-             f'{total / 1000:.1f} ms of kernel time in {sum(v[0] for v in agg.values())} launches']
+    lines = [f'one iteration ({"Gmain+Dmain" if args.main_only else "all four phases"}), res {args.res}, batch {args.batch} in rounds of {args.batch_gpu}: '
+             f'{total / 1000:.1f} ms of kernel time in {sum(v[0] for v in agg.values())} launches; wall clock of the same iteration without the profiler {wall_ms:.1f} ms']
     for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
         lines.append(f'{us / 1000:10.2f} ms {100 * us / total:5.1f}%  {n:6d}x  {name}')
     text = '\n'.join(lines)
