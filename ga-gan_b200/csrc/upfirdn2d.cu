@@ -227,6 +227,18 @@ __global__ void __launch_bounds__(256) fir_stream(StreamP p) {
     float K[4][4];
 #pragma unroll
     for (int i = 0; i < 16; ++i) K[i >> 2][i & 3] = sK[i];
+    // K == fy (x) fx ?  (exact test on the 16 coefficients; warp- and grid-uniform)
+    float fx[4], fy[4];
+    bool separable = K[0][0] != 0.f;
+    {
+        float amax = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) amax = fmaxf(amax, fabsf(K[i >> 2][i & 3]));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { fx[i] = K[0][i]; fy[i] = separable ? K[i][0] / K[0][0] : 0.f; }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) separable = separable && fabsf(K[i >> 2][i & 3] - fy[i >> 2] * fx[i & 3]) <= 1e-7f * amax;
+    }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x0 = (blockIdx.x * 32 + lane) * OXT;
@@ -300,14 +312,30 @@ __global__ void __launch_bounds__(256) fir_stream(StreamP p) {
                     in[j] = buf[ph][4 + (d - ph) / 2];
                 }
             }
-#pragma unroll
-            for (int ky = 0; ky < 4; ++ky) {
-                const int yy = rr - ky;                          // output row (relative) fed through filter row ky
-                if (yy < 0 || yy >= RY) continue;                // compile-time after unrolling
+            if (separable) {
+                // rank-1 filter (setup_filter builds the 2-D [1,3,3,1] filter as an outer product): horizontal pass once per input
+                // row, then one FMA per output row -- 8 instead of 16 FMAs per output
+                float h[OXT];
 #pragma unroll
                 for (int t = 0; t < OXT; ++t)
+                    h[t] = fmaf(fx[3], in[t + 3], fmaf(fx[2], in[t + 2], fmaf(fx[1], in[t + 1], fx[0] * in[t])));
 #pragma unroll
-                    for (int kx = 0; kx < 4; ++kx) acc[yy][t] = fmaf(K[ky][kx], in[t + kx], acc[yy][t]);
+                for (int ky = 0; ky < 4; ++ky) {
+                    const int yy = rr - ky;
+                    if (yy < 0 || yy >= RY) continue;
+#pragma unroll
+                    for (int t = 0; t < OXT; ++t) acc[yy][t] = fmaf(fy[ky], h[t], acc[yy][t]);
+                }
+            } else {
+#pragma unroll
+                for (int ky = 0; ky < 4; ++ky) {
+                    const int yy = rr - ky;                      // output row (relative) fed through filter row ky
+                    if (yy < 0 || yy >= RY) continue;            // compile-time after unrolling
+#pragma unroll
+                    for (int t = 0; t < OXT; ++t)
+#pragma unroll
+                        for (int kx = 0; kx < 4; ++kx) acc[yy][t] = fmaf(K[ky][kx], in[t + kx], acc[yy][t]);
+                }
             }
         }
 
