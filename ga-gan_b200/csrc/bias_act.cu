@@ -22,6 +22,8 @@ struct Params {
     int64_t sizeX;
     int sizeB;
     int64_t stepB;
+    const float* noise;      // optional [Nn, stepB] plane(s) added before the activation (forward only): the per-pixel noise of
+    int64_t noise_bs;        // SynthesisLayer (networks.py:904-917), broadcast over channels; batch stride 0 = one shared plane
 };
 
 // One element.  A = the reference's cuda_idx, G = grad order.  Mirrors the case table of
@@ -126,11 +128,17 @@ __global__ void __launch_bounds__(256) bias_act_vec4(Params p) {
         float4 r = (G > 0 && A == 9) ? vr[it] : make_float4(0, 0, 0, 0);
         float4 yr = (G > 0) ? vy[it] : make_float4(0, 0, 0, 0);
         float4 d = (G == 2) ? vd[it] : make_float4(1, 1, 1, 1);
+        float4 nz = make_float4(0, 0, 0, 0);
+        if (G == 0 && p.noise && ok) {                  // element e = 4*i4 sits at pixel e % stepB of sample e / (stepB*sizeB)
+            const int64_t e = i4 << 2;
+            const int64_t plane = e / p.stepB;
+            nz = __ldg(reinterpret_cast<const float4*>(p.noise + (plane / p.sizeB) * p.noise_bs + (e - plane * p.stepB)));
+        }
         float4 o;
-        o.x = eval<A, G>(vx[it].x, b, r.x, yr.x, d.x, p);
-        o.y = eval<A, G>(vx[it].y, b, r.y, yr.y, d.y, p);
-        o.z = eval<A, G>(vx[it].z, b, r.z, yr.z, d.z, p);
-        o.w = eval<A, G>(vx[it].w, b, r.w, yr.w, d.w, p);
+        o.x = eval<A, G>(vx[it].x, b + nz.x, r.x, yr.x, d.x, p);
+        o.y = eval<A, G>(vx[it].y, b + nz.y, r.y, yr.y, d.y, p);
+        o.z = eval<A, G>(vx[it].z, b + nz.z, r.z, yr.z, d.z, p);
+        o.w = eval<A, G>(vx[it].w, b + nz.w, r.w, yr.w, d.w, p);
         if (ok) reinterpret_cast<float4*>(p.y)[i4] = o;
         if (p.dbias) {
             float s = ok ? (o.x + o.y) + (o.z + o.w) : 0.f;
@@ -157,8 +165,9 @@ __global__ void __launch_bounds__(256) bias_act_scalar(Params p) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < p.sizeX; i += stride) {
-        int c = (p.b || p.dbias) ? (int)((i / p.stepB) % p.sizeB) : 0;
+        int c = (p.b || p.dbias || p.noise) ? (int)((i / p.stepB) % p.sizeB) : 0;
         float b = p.b ? __ldg(p.b + c) : 0.f;
+        if (G == 0 && p.noise) { const int64_t plane = i / p.stepB; b += __ldg(p.noise + (plane / p.sizeB) * p.noise_bs + (i - plane * p.stepB)); }
         float xr = (G > 0 && p.xref) ? __ldg(p.xref + i) : 0.f;
         float yr = (G > 0 && p.yref) ? __ldg(p.yref + i) : 0.f;
         float d = (G == 2 && p.dy) ? __ldg(p.dy + i) : 1.f;
@@ -171,7 +180,7 @@ __global__ void __launch_bounds__(256) bias_act_scalar(Params p) {
 template <int A, int G>
 int launch(const Params& p, cudaStream_t st) {
     auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-    bool vec = (p.sizeX % 4 == 0) && (p.stepB % 4 == 0) && al16(p.x) && al16(p.xref) && al16(p.yref) && al16(p.dy) && al16(p.y);
+    bool vec = (p.sizeX % 4 == 0) && (p.stepB % 4 == 0) && al16(p.noise) && (p.noise_bs % 4 == 0) && al16(p.x) && al16(p.xref) && al16(p.yref) && al16(p.dy) && al16(p.y);
     if (vec) {
         const int64_t per_block = 8 /*warps*/ * 32 * 8 /*ITER*/ * 4;
         int64_t grid = (p.sizeX + per_block - 1) / per_block;
@@ -194,9 +203,9 @@ int launch_g(const Params& p, int grad, cudaStream_t st) {
 
 }  // namespace
 
-extern "C" GG_API int gg_bias_act_f32(const float* x, const float* b, const float* xref, const float* yref, const float* dy,
-                               float* y, float* dbias, int grad, int act, float alpha, float gain, float clamp,
-                               int64_t sizeX, int sizeB, int64_t stepB, gg_stream_t stream) {
+static int bias_act_impl(const float* x, const float* b, const float* xref, const float* yref, const float* dy,
+                         float* y, float* dbias, int grad, int act, float alpha, float gain, float clamp,
+                         int64_t sizeX, int sizeB, int64_t stepB, const float* noise, int64_t noise_bs, gg_stream_t stream) {
     GG_REQUIRE(x != nullptr && y != nullptr, "bias_act: x and y must be non-null");
     GG_REQUIRE(sizeX >= 0 && sizeX <= 0x7fffffffLL, "bias_act: x is too large");  // bias_act.cpp:40
     GG_REQUIRE(grad >= 0 && grad <= 2, "bias_act: grad must be 0, 1 or 2");
@@ -204,8 +213,9 @@ extern "C" GG_API int gg_bias_act_f32(const float* x, const float* b, const floa
     GG_REQUIRE(b == nullptr || (sizeB >= 1 && stepB >= 1), "bias_act: b has wrong number of elements");
     GG_REQUIRE(dbias == nullptr || (sizeB >= 1 && stepB >= 1), "bias_act: dbias needs sizeB/stepB");
     if (sizeX == 0) return GG_OK;
-    if (b == nullptr && dbias == nullptr) { sizeB = 1; stepB = (int64_t)1 << 30; }   // no per-channel work: any layout vectorises
-    Params p{x, b, xref, yref, dy, y, dbias, alpha, gain, clamp, sizeX, sizeB < 1 ? 1 : sizeB, stepB < 1 ? 1 : stepB};
+    GG_REQUIRE(noise == nullptr || (grad == 0 && sizeB >= 1 && stepB >= 1 && noise_bs >= 0), "bias_act: noise needs grad == 0 and sizeB/stepB");
+    if (b == nullptr && dbias == nullptr && noise == nullptr) { sizeB = 1; stepB = (int64_t)1 << 30; }   // no per-channel work: any layout vectorises
+    Params p{x, b, xref, yref, dy, y, dbias, alpha, gain, clamp, sizeX, sizeB < 1 ? 1 : sizeB, stepB < 1 ? 1 : stepB, noise, noise_bs};
     cudaStream_t st = (cudaStream_t)stream;
     switch (act) {
         case 1: return launch_g<1>(p, grad, st);
@@ -218,4 +228,15 @@ extern "C" GG_API int gg_bias_act_f32(const float* x, const float* b, const floa
         case 8: return launch_g<8>(p, grad, st);
         default: return launch_g<9>(p, grad, st);
     }
+}
+
+extern "C" GG_API int gg_bias_act_f32(const float* x, const float* b, const float* xref, const float* yref, const float* dy,
+                               float* y, float* dbias, int grad, int act, float alpha, float gain, float clamp,
+                               int64_t sizeX, int sizeB, int64_t stepB, gg_stream_t stream) {
+    return bias_act_impl(x, b, xref, yref, dy, y, dbias, grad, act, alpha, gain, clamp, sizeX, sizeB, stepB, nullptr, 0, stream);
+}
+
+extern "C" GG_API int gg_bias_act_noise_f32(const float* x, const float* b, const float* noise, int64_t noise_batch_stride, float* y, int act,
+                                     float alpha, float gain, float clamp, int64_t sizeX, int sizeB, int64_t stepB, gg_stream_t stream) {
+    return bias_act_impl(x, b, nullptr, nullptr, nullptr, y, nullptr, 0, act, alpha, gain, clamp, sizeX, sizeB, stepB, noise, noise_batch_stride, stream);
 }

@@ -67,6 +67,8 @@ _SIGNATURES = {
     'gg_bias_act_f32': (ctypes.c_int, [_c_float_p] * 7 + [ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
                                                           ctypes.c_float, ctypes.c_int64, ctypes.c_int, ctypes.c_int64,
                                                           ctypes.c_void_p]),
+    'gg_bias_act_noise_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int64, _c_float_p, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                             ctypes.c_float, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p]),
     'gg_upfirdn2d_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 15 + [ctypes.c_float, ctypes.c_int, ctypes.c_int,
                                                            ctypes.c_void_p]),
     'gg_fir4_pm_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 7 + [ctypes.c_float] + [ctypes.c_int] * 8 + [ctypes.c_void_p]),
@@ -185,6 +187,28 @@ class _Plugin:
             _check(self._lib.gg_bias_act_f32(_ptr(x), _ptr(b), _ptr(xref), _ptr(yref), _ptr(dy), _ptr(y), _ptr(dbias),
                                             int(grad), int(act), float(alpha), float(gain), float(clamp),
                                             x.numel(), int(size_b), int(step_b), _stream(x)), 'bias_act')
+        return y
+
+    # forward bias_act with per-pixel noise (include/gagan_b200.h: gg_bias_act_noise_f32); x dense NCHW, dim == 1
+    def bias_act_noise(self, x, b, noise, act, alpha, gain, clamp):
+        _require_cuda(x, 'x')
+        _check_device(x)
+        if x.dim() != 4 or not x.is_contiguous():
+            raise RuntimeError('bias_act(noise=...): x must be dense NCHW')
+        N, C, H, W = x.shape
+        noise = noise.contiguous()
+        if noise.numel() == H * W:
+            nbs = 0
+        elif noise.numel() == N * H * W:
+            nbs = H * W
+        else:
+            raise RuntimeError('bias_act(noise=...): noise must be [H,W] or [N,1,H,W]')
+        if b.numel() != 0 and b.numel() != C:
+            raise RuntimeError('b has wrong number of elements')
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _check(self._lib.gg_bias_act_noise_f32(_ptr(x), _ptr(b), _ptr(noise), nbs, _ptr(y), int(act), float(alpha), float(gain),
+                                                  float(clamp), x.numel(), C, H * W, _stream(x)), 'bias_act')
         return y
 
     # upfirdn2d.cpp:16-94

@@ -51,7 +51,7 @@ def _null_like(x):
 
 # ----------------------------------------------------------------------------
 
-def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, impl='cuda'):
+def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, impl='cuda', noise=None):
     r"""Fused bias and activation function: `clamp(act(x + b) * gain)`.
 
     Args / semantics identical to the reference (bias_act.py:88-122).  Supports first and second
@@ -64,6 +64,12 @@ def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, 
     if x.device.type != 'cuda':
         raise RuntimeError('bias_act: the B200 build has no CPU path; x must be a CUDA tensor')
     _init()
+    if noise is not None:
+        # extension: per-pixel noise ([H,W] or [N,1,H,W]) added before the activation inside the same kernel -- the
+        # `x.add_(noise)` / fma pass of the SynthesisLayer (networks.py:648-653)
+        if dim != 1 or x.ndim != 4:
+            raise RuntimeError('bias_act(noise=...) needs an NCHW tensor with dim == 1')
+        return _bias_act_cuda(dim=dim, act=act, alpha=alpha, gain=gain, clamp=clamp).apply(x, b, noise)
     return _bias_act_cuda(dim=dim, act=act, alpha=alpha, gain=gain, clamp=clamp).apply(x, b)
 
 
@@ -92,15 +98,20 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
     # Forward op.
     class BiasActCuda(torch.autograd.Function):
         @staticmethod
-        def forward(ctx, x, b):  # pylint: disable=arguments-differ
+        def forward(ctx, x, b, noise=None):  # pylint: disable=arguments-differ
             if x.dtype != torch.float32:
                 raise RuntimeError('bias_act: this build serves fp32 only')
             ctx.memory_format = torch.channels_last if x.ndim > 2 and x.stride()[1] == 1 else torch.contiguous_format
+            ctx.noise_shape = tuple(noise.shape) if noise is not None else None
+            if noise is not None:
+                ctx.memory_format = torch.contiguous_format
             x = x.contiguous(memory_format=ctx.memory_format)
             b = b.contiguous() if b is not None else _null_like(x)
             null = _null_like(x)
             y = x
-            if (not is_identity or b.numel() != 0) and x.numel() != 0:
+            if noise is not None and x.numel() != 0:
+                y = _plugin.bias_act_noise(x, b, noise.to(x.dtype), spec.cuda_idx, alpha, gain, clamp)
+            elif (not is_identity or b.numel() != 0) and x.numel() != 0:
                 y = _plugin.bias_act(x, b, null, null, null, 0, dim, spec.cuda_idx, alpha, gain, clamp)
             ctx.save_for_backward(
                 x if 'x' in spec.ref or spec.has_2nd_grad else null,
@@ -114,7 +125,8 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
             x, b, y = ctx.saved_tensors
             dx = None
             db = None
-            if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            want_dn = ctx.noise_shape is not None and len(ctx.needs_input_grad) > 2 and ctx.needs_input_grad[2]
+            if ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or want_dn:
                 want_db = bool(ctx.needs_input_grad[1])
                 if is_identity:
                     dx = dy
@@ -124,7 +136,15 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
                     dx, db = BiasActCudaGrad.apply(dy, x, b, y, want_db)
                     if not want_db:
                         db = None
-            return dx, db
+            if ctx.noise_shape is None:
+                return dx, db
+            dn = None
+            if want_dn:                                   # the noise enters like a bias that varies per pixel instead of per channel
+                dn = dx.sum(dim=1, keepdim=True)
+                if len(ctx.noise_shape) == 2:
+                    dn = dn.sum(dim=[0, 1])
+                dn = dn.reshape(ctx.noise_shape)
+            return (dx if ctx.needs_input_grad[0] else None), db, dn
 
     # Backward op: (dx, db) = grad-1 kernel with the bias reduction fused in.
     class BiasActCudaGrad(torch.autograd.Function):

@@ -133,6 +133,11 @@ class Conv2dLayer(torch.nn.Module):
         w = self.weight * self.weight_gain
         b = self.bias.to(x.dtype) if self.bias is not None else None
         flip_weight = (self.up == 1)
+        if b is None and self.activation == 'linear' and self.conv_clamp is None:
+            # bias-free linear layer (the resnet skip path): act(x)*gain is a rescaling of the (tiny) weight tensor
+            w = w * (self.act_gain * gain)
+            return conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, up=self.up, down=self.down,
+                                                   padding=self.padding, flip_weight=flip_weight)
         x = conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, up=self.up, down=self.down,
                                             padding=self.padding, flip_weight=flip_weight)
         act_gain = self.act_gain * gain
@@ -251,11 +256,13 @@ class SynthesisLayer(torch.nn.Module):
         if self.use_noise and noise_mode == 'const':
             noise = self.noise_const * self.noise_strength
         flip_weight = (self.up == 1)
-        x = modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
+        # the noise is added by the bias_act kernel (one pass instead of add + bias_act); modulated_conv2d(noise=...) itself
+        # still accepts it for API compatibility
+        x = modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=None, up=self.up, padding=self.padding,
                              resample_filter=self.resample_filter, flip_weight=flip_weight, fused_modconv=fused_modconv)
         act_gain = self.act_gain * gain
         act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
-        return bias_act.bias_act(x, self.bias.to(x.dtype), act=self.activation, gain=act_gain, clamp=act_clamp)
+        return bias_act.bias_act(x, self.bias.to(x.dtype), act=self.activation, gain=act_gain, clamp=act_clamp, noise=noise)
 
 
 class ToRGBLayer(torch.nn.Module):

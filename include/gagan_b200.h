@@ -77,6 +77,13 @@ GG_API int gg_bias_act_f32(const float* x, const float* b, const float* xref, co
                     float* y, float* dbias, int grad, int act, float alpha, float gain, float clamp,
                     int64_t sizeX, int sizeB, int64_t stepB, gg_stream_t stream);
 
+/* Forward bias_act with the SynthesisLayer's per-pixel noise folded in (training/networks.py:904-921 adds
+ * `noise [N,1,H,W]` or `[H,W]` to the conv output with a separate full-tensor pass before bias_act):
+ *   y[i] = clamp(act(x[i] + b[c(i)] + noise[n(i) * noise_batch_stride + i % stepB]) * gain),   n(i) = i / (stepB * sizeB)
+ * x is dense NCHW with stepB = H*W and sizeB = C; noise_batch_stride = 0 broadcasts one plane over the batch. */
+GG_API int gg_bias_act_noise_f32(const float* x, const float* b, const float* noise, int64_t noise_batch_stride, float* y, int act,
+                          float alpha, float gain, float clamp, int64_t sizeX, int sizeB, int64_t stepB, gg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * upfirdn2d -- replaces `_plugin.upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1,
  * flip, gain)` (torch_utils/ops/upfirdn2d.cpp:16-94, kernels upfirdn2d.cu:29-200).

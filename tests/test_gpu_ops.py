@@ -504,3 +504,23 @@ def test_full_size_elementwise_properties(ops, device):
     ones = torch.ones(2, 8, 256, 256, device=device)
     assert_close(ops.upfirdn2d.upsample2d(ones, f)[:, :, 4:-4, 4:-4], torch.ones(2, 8, 504, 504), 1e-6, 'up2 DC gain')
     assert_close(ops.upfirdn2d.downsample2d(ones, f)[:, :, 2:-2, 2:-2], torch.ones(2, 8, 124, 124), 1e-6, 'down2 DC gain')
+
+
+@pytest.mark.parametrize('shape,const_noise', [((3, 8, 16, 20), False), ((2, 5, 7, 9), True), ((2, 16, 32, 32), True)])
+def test_bias_act_with_folded_noise(ops, device, shape, const_noise):
+    # bias_act(x, b, noise=n) == bias_act(x + n, b) of the reference (networks.py:904-921: noise add, then bias_act), with
+    # gradients for x, b and the noise
+    g = torch.Generator().manual_seed(sum(shape))
+    N, C, H, W = shape
+    x = torch.randn(shape, generator=g); b = torch.randn(C, generator=g)
+    nz = torch.randn(H, W, generator=g) if const_noise else torch.randn(N, 1, H, W, generator=g)
+    dy = torch.randn(shape, generator=g)
+    xs = [t_.clone().requires_grad_(True) for t_ in (x, b, nz)]
+    want = R.bias_act(xs[0] + xs[2], xs[1], act='lrelu', gain=1.3, clamp=2.0)
+    wg = torch.autograd.grad(want, xs, dy)
+    ds = [t_.to(device).requires_grad_(True) for t_ in (x, b, nz)]
+    got = ops.bias_act.bias_act(ds[0], ds[1], act='lrelu', gain=1.3, clamp=2.0, noise=ds[2])
+    assert_close(got, want, 1e-6, 'y')
+    gg_ = torch.autograd.grad(got, ds, dy.to(device))
+    for name, a_, b_ in zip(['dx', 'db', 'dnoise'], gg_, wg):
+        assert_close(a_, b_, 2e-6, name)
