@@ -35,7 +35,8 @@ int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int
               int pad_x, int flip_w, int w_is_IO, const float* in_scale, const float* out_scale, int nprod, cudaStream_t st);
 bool wgrad_tc_eligible(int N, int A, int HA, int WA, int B, int HB, int WB, int KH, int KW, int stride, int pad_y, int pad_x);
 int wgrad_tc(const float* a, const float* b, float* dw, int N, int A, int HA, int WA, int B, int HB, int WB, int KH, int KW,
-             int pad_y, int pad_x, int flip_w, int out_layout, const float* a_scale, const float* b_scale, int nprod, cudaStream_t st);
+             int pad_y, int pad_x, int flip_w, int out_layout, const float* a_scale, const float* b_scale, int nprod, int pm_dim,
+             unsigned pm_dead, cudaStream_t st);
 
 }  // namespace gg
 
@@ -94,6 +95,15 @@ extern "C" GG_API int gg_conv2d_f32(const float* x, const float* w, float* y, in
 extern "C" GG_API int gg_conv2d_wgrad_f32(const float* a, const float* b, float* dw, int N, int A, int HA, int WA, int B, int HB, int WB,
                                    int KH, int KW, int stride, int pad_y, int pad_x, int flip_w, int out_layout,
                                    const float* a_scale, const float* b_scale, int prec, int* used_prec, gg_stream_t stream) {
+    return gg_conv2d_wgrad_pm_f32(a, b, dw, N, A, HA, WA, B, HB, WB, KH, KW, stride, pad_y, pad_x, flip_w, out_layout, a_scale, b_scale,
+                                  prec, used_prec, 0, 0u, stream);
+}
+
+extern "C" GG_API int gg_conv2d_wgrad_pm_f32(const float* a, const float* b, float* dw, int N, int A, int HA, int WA, int B, int HB, int WB,
+                                      int KH, int KW, int stride, int pad_y, int pad_x, int flip_w, int out_layout,
+                                      const float* a_scale, const float* b_scale, int prec, int* used_prec, int pm_dim,
+                                      unsigned pm_dead, gg_stream_t stream) {
+    GG_REQUIRE(pm_dim >= 0 && pm_dim <= 2 && pm_dead <= 0xffffu, "conv2d_wgrad: bad phase-major hint");
     GG_REQUIRE(a && b && dw, "conv2d_wgrad: null pointer");
     GG_REQUIRE(N >= 0 && A >= 1 && B >= 1 && HA >= 1 && WA >= 1 && HB >= 1 && WB >= 1 && KH >= 1 && KW >= 1, "conv2d_wgrad: bad shape");
     GG_REQUIRE(stride >= 1 && pad_y >= 0 && pad_x >= 0, "conv2d_wgrad: bad stride/padding");
@@ -114,5 +124,5 @@ extern "C" GG_API int gg_conv2d_wgrad_f32(const float* a, const float* b, float*
     if (use == GG_PREC_FP32_SIMT)
         return gg::conv2d_wgrad_simt(a, b, dw, N, A, HA, WA, B, HB, WB, KH, KW, stride, pad_y, pad_x, flip_w, out_layout, a_scale,
                                      b_scale, st);
-    return gg::wgrad_tc(a, b, dw, N, A, HA, WA, B, HB, WB, KH, KW, pad_y, pad_x, flip_w, out_layout, a_scale, b_scale, use, st);
+    return gg::wgrad_tc(a, b, dw, N, A, HA, WA, B, HB, WB, KH, KW, pad_y, pad_x, flip_w, out_layout, a_scale, b_scale, use, pm_dim, pm_dead, st);
 }

@@ -501,23 +501,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static std::atomic<int> state{0};
-    if (state.load() == 2) return fn;
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
-        return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    state.store(2);
-    return fn;
-}
-
 // The stream-ordered scratch comes from the device's default memory pool.  Its default release threshold of 0 hands the
 // memory back to the driver at every synchronisation, which makes the next cudaMallocAsync cost ~1 ms; keep it cached.
 void keep_pool_memory() {
@@ -549,6 +532,19 @@ int launch_conv_tc(const CUtensorMap& xmap, const TcP& p, cudaStream_t st) {
 }
 
 }  // namespace
+
+gg::EncodeTiledFn gg::get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::atomic<int> state{0};
+    if (state.load() == 2) return fn;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    state.store(2);
+    return fn;
+}
 
 namespace gg {
 
@@ -597,7 +593,7 @@ int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int
     }
 
     // 2. TMA descriptor of x as a 4-D tensor {W, H, C, N}; box {rawW, boxH, 16, 1}; OOB elements read as zero
-    EncodeTiledFn encode = get_encode_fn();
+    gg::EncodeTiledFn encode = gg::get_encode_fn();
     if (!encode) { cudaFreeAsync(wp, st); set_error("conv2d(tc): cuTensorMapEncodeTiled is unavailable"); return GG_ECUDA; }
     CUtensorMap xmap;
     cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)I, (cuuint64_t)N};

@@ -3,6 +3,14 @@
 #include "common.cuh"
 #include <cuda.h>
 
+namespace gg {
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency); defined in conv_tc.cu
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn();
+}  // namespace gg
+
 namespace ggtc {
 
 // ------------------------------------------------------------------------------------------------ PTX helpers

@@ -414,8 +414,18 @@ bool wgrad_tc_eligible(int N, int A, int HA, int WA, int B, int HB, int WB, int 
     return true;
 }
 
+// wgrad_tma.cu: the TMA-fed kernel (16-byte aligned operands)
+bool wgrad_tma_eligible(const float* a, const float* b, int WA, int WB);
+int wgrad_tma(const float* a, const float* b, float* dw, int N, int A, int HA, int WA, int B, int HB, int WB, int K,
+              int pad_y, int pad_x, int flip_w, int out_layout, const float* a_scale, const float* b_scale, int nprod,
+              int pm_dim, unsigned pm_dead, cudaStream_t st);
+
 int wgrad_tc(const float* a, const float* b, float* dw, int N, int A, int HA, int WA, int B, int HB, int WB, int K, int /*KW*/,
-             int pad_y, int pad_x, int flip_w, int out_layout, const float* a_scale, const float* b_scale, int nprod, cudaStream_t st) {
+             int pad_y, int pad_x, int flip_w, int out_layout, const float* a_scale, const float* b_scale, int nprod, int pm_dim,
+             unsigned pm_dead, cudaStream_t st) {
+    { const char* e = getenv("GG_WG_LDG");      // development switch: force the global-load kernel below
+      if (!(e && atoi(e)) && wgrad_tma_eligible(a, b, WA, WB))
+          return wgrad_tma(a, b, dw, N, A, HA, WA, B, HB, WB, K, pad_y, pad_x, flip_w, out_layout, a_scale, b_scale, nprod, pm_dim, pm_dead, st); }
     WgP p{};
     p.X = a; p.G = b; p.dw = dw; p.xs = a_scale; p.gs = b_scale;
     p.N = N; p.A = A; p.HA = HA; p.WA = WA; p.B = B; p.HB = HB; p.WB = WB; p.K = K; p.pad_y = pad_y; p.pad_x = pad_x;

@@ -77,6 +77,9 @@ _SIGNATURES = {
                                                         ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
     'gg_conv2d_wgrad_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 14 + [_c_float_p, _c_float_p, ctypes.c_int,
                                                               ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
+    'gg_conv2d_wgrad_pm_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 14 + [_c_float_p, _c_float_p, ctypes.c_int,
+                                                                 ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_uint,
+                                                                 ctypes.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())
 
@@ -329,7 +332,9 @@ class _Plugin:
 
     # replaces aten::cudnn_convolution(_transpose)_backward_weight (conv2d_gradfix.py:178-188)
     def conv2d_wgrad(self, a, b, kernel_size, stride=1, padding=(0, 0), flip_w=False, out_layout=0, a_scale=None,
-                     b_scale=None, prec=None, flop_scale=1.0):
+                     b_scale=None, prec=None, flop_scale=1.0, pm=None):
+        """`pm=(pm_dim, pm_dead)`: structural hint for the phase-major stride-2 weights (include/gagan_b200.h:
+        gg_conv2d_wgrad_pm_f32) -- entries of dw that are zero by construction in the weight may be left zero."""
         _require_cuda(a, 'input')
         _require_cuda(b, 'grad_output')
         _check_device(a)
@@ -345,10 +350,11 @@ class _Plugin:
         used = ctypes.c_int(0)
         ev0 = _prof_begin(a)
         with torch.cuda.device(a.device):
-            _check(self._lib.gg_conv2d_wgrad_f32(_ptr(a), _ptr(b), _ptr(dw), N, A, HA, WA, B, HB, WB, KH, KW, int(stride),
-                                                int(padding[0]), int(padding[1]), 1 if flip_w else 0, int(out_layout),
-                                                _ptr(a_scale), _ptr(b_scale), int(conv_precision if prec is None else prec),
-                                                ctypes.byref(used), _stream(a)), 'conv2d_wgrad')
+            _check(self._lib.gg_conv2d_wgrad_pm_f32(_ptr(a), _ptr(b), _ptr(dw), N, A, HA, WA, B, HB, WB, KH, KW, int(stride),
+                                                   int(padding[0]), int(padding[1]), 1 if flip_w else 0, int(out_layout),
+                                                   _ptr(a_scale), _ptr(b_scale), int(conv_precision if prec is None else prec),
+                                                   ctypes.byref(used), int(pm[0]) if pm else 0, int(pm[1]) if pm else 0,
+                                                   _stream(a)), 'conv2d_wgrad')
         self.last_wgrad_prec = used.value
         _prof_end(a, ev0, 'wgrad', flop_scale * 2.0 * N * A * B * KH * KW * HB * WB, used.value)
         return dw

@@ -125,7 +125,7 @@ def _run_wgrad(grad_output, input, weight_shape, transpose, stride, padding, gro
 _conv2d_s1_cache = dict()
 
 
-def conv2d_s1(x, w, padding=(0, 0), out_hw=None, io=False, flip=False, live=1.0, in_scale=None, out_scale=None):
+def conv2d_s1(x, w, padding=(0, 0), out_hw=None, io=False, flip=False, live=1.0, in_scale=None, out_scale=None, pm=None):
     """`in_scale [N,I]` / `out_scale [N,O]`: per-sample channel scales folded into the kernel's operand conversion and
     epilogue -- y = out_scale * conv(in_scale * x, w) -- i.e. the style modulation / demodulation of modulated_conv2d
     (networks.py:642,648-651) without their full-tensor multiply passes."""
@@ -134,7 +134,7 @@ def conv2d_s1(x, w, padding=(0, 0), out_hw=None, io=False, flip=False, live=1.0,
     padding = _tuple_of_ints(padding, 2)
     if out_hw is None:
         out_hw = (x.shape[2] + 2 * padding[0] - kh + 1, x.shape[3] + 2 * padding[1] - kw + 1)
-    key = (tuple(w.shape), padding, (int(out_hw[0]), int(out_hw[1])), bool(io), bool(flip), float(live))
+    key = (tuple(w.shape), padding, (int(out_hw[0]), int(out_hw[1])), bool(io), bool(flip), float(live), (tuple(pm) if pm else None))
     if in_scale is None and out_scale is None:
         return _conv2d_s1(*key).apply(x, w)
     if fuse_scales is False:            # debug switch: explicit multiply passes around the unscaled kernel
@@ -147,8 +147,8 @@ fuse_scales = True
 _scaled_conv2d_s1_cache = dict()
 
 
-def _scaled_conv2d_s1(weight_shape, padding, out_hw, io, flip, live, has_a, has_b):
-    key = (weight_shape, padding, out_hw, io, flip, live, has_a, has_b)
+def _scaled_conv2d_s1(weight_shape, padding, out_hw, io, flip, live, pm, has_a, has_b):
+    key = (weight_shape, padding, out_hw, io, flip, live, pm, has_a, has_b)
     if key in _scaled_conv2d_s1_cache:
         return _scaled_conv2d_s1_cache[key]
     kh, kw = weight_shape[2], weight_shape[3]
@@ -179,8 +179,8 @@ def _scaled_conv2d_s1(weight_shape, padding, out_hw, io, flip, live, has_a, has_
                 # out with differentiable ops and the closed, unscaled primitives so that autograd can differentiate them again.
                 # (Re-running the forward and calling autograd.grad on it would be wrong: out_scale = dcoefs is itself a function
                 # of in_scale = styles, and the total derivative would count that path twice.)
-                conv = _conv2d_s1(weight_shape, padding, out_hw, io, flip, live)
-                conv_t = _conv2d_s1(weight_shape, dpad, (x.shape[2], x.shape[3]), not io, not flip, live)
+                conv = _conv2d_s1(weight_shape, padding, out_hw, io, flip, live, pm)
+                conv_t = _conv2d_s1(weight_shape, dpad, (x.shape[2], x.shape[3]), not io, not flip, live, pm)
                 xa = x * a[:, :, None, None] if a is not None else x
                 dyb = dy * b[:, :, None, None] if b is not None else dy
                 dx = dw = da = db = None
@@ -208,7 +208,7 @@ def _scaled_conv2d_s1(weight_shape, padding, out_hw, io, flip, live, has_a, has_
                     dx = None
             if ctx.needs_input_grad[1] and not weight_gradients_disabled:
                 dw = _plugin.conv2d_wgrad(x, dy, (kh, kw), stride=1, padding=padding, flip_w=flip, out_layout=(1 if io else 0),
-                                          flop_scale=live, a_scale=a, b_scale=b)
+                                          flop_scale=live, a_scale=a, b_scale=b, pm=pm)
             if b is not None and ctx.needs_input_grad[3]:
                 # d/db[n,o] = sum_p dy * conv(a*x, w) = sum_p dy * y / b
                 db = _plugin.chan_dot(dy, y) / torch.where(b == 0, torch.ones_like(b), b)
@@ -218,10 +218,12 @@ def _scaled_conv2d_s1(weight_shape, padding, out_hw, io, flip, live, has_a, has_
     return ScaledConvS1
 
 
-def _conv2d_s1(weight_shape, padding, out_hw, io, flip, live=1.0):
+def _conv2d_s1(weight_shape, padding, out_hw, io, flip, live=1.0, pm=None):
     # `live` = fraction of structurally non-zero weight blocks (9/16 for the phase-major stride-2 forms); it only scales
     # the algorithmic-FLOP accounting of bench.py so that skipped zero blocks are never counted as work.
-    key = (weight_shape, padding, out_hw, io, flip, live)
+    # `pm` = (pm_dim, pm_dead): which entries of the weight are zero by construction (gg_conv2d_wgrad_pm_f32): the weight-gradient
+    # kernel skips them.
+    key = (weight_shape, padding, out_hw, io, flip, live, pm)
     if key in _conv2d_s1_cache:
         return _conv2d_s1_cache[key]
     kh, kw = weight_shape[2], weight_shape[3]
@@ -246,7 +248,7 @@ def _conv2d_s1(weight_shape, padding, out_hw, io, flip, live=1.0):
             x, w = ctx.saved_tensors
             dx = dw = None
             if ctx.needs_input_grad[0]:
-                dx = _conv2d_s1(weight_shape, dpad, (x.shape[2], x.shape[3]), not io, not flip, live).apply(dy, w)
+                dx = _conv2d_s1(weight_shape, dpad, (x.shape[2], x.shape[3]), not io, not flip, live, pm).apply(dy, w)
             if ctx.needs_input_grad[1] and not weight_gradients_disabled:
                 dw = WgradS1.apply(dy, x)
             return dx, dw
@@ -255,16 +257,16 @@ def _conv2d_s1(weight_shape, padding, out_hw, io, flip, live=1.0):
         @staticmethod
         def forward(ctx, dy, x):
             ctx.save_for_backward(dy, x)
-            return _plugin.conv2d_wgrad(x, dy, (kh, kw), stride=1, padding=padding, flip_w=flip, out_layout=(1 if io else 0), flop_scale=live)
+            return _plugin.conv2d_wgrad(x, dy, (kh, kw), stride=1, padding=padding, flip_w=flip, out_layout=(1 if io else 0), flop_scale=live, pm=pm)
 
         @staticmethod
         def backward(ctx, ggw):
             dy, x = ctx.saved_tensors
             g_dy = g_x = None
             if ctx.needs_input_grad[0]:
-                g_dy = _conv2d_s1(weight_shape, padding, (dy.shape[2], dy.shape[3]), io, flip, live).apply(x, ggw)
+                g_dy = _conv2d_s1(weight_shape, padding, (dy.shape[2], dy.shape[3]), io, flip, live, pm).apply(x, ggw)
             if ctx.needs_input_grad[1]:
-                g_x = _conv2d_s1(weight_shape, dpad, (x.shape[2], x.shape[3]), not io, not flip, live).apply(dy, ggw)
+                g_x = _conv2d_s1(weight_shape, dpad, (x.shape[2], x.shape[3]), not io, not flip, live, pm).apply(dy, ggw)
             return g_dy, g_x
 
     ConvS1.Wgrad = WgradS1

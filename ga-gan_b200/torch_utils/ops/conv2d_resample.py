@@ -43,6 +43,27 @@ def _conv2d_wrapper(x, w, stride=1, padding=0, groups=1, transpose=False, flip_w
 _PM_LIVE = 9.0 / 16.0
 
 
+class _Live(float):
+    """Fraction of structurally non-zero (phase, tap) weight blocks of a phase-major weight, carrying the structure itself:
+    `pm = (pm_dim, pm_dead)` as defined by gg_conv2d_wgrad_pm_f32 (include/gagan_b200.h) so that the weight-gradient kernel
+    can skip the blocks that are zero by construction."""
+    pm = None
+
+
+def _pm_live(kind, kh, kw):
+    dead = 0
+    for py in range(2):
+        for px in range(2):
+            for a in range(2):
+                for b in range(2):
+                    ky, kx = (2 * a + py, 2 * b + px) if kind == 'down' else (py + 2 * (1 - a), px + 2 * (1 - b))
+                    if ky >= kh or kx >= kw:
+                        dead |= 1 << ((py * 2 + px) * 4 + a * 2 + b)
+    live = _Live(_PM_LIVE)
+    live.pm = (2 if kind == 'down' else 1, dead)       # down: dim 1 of W2 [O,4I,2,2] is phase-grouped; up: dim 0 of W2 [4O,I,2,2]
+    return live
+
+
 def phase_major_weight_down(w):
     """[O,I,kh,kw] (kh,kw <= 4) -> [O,4I,2,2]:  W2[o,(py,px,i),a,b] = w[o,i,2a+py,2b+px]  (0 beyond the kernel)."""
     O, I, kh, kw = w.shape
@@ -77,21 +98,22 @@ def down2_phase_major(x, w, f, fir_pad, flip_weight, flip_filter, conv_s1, fir_t
     if not flip_weight:
         w = w.flip([2, 3])
     xs = fir_to_pm(x, f, fir_pad, flip_filter, 1, oh + 1, _round_up(ow + 1, 4))   # width % 4: TMA row pitch must be 16-byte aligned
-    return conv_s1(xs, phase_major_weight_down(w), (0, 0), (oh, ow), _PM_LIVE)
+    return conv_s1(xs, phase_major_weight_down(w), (0, 0), (oh, ow), _pm_live('down', kh, kw))
 
 
 def up2_phase_major(x, w, f, fir_pad, flip_weight, flip_filter, conv_s1, fir_from_pm, in_scale=None, out_scale=None):
     """conv2d_resample.py:125-139 (stride-2 transposed conv with pad 0, then FIR with gain 4) in phase-major form;
     `fir_from_pm(z, f, padding, flip_filter, gain, valid_hw)` reads the phase-major conv output directly."""
     N, I, H, W = x.shape
+    live = _pm_live('up', int(w.shape[2]), int(w.shape[3]))
     if flip_weight:                      # the reference hands `not flip_weight` to the transposed conv (:138)
         w = w.flip([2, 3])
     xs_w = _round_up(W + 1, 4)           # the gradient of this tensor is a TMA source in backward: keep the width aligned
     if in_scale is not None or out_scale is not None:      # per-sample scales: the 4 output phases of channel o share out_scale[:, o]
-        z = conv_s1(x, phase_major_weight_up(w), (1, 1), (H + 1, xs_w), _PM_LIVE, in_scale=in_scale,
+        z = conv_s1(x, phase_major_weight_up(w), (1, 1), (H + 1, xs_w), live, in_scale=in_scale,
                     out_scale=(out_scale.repeat(1, 4) if out_scale is not None else None))
     else:
-        z = conv_s1(x, phase_major_weight_up(w), (1, 1), (H + 1, xs_w), _PM_LIVE)   # [N,4O,H+1,xs_w]; valid logical extent 2H+1 x 2W+1
+        z = conv_s1(x, phase_major_weight_up(w), (1, 1), (H + 1, xs_w), live)   # [N,4O,H+1,xs_w]; valid logical extent 2H+1 x 2W+1
     return fir_from_pm(z, f, fir_pad, flip_filter, 4, (2 * H + 1, 2 * W + 1))
 
 
@@ -124,7 +146,8 @@ def plan(w_shape, f, up, down, padding):
 
 
 def _conv_s1(x, w, padding, out_hw, live, in_scale=None, out_scale=None):
-    return conv2d_gradfix.conv2d_s1(x, w, padding=padding, out_hw=out_hw, live=live, in_scale=in_scale, out_scale=out_scale)
+    return conv2d_gradfix.conv2d_s1(x, w, padding=padding, out_hw=out_hw, live=float(live), in_scale=in_scale, out_scale=out_scale,
+                                    pm=getattr(live, 'pm', None))
 
 
 def _fir_to_pm(x, f, padding, flip_filter, gain, ys, xs):

@@ -147,6 +147,16 @@ GG_API int gg_conv2d_wgrad_f32(const float* a, const float* b, float* dw, int N,
                         int KH, int KW, int stride, int pad_y, int pad_x, int flip_w, int out_layout,
                         const float* a_scale, const float* b_scale, int prec, int* used_prec, gg_stream_t stream);
 
+/* Same weight gradient with a structural hint for the phase-major stride-2 forms of conv2d_resample.py:119-142 (this repo's
+ * torch_utils/ops/conv2d_resample.py: phase_major_weight_down / _up): dimension `pm_dim - 1` of dw (pm_dim = 1 or 2; 0 = no
+ * hint) consists of 4 equal groups, one per sub-pixel phase (py,px), and bit (group*4 + ky*2 + kx) of `pm_dead` marks the taps of
+ * that group that are zero BY CONSTRUCTION in the weight (7 of the 16 for a 3x3 kernel).  Those entries of dw may be left zero
+ * instead of being computed: the host discards them.  KH == KW == 2 only; ignored otherwise. */
+GG_API int gg_conv2d_wgrad_pm_f32(const float* a, const float* b, float* dw, int N, int A, int HA, int WA, int B, int HB, int WB,
+                           int KH, int KW, int stride, int pad_y, int pad_x, int flip_w, int out_layout,
+                           const float* a_scale, const float* b_scale, int prec, int* used_prec, int pm_dim, unsigned pm_dead,
+                           gg_stream_t stream);
+
 /* out[r] = sum_p a[r,p] * b[r,p] for `rows` rows of P contiguous floats (row = one (sample, channel) plane): the style and
  * demodulation-coefficient gradients of modulated_conv2d once the per-sample scales live inside the conv kernels
  * (training/networks.py:642,648-651 and their autograd reductions).  out is overwritten. */
