@@ -1,22 +1,27 @@
-// tcgen05 / TMEM weight-gradient kernel, TMA-fed (the path every aligned layer of the networks takes).
+// tcgen05 / TMEM weight-gradient kernel, TMA-fed, G operand in tensor memory (the path every aligned layer takes).
 //
 // Same contraction, GEMM view, work units and accumulation scheme as wgrad_tc.cu (read its header first):
 //
 //   dw[b,a,ky,kx] = sum_{n,y,x} (gs[n,b] * G[n,b,y,x]) * (xs[n,a] * X[n,a,y+ky-py,x+kx-px])
 //   D_ky[m = (kx slot, grad channel b), n = input channel a] += sum_{pixels} Gshift[m, pix] * X_ky[n, pix]
 //
-// What is different is how the operands reach shared memory.  ncu on wgrad_tc_kernel showed the converter warps, not the
-// tensor core, setting the pace: ~530 warp instructions per 16-pixel row task (address arithmetic, bounds tests, global-load
-// latency with only two tasks in flight per SM) against ~160 that the hi/lo split itself needs.  Here
+// What is different is how the operands reach the tensor core.  ncu on wgrad_tc_kernel showed (1) the converter warps
+// setting the pace (~530 warp instructions per 16-pixel row task: address arithmetic, bounds tests, global-load latency with
+// two tasks in flight per SM, against ~160 that the hi/lo split needs) and, once that was fixed, (2) the shared-memory port
+// saturated: 18 SS-mode MMAs per task read 108 KB of operands, the converters move another 60 KB.  Here
 //
-//   * one producer thread issues TMA box loads {16 (+8 apron for G) pixels, 1 row, NTA or RB channels, 1 sample} of the raw fp32
-//     rows into a 4-deep staging ring.  Image borders, channel tails and the zero padding are TMA out-of-bounds zero fill:
+//   * one producer thread issues TMA box loads {16 (+12 apron for G) pixels, 1 row, NTA or RB channels, 1 sample} of the raw
+//     fp32 rows into a staging ring.  Image borders, channel tails and the zero padding are TMA out-of-bounds zero fill:
 //     no bounds test is left in the kernel.  (A box has to start on a 16-byte boundary of global memory, so the kx shift of
-//     the G operand is applied by the converters: two aligned 128-bit reads and a register select per 4 pixels.)
-//   * the converter warps read a staged row (LDS.128), scale, split into tf32 hi/lo and write the UMMA K-major images --
-//     every address is a per-thread constant plus a ring offset;
+//     the G operand is applied by the converters when they pick their 16 pixels out of the apron row.)
+//   * the G operand (M = 128 rows) lives in TENSOR MEMORY: converter thread m owns MMA row m = TMEM lane m, reads its staged row
+//     (row pitch 112 B: conflict-free 128-bit reads), scales, splits into tf32 hi/lo and writes 2 x 16 columns with tcgen05.st;
+//     the MMAs are issued in the TS form (A from TMEM), so only the 64 X rows of an MMA cross the shared-memory port:
+//     36 KB instead of 108 KB per task, and no st.shared for G at all;
+//   * the X operand (N = NTA rows) is converted into the K-major UMMA shared-memory image as before, with a rotated
+//     chunk <-> lane mapping that makes both the staged read and the image stores bank-conflict free;
 //   * structurally dead taps of the phase-major stride-2 weights (conv2d_resample.py: 7 of the 16 (phase, tap) blocks are
-//     zero by construction) are skipped per (tile, ky): no loads, no MMAs, no flush.
+//     zero by construction) are skipped per (tile, ky): no MMAs, no drain, no flush; a tile without a live tap exits.
 //
 // Requirements (checked by wgrad_tma_eligible, otherwise wgrad_tc.cu's kernel runs): 16-byte aligned base pointers and row
 // pitches (WA % 4 == 0, WB % 4 == 0) -- the TMA global-stride rule.
@@ -33,13 +38,12 @@ constexpr int GROUP_THREADS = GROUP_WARPS * 32;
 constexpr int PROD_WARPS = 4;                           // w0 = MMA issuer + TMEM owner, w1 = TMA producer, w2..w3 idle (one warpgroup for setmaxnreg)
 constexpr int THREADS = (PROD_WARPS + CONS_WARPS) * 32;
 constexpr int UW = 16;                                  // image columns per strip (two K=8 steps)
-constexpr int GS = 4;                                   // G-row ring slots
-constexpr int XS = 8;                                   // X-row ring slots (k live rows + rows in flight)
-constexpr int ST = 4;                                   // staging slots (raw fp32 rows in flight from TMA)
-constexpr uint32_t LBO_A = 128 * 16;                    // chunk pitch of the G image
+constexpr int GS = 4;                                   // G-row slots in tensor memory (32 columns each: 16 hi + 16 lo)
+constexpr int XS = 8;                                   // X-row ring slots in shared memory (k live rows + rows in flight)
+constexpr int ST = 6;                                   // staging slots (raw fp32 rows in flight from TMA)
 constexpr uint32_t ROW_B = UW * 4;                      // bytes of one staged X row (16 pixels)
-constexpr int GW = UW + 8;                              // staged G row: pixels u0-4 .. u0+19 (serves every kx shift of the tile)
-constexpr uint32_t GROW_B = GW * 4;
+constexpr int GW = UW + 12;                             // staged G row: pixels u0-4 .. u0+23; 20 are needed (every kx shift), 28 give a
+constexpr uint32_t GROW_B = GW * 4;                     // row pitch of 7 x 16 B: consecutive rows fall into different bank groups
 constexpr uint32_t STG_G = 128 * GROW_B;                // staged G rows (up to 128 channels), then the X rows
 
 struct WtP {
@@ -67,6 +71,13 @@ __device__ __forceinline__ void mbar_wait_block(uint32_t bar, uint32_t parity) {
         if (ok) return;
         if (it > (1u << 24)) { *reinterpret_cast<volatile int*>(8) = (int)bar; __trap(); }   // a pipeline bug must not hang the GPU
     }
+}
+
+// 128-bit shared-memory read that the compiler may not split into narrower (bank-conflicting) accesses
+__device__ __forceinline__ float4 lds128(const void* ptr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(ptr)));
+    return v;
 }
 
 struct Tile { int b0, a0, kx0, ns; uint32_t ky_live; };
@@ -113,19 +124,19 @@ __device__ __forceinline__ Strip decode_strip(int strip, const WtP& p) {
 template <int NTA>
 __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap gmap, WtP p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     constexpr uint32_t LBO_B = NTA * 16;
-    constexpr uint32_t G_HALF = 4 * LBO_A, G_SLOT = 2 * G_HALF;          // hi image, lo image
-    constexpr uint32_t X_HALF = 4 * LBO_B, X_SLOT = 2 * X_HALF;
-    constexpr uint32_t STG_SLOT = STG_G + NTA * ROW_B;                   // 16 KB (NTA = 64) / 14 KB (NTA = 32)
-    constexpr uint32_t OFF_G = 0, OFF_X = OFF_G + GS * G_SLOT, OFF_STG = OFF_X + XS * X_SLOT, OFF_BAR = OFF_STG + ST * STG_SLOT,
-                       OFF_SLOT = OFF_BAR + 512;
-    static_assert(OFF_STG % 128 == 0 && STG_SLOT % 128 == 0, "TMA destinations must be 128-byte aligned");
+    constexpr uint32_t X_HALF = 4 * LBO_B, X_SLOT = 2 * X_HALF;          // hi image, lo image
+    constexpr uint32_t STG_SLOT = STG_G + NTA * ROW_B;                   // 18 KB (NTA = 64) / 16 KB (NTA = 32)
+    constexpr uint32_t OFF_X = 0, OFF_STG = OFF_X + XS * X_SLOT, OFF_BAR = OFF_STG + ST * STG_SLOT, OFF_SLOT = OFF_BAR + 512;
+    static_assert(OFF_STG % 128 == 0 && STG_SLOT % 128 == 0 && STG_G % 128 == 0, "TMA destinations must be 128-byte aligned");
     constexpr uint32_t ACC_STRIDE = 3 * NTA;                             // TMEM columns of one accumulator set (ky-major)
-    constexpr uint32_t TMEM_COLS = (2 * ACC_STRIDE <= 256) ? 256 : 512;
+    constexpr uint32_t TM_G = 2 * ACC_STRIDE;                            // first column of the G slots
+    constexpr uint32_t TMEM_COLS = 512;                                  // 2 accumulator sets + GS x 32 columns of G (384 + 128 at NTA = 64)
+    static_assert(TM_G + GS * 32 <= TMEM_COLS, "tensor memory budget");
 
     const uint32_t bar0 = base + OFF_BAR;
     auto BAR_G_FULL = [&](int s) { return bar0 + 8u * s; };
@@ -162,13 +173,12 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
     if (warp < PROD_WARPS) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (warp == 0 && elect_one()) {
-            // ===== MMA issuer (one thread)
+            // ===== MMA issuer (one thread): D_ky[tmem] += G[tmem] * X_ky[smem]
             const uint32_t idesc = umma_idesc_tf32(128, NTA, 0, 0);
-            const uint64_t a_word = ((uint64_t)(8u | (1u << 14)) << 32) | ((uint64_t)(LBO_A >> 4) << 16);   // SBO 128 B, LBO
-            const uint64_t b_word = ((uint64_t)(8u | (1u << 14)) << 32) | ((uint64_t)(LBO_B >> 4) << 16);
-            constexpr uint32_t a_ks = 2 * (LBO_A >> 4), b_ks = 2 * (LBO_B >> 4);
+            const uint64_t b_word = ((uint64_t)(8u | (1u << 14)) << 32) | ((uint64_t)(LBO_B >> 4) << 16);   // SBO 128 B, LBO
+            constexpr uint32_t b_ks = 2 * (LBO_B >> 4);
             uint32_t gq = 0, xq = 0, sc = 0;        // running G-row, X-row and strip counters (ring positions)
-            const uint32_t g0_16 = (base + OFF_G) >> 4, x0_16 = (base + OFF_X) >> 4;
+            const uint32_t x0_16 = (base + OFF_X) >> 4;
             for (int strip = strip_beg; strip < strip_end; ++strip) {
                 const int r0 = ((strip / p.ustrips) % p.rstrips) * p.RR;
                 const int rows = min(p.RR, p.HB - r0);
@@ -181,7 +191,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
                     mbar_wait_spin(BAR_G_FULL(gslot), (gq / GS) & 1);
                     mbar_wait_spin(BAR_X_FULL(xlast & (XS - 1)), (xlast / XS) & 1);          // X rows i .. i+K-2 were waited for earlier
                     tc_fence_after();
-                    const uint64_t g_hi = a_word + (g0_16 + gslot * (G_SLOT >> 4)), g_lo = g_hi + (G_HALF >> 4);
+                    const uint32_t g_hi = tmem_base + TM_G + gslot * 32, g_lo = g_hi + 16;   // columns: 16 pixels hi, 16 pixels lo
                     const uint32_t accf = i > 0 ? 1u : 0u;
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky) {
@@ -189,15 +199,15 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
                         const uint64_t x_hi = b_word + (x0_16 + ((xq + ky) & (XS - 1)) * (X_SLOT >> 4)), x_lo = x_hi + (X_HALF >> 4);
                         const uint32_t d = d0 + (uint32_t)ky * NTA;
                         if (p.nprod == 3) {
-                            umma_tf32(d, g_hi, x_hi, idesc, accf);
-                            umma_tf32(d, g_hi, x_lo, idesc, 1u);
-                            umma_tf32(d, g_lo, x_hi, idesc, 1u);
-                            umma_tf32(d, g_hi + a_ks, x_hi + b_ks, idesc, 1u);
-                            umma_tf32(d, g_hi + a_ks, x_lo + b_ks, idesc, 1u);
-                            umma_tf32(d, g_lo + a_ks, x_hi + b_ks, idesc, 1u);
+                            umma_tf32_ts(d, g_hi, x_hi, idesc, accf);
+                            umma_tf32_ts(d, g_hi, x_lo, idesc, 1u);
+                            umma_tf32_ts(d, g_lo, x_hi, idesc, 1u);
+                            umma_tf32_ts(d, g_hi + 8, x_hi + b_ks, idesc, 1u);
+                            umma_tf32_ts(d, g_hi + 8, x_lo + b_ks, idesc, 1u);
+                            umma_tf32_ts(d, g_lo + 8, x_hi + b_ks, idesc, 1u);
                         } else {
-                            umma_tf32(d, g_hi, x_hi, idesc, accf);
-                            umma_tf32(d, g_hi + a_ks, x_hi + b_ks, idesc, 1u);
+                            umma_tf32_ts(d, g_hi, x_hi, idesc, accf);
+                            umma_tf32_ts(d, g_hi + 8, x_hi + b_ks, idesc, 1u);
                         }
                     }
                     umma_commit(BAR_G_EMPTY(gslot));
@@ -217,23 +227,23 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
                 const Strip s = decode_strip(strip, p);
                 const int ntask = s.rows + K - 1;
                 for (int j = 0; j < ntask; ++j, ++tc) {
-                    const uint32_t slot = tc & (ST - 1);
+                    const uint32_t slot = tc % ST;
                     mbar_wait_spin(BAR_STG_EMPTY(slot), ((tc / ST) & 1) ^ 1);
                     const bool has_g = j >= K - 1;
                     mbar_expect_tx(BAR_STG_FULL(slot), NTA * ROW_B + (has_g ? (uint32_t)p.RB * GROW_B : 0u));
                     const uint32_t dst = stg0 + slot * STG_SLOT;
                     tma_load_4d(dst + STG_G, &xmap, BAR_STG_FULL(slot), s.u0, s.r0 - p.pad_y + j, T.a0, s.n);
                     // A TMA box must start on a 16-byte boundary of global memory, so the kx shift cannot be put into the box
-                    // coordinate: ONE aligned box with a 4-pixel apron on both sides serves all shifts (the converters pick).
+                    // coordinate: ONE aligned box with a 4-pixel apron on the left serves all shifts (the converters pick).
                     if (has_g) tma_load_4d(dst, &gmap, BAR_STG_FULL(slot), s.u0 - 4, s.r0 - (K - 1) + j, T.b0, s.n);
                 }
             }
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-        // ===== converter warps: staged fp32 rows -> tf32 hi/lo UMMA images; then drain strip s-1 from TMEM into registers
+        // ===== converter warps: staged fp32 rows -> tf32 hi/lo (G: tensor memory, X: UMMA shared-memory image); then drain strip s-1
         const int ct = threadIdx.x - PROD_WARPS * 32;      // 0..255
-        const int q = warp & 3;                            // TMEM lane quarter
+        const int q = warp & 3;                            // TMEM lane quarter this warp may access
         const int grp = (warp - PROD_WARPS) >> 2;          // converter group = half of the accumulator columns this warp owns
         const int half = grp;
         constexpr int HN = NTA / 2;                        // input channels per thread and ky
@@ -243,34 +253,28 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
         for (int j = 0; j < HC; ++j) acc[j] = 0.f;
 
         constexpr int XI = NTA * 4 / GROUP_THREADS;        // X items per thread (2 for NTA = 64, 1 for 32)
-        constexpr int GI = 512 / GROUP_THREADS;            // G items per thread (4)
         const int gt = ct & (GROUP_THREADS - 1);           // thread index inside the group
-        // Item k of this thread: row row0 + 32 k, 16-byte chunk ce.  Within a quarter-warp (8 lanes = 8 consecutive rows) the chunk
-        // index rotates with the row, so that BOTH the 128-bit reads of the staged row-major tile (row pitch 64 B for X, 96 B
-        // for G) and the 128-bit stores into the chunk-major UMMA images (row pitch 16 B) touch eight different 16-byte bank
-        // groups: conflict free without a TMA swizzle.  X: ce = c0 ^ ((row >> 1) & 3); G: ce = (c0 + ((row >> 2) & 1)) & 3.
+        // X item k of this thread: row row0 + 32 k, 16-byte chunk cex.  Within a quarter-warp (8 lanes = 8 consecutive rows) the
+        // chunk index rotates with the row pair, cex = c0 ^ ((row >> 1) & 3), so that BOTH the 128-bit read of the staged
+        // row-major tile (row pitch 64 B) and the 128-bit stores into the chunk-major UMMA image (row pitch 16 B) touch eight
+        // different 16-byte bank groups: conflict free without a TMA swizzle.
         const int c0 = item_chunk(gt), row0 = item_row(gt);
-        const int cex = c0 ^ ((row0 >> 1) & 3), ceg = (c0 + ((row0 >> 2) & 1)) & 3;
+        const int cex = c0 ^ ((row0 >> 1) & 3);
         const uint32_t xsrc0 = STG_G + (uint32_t)row0 * ROW_B + (uint32_t)(cex << 4);
-        const uint32_t xdst0 = (uint32_t)cex * LBO_B + (uint32_t)row0 * 16, gdst0 = (uint32_t)ceg * LBO_A + (uint32_t)row0 * 16;
-        // G item k = row m = row0 + 32 k of the MMA = (kx slot sft, channel b): chunk ceg holds pixels u0 + 4 ceg - sh .. + 3 with
-        // sh = kx - pad_x, i.e. staged pixels 4 (ceg + cq) + e0 .. + 3 where 4 cq + e0 = 4 - sh: two aligned 128-bit reads + a select
-        uint32_t gsrc[GI];
-        int ge0[GI];
-        bool gzero[GI];                                    // rows of kx slots this tile does not have: written as zeros
-#pragma unroll
-        for (int k = 0; k < GI; ++k) {
-            const int m = row0 + 32 * k, sft = m >> p.rb_shift, b = m & (p.RB - 1);
-            const int t = 4 - (T.kx0 + sft - p.pad_x);     // 2 .. 6
-            gsrc[k] = (uint32_t)b * GROW_B + (uint32_t)((ceg + (t >> 2)) << 4);
-            ge0[k] = t & 3;
-            gzero[k] = sft >= T.ns;
-        }
-        float xsc[XI], gsc[GI];
+        const uint32_t xdst0 = (uint32_t)cex * LBO_B + (uint32_t)row0 * 16;
+        // G: this thread owns MMA row m = TMEM lane m = (kx slot sft, channel b).  Its 16 pixels u0 - sh .. u0 - sh + 15
+        // (sh = kx - pad_x) are the staged pixels t .. t + 15 with t = 4 - sh in 2 .. 6: five aligned 128-bit reads starting at
+        // chunk t >> 2, then a (warp-uniform) register pick by t & 3.
+        const int m = q * 32 + lane;
+        const int g_sft = m >> p.rb_shift, g_b = m & (p.RB - 1);
+        const int g_t = 4 - (T.kx0 + g_sft - p.pad_x);
+        const uint32_t gsrc = (uint32_t)g_b * GROW_B + (uint32_t)((g_t >> 2) << 4);
+        const int g_e0 = g_t & 3;
+        const bool g_zero = g_sft >= T.ns;                 // rows of kx slots this tile does not have: written as zeros
+        const uint32_t g_taddr = tmem_base + ((uint32_t)(q * 32) << 16) + TM_G;
+        float xsc[XI], gsc = 1.f;
 #pragma unroll
         for (int k = 0; k < XI; ++k) xsc[k] = 1.f;
-#pragma unroll
-        for (int k = 0; k < GI; ++k) gsc[k] = 1.f;
         int cur_n = -1;
 
         auto store_split = [&](uint8_t* hi_addr, uint32_t half_bytes, const float4& val, float sc_) {
@@ -302,7 +306,6 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
             if (lane == 0) mbar_arrive(BAR_ACC_EMPTY(buf));
         };
         auto flush = [&]() {                               // registers -> dw (fp32 atomics; dw was zero-filled by the host)
-            const int m = q * 32 + lane;
             const int s = m >> p.rb_shift, bc = T.b0 + (m & (p.RB - 1));
             const bool row_ok = s < T.ns && bc < p.B;
             int kx = T.kx0 + s;
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
             }
         };
 
-        uint32_t sc = 0, tbase = 0, xbase = 0, gq0 = 0;   // strip counter; staging / X-ring / G-ring positions of the strip's first task
+        uint32_t sc = 0, tbase = 0, xbase = 0, gq0 = 0;   // strip counter; staging / X-ring / G-slot positions of the strip's first task
         bool pend = false;
         int pend_rows = 0;
         uint32_t pend_sc = 0;
@@ -338,30 +341,40 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
                     const int ac = T.a0 + row0 + 32 * k;
                     xsc[k] = (p.xs && ac < p.A) ? __ldg(p.xs + (size_t)s.n * p.A + ac) : 1.f;
                 }
-#pragma unroll
-                for (int k = 0; k < GI; ++k) {
-                    const int bc = T.b0 + ((row0 + 32 * k) & (p.RB - 1));
-                    gsc[k] = (p.gs && bc < p.B) ? __ldg(p.gs + (size_t)s.n * p.B + bc) : 1.f;
-                }
+                const int bc = T.b0 + g_b;
+                gsc = (p.gs && bc < p.B) ? __ldg(p.gs + (size_t)s.n * p.B + bc) : 1.f;
             }
             for (int j = grp; j < ntask; j += 2) {
-                const uint32_t tcn = tbase + (uint32_t)j, slot = tcn & (ST - 1);
+                const uint32_t tcn = tbase + (uint32_t)j, slot = tcn % ST;
                 const uint32_t xc = xbase + (uint32_t)j, xslot = xc & (XS - 1);
                 const bool has_g = j >= K - 1;
                 const uint32_t gc = gq0 + (uint32_t)(j - (K - 1)), gslot = gc & (GS - 1);
                 mbar_wait_block(BAR_STG_FULL(slot), (tcn / ST) & 1);
                 const uint8_t* stg = gbase + OFF_STG + slot * STG_SLOT;
-                float4 xv[XI], gv[GI];
+                float4 xv[XI];
 #pragma unroll
-                for (int k = 0; k < XI; ++k) xv[k] = *reinterpret_cast<const float4*>(stg + xsrc0 + k * 32 * ROW_B);
+                for (int k = 0; k < XI; ++k) xv[k] = lds128(stg + xsrc0 + k * 32 * ROW_B);
+                float g[16];
                 if (has_g) {
+                    float v[20];
 #pragma unroll
-                    for (int k = 0; k < GI; ++k) {
-                        const float4 lo = *reinterpret_cast<const float4*>(stg + gsrc[k]);
-                        if (ge0[k] == 0) { gv[k] = lo; continue; }                 // warp-uniform: a warp's 8 rows share the kx slot
-                        const float4 hi = *reinterpret_cast<const float4*>(stg + gsrc[k] + 16);
-                        gv[k] = ge0[k] == 1 ? make_float4(lo.y, lo.z, lo.w, hi.x) : ge0[k] == 2 ? make_float4(lo.z, lo.w, hi.x, hi.y)
-                                                                                                : make_float4(lo.w, hi.x, hi.y, hi.z);
+                    for (int c = 0; c < 5; ++c) {
+                        const float4 t4 = lds128(stg + gsrc + 16 * c);
+                        v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w;
+                    }
+                    // warp-uniform pick: all 32 rows of a warp belong to the same kx slot
+                    if (g_e0 == 0) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) g[e] = v[e];
+                    } else if (g_e0 == 1) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) g[e] = v[e + 1];
+                    } else if (g_e0 == 2) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) g[e] = v[e + 2];
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) g[e] = v[e + 3];
                     }
                 }
                 mbar_wait_block(BAR_X_EMPTY(xslot), ((xc / XS) & 1) ^ 1);
@@ -369,13 +382,22 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
 #pragma unroll
                 for (int k = 0; k < XI; ++k) store_split(xb + k * 32 * 16, X_HALF, xv[k], xsc[k]);
                 if (has_g) {
-                    mbar_wait_block(BAR_G_EMPTY(gslot), ((gc / GS) & 1) ^ 1);
-                    uint8_t* gb = gbase + OFF_G + gslot * G_SLOT + gdst0;
+                    uint32_t hi[16], lo[16];
+                    const float gs_ = g_zero ? 0.f : gsc;
 #pragma unroll
-                    for (int k = 0; k < GI; ++k)
-                        store_split(gb + k * 32 * 16, G_HALF, gzero[k] ? make_float4(0.f, 0.f, 0.f, 0.f) : gv[k], gsc[k]);
+                    for (int e = 0; e < 16; ++e) {
+                        float h, l;
+                        split_tf32(g[e] * gs_, h, l);
+                        hi[e] = __float_as_uint(h); lo[e] = __float_as_uint(l);
+                    }
+                    mbar_wait_block(BAR_G_EMPTY(gslot), ((gc / GS) & 1) ^ 1);
+                    tc_fence_after();
+                    tmem_st16(g_taddr + gslot * 32, hi);
+                    tmem_st16(g_taddr + gslot * 32 + 16, lo);
+                    tmem_wait_st();
+                    tc_fence_before();
                 }
-                fence_proxy_async();                       // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                fence_proxy_async();                       // generic-proxy stores (X image) -> visible to the tensor core's async-proxy reads
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(BAR_STG_EMPTY(slot));
@@ -402,7 +424,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
 template <int NTA>
 int launch_wgrad_tma(const CUtensorMap& xmap, const CUtensorMap& gmap, const WtP& p, int grid, cudaStream_t st) {
     constexpr uint32_t LBO_B = NTA * 16;
-    const size_t smem = GS * 2 * 4 * LBO_A + XS * 2 * 4 * LBO_B + ST * (STG_G + NTA * ROW_B) + 512 + 16 + 1024;
+    const size_t smem = XS * 2 * 4 * LBO_B + ST * (STG_G + NTA * ROW_B) + 512 + 16 + 128;
     static std::atomic<int> attr_set{0};
     if (!attr_set.load()) {
         GG_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<NTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
