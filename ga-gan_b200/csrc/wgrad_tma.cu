@@ -27,6 +27,7 @@
 // pitches (WA % 4 == 0, WB % 4 == 0) -- the TMA global-stride rule.
 #include "tc_common.cuh"
 #include <stdlib.h>
+#include <limits.h>
 
 using namespace ggtc;
 
@@ -128,10 +129,14 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    constexpr uint32_t LBO_B = NTA * 16;
-    constexpr uint32_t X_HALF = 4 * LBO_B, X_SLOT = 2 * X_HALF;          // hi image, lo image
+    // X image in shared memory: [hi | lo][16-byte pixel chunk][ring slot][channel row] x 16 B.  Rows of CONSECUTIVE ring slots are
+    // contiguous inside a chunk, so one UMMA descriptor with N = K*NTA rows covers the X rows of all K filter rows ky at once
+    // (their accumulators D_ky are adjacent TMEM column ranges): 6 wide MMAs per task instead of 18 narrow ones.
+    constexpr uint32_t X_ROWS = NTA * 16;                                // one ring slot inside a chunk
+    constexpr uint32_t LBO_B = XS * X_ROWS;                              // chunk pitch
+    constexpr uint32_t X_HALF = 4 * LBO_B;                               // hi image, then lo image
     constexpr uint32_t STG_SLOT = STG_G + NTA * ROW_B;                   // 18 KB (NTA = 64) / 16 KB (NTA = 32)
-    constexpr uint32_t OFF_X = 0, OFF_STG = OFF_X + XS * X_SLOT, OFF_BAR = OFF_STG + ST * STG_SLOT, OFF_SLOT = OFF_BAR + 512;
+    constexpr uint32_t OFF_X = 0, OFF_STG = OFF_X + 2 * X_HALF, OFF_BAR = OFF_STG + ST * STG_SLOT, OFF_SLOT = OFF_BAR + 512;
     static_assert(OFF_STG % 128 == 0 && STG_SLOT % 128 == 0 && STG_G % 128 == 0, "TMA destinations must be 128-byte aligned");
     constexpr uint32_t ACC_STRIDE = 3 * NTA;                             // TMEM columns of one accumulator set (ky-major)
     constexpr uint32_t TM_G = 2 * ACC_STRIDE;                            // first column of the G slots
@@ -175,10 +180,13 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
         if (warp == 0 && elect_one()) {
             // ===== MMA issuer (one thread): D_ky[tmem] += G[tmem] * X_ky[smem]
             const uint32_t idesc = umma_idesc_tf32(128, NTA, 0, 0);
+            const uint32_t idesc_w = umma_idesc_tf32(128, K * NTA, 0, 0);          // all ky in one instruction
+            const bool all_live = T.ky_live == (1u << K) - 1u;
             const uint64_t b_word = ((uint64_t)(8u | (1u << 14)) << 32) | ((uint64_t)(LBO_B >> 4) << 16);   // SBO 128 B, LBO
             constexpr uint32_t b_ks = 2 * (LBO_B >> 4);
             uint32_t gq = 0, xq = 0, sc = 0;        // running G-row, X-row and strip counters (ring positions)
             const uint32_t x0_16 = (base + OFF_X) >> 4;
+            const bool three = p.nprod == 3;
             for (int strip = strip_beg; strip < strip_end; ++strip) {
                 const int r0 = ((strip / p.ustrips) % p.rstrips) * p.RR;
                 const int rows = min(p.RR, p.HB - r0);
@@ -187,31 +195,33 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
                 const uint32_t d0 = tmem_base + buf * ACC_STRIDE;
                 for (int j = 0; j < K - 1; ++j) mbar_wait_spin(BAR_X_FULL((xq + j) & (XS - 1)), ((xq + j) / XS) & 1);
                 for (int i = 0; i < rows; ++i) {
-                    const uint32_t gslot = gq & (GS - 1), xlast = xq + K - 1;
+                    const uint32_t gslot = gq & (GS - 1), xlast = xq + K - 1, xfirst = xq & (XS - 1);
                     mbar_wait_spin(BAR_G_FULL(gslot), (gq / GS) & 1);
                     mbar_wait_spin(BAR_X_FULL(xlast & (XS - 1)), (xlast / XS) & 1);          // X rows i .. i+K-2 were waited for earlier
                     tc_fence_after();
                     const uint32_t g_hi = tmem_base + TM_G + gslot * 32, g_lo = g_hi + 16;   // columns: 16 pixels hi, 16 pixels lo
                     const uint32_t accf = i > 0 ? 1u : 0u;
+                    if (all_live && xfirst + K <= XS) {
+                        // the K ring slots of this row's window are consecutive in memory: one N = K*NTA instruction per product
+                        const uint64_t x_hi = b_word + (x0_16 + xfirst * (X_ROWS >> 4)), x_lo = x_hi + (X_HALF >> 4);
+                        umma_tf32_ts(d0, g_hi, x_hi, idesc_w, accf);
+                        if (three) { umma_tf32_ts(d0, g_hi, x_lo, idesc_w, 1u); umma_tf32_ts(d0, g_lo, x_hi, idesc_w, 1u); }
+                        umma_tf32_ts(d0, g_hi + 8, x_hi + b_ks, idesc_w, 1u);
+                        if (three) { umma_tf32_ts(d0, g_hi + 8, x_lo + b_ks, idesc_w, 1u); umma_tf32_ts(d0, g_lo + 8, x_hi + b_ks, idesc_w, 1u); }
+                    } else {
 #pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        if (ky >= K || !((T.ky_live >> ky) & 1u)) continue;
-                        const uint64_t x_hi = b_word + (x0_16 + ((xq + ky) & (XS - 1)) * (X_SLOT >> 4)), x_lo = x_hi + (X_HALF >> 4);
-                        const uint32_t d = d0 + (uint32_t)ky * NTA;
-                        if (p.nprod == 3) {
+                        for (int ky = 0; ky < 3; ++ky) {
+                            if (ky >= K || !((T.ky_live >> ky) & 1u)) continue;
+                            const uint64_t x_hi = b_word + (x0_16 + ((xq + ky) & (XS - 1)) * (X_ROWS >> 4)), x_lo = x_hi + (X_HALF >> 4);
+                            const uint32_t d = d0 + (uint32_t)ky * NTA;
                             umma_tf32_ts(d, g_hi, x_hi, idesc, accf);
-                            umma_tf32_ts(d, g_hi, x_lo, idesc, 1u);
-                            umma_tf32_ts(d, g_lo, x_hi, idesc, 1u);
+                            if (three) { umma_tf32_ts(d, g_hi, x_lo, idesc, 1u); umma_tf32_ts(d, g_lo, x_hi, idesc, 1u); }
                             umma_tf32_ts(d, g_hi + 8, x_hi + b_ks, idesc, 1u);
-                            umma_tf32_ts(d, g_hi + 8, x_lo + b_ks, idesc, 1u);
-                            umma_tf32_ts(d, g_lo + 8, x_hi + b_ks, idesc, 1u);
-                        } else {
-                            umma_tf32_ts(d, g_hi, x_hi, idesc, accf);
-                            umma_tf32_ts(d, g_hi + 8, x_hi + b_ks, idesc, 1u);
+                            if (three) { umma_tf32_ts(d, g_hi + 8, x_lo + b_ks, idesc, 1u); umma_tf32_ts(d, g_lo + 8, x_hi + b_ks, idesc, 1u); }
                         }
                     }
                     umma_commit(BAR_G_EMPTY(gslot));
-                    umma_commit(BAR_X_EMPTY(xq & (XS - 1)));                           // X row i is not needed by later G rows
+                    umma_commit(BAR_X_EMPTY(xfirst));                                  // X row i is not needed by later G rows
                     ++gq; ++xq;
                 }
                 for (int j = 0; j < K - 1; ++j) umma_commit(BAR_X_EMPTY((xq + j) & (XS - 1)));   // the strip's bottom halo rows
@@ -261,7 +271,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
         const int c0 = item_chunk(gt), row0 = item_row(gt);
         const int cex = c0 ^ ((row0 >> 1) & 3);
         const uint32_t xsrc0 = STG_G + (uint32_t)row0 * ROW_B + (uint32_t)(cex << 4);
-        const uint32_t xdst0 = (uint32_t)cex * LBO_B + (uint32_t)row0 * 16;
+        const uint32_t xdst0 = (uint32_t)cex * LBO_B + (uint32_t)row0 * 16;      // + ring slot * X_ROWS
         // G: this thread owns MMA row m = TMEM lane m = (kx slot sft, channel b).  Its 16 pixels u0 - sh .. u0 - sh + 15
         // (sh = kx - pad_x) are the staged pixels t .. t + 15 with t = 4 - sh in 2 .. 6: five aligned 128-bit reads starting at
         // chunk t >> 2, then a (warp-uniform) register pick by t & 3.
@@ -378,7 +388,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
                     }
                 }
                 mbar_wait_block(BAR_X_EMPTY(xslot), ((xc / XS) & 1) ^ 1);
-                uint8_t* xb = gbase + OFF_X + xslot * X_SLOT + xdst0;
+                uint8_t* xb = gbase + OFF_X + xslot * X_ROWS + xdst0;
 #pragma unroll
                 for (int k = 0; k < XI; ++k) store_split(xb + k * 32 * 16, X_HALF, xv[k], xsc[k]);
                 if (has_g) {
@@ -423,8 +433,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
 
 template <int NTA>
 int launch_wgrad_tma(const CUtensorMap& xmap, const CUtensorMap& gmap, const WtP& p, int grid, cudaStream_t st) {
-    constexpr uint32_t LBO_B = NTA * 16;
-    const size_t smem = XS * 2 * 4 * LBO_B + ST * (STG_G + NTA * ROW_B) + 512 + 16 + 128;
+    const size_t smem = XS * 2 * 4 * (NTA * 16) + ST * (STG_G + NTA * ROW_B) + 512 + 16 + 128;
     static std::atomic<int> attr_set{0};
     if (!attr_set.load()) {
         GG_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<NTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -486,9 +495,16 @@ int wgrad_tma(const float* a, const float* b, float* dw, int N, int A, int HA, i
         if (ch % 4 == 0) { p.pm_side = on_a ? 1 : 2; p.pm_group = ch / 4; p.pm_dead = pm_dead; }
     }
     const int ntiles = p.btiles * p.atiles * p.zgroups;
-    int64_t parts = (2LL * GG_NUM_SMS + ntiles - 1) / ntiles;          // ~2 waves of CTAs; one atomic flush per CTA
-    if (parts > S) parts = S;
-    if (parts < 1) parts = 1;
+    // Strip partitions per tile: one CTA per SM is resident, so the kernel takes ceil(grid / 148) rounds of `strips per CTA`
+    // each; pick the partition count (>= ~2 waves for balance, one atomic flush per CTA) that minimises rounds x strips.
+    int64_t parts = 1, best = INT64_MAX;
+    const int64_t pmin = (2LL * GG_NUM_SMS + ntiles - 1) / ntiles;
+    for (int64_t c = pmin < S ? pmin : S; c <= S && c <= pmin + 40; ++c) {
+        if (c < 1) continue;
+        const int64_t per = (S + c - 1) / c, ctas = ((S + per - 1) / per) * ntiles;
+        const int64_t cost = ((ctas + GG_NUM_SMS - 1) / GG_NUM_SMS) * (per + 1);      // +1: fixed cost of a CTA (setup, drain, flush)
+        if (cost < best) { best = cost; parts = c; }
+    }
     p.units_per_cta = (int)((S + parts - 1) / parts);                  // strips per CTA
     parts = (S + p.units_per_cta - 1) / p.units_per_cta;
     const int grid = (int)(parts * ntiles);
