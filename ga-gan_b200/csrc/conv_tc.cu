@@ -90,7 +90,12 @@ constexpr int MAX_W_STAGES = 4;
 // Tile configurations <NT, SUBS>: <32|64|128, 2> and <256, 1>.  The operand fetch of an MMA reads 128 A rows whatever N is, and the
 // kernel is shared-memory-bandwidth bound, so layers with >= 256 output channels use N = 256 (half the A traffic per FLOP).
 __host__ __device__ constexpr int w_stages_for(int NT) { return NT == 256 ? 3 : 4; }
-constexpr int CHUNK_TAPS = 3;   // live taps accumulated in TMEM before the partial sum is drained (18 truncating accumulates)
+constexpr int CHUNK_TAPS = 3;   // live taps accumulated in TMEM before the partial sum is drained (18 truncating accumulates).
+// Longer chunks were tried (GG_CHUNK_TAPS, up to 9 = one drain per K-block: +5..25 % throughput) and rejected: truncation
+// removes ~0.5 ulp of the RUNNING sum at every accumulate, i.e. term i of an n-term chain ends up weighted by 1 - beta (n - i):
+// after the mean compensation a linear ramp of +-beta n/2 over the chain is left, which acts like a tiny but COHERENT
+// perturbation of the filter taps.  A single conv stays at 2e-6, but gradient sums over all pixels (noise strengths, biases,
+// weights) add that error coherently against a random-walk-sized signal: the Gmain parity test goes from 4e-6 to 1.3e-3.
 constexpr int CONS_WARPS = 8;
 constexpr int CONS_THREADS = CONS_WARPS * 32;
 constexpr int PROD_WARPS = 4;           // one warpgroup: TMA(x), TMA(weights), MMA, idle -- so that setmaxnreg can shift registers
@@ -103,6 +108,7 @@ struct TcP {
     int Nimg, I, O, OH, OW, K, pad_y, pad_x;
     int tiles_x, tiles_y, n_tiles, num_kb, nprod, total_tiles;
     int boxW, boxH;            // converted halo tile in pixels; boxW is its smem pixel pitch
+    int chunk_taps;            // live taps accumulated in TMEM before the partial sum is drained (<= CHUNK_TAPS)
     int rawW;                  // width of the raw TMA box (>= boxW: the box must start on a 16-byte boundary in global memory)
 };
 
@@ -328,7 +334,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
                             accf = 1u;
                             --left;
-                            if (++in_chunk == CHUNK_TAPS || left == 0) {   // close the chunk: its partial sums are complete in TMEM
+                            if (++in_chunk == p.chunk_taps || left == 0) {   // close the chunk: its partial sums are complete in TMEM
                                 umma_commit(BAR_ACC_FULL(ac & 1));
                                 ++ac; in_chunk = 0;
                             }
@@ -407,8 +413,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         };
 
         auto drain = [&](uint32_t first_chunk, int live) {   // all chunks of one K-block, with the truncation compensation
-            for (int c = 0; live > 0; ++c, live -= CHUNK_TAPS)
-                drain_chunk(first_chunk + c, rz_compensation(2 * min(live, CHUNK_TAPS), p.nprod));
+            for (int c = 0; live > 0; ++c, live -= p.chunk_taps)
+                drain_chunk(first_chunk + c, rz_compensation(2 * min(live, p.chunk_taps), p.nprod));
         };
 
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -448,8 +454,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 const float* raw = reinterpret_cast<const float*>(gbase + L.raw(s));
                 float4* hi = reinterpret_cast<float4*>(gbase + L.cvt(s, 0));
                 float4* lo = reinterpret_cast<float4*>(gbase + L.cvt(s, 1));
-                // The conversion of K-block j is interleaved with draining the chunks of K-block j-1: each chunk is read out of
-                // TMEM shortly after the tensor core finished it, so the issuer never waits for a free accumulator set.
+                // K-block j is converted and published FIRST, then the partial sums of K-block j-1 are drained: the tensor core goes
+                // from the MMAs of j-1 straight to those of j (other TMEM set) while the drain of j-1 runs next to them.
                 int pend_left = pend ? pend_live : 0;
                 uint32_t pend_chunk = pend_ac;
 #pragma unroll
@@ -471,22 +477,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         hi[idx] = h;
                         lo[idx] = l;
                     }
-                    if ((it & 1) && it + 1 < CVT_ITEMS && pend_left > 0) {     // after every second item: one finished chunk
-                        drain_chunk(pend_chunk++, rz_compensation(2 * min(pend_left, CHUNK_TAPS), p.nprod));
-                        pend_left -= CHUNK_TAPS;
-                    }
                 }
                 fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(BAR_CVT_FULL(s)); mbar_arrive(BAR_RAW_EMPTY(s)); }
                 if (pend) {
-                    for (; pend_left > 0; pend_left -= CHUNK_TAPS)
-                        drain_chunk(pend_chunk++, rz_compensation(2 * min(pend_left, CHUNK_TAPS), p.nprod));
+                    for (; pend_left > 0; pend_left -= p.chunk_taps)
+                        drain_chunk(pend_chunk++, rz_compensation(2 * min(pend_left, p.chunk_taps), p.nprod));
                     if (pend_last) store_tile(pend_tc);
                 }
                 pend = true; pend_last = (kb == M.last_kb); pend_tc = tc;
                 pend_ac = ac; pend_live = __popc(live);
-                ac += (pend_live + CHUNK_TAPS - 1) / CHUNK_TAPS;
+                ac += (pend_live + p.chunk_taps - 1) / p.chunk_taps;
                 ++kbc;
             }
         }
@@ -615,6 +617,7 @@ int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int
     if (total > 0x7fffffffLL) { cudaFreeAsync(wp, st); set_error("conv2d(tc): too many tiles"); return GG_EINVAL; }
     p.total_tiles = (int)total;
     p.boxW = boxW; p.boxH = boxH; p.rawW = rawW;
+    { const char* e = getenv("GG_CHUNK_TAPS"); const int v = e ? atoi(e) : CHUNK_TAPS; p.chunk_taps = v < 1 ? 1 : (v > 9 ? 9 : v); }
     int rc;
     if (NT == 256) rc = launch_conv_tc<256, 1>(xmap, p, st);
     else if (NT == 128) rc = launch_conv_tc<128, 2>(xmap, p, st);
