@@ -188,35 +188,188 @@ int launch_tile(const Params& p, cudaStream_t st) {
 
 
 // ------------------------------------------------------------------------------------------------
-// fir_stream<IN_PM, OUT_PM>: 4x4 FIR at unit rate (up = down = 1) that streams rows through registers and reads / writes
-// the PHASE-MAJOR layout of conv2d_resample.py on the fly, so that the space-to-depth / depth-to-space passes around the
-// tensor-core convolutions of the stride-2 layers cost no extra HBM traffic:
+// fir_stream<LAYOUT, PX0>: 4x4 FIR at unit rate (up = down = 1) that reads / writes the PHASE-MAJOR layout of
+// conv2d_resample.py on the fly, so that the space-to-depth / depth-to-space passes around the tensor-core convolutions of
+// the stride-2 layers cost no extra HBM traffic:
 //
 //   phase-major tensor  t_pm[n, (py,px,c), Y, X]  <->  logical image  t[n, c, 2Y+py, 2X+px]
 //
-//   IN_PM : the input is phase-major [N,4C,pmH,pmW]; logical pixels outside (validH, validW) count as zero
-//   OUT_PM: the output is phase-major [N,4C,pmH,pmW]; logical pixels outside (outH, outW) are written as zero
+//   LAYOUT 0: plain -> plain
+//   LAYOUT 1: the input is phase-major [N,4C,ipH,ipW]; logical pixels outside (inH, inW) count as zero
+//   LAYOUT 2: the output is phase-major [N,4C,opH,opW]; logical pixels outside (outH, outW) are written as zero
 //
-// One thread produces OXT consecutive output columns of RY consecutive rows: every input row is loaded once (scalar,
-// coalesced across the warp; the 3-column overlap between neighbouring threads is an L1 hit) and feeds the up-to-4 output
-// rows it contributes to.  Stores are 128-bit.
+// One thread owns 8 output columns and MARCHES DOWN a strip of RS rows: every input row is loaded once (the 3 halo rows of a
+// strip twice), runs through the horizontal taps, and updates three running partial sums -- the rows of the vertical taps that
+// are still open -- so an output row leaves the thread three input rows after its first contribution.  The loads of the row
+// two steps ahead are in flight while a row is processed (~200 bytes per thread in flight, 4-5 CTAs of 128 threads per SM:
+// enough to cover the HBM latency-bandwidth product).  PX0 = padx0 (0..3) is a template parameter: the position of every
+// needed column relative to the thread's aligned 8-column block is a compile-time constant, so a row is 2 aligned 128-bit
+// loads plus the left / right halo (a 128-bit load each, of which only the needed lanes are kept); threads whose blocks stick
+// out of the image (and rows outside it) take guarded scalar loads -- that is the zero padding.  Index math is integer and exact.
 struct StreamP {
     const float* x; const float* f; float* y;
-    int N, C, inH, inW, padx0, pady0, flip;     // logical input extent (IN_PM: the valid extent)
+    int N, C, inH, inW, padx0, pady0, flip;     // logical input extent (LAYOUT 1: the valid extent)
     float gain;
     int outH, outW;                             // logical (valid) output extent
-    int ipH, ipW, opH, opW;                     // phase-major plane sizes (IN_PM / OUT_PM)
+    int ipH, ipW, opH, opW;                     // phase-major plane sizes (LAYOUT 1 / 2)
+    int RS, ncg, nst;                           // rows per strip, 8-column groups per row, strips per plane
 };
 
-// LAYOUT 0: plain -> plain, 1: phase-major in -> plain out, 2: plain in -> phase-major out.  PX0 = padx0 (0..3) is a template
-// parameter so that the position of every needed input column inside the aligned 128-bit blocks is known at compile time.
-// One thread = 8 output columns x 8 output rows; per input row it issues 4 (plain) or 6 (phase-major: 3 per column phase)
-// aligned 128-bit loads; rows and column blocks that stick out of the image take a guarded scalar path.
-template <int LAYOUT, int PX0>
-__global__ void __launch_bounds__(256) fir_stream(StreamP p) {
+template <int LAYOUT, int PX0, bool SEP>
+__device__ __forceinline__ void fir_march(const StreamP& p, const float (&K)[4][4], const float (&fx)[4], const float (&fy)[4],
+                                          int x0, int y0, int n, int c) {
     constexpr bool IN_PM = LAYOUT == 1, OUT_PM = LAYOUT == 2;
-    constexpr int OXT = 8, RY = 8;
-    constexpr int NB = IN_PM ? 3 : 4;                 // 128-bit blocks per row (and per column phase for IN_PM)
+    const int fullH = OUT_PM ? 2 * p.opH : p.outH;
+    const int nrows = min(p.RS, fullH - y0);
+    const int nt = nrows + 3;                                   // input rows this strip touches
+    const int rbase = y0 - p.pady0;                             // logical input row of step 0
+    const int pitch = IN_PM ? p.ipW : p.inW;
+    const size_t iplane = IN_PM ? (size_t)p.ipH * p.ipW : (size_t)p.inH * p.inW;
+    const float* xin = p.x + (IN_PM ? ((size_t)n * 4 * p.C + c) * iplane : ((size_t)n * p.C + c) * iplane);
+    const int h0 = x0 >> 1;                                     // IN_PM: first phase-major column of the thread's block
+
+    // One input row -> in[0..10] = logical columns x0 - PX0 .. x0 - PX0 + 10 (zero outside the image).
+    auto load_row = [&](int rr, float (&in)[11]) {
+        const int r = rbase + rr;
+        const bool row_ok = (unsigned)r < (unsigned)p.inH;
+        if (!IN_PM) {
+            const float* rowp = xin + (size_t)(row_ok ? r : 0) * pitch + x0;
+            float buf[16];                                       // columns x0-4 .. x0+11
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                if (b == 0 && PX0 == 0) continue;                // left halo not needed
+                if (b == 3 && PX0 == 3) continue;                // right halo not needed
+                const int cb = x0 - 4 + 4 * b;
+                if (row_ok && cb >= 0 && cb + 3 < p.inW) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(rowp - 4 + 4 * b));
+                    buf[4 * b] = v.x; buf[4 * b + 1] = v.y; buf[4 * b + 2] = v.z; buf[4 * b + 3] = v.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        buf[4 * b + e] = (row_ok && cb + e >= 0 && cb + e < p.inW) ? __ldg(rowp - 4 + 4 * b + e) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 11; ++j) in[j] = buf[4 - PX0 + j];
+        } else {
+            // logical column x0 - PX0 + j lives in column phase ph = (j - PX0) & 1 at phase-major column h0 + (j - PX0 - ph) / 2
+            float buf[2][8];                                     // phase-major columns h0-2 .. h0+5 of both column phases
+            const int py = r & 1;
+#pragma unroll
+            for (int ph = 0; ph < 2; ++ph) {
+                const float* rowp = xin + (size_t)((py * 2 + ph) * p.C) * iplane + (size_t)(row_ok ? (r >> 1) : 0) * pitch + h0;
+                const int vcols = (p.inW - ph + 1) >> 1;        // valid phase-major columns of this phase
+                // left pair (h0-2, h0-1), middle quad (h0 .. h0+3), right pair (h0+4, h0+5)
+                if (row_ok && h0 >= 2 && h0 - 1 < vcols) {
+                    const float2 v = __ldg(reinterpret_cast<const float2*>(rowp - 2));
+                    buf[ph][0] = v.x; buf[ph][1] = v.y;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) buf[ph][e] = (row_ok && h0 - 2 + e >= 0 && h0 - 2 + e < vcols) ? __ldg(rowp - 2 + e) : 0.f;
+                }
+                if (row_ok && h0 + 3 < vcols) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(rowp));
+                    buf[ph][2] = v.x; buf[ph][3] = v.y; buf[ph][4] = v.z; buf[ph][5] = v.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) buf[ph][2 + e] = (row_ok && h0 + e < vcols) ? __ldg(rowp + e) : 0.f;
+                }
+                if (row_ok && h0 + 5 < vcols) {
+                    const float2 v = __ldg(reinterpret_cast<const float2*>(rowp + 4));
+                    buf[ph][6] = v.x; buf[ph][7] = v.y;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) buf[ph][6 + e] = (row_ok && h0 + 4 + e < vcols) ? __ldg(rowp + 4 + e) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 11; ++j) {
+                const int d = j - PX0;                           // compile-time after unrolling
+                const int ph = d & 1;
+                in[j] = buf[ph][(d - ph) / 2 + 2];
+            }
+        }
+    };
+
+    float* yout = OUT_PM ? p.y + ((size_t)n * 4 * p.C + c) * ((size_t)p.opH * p.opW) : p.y + ((size_t)n * p.C + c) * ((size_t)p.outH * p.outW);
+    const bool vec_out = OUT_PM || ((p.outW & 3) == 0 && x0 + 7 < p.outW && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+    auto store_row = [&](int y, const float (&o)[8]) {
+        if (OUT_PM) {
+            // logical (y, x0 + 2X' + px) -> plane (y&1, px, c), row y>>1, columns x0/2 + X'
+            float v[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = (y < p.outH && x0 + t < p.outW) ? o[t] : 0.f;
+            const size_t oplane = (size_t)p.opH * p.opW;
+            float* base = yout + (size_t)((y & 1) * 2) * p.C * oplane + (size_t)(y >> 1) * p.opW + (x0 >> 1);
+            *reinterpret_cast<float4*>(base) = make_float4(v[0], v[2], v[4], v[6]);
+            *reinterpret_cast<float4*>(base + (size_t)p.C * oplane) = make_float4(v[1], v[3], v[5], v[7]);
+        } else {
+            if (y >= p.outH) return;
+            float* dst = yout + (size_t)y * p.outW + x0;
+            if (vec_out) {
+                *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    if (x0 + t < p.outW) dst[t] = o[t];
+            }
+        }
+    };
+
+    // running partial sums of the three output rows that are still open: A is the oldest (one vertical tap missing)
+    float A[8], B[8], Cc[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { A[t] = 0.f; B[t] = 0.f; Cc[t] = 0.f; }
+    auto step = [&](int rr, const float (&in)[11]) {
+        float o[8];
+        if (SEP) {
+            // rank-1 filter (setup_filter builds the 2-D [1,3,3,1] filter as an outer product): horizontal pass once per input
+            // row, then one FMA per open output row
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const float h = fmaf(fx[3], in[t + 3], fmaf(fx[2], in[t + 2], fmaf(fx[1], in[t + 1], fx[0] * in[t])));
+                o[t] = fmaf(fy[3], h, A[t]);
+                A[t] = fmaf(fy[2], h, B[t]);
+                B[t] = fmaf(fy[1], h, Cc[t]);
+                Cc[t] = fy[0] * h;
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                float o3 = A[t], o2 = B[t], o1 = Cc[t], o0 = 0.f;
+#pragma unroll
+                for (int kx = 0; kx < 4; ++kx) {
+                    o3 = fmaf(K[3][kx], in[t + kx], o3);
+                    o2 = fmaf(K[2][kx], in[t + kx], o2);
+                    o1 = fmaf(K[1][kx], in[t + kx], o1);
+                    o0 = fmaf(K[0][kx], in[t + kx], o0);
+                }
+                o[t] = o3; A[t] = o2; B[t] = o1; Cc[t] = o0;
+            }
+        }
+        if (rr >= 3) store_row(y0 + rr - 3, o);
+    };
+
+    float r0[11], r1[11], r2[11];
+    load_row(0, r0);
+    load_row(1, r1);
+    for (int rr = 0; rr < nt; rr += 3) {
+        if (rr + 2 < nt) load_row(rr + 2, r2);
+        step(rr, r0);
+        if (rr + 1 < nt) {
+            if (rr + 3 < nt) load_row(rr + 3, r0);
+            step(rr + 1, r1);
+        }
+        if (rr + 2 < nt) {
+            if (rr + 4 < nt) load_row(rr + 4, r1);
+            step(rr + 2, r2);
+        }
+    }
+}
+
+template <int LAYOUT, int PX0>
+__global__ void __launch_bounds__(128, 4) fir_stream(StreamP p) {
     __shared__ float sK[16];
     if (threadIdx.x < 16) {
         int ky = threadIdx.x >> 2, kx = threadIdx.x & 3;
@@ -239,141 +392,29 @@ __global__ void __launch_bounds__(256) fir_stream(StreamP p) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) separable = separable && fabsf(K[i >> 2][i & 3] - fy[i >> 2] * fx[i & 3]) <= 1e-7f * amax;
     }
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x0 = (blockIdx.x * 32 + lane) * OXT;
-    const int y0 = (blockIdx.y * 8 + warp) * RY;
-    const int fullW = OUT_PM ? 2 * p.opW : p.outW, fullH = OUT_PM ? 2 * p.opH : p.outH;
-    if (x0 >= fullW || y0 >= fullH) return;
-    const int pitch = IN_PM ? p.ipW : p.inW;          // floats per stored input row
-    const size_t iplane = IN_PM ? (size_t)p.ipH * p.ipW : (size_t)p.inH * p.inW;
-    // first column of block 0 in the stored row: logical x0-4 (plain) or phase-major column x0/2-4
-    const int cb0 = IN_PM ? (x0 >> 1) - 4 : x0 - 4;
-    const int climit = IN_PM ? p.ipW : p.inW;         // stored columns
-    // the valid extent may end inside the stored row (IN_PM): logical col < inW  <=>  2X+px < inW
-    for (int nc = blockIdx.z; nc < p.N * p.C; nc += gridDim.z) {
-        const int n = nc / p.C, c = nc - n * p.C;
-        const float* xin = p.x + (IN_PM ? ((size_t)n * 4 * p.C + c) * iplane : (size_t)nc * iplane);
-
-        float acc[RY][OXT];
-#pragma unroll
-        for (int r = 0; r < RY; ++r)
-#pragma unroll
-            for (int t = 0; t < OXT; ++t) acc[r][t] = 0.f;
-
-#pragma unroll
-        for (int rr = 0; rr < RY + 3; ++rr) {
-            const int r = y0 + rr - p.pady0;                    // logical input row
-            const bool row_ok = r >= 0 && r < p.inH;
-            float in[OXT + 3];
-            if (!IN_PM) {
-                float buf[4 * NB];
-                const float* rowp = xin + (size_t)(row_ok ? r : 0) * pitch;
-#pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    const int cb = cb0 + 4 * b;
-                    if (row_ok && cb >= 0 && cb + 3 < climit) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(rowp + cb));
-                        buf[4 * b] = v.x; buf[4 * b + 1] = v.y; buf[4 * b + 2] = v.z; buf[4 * b + 3] = v.w;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            buf[4 * b + e] = (row_ok && cb + e >= 0 && cb + e < climit) ? __ldg(rowp + cb + e) : 0.f;
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < OXT + 3; ++j) in[j] = buf[4 - PX0 + j];
-            } else {
-                // logical column x0 - PX0 + j lives in column phase ph = (j - PX0) & 1 at phase-major column x0/2 + (j - PX0 - ph)/2
-                float buf[2][4 * NB];
-                const int py = r & 1;
-#pragma unroll
-                for (int ph = 0; ph < 2; ++ph) {
-                    const float* rowp = xin + (size_t)((py * 2 + ph) * p.C) * iplane + (size_t)(row_ok ? (r >> 1) : 0) * pitch;
-                    const int vcols = (p.inW - ph + 1) >> 1;    // valid phase-major columns of this phase
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) {
-                        const int cb = cb0 + 4 * b;
-                        if (row_ok && cb >= 0 && cb + 3 < vcols) {
-                            const float4 v = __ldg(reinterpret_cast<const float4*>(rowp + cb));
-                            buf[ph][4 * b] = v.x; buf[ph][4 * b + 1] = v.y; buf[ph][4 * b + 2] = v.z; buf[ph][4 * b + 3] = v.w;
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                buf[ph][4 * b + e] = (row_ok && cb + e >= 0 && cb + e < vcols) ? __ldg(rowp + cb + e) : 0.f;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < OXT + 3; ++j) {
-                    constexpr int dummy = 0; (void)dummy;
-                    const int d = j - PX0;                       // compile-time after unrolling
-                    const int ph = d & 1;
-                    in[j] = buf[ph][4 + (d - ph) / 2];
-                }
-            }
-            if (separable) {
-                // rank-1 filter (setup_filter builds the 2-D [1,3,3,1] filter as an outer product): horizontal pass once per input
-                // row, then one FMA per output row -- 8 instead of 16 FMAs per output
-                float h[OXT];
-#pragma unroll
-                for (int t = 0; t < OXT; ++t)
-                    h[t] = fmaf(fx[3], in[t + 3], fmaf(fx[2], in[t + 2], fmaf(fx[1], in[t + 1], fx[0] * in[t])));
-#pragma unroll
-                for (int ky = 0; ky < 4; ++ky) {
-                    const int yy = rr - ky;
-                    if (yy < 0 || yy >= RY) continue;
-#pragma unroll
-                    for (int t = 0; t < OXT; ++t) acc[yy][t] = fmaf(fy[ky], h[t], acc[yy][t]);
-                }
-            } else {
-#pragma unroll
-                for (int ky = 0; ky < 4; ++ky) {
-                    const int yy = rr - ky;                      // output row (relative) fed through filter row ky
-                    if (yy < 0 || yy >= RY) continue;            // compile-time after unrolling
-#pragma unroll
-                    for (int t = 0; t < OXT; ++t)
-#pragma unroll
-                        for (int kx = 0; kx < 4; ++kx) acc[yy][t] = fmaf(K[ky][kx], in[t + kx], acc[yy][t]);
-                }
-            }
-        }
-
-#pragma unroll
-        for (int r = 0; r < RY; ++r) {
-            const int y = y0 + r;
-            if (y >= fullH) continue;
-            if (OUT_PM) {
-                // logical (y, x0 + 2X' + px) -> plane (y&1, px, c), row y>>1, columns x0/2 + X'
-                float v[OXT];
-#pragma unroll
-                for (int t = 0; t < OXT; ++t) v[t] = (y < p.outH && x0 + t < p.outW) ? acc[r][t] : 0.f;
-                const size_t oplane = (size_t)p.opH * p.opW;
-                float* base = p.y + ((size_t)n * 4 * p.C + (size_t)((y & 1) * 2) * p.C + c) * oplane + (size_t)(y >> 1) * p.opW + (x0 >> 1);
-                *reinterpret_cast<float4*>(base) = make_float4(v[0], v[2], v[4], v[6]);
-                *reinterpret_cast<float4*>(base + (size_t)p.C * oplane) = make_float4(v[1], v[3], v[5], v[7]);
-            } else {
-                float* dst = p.y + (size_t)nc * p.outH * p.outW + (size_t)y * p.outW + x0;
-                if ((p.outW & 3) == 0 && x0 + 7 < p.outW) {
-                    *reinterpret_cast<float4*>(dst) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-                    *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
-                } else {
-#pragma unroll
-                    for (int t = 0; t < OXT; ++t)
-                        if (x0 + t < p.outW) dst[t] = acc[r][t];
-                }
-            }
-        }
-    }
+    // thread -> (8-column group, row strip, plane); column groups fastest, so a warp reads contiguous row segments and narrow
+    // images still fill their warps (with neighbouring strips / planes)
+    const long long id = (long long)blockIdx.x * 128 + threadIdx.x;
+    const int cg = (int)(id % p.ncg);
+    const long long r = id / p.ncg;
+    const int st = (int)(r % p.nst);
+    const long long nc = r / p.nst;
+    if (nc >= (long long)p.N * p.C) return;
+    const int n = (int)(nc / p.C), c = (int)(nc - (long long)n * p.C);
+    if (separable) fir_march<LAYOUT, PX0, true>(p, K, fx, fy, cg * 8, st * p.RS, n, c);
+    else fir_march<LAYOUT, PX0, false>(p, K, fx, fy, cg * 8, st * p.RS, n, c);
 }
 
 template <int LAYOUT, int PX0>
-int launch_stream2(const StreamP& p, cudaStream_t st) {
-    constexpr int OXT = 8, RY = 8;
+int launch_stream2(StreamP p, cudaStream_t st) {
     const int fullW = LAYOUT == 2 ? 2 * p.opW : p.outW, fullH = LAYOUT == 2 ? 2 * p.opH : p.outH;
-    dim3 grid((unsigned)((fullW + 32 * OXT - 1) / (32 * OXT)), (unsigned)((fullH + 8 * RY - 1) / (8 * RY)),
-              (unsigned)(p.N * p.C < 65535 ? p.N * p.C : 65535));
-    fir_stream<LAYOUT, PX0><<<grid, 256, 0, st>>>(p);
+    p.RS = fullH >= 128 ? 32 : (fullH >= 32 ? 16 : 8);
+    p.ncg = (fullW + 7) / 8;
+    p.nst = (fullH + p.RS - 1) / p.RS;
+    const long long threads = (long long)p.ncg * p.nst * p.N * p.C;
+    const long long blocks = (threads + 127) / 128;
+    if (blocks > 0x7fffffffLL) { gg::set_error("upfirdn2d: grid too large"); return GG_EINVAL; }
+    fir_stream<LAYOUT, PX0><<<(unsigned)blocks, 128, 0, st>>>(p);
     return gg::check_launch("upfirdn2d(fir_stream)");
 }
 
@@ -415,7 +456,7 @@ extern "C" GG_API int gg_upfirdn2d_f32(const float* x, const float* f, float* y,
 
     const bool f4 = (fH == 4 && fW == 4) && upx == upy && downx == downy && outW >= 48;
     if (f4 && upx == 1 && downx == 1) {   // unit rate: the register-streaming kernel (also serves the phase-major layouts)
-        StreamP sp{x, f, y, N, C, inH, inW, padx0, pady0, flip, gain, outH, outW, 0, 0, 0, 0};
+        StreamP sp{x, f, y, N, C, inH, inW, padx0, pady0, flip, gain, outH, outW, 0, 0, 0, 0, 0, 0, 0};
         if (stream_ok(sp, false)) return launch_stream<0>(sp, st);
         return launch_tile<1, 1, 0, 4, 4>(p, st);
     }
@@ -445,7 +486,7 @@ extern "C" GG_API int gg_fir4_pm_f32(const float* x, const float* f, float* y, i
     GG_REQUIRE((int64_t)N * C * (in_pm ? 4LL * in_pmH * in_pmW : (int64_t)inH * inW) <= 0x7fffffffLL &&
                (int64_t)N * C * (out_pm ? 4LL * out_pmH * out_pmW : (int64_t)outH * outW) <= 0x7fffffffLL, "fir4_pm: tensor is too large");
     if (N == 0) return GG_OK;
-    StreamP p{x, f, y, N, C, inH, inW, padx0, pady0, flip, gain, outH, outW, in_pmH, in_pmW, out_pmH, out_pmW};
+    StreamP p{x, f, y, N, C, inH, inW, padx0, pady0, flip, gain, outH, outW, in_pmH, in_pmW, out_pmH, out_pmW, 0, 0, 0};
     cudaStream_t st = (cudaStream_t)stream;
     GG_REQUIRE(stream_ok(p, in_pm != 0), "fir4_pm: needs 0 <= padx0 <= 3 and 16-byte aligned input rows (width %% 4 == 0)");
     if (in_pm) return launch_stream<1>(p, st);

@@ -524,3 +524,98 @@ def test_bias_act_with_folded_noise(ops, device, shape, const_noise):
     gg_ = torch.autograd.grad(got, ds, dy.to(device))
     for name, a_, b_ in zip(['dx', 'db', 'dnoise'], gg_, wg):
         assert_close(a_, b_, 2e-6, name)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# TMA-fed weight-gradient kernel (csrc/wgrad_tma.cu): G operand in tensor memory, kx shift applied by the converters
+
+def _wgrad_oracle(x, dy, k, pad, a=None, b=None):
+    """dw[o,i,ky,kx] = sum dy[n,o,y,x] * x[n,i,y+ky-pad,x+kx-pad] in fp64 through autograd of the CPU conv
+    (conv2d_gradfix.py:175-191); dy may be smaller / larger than the natural output: positions outside x read as zero."""
+    xd = (x if a is None else x * a[:, :, None, None]).double()
+    dyd = (dy if b is None else dy * b[:, :, None, None]).double()
+    N, I, H, W = xd.shape
+    OH, OW = dyd.shape[2:]
+    # pad x on the bottom/right so that the natural output covers dy's extent (extra rows/cols are zero = "outside x")
+    eh, ew = max(0, OH + k - 1 - 2 * pad - H), max(0, OW + k - 1 - 2 * pad - W)
+    xp = torch.nn.functional.pad(xd, (0, ew, 0, eh))
+    w = torch.zeros(dyd.shape[1], I, k, k, dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.conv2d(xp, w, padding=pad)[:, :, :OH, :OW]
+    dw, = torch.autograd.grad(y, w, dyd)
+    return dw
+
+
+@pytest.mark.parametrize('case', [
+    # N, A, HA, WA, B, HB, WB, k, pad
+    (4, 32, 16, 16, 32, 16, 16, 3, 1),      # 32-channel tile: three kx slots stacked in one MMA
+    (2, 64, 32, 32, 64, 32, 32, 3, 1),      # two kx slots + one
+    (2, 48, 24, 24, 40, 24, 24, 3, 1),      # channel tails on both operands
+    (1, 160, 16, 20, 136, 16, 20, 3, 1),    # several tiles per operand, one kx per CTA group, width % 16 != 0
+    (2, 64, 17, 20, 32, 16, 16, 2, 0),      # phase-major down form: a larger than b
+    (2, 32, 16, 16, 128, 17, 20, 2, 1),     # phase-major up form: b larger than a (reads outside a count as zero)
+    (3, 96, 12, 12, 96, 12, 12, 1, 0),      # 1x1
+    (2, 32, 40, 8, 32, 40, 8, 3, 1),        # narrow maps (width < one 16-pixel strip)
+    (2, 32, 35, 36, 64, 35, 36, 3, 2),      # rows % 16 != 0, "full" padding
+])
+@pytest.mark.parametrize('flip,layout', [(False, 0), (True, 1)])
+def test_wgrad_tma_kernel_vs_oracle(ops, device, case, flip, layout):
+    N, A, HA, WA, B, HB, WB, k, pad = case
+    co = ops.custom_ops
+    plugin = co.get_plugin('conv2d_plugin')
+    g = torch.Generator().manual_seed(A * 31 + B + k)
+    x = torch.randn(N, A, HA, WA, generator=g); dy = torch.randn(N, B, HB, WB, generator=g)
+    a = torch.rand(N, A, generator=g) + 0.5; b = torch.rand(N, B, generator=g) + 0.5
+    want = _wgrad_oracle(x, dy, k, pad, a, b)
+    if flip:
+        want = want.flip([2, 3])
+    if layout:
+        want = want.transpose(0, 1)
+    got = plugin.conv2d_wgrad(x.to(device), dy.to(device), (k, k), padding=(pad, pad), flip_w=flip, out_layout=layout,
+                              a_scale=a.to(device), b_scale=b.to(device), prec=co.PREC_TF32X3)
+    assert plugin.last_wgrad_prec == 3 and tuple(got.shape) == tuple(want.shape)
+    assert_close(got, want.float(), 1e-5, 'wgrad(tma)')
+
+
+def test_wgrad_unaligned_rows_take_the_global_load_kernel(ops, device):
+    # row pitches that are not multiples of 16 bytes cannot be TMA sources: wgrad_tc.cu's kernel serves them, same results
+    co = ops.custom_ops
+    plugin = co.get_plugin('conv2d_plugin')
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 32, 33, 21, generator=g); dy = torch.randn(2, 32, 33, 21, generator=g)
+    want = _wgrad_oracle(x, dy, 3, 1)
+    got = plugin.conv2d_wgrad(x.to(device), dy.to(device), (3, 3), padding=(1, 1), prec=co.PREC_TF32X3)
+    assert_close(got, want.float(), 1e-5, 'wgrad(ldg)')
+
+
+@pytest.mark.parametrize('kind,N,I,O,R,skips', [('down', 2, 64, 128, 32, True), ('down', 2, 32, 64, 64, True), ('up', 2, 128, 128, 16, True),
+                                                ('up', 2, 64, 32, 32, False),     # all four phases share one 128-row tile: nothing to skip
+                                                ('up', 2, 32, 64, 16, True)])
+def test_wgrad_phase_major_hint_skips_only_dead_taps(ops, device, kind, N, I, O, R, skips):
+    """gg_conv2d_wgrad_pm_f32: with the structural hint the entries that are zero by construction in the phase-major weight
+    (conv2d_resample.phase_major_weight_down / _up) may be left zero; every live entry must be unchanged."""
+    co = ops.custom_ops
+    cr = ops.conv2d_resample
+    plugin = co.get_plugin('conv2d_plugin')
+    g = torch.Generator().manual_seed(R + I)
+    w2 = (cr.phase_major_weight_down if kind == 'down' else cr.phase_major_weight_up)(torch.ones(O, I, 3, 3))
+    live = cr._pm_live(kind, 3, 3)
+    if kind == 'down':      # x phase-major [N,4I,R/2+1,..], dy [N,O,R/2,R/2], pad 0
+        x = torch.randn(N, 4 * I, R // 2 + 1, (R // 2 + 1 + 3) // 4 * 4, generator=g); dy = torch.randn(N, O, R // 2, R // 2, generator=g)
+        pad = 0
+    else:                   # x [N,I,R,R], dy phase-major [N,4O,R+1,..], pad 1
+        x = torch.randn(N, I, R, R, generator=g); dy = torch.randn(N, 4 * O, R + 1, (R + 1 + 3) // 4 * 4, generator=g)
+        pad = 1
+    for flip, layout in ((False, 0), (True, 1)):
+        full = plugin.conv2d_wgrad(x.to(device), dy.to(device), (2, 2), padding=(pad, pad), flip_w=flip, out_layout=layout, prec=co.PREC_TF32X3)
+        # the hint describes dw in the layout of the weight tensor itself; with out_layout=1 dim 0 <-> dim 1 swap roles
+        pm = live.pm if not layout else (3 - live.pm[0], live.pm[1])
+        hint = plugin.conv2d_wgrad(x.to(device), dy.to(device), (2, 2), padding=(pad, pad), flip_w=flip, out_layout=layout, prec=co.PREC_TF32X3, pm=pm)
+        mask = (w2 != 0)
+        if layout:
+            mask = mask.transpose(0, 1)
+        mask = mask.to(device)
+        assert float((hint - full).abs()[mask].max()) <= 1e-6 * float(full.abs().max()), 'live entries changed'
+        dead = hint[~mask]
+        assert (float((dead != 0).float().mean()) < 1.0) == skips   # something was skipped (when a tile lies inside a phase pair) ...
+        tol = 1e-6 * float(full.abs().max())                     # (atomic flush order differs between two launches)
+        assert bool(((dead == 0) | ((dead - full[~mask]).abs() <= tol)).all())  # ... and what was not skipped is the plain result
