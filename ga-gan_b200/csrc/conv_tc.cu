@@ -29,6 +29,7 @@
 //                setmaxnreg moves registers from the producer warpgroup to the two consumer warpgroups (128 accumulators/thread).
 #include "tc_common.cuh"
 #include <stdlib.h>
+#include <limits.h>
 
 using namespace ggtc;
 
@@ -208,10 +209,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
             mbar_init(BAR_RAW_FULL(s), 1); mbar_init(BAR_RAW_EMPTY(s), CONS_WARPS);
-            mbar_init(BAR_CVT_FULL(s), CONS_WARPS); mbar_init(BAR_CVT_EMPTY(s), 1);
-            mbar_init(BAR_ACC_FULL(s), 1); mbar_init(BAR_ACC_EMPTY(s), CONS_WARPS);
+            mbar_init(BAR_CVT_FULL(s), CONS_WARPS); mbar_init(BAR_CVT_EMPTY(s), SUBS);    // one commit per MMA issuer (one per sub-tile)
+            mbar_init(BAR_ACC_FULL(s), SUBS); mbar_init(BAR_ACC_EMPTY(s), CONS_WARPS);
         }
-        for (int s = 0; s < W_STAGES; ++s) { mbar_init(BAR_W_FULL(s), 1); mbar_init(BAR_W_EMPTY(s), 1); }
+        for (int s = 0; s < W_STAGES; ++s) { mbar_init(BAR_W_FULL(s), 1); mbar_init(BAR_W_EMPTY(s), SUBS); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(base + L.tmem_slot, TMEM_COLS);
@@ -263,10 +264,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 }
             }
         }
-    } else if (warp == 2) {
-        // ===== MMA issuer (one thread).  Descriptors are 64-bit adds on per-K-block bases: the issue loop has to stay well
-        // under the 64-cycle tensor-core time of one M=128 x N=128 x K=8 instruction.
+    } else if (warp == 2 || (SUBS == 2 && warp == 3)) {
+        // ===== MMA issuers: ONE THREAD PER SUB-TILE (warp 2: sub-tile 0, warp 3: sub-tile 1).  The issue loop is scalar code of a
+        // single thread -- ~100 dependent instructions per filter tap for 12 MMAs, ~7 cycles each (ncu source view) -- and for
+        // N <= 128 that, not the tensor core, set the pace.  The two sub-tiles have independent accumulators, so two threads on
+        // two different schedulers issue them side by side; every "empty" / "accumulator full" barrier counts one
+        // tcgen05.commit per issuer (a commit covers the MMAs of the thread that executes it).
         if (elect_one()) {
+            const uint32_t sub = (uint32_t)(warp - 2);
             uint32_t kbc = 0, ws = 0, wph = 0, ac = 0;          // K-block, weight-stage and accumulator-chunk counters
             const uint32_t idesc = umma_idesc_tf32(128, NT, 0, 0);
             // descriptor: bits [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, bit 46 = version 1
@@ -276,6 +281,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             const uint64_t b_word = ((uint64_t)(8u | (1u << 14)) << 32) | (((uint32_t)NT & 0x3FFFu) << 16);
             const uint32_t a_ks = 2u * (uint32_t)npix;          // second K=8 step: two 4-channel chunks further (16-byte units)
             constexpr uint32_t b_ks = 2u * NT, b_lo_off = 4u * NT;
+            const bool three = p.nprod == 3;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(t, p);
                 const uint32_t* mrow = p.mask + (size_t)tc.nt * p.num_kb;
@@ -287,8 +293,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     const uint32_t cs = kbc & 1, cph = (kbc >> 1) & 1;
                     mbar_wait(BAR_CVT_FULL(cs), cph);
                     tc_fence_after();
-                    const uint64_t a_hi0 = a_word + ((base + L.cvt(cs, 0)) >> 4), a_lo0 = a_word + ((base + L.cvt(cs, 1)) >> 4);
-                    uint32_t d0 = 0, d1 = 0;
+                    // sub-tile `sub` starts 8 pixels (8 x 16 bytes) to the right
+                    const uint64_t a_hi0 = a_word + ((base + L.cvt(cs, 0)) >> 4) + 8u * sub, a_lo0 = a_word + ((base + L.cvt(cs, 1)) >> 4) + 8u * sub;
+                    uint32_t d = 0;
                     uint32_t accf = 0u;                               // first MMA of a chunk overwrites the accumulator
                     uint32_t tap = 0;
                     int in_chunk = 0, left = __popc(m);
@@ -298,7 +305,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             if (in_chunk == 0) {                      // open a chunk: TMEM accumulator set ac & 1, drained two chunks ago
                                 const uint32_t as = ac & 1;
                                 mbar_wait(BAR_ACC_EMPTY(as), ((ac >> 1) & 1) ^ 1);
-                                d0 = tmem_base + as * SET_COLS; d1 = d0 + NT;
+                                d = tmem_base + as * SET_COLS + sub * NT;
                                 accf = 0u;
                             }
                             mbar_wait(BAR_W_FULL(ws), wph);
@@ -306,30 +313,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             const uint32_t toff = (uint32_t)(ky * p.boxW + kx);
                             const uint64_t b_hi0 = b_word + ((base + L.wst(ws)) >> 4), b_lo0 = b_hi0 + b_lo_off;
                             const uint64_t ah0 = a_hi0 + toff, al0 = a_lo0 + toff;
-                            if (p.nprod == 3) {
-                                // sub-tile 0 (x offset 0), K steps 0 and 1; then sub-tile 1 (x offset 8 pixels)
-                                umma_tf32(d0, ah0, b_hi0, idesc, accf);
-                                umma_tf32(d0, ah0, b_lo0, idesc, 1u);
-                                umma_tf32(d0, al0, b_hi0, idesc, 1u);
-                                umma_tf32(d0, ah0 + a_ks, b_hi0 + b_ks, idesc, 1u);
-                                umma_tf32(d0, ah0 + a_ks, b_lo0 + b_ks, idesc, 1u);
-                                umma_tf32(d0, al0 + a_ks, b_hi0 + b_ks, idesc, 1u);
-                                if (SUBS == 2) {
-                                    umma_tf32(d1, ah0 + 8u, b_hi0, idesc, accf);
-                                    umma_tf32(d1, ah0 + 8u, b_lo0, idesc, 1u);
-                                    umma_tf32(d1, al0 + 8u, b_hi0, idesc, 1u);
-                                    umma_tf32(d1, ah0 + 8u + a_ks, b_hi0 + b_ks, idesc, 1u);
-                                    umma_tf32(d1, ah0 + 8u + a_ks, b_lo0 + b_ks, idesc, 1u);
-                                    umma_tf32(d1, al0 + 8u + a_ks, b_hi0 + b_ks, idesc, 1u);
-                                }
-                            } else {
-                                umma_tf32(d0, ah0, b_hi0, idesc, accf);
-                                umma_tf32(d0, ah0 + a_ks, b_hi0 + b_ks, idesc, 1u);
-                                if (SUBS == 2) {
-                                    umma_tf32(d1, ah0 + 8u, b_hi0, idesc, accf);
-                                    umma_tf32(d1, ah0 + 8u + a_ks, b_hi0 + b_ks, idesc, 1u);
-                                }
-                            }
+                            umma_tf32(d, ah0, b_hi0, idesc, accf);                       // K step 0
+                            if (three) { umma_tf32(d, ah0, b_lo0, idesc, 1u); umma_tf32(d, al0, b_hi0, idesc, 1u); }
+                            umma_tf32(d, ah0 + a_ks, b_hi0 + b_ks, idesc, 1u);           // K step 1
+                            if (three) { umma_tf32(d, ah0 + a_ks, b_lo0 + b_ks, idesc, 1u); umma_tf32(d, al0 + a_ks, b_hi0 + b_ks, idesc, 1u); }
                             umma_commit(BAR_W_EMPTY(ws));          // frees the weight stage when these MMAs have read it
                             if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
                             accf = 1u;
@@ -368,6 +355,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         int pend_live = 0;                              // live taps of the pending K-block
         TileCoord pend_tc{0, 0, 0, 0};
         const size_t plane = (size_t)p.OH * p.OW;
+        int cvt_src[CVT_ITEMS];                         // conversion plan: source index in the raw box per (chunk, pixel) item
+        int plan_dx = INT_MIN, plan_dy = INT_MIN;
 
         auto store_tile = [&](const TileCoord& tc) {
             const int m = q * 32 + lane;                // accumulator row = pixel inside the 8x16 sub-tile
@@ -436,14 +425,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             const int ox0 = tc.tx * TILE_W, oy0 = tc.ty * TILE_H;
             const int cx = max((ox0 - p.pad_x) & ~3, 0), cy = max(oy0 - p.pad_y, 0);
             const int dx = (ox0 - p.pad_x) - cx, dy = (oy0 - p.pad_y) - cy;       // converted (r,c) <- raw (r+dy, c+dx)
-            int cvt_src[CVT_ITEMS];
+            // (the plan only depends on how the box had to be shifted / clamped, i.e. on (dx, dy): interior tiles share one plan,
+            //  and its ~60 integer divisions per thread are not repeated for every tile)
+            if (dx != plan_dx || dy != plan_dy) {
+                plan_dx = dx; plan_dy = dy;
 #pragma unroll
-            for (int it = 0; it < CVT_ITEMS; ++it) {
-                const int idx = ct + it * CONS_THREADS;
-                const int chunk = idx / npix, px = idx - chunk * npix;
-                const int rr = px / p.boxW + dy, cc = px % p.boxW + dx;
-                cvt_src[it] = (chunk < 4 && rr >= 0 && cc >= 0 && rr < p.boxH && cc < p.rawW) ? (chunk * 4) * rpix + rr * p.rawW + cc
-                                                                                               : (chunk < 4 ? -1 : -2);
+                for (int it = 0; it < CVT_ITEMS; ++it) {
+                    const int idx = ct + it * CONS_THREADS;
+                    const int chunk = idx / npix, px = idx - chunk * npix;
+                    const int rr = px / p.boxW + dy, cc = px % p.boxW + dx;
+                    cvt_src[it] = (chunk < 4 && rr >= 0 && cc >= 0 && rr < p.boxH && cc < p.rawW) ? (chunk * 4) * rpix + rr * p.rawW + cc
+                                                                                                   : (chunk < 4 ? -1 : -2);
+                }
             }
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 const uint32_t live = M.get(kb);
