@@ -277,14 +277,25 @@ def main():
     all_conv_ms = sum(v[2] for v in by_kind.values())
     tf32_peak = peaks['bf16_sustained'] / 2.0
     achieved = dom_flops / (dom_ms / 1000.0) / 1e12 if dom_ms > 0 else 0.0
-    roofline = dict(bound='tensor', achieved=achieved, peak=tf32_peak, unit='TFLOP/s', frac=achieved / tf32_peak, traffic=None,
+    # DRAM bytes per launch of the same kernel from the committed ncu --set full capture of this command (profiles/): bench.py cannot
+    # run a profiler itself, so the figure is read from the summary that tools/ncu_traffic.py wrote; null if there is none
+    traffic, traffic_note = None, 'no ncu capture committed'
+    tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if os.path.isfile(tpath):
+        try:
+            tj = json.load(open(tpath))
+            traffic, traffic_note = tj['conv_tc_kernel']['dram_bytes_per_launch'], tj['conv_tc_kernel']['note']
+        except Exception as e:      # a malformed summary must not break the bench line
+            traffic_note = f'unreadable {tpath}: {e}'
+    roofline = dict(bound='tensor', achieved=achieved, peak=tf32_peak, unit='TFLOP/s', frac=achieved / tf32_peak, traffic=traffic,
+                    traffic_note=traffic_note,
                     kernel='conv_tc_kernel (tcgen05 implicit-GEMM conv: forward + data gradient of every conv layer)',
                     launches=dom_launches, avg_launch_ms=(dom_ms / dom_launches if dom_launches else None),
                     algorithmic_flops_per_launch=(dom_flops / dom_launches if dom_launches else None),
                     share_of_step=dom_ms / ms_total, all_conv_kernels_share_of_step=all_conv_ms / ms_total,
                     peak_source=f'{peaks["source"]}: bf16 sustained {peaks["bf16_sustained"]} TF/s / 2 (TF32 dense = half of bf16)',
                     note='fp32 parity needs 3 TF32 products per MAC (hi*hi + hi*lo + lo*hi): the tensor pipe does 3x the algorithmic FLOPs, '
-                         'so frac <= 0.333 by construction; traffic (dram bytes per launch) is in profiles/r1f_conv_tc_*.txt for two layer shapes',
+                         'so frac <= 0.333 by construction',
                     by_kind={k: dict(launches=v[0], tflops=(v[1] / (v[2] / 1000.0) / 1e12 if v[2] > 0 else 0.0), ms=v[2]) for k, v in by_kind.items()})
 
     if rank != 0:
