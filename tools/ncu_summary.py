@@ -3,7 +3,7 @@
     python tools/ncu_summary.py gpurun_out/x.ncu-rep > profiles/x.txt"""
 import csv, io, re, subprocess, sys
 KEYS = [r'^gpu__time_duration\.sum$', r'^dram__bytes_read\.sum$', r'^dram__bytes_write\.sum$', r'^gpu__dram_throughput\.avg\.pct_of_peak_sustained_elapsed$',
-        r'sm__pipe_tensor_cycles_active_realtime\.avg\.pct_of_peak_sustained_elapsed$', r'^sm__throughput\.avg\.pct_of_peak_sustained_elapsed$',
+        r'sm__pipe_tensor_cycles_active_realtime\.avg\.pct_of_peak_sustained_elapsed$', r'^sm__throughput\.avg\.pct_of_peak_sustained_elapsed$', r'^sm__pipe_tensor_cycles_active\.avg\.pct_of_peak_sustained_(active|elapsed)$',
         r'^sm__warps_active\.avg\.pct_of_peak_sustained_active$', r'^launch__registers_per_thread$', r'^launch__grid_size$', r'^launch__block_size$',
         r'^launch__shared_mem_per_block_dynamic$', r'^lts__t_sector_hit_rate\.pct$', r'^l1tex__data_bank_conflicts_pipe_lsu_mem_shared\.sum$',
         r'^l1tex__data_pipe_lsu_wavefronts_mem_shared\.sum$', r'^smsp__inst_executed\.sum$', r'^sm__cycles_elapsed\.max$',
