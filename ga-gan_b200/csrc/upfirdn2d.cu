@@ -428,6 +428,198 @@ int launch_stream(const StreamP& p, cudaStream_t st) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fir_resample2<UP, PX0>: the true 2x cases of the 4x4 filter -- down2 (UP = false: D skip path, upfirdn2d.py:369-404) and
+// up2 (UP = true: image upsampling, the gradient of the skip path, upfirdn2d.py:329-364) -- with the marching scheme of
+// fir_stream: one thread walks down the INPUT rows of a strip, 128-bit aligned loads, running partial sums of the output rows
+// that are still open, 128-bit stores.
+//   down2: thread = 4 output columns (8 input columns + halo); input row j (relative to the first tap row of the strip) feeds
+//          filter rows ky = j mod 2 and ky + 2 of two output rows.
+//   up2  : thread = 8 output columns (4 input columns + halo); polyphase: every output has 2x2 live taps; input row r
+//          completes output rows q = 2r-3, 2r-2 and opens q = 2r-1, 2r   (q = oy - pady0).
+struct Res2P {
+    const float* x; const float* f; float* y;
+    int NC, inH, inW, padx0, pady0, flip;
+    float gain;
+    int outH, outW, RS, ncg, nst;               // RS = output rows per strip
+};
+
+template <bool UP, int PX0>
+__global__ void __launch_bounds__(128, 4) fir_resample2(Res2P p) {
+    __shared__ float sK[16];
+    if (threadIdx.x < 16) {
+        int ky = threadIdx.x >> 2, kx = threadIdx.x & 3;
+        int sy = p.flip ? ky : 3 - ky, sx = p.flip ? kx : 3 - kx;
+        sK[threadIdx.x] = p.gain * __ldg(p.f + sy * 4 + sx);
+    }
+    __syncthreads();
+    float K[4][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) K[i >> 2][i & 3] = sK[i];
+    const long long id = (long long)blockIdx.x * 128 + threadIdx.x;
+    const int cg = (int)(id % p.ncg);
+    const long long rr_ = id / p.ncg;
+    const int st = (int)(rr_ % p.nst);
+    const long long nc = rr_ / p.nst;
+    if (nc >= p.NC) return;
+    const float* xin = p.x + (size_t)nc * p.inH * p.inW;
+    float* yout = p.y + (size_t)nc * p.outH * p.outW;
+    const int oy0 = st * p.RS, nrows = min(p.RS, p.outH - oy0);
+    const bool y_al = (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 && (p.outW & 3) == 0;
+
+    if (!UP) {
+        const int ox0 = cg * 4, x0 = 2 * ox0;                   // x0: first input column of the aligned 8-column block
+        // in[j] = input column x0 - PX0 + j, j = 0..9 (zero outside the image)
+        auto load_row = [&](int r, float (&in)[11]) {
+            const bool row_ok = (unsigned)r < (unsigned)p.inH;
+            const float* rowp = xin + (size_t)(row_ok ? r : 0) * p.inW + x0;
+            float buf[16];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                if (b == 0 && PX0 == 0) continue;
+                if (b == 3 && PX0 >= 2) continue;                // columns up to x0 - PX0 + 9
+                const int cb = x0 - 4 + 4 * b;
+                if (row_ok && cb >= 0 && cb + 3 < p.inW) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(rowp - 4 + 4 * b));
+                    buf[4 * b] = v.x; buf[4 * b + 1] = v.y; buf[4 * b + 2] = v.z; buf[4 * b + 3] = v.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        buf[4 * b + e] = (row_ok && cb + e >= 0 && cb + e < p.inW) ? __ldg(rowp - 4 + 4 * b + e) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 10; ++j) in[j] = buf[4 - PX0 + j];
+            in[10] = 0.f;
+        };
+        float prev[4], cur[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { prev[t] = 0.f; cur[t] = 0.f; }
+        const int rbase = 2 * oy0 - p.pady0;                     // input row of relative tap row j = 0
+        const int nt = 2 * nrows + 2;
+        auto hsum = [&](const float (&in)[11], int ky, int t, float a) {
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) a = fmaf(K[ky][kx], in[2 * t + kx], a);
+            return a;
+        };
+        auto step = [&](int j, const float (&in)[11]) {
+            if (!(j & 1)) {                                      // even: filter rows 2 (older output row) and 0 (opens a row)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) { prev[t] = hsum(in, 2, t, prev[t]); cur[t] = hsum(in, 0, t, 0.f); }
+            } else {                                             // odd: filter row 3 completes the older row, 1 continues the newer
+                float o[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) { o[t] = hsum(in, 3, t, prev[t]); prev[t] = hsum(in, 1, t, cur[t]); }
+                const int oy = oy0 + (j - 3) / 2;
+                if (j >= 3) {
+                    float* dst = yout + (size_t)oy * p.outW + ox0;
+                    if (y_al && ox0 + 3 < p.outW) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                    else {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) if (ox0 + t < p.outW) dst[t] = o[t];
+                    }
+                }
+            }
+        };
+        float r0[11], r1[11], r2[11];
+        load_row(rbase, r0);
+        load_row(rbase + 1, r1);
+        for (int j = 0; j < nt; j += 6) {                        // steps of 6 keep the parity of j compile-time inside the body
+            if (j + 2 < nt) load_row(rbase + j + 2, r2);
+            step(j, r0);
+            if (j + 1 < nt) { if (j + 3 < nt) load_row(rbase + j + 3, r0); step(j + 1, r1); }
+            if (j + 2 < nt) { if (j + 4 < nt) load_row(rbase + j + 4, r1); step(j + 2, r2); }
+            if (j + 3 < nt) { if (j + 5 < nt) load_row(rbase + j + 5, r2); step(j + 3, r0); }
+            if (j + 4 < nt) { if (j + 6 < nt) load_row(rbase + j + 6, r0); step(j + 4, r1); }
+            if (j + 5 < nt) { if (j + 7 < nt) load_row(rbase + j + 7, r1); step(j + 5, r2); }
+        }
+    } else {
+        const int ox0 = cg * 8, h0 = ox0 >> 1;                   // h0: first input column of the aligned 4-column block
+        // in[e + 2] = input column h0 + e, e = -2..5 (zero outside the image)
+        auto load_row = [&](int r, float (&in)[8]) {
+            const bool row_ok = (unsigned)r < (unsigned)p.inH;
+            const float* rowp = xin + (size_t)(row_ok ? r : 0) * p.inW + h0;
+            if (row_ok && h0 >= 2 && h0 - 1 < p.inW) { const float2 v = __ldg(reinterpret_cast<const float2*>(rowp - 2)); in[0] = v.x; in[1] = v.y; }
+            else {                                               // (h0 is a multiple of 4: h0 < 2 means columns -2, -1 = padding)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) in[e] = (row_ok && h0 - 2 + e >= 0 && h0 - 2 + e < p.inW) ? __ldg(rowp - 2 + e) : 0.f;
+            }
+            if (row_ok && h0 + 3 < p.inW) { const float4 v = __ldg(reinterpret_cast<const float4*>(rowp)); in[2] = v.x; in[3] = v.y; in[4] = v.z; in[5] = v.w; }
+            else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) in[2 + e] = (row_ok && h0 + e < p.inW) ? __ldg(rowp + e) : 0.f;
+            }
+            if (row_ok && h0 + 5 < p.inW) { const float2 v = __ldg(reinterpret_cast<const float2*>(rowp + 4)); in[6] = v.x; in[7] = v.y; }
+            else {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) in[6 + e] = (row_ok && h0 + 4 + e < p.inW) ? __ldg(rowp + 4 + e) : 0.f;
+            }
+        };
+        float podd[8], pevn[8];                                   // open output rows q = 2r-1 (filter row 1 done) and q = 2r (row 0 done)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { podd[t] = 0.f; pevn[t] = 0.f; }
+        // horizontal polyphase sum of filter row ky for output column t: taps kx with (t + kx - PX0) even
+        auto hsum = [&](const float (&in)[8], int ky, int t, float a) {
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx)
+                if (((t + kx - PX0) & 1) == 0) a = fmaf(K[ky][kx], in[(t + kx - PX0) / 2 + 2], a);   // compile-time after unrolling
+            return a;
+        };
+        const int q0 = oy0 - p.pady0;                            // q of the strip's first output row
+        const int r_lo = (q0 + 1) >> 1, r_hi = ((q0 + nrows) >> 1) + 1;      // ceil(q0/2) .. ceil((q0+nrows-1)/2)+1  (arithmetic shift = floor)
+        auto store = [&](int q, const float (&o)[8]) {
+            const int oy = q + p.pady0;
+            if (oy < oy0 || oy >= oy0 + nrows) return;
+            float* dst = yout + (size_t)oy * p.outW + ox0;
+            if (y_al && ox0 + 7 < p.outW) {
+                *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) if (ox0 + t < p.outW) dst[t] = o[t];
+            }
+        };
+        auto step = [&](int r, const float (&in)[8]) {
+            float o3[8], o2[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                o3[t] = hsum(in, 3, t, podd[t]);                 // q = 2r-3: filter row 1 came from input row r-1
+                o2[t] = hsum(in, 2, t, pevn[t]);                 // q = 2r-2: filter row 0 came from input row r-1
+                podd[t] = hsum(in, 1, t, 0.f);                   // opens q = 2r-1
+                pevn[t] = hsum(in, 0, t, 0.f);                   // opens q = 2r
+            }
+            store(2 * r - 3, o3);
+            store(2 * r - 2, o2);
+        };
+        float a0[8], a1[8], a2[8];
+        load_row(r_lo, a0);
+        load_row(r_lo + 1, a1);
+        for (int r = r_lo; r <= r_hi; r += 3) {
+            if (r + 2 <= r_hi) load_row(r + 2, a2);
+            step(r, a0);
+            if (r + 1 <= r_hi) { if (r + 3 <= r_hi) load_row(r + 3, a0); step(r + 1, a1); }
+            if (r + 2 <= r_hi) { if (r + 4 <= r_hi) load_row(r + 4, a1); step(r + 2, a2); }
+        }
+    }
+}
+
+template <bool UP>
+int launch_resample2(Res2P p, cudaStream_t st) {
+    p.RS = p.outH >= 128 ? 32 : (p.outH >= 32 ? 16 : 8);
+    p.ncg = UP ? (p.outW + 7) / 8 : (p.outW + 3) / 4;
+    p.nst = (p.outH + p.RS - 1) / p.RS;
+    const long long threads = (long long)p.ncg * p.nst * p.NC;
+    const long long blocks = (threads + 127) / 128;
+    if (blocks > 0x7fffffffLL) { gg::set_error("upfirdn2d: grid too large"); return GG_EINVAL; }
+    switch (p.padx0) {
+        case 0: fir_resample2<UP, 0><<<(unsigned)blocks, 128, 0, st>>>(p); break;
+        case 1: fir_resample2<UP, 1><<<(unsigned)blocks, 128, 0, st>>>(p); break;
+        case 2: fir_resample2<UP, 2><<<(unsigned)blocks, 128, 0, st>>>(p); break;
+        default: fir_resample2<UP, 3><<<(unsigned)blocks, 128, 0, st>>>(p); break;
+    }
+    return gg::check_launch("upfirdn2d(fir_resample2)");
+}
+
 // 128-bit row loads need 16-byte aligned rows; padx0 must be one of the four instantiations
 bool stream_ok(const StreamP& p, bool in_pm) {
     const int pitch = in_pm ? p.ipW : p.inW;
@@ -459,6 +651,16 @@ extern "C" GG_API int gg_upfirdn2d_f32(const float* x, const float* f, float* y,
         StreamP sp{x, f, y, N, C, inH, inW, padx0, pady0, flip, gain, outH, outW, 0, 0, 0, 0, 0, 0, 0};
         if (stream_ok(sp, false)) return launch_stream<0>(sp, st);
         return launch_tile<1, 1, 0, 4, 4>(p, st);
+    }
+    // true 2x resampling: the marching kernels need 16-byte aligned input rows, 0 <= pad0 <= 3 and (up2) no pad0 beyond the filter reach
+    const bool march_ok = f4 && padx0 >= 0 && padx0 <= 3 && pady0 >= 0 && pady0 <= 3 && inW % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    if (march_ok && upx == 1 && downx == 2) {
+        Res2P rp{x, f, y, N * C, inH, inW, padx0, pady0, flip, gain, outH, outW, 0, 0, 0};
+        return launch_resample2<false>(rp, st);
+    }
+    if (march_ok && upx == 2 && downx == 1) {
+        Res2P rp{x, f, y, N * C, inH, inW, padx0, pady0, flip, gain, outH, outW, 0, 0, 0};
+        return launch_resample2<true>(rp, st);
     }
     if (f4 && upx == 1 && downx == 2) return launch_tile<1, 2, 0, 2, 2>(p, st);
     if (f4 && upx == 2 && downx == 1) {
