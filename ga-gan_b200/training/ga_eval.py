@@ -76,11 +76,17 @@ def default_fitness(G, D, ws, c):
 
 
 @torch.no_grad()
-def evaluate_population(G, D, population, z, c=None, rank=0, world=1, fitness_fn=None):
+def evaluate_population(G, D, population, z, c=None, rank=0, world=1, fitness_fn=None, cuda_graph=True):
     """Fitness [P] of every individual, identical on all ranks.
 
     G, D: this rank's replicas (G built with additive domain modulation); population: [P, genome] (same on every rank);
     z: the shared latent batch [B, z_dim] on this rank's device.  `fitness_fn(G, D, ws, c)` defaults to the mean logit.
+
+    One individual is ~130 library launches plus a few hundred small torch ops for ~10 ms of device work at 256^2, partly
+    launch-bound from Python.  With `cuda_graph=True` (CUDA only, shards of >= 16 individuals) the evaluation of ONE individual is
+    captured into a CUDA graph after an eager warm-up and replayed for every other individual -- only the offsets (device
+    tensors, updated in place between replays) change.  The same kernels run either way and the results are identical
+    (measured: 82 -> 97 individuals/s at 256^2 paper256, batch 8, one B200; tools/ga_bench.py).
     """
     fitness_fn = fitness_fn or default_fitness
     device = z.device
@@ -89,10 +95,26 @@ def evaluate_population(G, D, population, z, c=None, rank=0, world=1, fitness_fn
     was_training = (G.training, D.training)
     G.eval(); D.eval()
     ws = G.mapping(z, c)                                  # shared by all individuals: offsets live in the synthesis layers only
+    mine = shard_indices(population.shape[0], rank, world)
     local = []
-    for i in shard_indices(population.shape[0], rank, world):
+    graph = static_out = None
+    if cuda_graph and device.type == 'cuda' and len(mine) >= 16:      # capturing costs ~0.1 s: only worth it for a long shard
+        load_individual(G, population[mine[0]])
+        side = torch.cuda.Stream(device)                  # warm-up on a side stream, as graph capture requires
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            fitness_fn(G, D, ws, c)                       # plugin / attribute / allocator initialisation happens here, not in the capture
+        torch.cuda.current_stream(device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_out = fitness_fn(G, D, ws, c)
+    for i in mine:
         load_individual(G, population[i])
-        local.append(fitness_fn(G, D, ws, c))
+        if graph is not None:
+            graph.replay()
+            local.append(static_out.clone())
+        else:
+            local.append(fitness_fn(G, D, ws, c))
     out = gather_fitness(local, population.shape[0], rank, world, device)
     G.train(was_training[0]); D.train(was_training[1])
     return out
