@@ -100,12 +100,22 @@ __global__ void __launch_bounds__(256) bias_act_vec4(Params p) {
     float acc = 0.f;     // partial dbias for channel acc_c (UNIFORM only)
     int acc_c = -1;
 
-    float4 vx[ITER], vr[ITER], vy[ITER], vd[ITER];
+    // sizeX <= INT_MAX (checked by the entry point): all element / plane arithmetic fits 32-bit unsigned, whose divisions cost a
+    // fraction of the 64-bit ones (two of them per 128-element span were a measurable share of this memory-bound kernel)
+    const uint32_t stepB = (uint32_t)p.stepB, sizeB = (uint32_t)p.sizeB;
+    float4 vx[ITER], vr[ITER], vy[ITER], vd[ITER], vn[ITER];
 #pragma unroll
     for (int it = 0; it < ITER; ++it) {           // issue all loads first (memory-level parallelism)
         int64_t i4 = base4 + it * 32;
         bool ok = i4 < n4;
         vx[it] = ok ? ld4(p.x, i4) : make_float4(0, 0, 0, 0);
+        if (G == 0) {
+            vn[it] = make_float4(0, 0, 0, 0);
+            if (p.noise && ok) {                        // element e = 4*i4 sits at pixel e % stepB of sample e / (stepB*sizeB)
+                const uint32_t e = (uint32_t)(i4 << 2), plane = e / stepB;
+                vn[it] = __ldg(reinterpret_cast<const float4*>(p.noise + (int64_t)(plane / sizeB) * p.noise_bs + (e - plane * stepB)));
+            }
+        }
         if (G > 0 && A == 9) vr[it] = (ok && p.xref) ? ld4(p.xref, i4) : make_float4(0, 0, 0, 0);
         if (G > 0) vy[it] = (ok && p.yref) ? ld4(p.yref, i4) : make_float4(0, 0, 0, 0);
         if (G == 2) vd[it] = (ok && p.dy) ? ld4(p.dy, i4) : make_float4(1, 1, 1, 1);
@@ -118,22 +128,17 @@ __global__ void __launch_bounds__(256) bias_act_vec4(Params p) {
         float b = 0.f;
         if (p.b || p.dbias) {
             if (UNIFORM) {
-                int64_t span0 = (warp * (32 * ITER) + it * 32) << 2;  // first element of this warp-span
-                c = (int)((span0 / p.stepB) % p.sizeB);
+                const uint32_t span0 = (uint32_t)((warp * (32 * ITER) + it * 32) << 2);  // first element of this warp-span
+                c = (int)((span0 / stepB) % sizeB);
             } else {
-                c = ok ? (int)(((i4 << 2) / p.stepB) % p.sizeB) : 0;
+                c = ok ? (int)(((uint32_t)(i4 << 2) / stepB) % sizeB) : 0;
             }
             if (p.b) b = __ldg(p.b + c);
         }
         float4 r = (G > 0 && A == 9) ? vr[it] : make_float4(0, 0, 0, 0);
         float4 yr = (G > 0) ? vy[it] : make_float4(0, 0, 0, 0);
         float4 d = (G == 2) ? vd[it] : make_float4(1, 1, 1, 1);
-        float4 nz = make_float4(0, 0, 0, 0);
-        if (G == 0 && p.noise && ok) {                  // element e = 4*i4 sits at pixel e % stepB of sample e / (stepB*sizeB)
-            const int64_t e = i4 << 2;
-            const int64_t plane = e / p.stepB;
-            nz = __ldg(reinterpret_cast<const float4*>(p.noise + (plane / p.sizeB) * p.noise_bs + (e - plane * p.stepB)));
-        }
+        const float4 nz = (G == 0) ? vn[it] : make_float4(0, 0, 0, 0);
         float4 o;
         o.x = eval<A, G>(vx[it].x, b + nz.x, r.x, yr.x, d.x, p);
         o.y = eval<A, G>(vx[it].y, b + nz.y, r.y, yr.y, d.y, p);

@@ -101,3 +101,22 @@ def test_ga_population_fitness_eval_on_the_device(device):
         base = D(G.synthesis(G.mapping(z, c), noise_mode='const'), c).mean()
     assert abs(float(fit[2] - base)) <= 1e-5 * max(1.0, abs(float(base)))
     assert len({round(float(v), 5) for v in fit}) == 5                      # different offsets, different fitness
+
+
+def test_ga_population_eval_cuda_graph_replay_matches_eager(device):
+    """Shards of >= 16 individuals are evaluated by replaying one captured CUDA graph (ga_eval.evaluate_population): the
+    same kernels, so the fitness vector must equal the eager loop's bit for bit (up to atomics-free determinism)."""
+    from training import networks, ga_eval
+    torch.manual_seed(4)
+    G = networks.Generator(z_dim=32, c_dim=0, w_dim=32, img_resolution=32, img_channels=3, mapping_kwargs=dict(num_layers=2),
+                           synthesis_kwargs=dict(channel_base=512, channel_max=32, use_domain_modulation=True,
+                                                 domain_modulation_parametrization='additive')).to(device)
+    D = networks.Discriminator(c_dim=0, img_resolution=32, img_channels=3, channel_base=512, channel_max=32).to(device)
+    pop = ga_eval.init_population(G, size=18, scale=0.1, seed=2)
+    z = torch.randn(4, 32, device=device)
+    eager = ga_eval.evaluate_population(G, D, pop, z, cuda_graph=False)
+    graph = ga_eval.evaluate_population(G, D, pop, z, cuda_graph=True)
+    again = ga_eval.evaluate_population(G, D, pop, z, cuda_graph=True)       # a second capture in the same process
+    assert torch.isfinite(graph).all() and len({round(float(v), 5) for v in graph}) == 18
+    assert float((graph - eager).abs().max()) <= 1e-6 * float(eager.abs().max())
+    assert float((again - graph).abs().max()) <= 1e-6 * float(eager.abs().max())
