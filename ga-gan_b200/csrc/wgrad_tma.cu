@@ -70,7 +70,7 @@ __device__ __forceinline__ void mbar_wait_block(uint32_t bar, uint32_t parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (ok) return;
-        if (it > (1u << 24)) { *reinterpret_cast<volatile int*>(8) = (int)bar; __trap(); }   // a pipeline bug must not hang the GPU
+        if (it > (1u << 28)) { *reinterpret_cast<volatile int*>(8) = (int)bar; __trap(); }   // (seconds) a pipeline bug must not hang the GPU
     }
 }
 
