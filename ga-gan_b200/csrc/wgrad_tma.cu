@@ -65,12 +65,17 @@ __device__ __forceinline__ int item_row(int id) { return (id & 7) | ((id >> 5) <
 // potentially-blocking wait (the hardware suspends the thread for a while): used by the many converter threads, which
 // would otherwise hammer the shared-memory pipe that the MMA operands and the barrier traffic of the single-thread roles need
 __device__ __forceinline__ void mbar_wait_block(uint32_t bar, uint32_t parity) {
+    long long t0 = 0;
     for (uint32_t it = 0;; ++it) {
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (ok) return;
-        if (it > (1u << 28)) { *reinterpret_cast<volatile int*>(8) = (int)bar; __trap(); }   // (seconds) a pipeline bug must not hang the GPU
+        if ((it & 1023u) == 1023u) {                     // watchdog, off the fast path: ~4 s of SM clocks, then fault instead of hanging the GPU
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000LL) { *reinterpret_cast<volatile int*>(8) = (int)bar; __trap(); }
+        }
     }
 }
 
