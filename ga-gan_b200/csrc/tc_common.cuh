@@ -25,18 +25,23 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Watchdog shared by the wait loops: off the fast path (the clock is read once per 1024 polls -- reading it around every wait
+// was a visible share of the single-thread issue loops), ~4 s of SM clocks, then a fault instead of a hung GPU.  A watchdog
+// expiry shows up as "illegal memory access" (null store), distinguishable from a hardware fault.
+__device__ __forceinline__ void mbar_watchdog(uint32_t it, long long& t0, uint32_t bar) {
+    if ((it & 1023u) != 1023u) return;
+    const long long now = clock64();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 8000000000LL) { *reinterpret_cast<volatile int*>(8) = (int)bar; __trap(); }
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    const long long t0 = clock64();
-    for (;;) {
+    long long t0 = 0;
+    for (uint32_t it = 0;; ++it) {
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (ok) return;
-        if (clock64() - t0 > 4000000000LL) {   // ~2 s: a pipeline bug must not hang the GPU
-            // distinguishable from a hardware fault: a watchdog expiry shows up as "illegal memory access" (null store)
-            *reinterpret_cast<volatile int*>(8) = (int)bar;
-            __trap();
-        }
+        mbar_watchdog(it, t0, bar);
     }
 }
 // One lane of a converged warp; ptxas treats the region guarded by elect.sync as single-threaded, which lets it keep the
@@ -49,13 +54,13 @@ __device__ __forceinline__ bool elect_one() {
 // Pure spin on mbarrier.test_wait (no hardware suspend): lower wake-up latency for the fine-grained producer/consumer
 // handshakes of the weight-gradient kernel, at the price of issue slots.
 __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
-    const long long t0 = clock64();
-    for (;;) {
+    long long t0 = 0;
+    for (uint32_t it = 0;; ++it) {
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (ok) return;
-        if (clock64() - t0 > 4000000000LL) { *reinterpret_cast<volatile int*>(8) = (int)bar; __trap(); }
+        mbar_watchdog(it, t0, bar);
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

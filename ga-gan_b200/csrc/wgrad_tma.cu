@@ -36,10 +36,9 @@ namespace {
 constexpr int CONS_WARPS = 8;
 constexpr int GROUP_WARPS = 4;                          // the converter warps work as two groups that alternate tasks
 constexpr int GROUP_THREADS = GROUP_WARPS * 32;
-constexpr int PROD_WARPS = 4;                           // w0 = MMA issuer + TMEM owner, w1 = TMA producer, w2..w3 idle (one warpgroup for setmaxnreg)
+constexpr int PROD_WARPS = 4;                           // w0 = MMA issuer + TMEM owner, w1 / w2 = TMA producers (X / G rows), w3 idle (one warpgroup for setmaxnreg)
 constexpr int THREADS = (PROD_WARPS + CONS_WARPS) * 32;
 constexpr int UW = 16;                                  // image columns per strip (two K=8 steps)
-constexpr int GS = 4;                                   // G-row slots in tensor memory (32 columns each: 16 hi + 16 lo)
 constexpr int XS = 8;                                   // X-row ring slots in shared memory (k live rows + rows in flight)
 constexpr int ST = 6;                                   // staging slots (raw fp32 rows in flight from TMA)
 constexpr uint32_t ROW_B = UW * 4;                      // bytes of one staged X row (16 pixels)
@@ -64,20 +63,7 @@ __device__ __forceinline__ int item_row(int id) { return (id & 7) | ((id >> 5) <
 
 // potentially-blocking wait (the hardware suspends the thread for a while): used by the many converter threads, which
 // would otherwise hammer the shared-memory pipe that the MMA operands and the barrier traffic of the single-thread roles need
-__device__ __forceinline__ void mbar_wait_block(uint32_t bar, uint32_t parity) {
-    long long t0 = 0;
-    for (uint32_t it = 0;; ++it) {
-        uint32_t ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (ok) return;
-        if ((it & 1023u) == 1023u) {                     // watchdog, off the fast path: ~4 s of SM clocks, then fault instead of hanging the GPU
-            const long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 8000000000LL) { *reinterpret_cast<volatile int*>(8) = (int)bar; __trap(); }
-        }
-    }
-}
+__device__ __forceinline__ void mbar_wait_block(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
 
 // 128-bit shared-memory read that the compiler may not split into narrower (bank-conflicting) accesses
 __device__ __forceinline__ float4 lds128(const void* ptr) {
@@ -138,6 +124,11 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
     // contiguous inside a chunk, so one UMMA descriptor with N = K*NTA rows covers the X rows of all K filter rows ky at once
     // (their accumulators D_ky are adjacent TMEM column ranges): 6 wide MMAs per task instead of 18 narrow ones.
     constexpr uint32_t X_ROWS = NTA * 16;                                // one ring slot inside a chunk
+    // G-row slots in tensor memory (32 columns each: 16 hi + 16 lo).  The slot ring is a latency loop (converter -> tcgen05.st ->
+    // barrier -> MMA issue -> tensor queue -> commit -> barrier -> converter, ~3 600 cycles): with 4 slots every shape ran at
+    // ~900 cycles per row task whatever its MMA time.  NTA = 32 has the TMEM columns for 8 slots; at NTA = 64 the two
+    // accumulator sets (2 x 192 columns) leave room for 4.
+    constexpr int GS = NTA == 32 ? 8 : 4;
     constexpr uint32_t LBO_B = XS * X_ROWS;                              // chunk pitch
     constexpr uint32_t X_HALF = 4 * LBO_B;                               // hi image, then lo image
     constexpr uint32_t STG_SLOT = STG_G + NTA * ROW_B;                   // 18 KB (NTA = 64) / 16 KB (NTA = 32)
@@ -162,7 +153,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
         for (int s = 0; s < GS; ++s) { mbar_init(BAR_G_FULL(s), GROUP_WARPS); mbar_init(BAR_G_EMPTY(s), 1); }
         for (int s = 0; s < XS; ++s) { mbar_init(BAR_X_FULL(s), GROUP_WARPS); mbar_init(BAR_X_EMPTY(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(BAR_ACC_FULL(s), 1); mbar_init(BAR_ACC_EMPTY(s), CONS_WARPS); }
-        for (int s = 0; s < ST; ++s) { mbar_init(BAR_STG_FULL(s), 1); mbar_init(BAR_STG_EMPTY(s), GROUP_WARPS); }
+        for (int s = 0; s < ST; ++s) { mbar_init(BAR_STG_FULL(s), 2); mbar_init(BAR_STG_EMPTY(s), GROUP_WARPS); }   // FULL: one arrive per producer
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(base + OFF_SLOT, TMEM_COLS);
@@ -234,23 +225,28 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
                 umma_commit(BAR_ACC_FULL(buf));
                 ++sc;
             }
-        } else if (warp == 1 && elect_one()) {
-            // ===== TMA producer (one thread): raw fp32 rows of task j of every strip -> staging ring
+        } else if ((warp == 1 || warp == 2) && elect_one()) {
+            // ===== TMA producers (one thread per operand: warp 1 = X rows, warp 2 = G rows): raw fp32 rows of task j of every strip
+            // -> staging ring (two threads so that the scalar issue code of one producer cannot set the pace of the kernel)
+            const bool is_g = warp == 2;
             uint32_t tc = 0;
-            const uint32_t stg0 = base + OFF_STG;
+            const uint32_t stg0 = base + OFF_STG + (is_g ? 0u : STG_G);
+            const CUtensorMap* map = is_g ? &gmap : &xmap;
+            const uint32_t bytes = is_g ? (uint32_t)p.RB * GROW_B : NTA * ROW_B;
+            const int ch0 = is_g ? T.b0 : T.a0;
             for (int strip = strip_beg; strip < strip_end; ++strip) {
                 const Strip s = decode_strip(strip, p);
                 const int ntask = s.rows + K - 1;
+                // A TMA box must start on a 16-byte boundary of global memory, so the kx shift cannot be put into the box
+                // coordinate: ONE aligned G box with a 4-pixel apron on the left serves all shifts (the converters pick).
+                const int cx = is_g ? s.u0 - 4 : s.u0;
+                const int cy = is_g ? s.r0 - (K - 1) : s.r0 - p.pad_y;
                 for (int j = 0; j < ntask; ++j, ++tc) {
                     const uint32_t slot = tc % ST;
                     mbar_wait_spin(BAR_STG_EMPTY(slot), ((tc / ST) & 1) ^ 1);
-                    const bool has_g = j >= K - 1;
-                    mbar_expect_tx(BAR_STG_FULL(slot), NTA * ROW_B + (has_g ? (uint32_t)p.RB * GROW_B : 0u));
-                    const uint32_t dst = stg0 + slot * STG_SLOT;
-                    tma_load_4d(dst + STG_G, &xmap, BAR_STG_FULL(slot), s.u0, s.r0 - p.pad_y + j, T.a0, s.n);
-                    // A TMA box must start on a 16-byte boundary of global memory, so the kx shift cannot be put into the box
-                    // coordinate: ONE aligned box with a 4-pixel apron on the left serves all shifts (the converters pick).
-                    if (has_g) tma_load_4d(dst, &gmap, BAR_STG_FULL(slot), s.u0 - 4, s.r0 - (K - 1) + j, T.b0, s.n);
+                    if (is_g && j < K - 1) { mbar_arrive(BAR_STG_FULL(slot)); continue; }      // the strip's top halo rows have no G row
+                    mbar_expect_tx(BAR_STG_FULL(slot), bytes);
+                    tma_load_4d(stg0 + slot * STG_SLOT, map, BAR_STG_FULL(slot), cx, cy + j, ch0, s.n);
                 }
             }
         }
