@@ -434,7 +434,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     const int idx = ct + it * CONS_THREADS;
                     const int chunk = idx / npix, px = idx - chunk * npix;
                     const int rr = px / p.boxW + dy, cc = px % p.boxW + dx;
-                    cvt_src[it] = (chunk < 4 && rr >= 0 && cc >= 0 && rr < p.boxH && cc < p.rawW) ? (chunk * 4) * rpix + rr * p.rawW + cc
+                    // bits 0..23: source index in the raw box, bits 24..25: the 4-channel chunk (so that the hot loop has no division)
+                    cvt_src[it] = (chunk < 4 && rr >= 0 && cc >= 0 && rr < p.boxH && cc < p.rawW) ? (((chunk * 4) * rpix + rr * p.rawW + cc) | (chunk << 24))
                                                                                                    : (chunk < 4 ? -1 : -2);
                 }
             }
@@ -453,14 +454,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 uint32_t pend_chunk = pend_ac;
 #pragma unroll
                 for (int it = 0; it < CVT_ITEMS; ++it) {
-                    const int src = cvt_src[it];
+                    const int plan = cvt_src[it], src = plan < 0 ? plan : (plan & 0xFFFFFF);
                     if (src != -2) {                    // -2: past the end of the tile
                         const int idx = ct + it * CONS_THREADS;
                         float4 h = make_float4(0.f, 0.f, 0.f, 0.f), l = h;
                         if (src >= 0) {
                             float v0 = raw[src], v1 = raw[src + rpix], v2 = raw[src + 2 * rpix], v3 = raw[src + 3 * rpix];
                             if (p.in_scale) {
-                                const int chunk = idx / npix;
+                                const int chunk = plan >> 24;
                                 const float4 sv = *reinterpret_cast<const float4*>(sc_s + kb * KB_CH + chunk * 4);
                                 v0 *= sv.x; v1 *= sv.y; v2 *= sv.z; v3 *= sv.w;
                             }
