@@ -386,14 +386,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             const int s = k & 1;
             mbar_wait(BAR_ACC_FULL(s), (k >> 1) & 1);
             tc_fence_after();
+            // TMEM loads are issued in pairs before one wait, so that their latencies overlap (one load + wait at a time made the
+            // drain a chain of ~16 dependent round trips at NT = 256)
+            constexpr int NLD = SUBS * HN / 16;               // 16-column loads of this thread: (sub, cb) in row-major order
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * SET_COLS + hcol * HN);
 #pragma unroll
-            for (int sub = 0; sub < SUBS; ++sub) {
+            for (int l = 0; l < NLD; l += 2) {
+                uint32_t v[2][16];
 #pragma unroll
-                for (int cb = 0; cb < HN; cb += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * SET_COLS + sub * NT + hcol * HN + cb), v);
+                for (int u = 0; u < 2; ++u)
+                    if (l + u < NLD) tmem_ld16_nowait(t0 + (uint32_t)(((l + u) / (HN / 16)) * NT + ((l + u) % (HN / 16)) * 16), v[u]);
+                tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[sub][cb + j] = fmaf(__uint_as_float(v[j]), kc, acc[sub][cb + j]);
+                for (int u = 0; u < 2; ++u) {
+                    if (l + u < NLD) {
+                        const int sub = (l + u) / (HN / 16), cb = ((l + u) % (HN / 16)) * 16;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[sub][cb + j] = fmaf(__uint_as_float(v[u][j]), kc, acc[sub][cb + j]);
+                    }
                 }
             }
             tc_fence_before();

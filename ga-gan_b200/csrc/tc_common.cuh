@@ -98,6 +98,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// the same load without the wait: issue several, then tmem_wait_ld() once, so that their latencies overlap
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // registers -> TMEM: 16 consecutive 32-bit columns of this thread's lane (warp w may only touch lanes 32*(w%4) .. +31)
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"

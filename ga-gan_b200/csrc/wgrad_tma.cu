@@ -303,13 +303,16 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
                 if (ky < K && ((T.ky_live >> ky) & 1u)) {
+                    // all loads of one filter row are issued before one wait, so that their latencies overlap
+                    uint32_t v[HN / 16][16];
 #pragma unroll
-                    for (int cb = 0; cb < HN; cb += 16) {
-                        uint32_t v[16];
-                        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_STRIDE + (uint32_t)(ky * NTA + half * HN + cb), v);
+                    for (int cb = 0; cb < HN; cb += 16)
+                        tmem_ld16_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_STRIDE + (uint32_t)(ky * NTA + half * HN + cb), v[cb / 16]);
+                    tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[ky * HN + cb + j] = fmaf(__uint_as_float(v[j]), kc, acc[ky * HN + cb + j]);
-                    }
+                    for (int cb = 0; cb < HN; cb += 16)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[ky * HN + cb + j] = fmaf(__uint_as_float(v[cb / 16][j]), kc, acc[ky * HN + cb + j]);
                 }
             }
             tc_fence_before();
