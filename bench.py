@@ -168,7 +168,11 @@ def run_reference_arm(args, rank):
               f'{args.cpu_batch}, {res}x{res} {args.cfg} fp32, oracle port of impl=ref; wall budget {budget_s:.0f}s')
     line = dict(metric=METRIC, value=value, unit=UNIT, impl='reference', n_gpus=args.gpus, steps=done, warmup=done_warm,
                 ms_per_step=1000.0 * args.cpu_batch / value, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
-                data='synthetic', config=dict(workload=f'StyleGAN2 {args.cfg} {res}x{res} G+D train iteration, CPU sample batch {args.cpu_batch}'),
+                data='synthetic',
+                # the same workload as the GPU arm (its `config.workload`, `global_batch`); what was actually timed is `cpu_baseline.sample`
+                config=dict(workload=f'StyleGAN2 {args.cfg} (config-f) {args.res}x{args.res} G+D train iteration fp32, batch {args.batch}/GPU '
+                                     f'in rounds of {min(args.batch_gpu, args.batch)}', global_batch=args.batch * max(args.gpus, 1),
+                            parallelism=f'dp{max(args.gpus, 1)}', reference_sample=f'batch {args.cpu_batch} at {res}x{res} on the host cores, scaled per image'),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=os.cpu_count(), kind='port', sample=sample,
                                   phase_seconds={k: round(v, 3) for k, v in phases.items()}),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
