@@ -59,7 +59,7 @@ def _pm_live(kind, kh, kw):
                     ky, kx = (2 * a + py, 2 * b + px) if kind == 'down' else (py + 2 * (1 - a), px + 2 * (1 - b))
                     if ky >= kh or kx >= kw:
                         dead |= 1 << ((py * 2 + px) * 4 + a * 2 + b)
-    live = _Live(_PM_LIVE)
+    live = _Live((16 - bin(dead).count('1')) / 16.0)       # 9/16 for a 3x3 kernel
     live.pm = (2 if kind == 'down' else 1, dead)       # down: dim 1 of W2 [O,4I,2,2] is phase-grouped; up: dim 0 of W2 [4O,I,2,2]
     return live
 

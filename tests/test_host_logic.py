@@ -164,3 +164,26 @@ def test_phase_major_forms_of_the_stride2_layers_match_the_oracle():
     assert int((w2.abs().sum(dim=(0, 2)) == 0).sum()) == 7
     w2 = cr.phase_major_weight_up(torch.ones(2, 3, 3, 3)).reshape(4, 2, 3, 4)
     assert int((w2.abs().sum(dim=(1, 2)) == 0).sum()) == 7
+
+
+@pytest.mark.parametrize('kind', ['down', 'up'])
+@pytest.mark.parametrize('k', [1, 2, 3, 4])
+def test_phase_major_dead_tap_mask_is_the_zero_pattern_of_the_weight(kind, k):
+    """The structural hint handed to gg_conv2d_wgrad_pm_f32 (conv2d_resample._pm_live) must mark exactly the (phase group,
+    tap) blocks that phase_major_weight_down / _up leave zero for ANY weight -- otherwise the kernel would skip live gradients."""
+    O, I = 3, 5
+    w = torch.rand(O, I, k, k) + 1.0                                   # no accidental zeros
+    w2 = (conv2d_resample.phase_major_weight_down if kind == 'down' else conv2d_resample.phase_major_weight_up)(w)
+    live = conv2d_resample._pm_live(kind, k, k)
+    pm_dim, dead = live.pm
+    assert pm_dim == (2 if kind == 'down' else 1)
+    grouped = w2.reshape(O, 4, I, 2, 2) if kind == 'down' else w2.reshape(4, O, I, 2, 2).transpose(0, 1)   # [O, group, I, a, b]
+    n_dead = 0
+    for g, a, b in itertools.product(range(4), range(2), range(2)):
+        block = grouped[:, g, :, a, b]
+        is_dead = bool((dead >> (g * 4 + a * 2 + b)) & 1)
+        assert bool((block == 0).all()) == is_dead, (kind, k, g, a, b)
+        assert is_dead or bool((block != 0).all())
+        n_dead += is_dead
+    if k == 3:
+        assert n_dead == 7 and abs(float(live) - 9.0 / 16.0) < 1e-12    # 9 of the 16 (phase, tap) blocks are live
