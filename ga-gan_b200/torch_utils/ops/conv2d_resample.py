@@ -40,7 +40,6 @@ def _conv2d_wrapper(x, w, stride=1, padding=0, groups=1, transpose=False, flip_w
 # way every dense contraction of the networks -- forward, data gradient and weight gradient -- runs through the ONE
 # stride-1 tensor-core kernel (conv2d_gradfix.conv2d_s1), with the same results as conv2d_resample.py:119-142.
 
-_PM_LIVE = 9.0 / 16.0
 
 
 class _Live(float):
