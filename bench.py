@@ -2,40 +2,50 @@
 """bench.py -- StyleGAN2 G+D training throughput (images/sec) on B200, BASELINE.json's metric.
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched per rank by torch.distributed.run)
-    python bench.py --impl reference ...                      (the reference's CPU impl='ref' algorithm, oracle port)
+    python bench.py --impl reference ...                      (the UNMODIFIED reference on its CPU impl='ref' operators)
+    python bench.py --workload ada | ga ...                   (BASELINE configs[2] / configs[3]; not the headline)
+    python bench.py --global-batch 32 --gpus N                (strong scaling: the reference's `--batch` semantics)
 
-Workload (config.workload): BASELINE.json configs[1] -- "StyleGAN2 config-f 1024^2 G+D forward-backward fp32,
-batch 32 on 1 B200": one step = one training iteration of the upstream loop (Gmain + Dmain every iteration,
-Greg every 4th, Dreg every 16th, Adam steps, G_ema), batch 32 PER GPU (weak scaling), run as `batch_gpu`-sized
-accumulation rounds exactly like training_loop.py:495-502.  Synthetic data, random-init weights.
+Default workload (config.workload): BASELINE.json configs[1] -- "StyleGAN2 config-f 1024^2 G+D forward-backward fp32,
+batch 32 on 1 B200": one step = one training iteration of the upstream loop (Gmain + Dmain every iteration, Greg every
+4th, Dreg every 16th, Adam steps, G_ema), batch 32 PER GPU (weak scaling), in `batch_gpu`-sized accumulation rounds exactly
+like training_loop.py:495-502.  Synthetic data, random-init weights.  The networks, the loss and (for `ada`) the augment
+pipe are the REFERENCE's own classes from the checkout in baseline/_ref (tools/vendor_reference.py), running on this build's
+operators through gagan_b200.install() -- the drop-in is what is measured.
 
 One JSON line on stdout (rank 0):
   value      images/sec, inputs resident in HBM when the timed region starts (CUDA events, max over ranks)
-  e2e        images/sec through the public API with HOST inputs: every step copies that step's uint8 image batch
-             and latents from pinned host memory, and reads the step's loss scalars back
-  roofline   the dominant kernel family (conv2d fwd/dgrad/wgrad): algorithmic FLOPs / CUDA-event time of every
-             conv launch inside the timed region, against the measured TF32 peak (= 1/2 of the measured bf16 peak)
-  cpu_baseline  the oracle port of the reference's impl='ref' CPU path, timed on this box's host cores (rank 0, N=1)
+  e2e        images/sec through the public API with HOST inputs: every step copies that step's uint8 image batch and
+             latents from pinned host memory, and reads the step's loss statistics back (training_stats collector)
+  roofline   the dominant kernel family (conv2d fwd/dgrad): algorithmic FLOPs / CUDA-event time of every conv launch inside
+             the timed region, against the measured TF32 peak (= 1/2 of the measured bf16 peak)
+  cpu_baseline  the reference itself (kind "reference": oracle/_ref through oracle/live_ref.py semantics) timed on this box's
+             host cores in a child process (rank 0, N=1)
+  fast_mode  the same step with ONE TF32 product per MAC instead of three (not fp32-faithful; reported, never the headline)
 """
+import io
 import os
 import sys
 import json
 import time
 import argparse
 import threading
+import contextlib
 import subprocess
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-PKG = os.path.join(ROOT, 'ga-gan_b200')
-for _p in (ROOT, PKG):
-    if _p not in sys.path:
-        sys.path.insert(0, _p)
+CHECKOUT = os.path.join(ROOT, 'baseline', '_ref', 'DissimilarDomains')
+ORACLE_REF = os.path.join(ROOT, 'oracle', '_ref', 'DissimilarDomains')
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 import numpy as np   # noqa: E402
 import torch         # noqa: E402
 
 METRIC = 'stylegan2_g_d_train_images_per_sec'
 UNIT = 'img/s'
+AFFINE_PLUS_PARTS = ['synt_affine', 'tRGB_affine', 'synt_weights_offset.b64', 'tRGB_weights_offset.b64']   # DD/README.md:191-196
+AFFINE_PLUS_PARAM = 'out_in_additive'
 
 
 def parse_args():
@@ -44,16 +54,35 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=16)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--res', type=int, default=1024)
-    ap.add_argument('--cfg', default='stylegan2')
-    ap.add_argument('--batch', type=int, default=32, help='images per GPU per iteration')
+    ap.add_argument('--workload', default='train', choices=['train', 'ada', 'ga'],
+                    help='train = BASELINE configs[1] (headline); ada = configs[2] (Affine+ few-shot 256^2 with ADA); ga = configs[3]')
+    ap.add_argument('--res', type=int, default=None)
+    ap.add_argument('--cfg', default=None)
+    ap.add_argument('--batch', type=int, default=None, help='images per GPU per iteration (weak scaling)')
+    ap.add_argument('--global-batch', type=int, default=None, help='total images per iteration over all GPUs (strong scaling, train.py --batch)')
     ap.add_argument('--batch-gpu', type=int, default=32, help='images per accumulation round (training_loop.py:495-502); one round of 32 fits '
-                    "the B200's 180 GB in fp32 and keeps the low-resolution layers' tiles full (4 -> 22, 8 -> 24, 16 -> 26, 32 -> 28+ img/s)")
+                    "the B200's 180 GB in fp32 and keeps the low-resolution layers' tiles full")
     ap.add_argument('--prec', default='auto', choices=['auto', 'simt', 'tf32x1', 'tf32x3'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-fast-mode', action='store_true')
+    ap.add_argument('--reference-forwards', action='store_true', help="run the reference's forwards untouched (no fused callers)")
     ap.add_argument('--cpu-res', type=int, default=0, help='resolution of the CPU sample (0 = same as --res)')
     ap.add_argument('--cpu-batch', type=int, default=2)
-    return ap.parse_args()
+    ap.add_argument('--population', type=int, default=64)
+    ap.add_argument('--latents', type=int, default=8)
+    a = ap.parse_args()
+    dflt = dict(train=('stylegan2', 1024, 32), ada=('paper256', 256, 8), ga=('paper256', 256, 8))[a.workload]
+    a.cfg = a.cfg or dflt[0]
+    a.res = a.res or dflt[1]
+    world = max(int(os.environ.get('WORLD_SIZE', '1')), 1)
+    if a.global_batch is not None:
+        assert a.global_batch % world == 0, '--global-batch must be divisible by the number of ranks'
+        a.batch = a.global_batch // world
+        a.scaling = 'strong'
+    else:
+        a.batch = a.batch or dflt[2]
+        a.scaling = 'weak'
+    return a
 
 
 def measured_peaks():
@@ -105,78 +134,165 @@ class ClockSampler:
                     samples=len(sm))
 
 
+def workload_text(args, world):
+    if args.workload == 'train':
+        return (f'StyleGAN2 {args.cfg} (config-f) {args.res}x{args.res} G+D train iteration fp32, batch {args.batch}/GPU '
+                f'in rounds of {min(args.batch_gpu, args.batch)}')
+    if args.workload == 'ada':
+        return (f'ADA Affine+ few-shot adaptation {args.res}x{args.res} {args.cfg} fp32 (parts {",".join(AFFINE_PLUS_PARTS)}; {AFFINE_PLUS_PARAM}; '
+                f'AugmentPipe bgc, ada_target 0.6; 10 synthetic target images), batch {args.batch}/GPU')
+    return (f'GA StyleSpace-direction population fitness eval: {args.population} individuals sharded i % {world}, {args.latents} shared latents, '
+            f'{args.res}x{args.res} {args.cfg} G (additive offsets) + D, eval mode, const noise')
+
+
 # ----------------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle port of the reference's impl='ref' path (the reference is Python and cannot travel
-# to the GPU box; oracle/ is pinned against it by tests/golden/make_golden.py).
+# Reference arm / CPU baseline: the UNMODIFIED reference (oracle/_ref, a byte-identical copy of the reference's packages made
+# by tools/vendor_reference.py) on CPU tensors, where every op takes its own impl='ref' branch.  Nothing of this build is on
+# that path: this function neither imports gagan_b200 nor loads libgagan_b200.so.
 
 
-def cpu_reference_iteration(res, cfg, batch, seed=0):
-    """One amortised training iteration on the host cores; returns (images/sec, seconds per phase)."""
-    from oracle import networks_ref as NR
-    from training.training_loop import CONFIGS
-    spec = CONFIGS[cfg]
+REF_CONFIGS = {   # train.py:219-228, for the arm that must not import this build
+    'stylegan2': dict(fmaps=1.0, lrate=0.002, gamma=10.0, map=8, mbstd=4), 'paper256': dict(fmaps=0.5, lrate=0.0025, gamma=1.0, map=8, mbstd=8),
+    'paper512': dict(fmaps=1.0, lrate=0.0025, gamma=0.5, map=8, mbstd=8), 'paper1024': dict(fmaps=1.0, lrate=0.002, gamma=2.0, map=8, mbstd=4)}
+REF_AUGPIPE_BGC = dict(xflip=1, rotate90=1, xint=1, scale=1, rotate=1, aniso=1, xfrac=1, brightness=1, contrast=1, lumaflip=1, hue=1,
+                       saturation=1)   # train.py:365-368
+
+
+def _load_plain_reference():
+    from oracle import live_ref                         # private import + the `img is None` guard applied from outside
+    return live_ref.load()
+
+
+def cpu_reference_iteration(L, args, batch, seed=0):
+    """One amortised training iteration of the reference on the host cores; returns (images/sec, seconds per phase)."""
+    spec = REF_CONFIGS[args.cfg]
+    res = args.cpu_res or args.res
     cb = int(spec['fmaps'] * 32768)
     torch.set_num_threads(os.cpu_count())
-    gen = torch.Generator().manual_seed(seed)
-    PG = {k: v.requires_grad_(v.dtype.is_floating_point and 'noise_const' not in k and 'w_avg' not in k)
-          for k, v in NR.init_G_params(res, cb, 512, 512, 512, spec['map'], generator=gen).items()}
-    PD = {k: v.requires_grad_(True) for k, v in NR.init_D_params(res, cb, 512, generator=gen).items()}
-    gl = [v for v in PG.values() if v.requires_grad]
-    dl = list(PD.values())
-    optG = torch.optim.Adam(gl, lr=spec['lrate'] * 0.8, betas=(0.0, 0.99 ** 0.8), eps=1e-8)
-    optD = torch.optim.Adam(dl, lr=spec['lrate'] * 16 / 17, betas=(0.0, 0.99 ** (16 / 17)), eps=1e-8)
-    z = torch.randn(batch, 512, generator=gen)
-    real = torch.rand(batch, 3, res, res, generator=gen) * 2 - 1
-    mb = spec['mbstd']
+    torch.manual_seed(seed)
+    L.conv2d_gradfix.enabled = True                      # training_loop.py:209-210
+    L.grid_sample_gradfix.enabled = True
+    extra = {}
+    if args.workload == 'ada':
+        extra = dict(use_domain_modulation=True, domain_modulation_parametrization=AFFINE_PLUS_PARAM, generator_requires_grad_parts=AFFINE_PLUS_PARTS)
+    with contextlib.redirect_stdout(io.StringIO()):
+        G = L.networks.Generator(z_dim=512, c_dim=0, w_dim=512, img_resolution=res, img_channels=3, mapping_kwargs=dict(num_layers=spec['map']),
+                                 synthesis_kwargs=dict(channel_base=cb, channel_max=512, num_fp16_res=0, conv_clamp=None, **extra)).train()
+        D = L.networks.Discriminator(c_dim=0, img_resolution=res, img_channels=3, channel_base=cb, channel_max=512, num_fp16_res=0,
+                                     conv_clamp=None, epilogue_kwargs=dict(mbstd_group_size=spec['mbstd'])).train()
+    pipe = None
+    if args.workload == 'ada':
+        pipe = L.augment.AugmentPipe(**REF_AUGPIPE_BGC).train().requires_grad_(False)
+        pipe.p.copy_(torch.as_tensor(0.3))
+    loss = L.loss.StyleGAN2Loss(device=torch.device('cpu'), G_mapping=G.mapping, G_synthesis=G.synthesis, D=D, augment_pipe=pipe,
+                                r1_gamma=spec['gamma'])
+    optG = torch.optim.Adam(G.parameters(), lr=spec['lrate'] * 0.8, betas=(0.0, 0.99 ** 0.8), eps=1e-8)
+    optD = torch.optim.Adam(D.parameters(), lr=spec['lrate'] * 16 / 17, betas=(0.0, 0.99 ** (16 / 17)), eps=1e-8)
+    z = torch.randn(batch, 512)
+    c = torch.zeros(batch, 0)
+    real = torch.rand(batch, 3, res, res) * 2 - 1
     t = {}
-
-    def phase(name, fn, params, opt):
+    for name, net, opt, gain in (('Gmain', G, optG, 1), ('Dmain', D, optD, 1), ('Greg', G, optG, 4), ('Dreg', D, optD, 16)):
         t0 = time.perf_counter()
-        for p in params:
-            p.grad = None
-        loss = fn()
-        loss.backward()
+        opt.zero_grad(set_to_none=True)
+        G.requires_grad_(False); D.requires_grad_(False)
+        if net is G and args.workload == 'ada':
+            for n, p in G.named_parameters():           # the Affine+ parts: affine layers + the b64 weight offsets
+                p.requires_grad_((('affine' in n) and 'synthesis' in n) or ('weights_offset' in n and 'synthesis.b64' in n))
+        else:
+            net.requires_grad_(True)
+        loss.accumulate_gradients(phase=name, real_img=real, real_c=c, gen_z=z, gen_c=c, sync=True, gain=gain)
         opt.step()
         t[name] = time.perf_counter() - t0
-
-    phase('Gmain', lambda: NR.loss_Gmain(PG, PD, z, res, mb, num_layers=spec['map']), gl, optG)
-    phase('Dmain', lambda: NR.loss_Dmain(PG, PD, z, real, res, mb, num_layers=spec['map']), dl, optD)
-    phase('Greg', lambda: NR.loss_Gpl(PG, z, res, torch.zeros([]), num_layers=spec['map'])[0] * 4, gl, optG)
-    phase('Dreg', lambda: NR.loss_Dr1(PD, real, res, spec['gamma'], mb) * 16, dl, optD)
     t_iter = t['Gmain'] + t['Dmain'] + t['Greg'] / 4 + t['Dreg'] / 16
     return batch / t_iter, t
 
 
+def cpu_reference_ga(L, args, individuals):
+    """Fitness of `individuals` GA individuals through the reference G/D on the host cores; returns images/sec."""
+    spec = REF_CONFIGS[args.cfg]
+    cb = int(spec['fmaps'] * 32768)
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        G = L.networks.Generator(z_dim=512, c_dim=0, w_dim=512, img_resolution=args.res, img_channels=3, mapping_kwargs=dict(num_layers=spec['map']),
+                                 synthesis_kwargs=dict(channel_base=cb, channel_max=512, num_fp16_res=0, conv_clamp=None, use_domain_modulation=True,
+                                                       domain_modulation_parametrization='additive')).eval()
+        D = L.networks.Discriminator(c_dim=0, img_resolution=args.res, img_channels=3, channel_base=cb, channel_max=512, num_fp16_res=0,
+                                     conv_clamp=None, epilogue_kwargs=dict(mbstd_group_size=spec['mbstd'])).eval()
+    z = torch.randn(args.latents, 512); c = torch.zeros(args.latents, 0)
+    layers = [m for m in G.synthesis.modules() if isinstance(getattr(m, 'offset', None), torch.nn.Parameter)]
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        ws = G.mapping(z, c)
+        for _ in range(individuals):
+            for m in layers:
+                m.offset.copy_(0.1 * torch.randn(m.offset.shape))
+            D(G.synthesis(ws, noise_mode='const'), c).mean().item()
+    return individuals * args.latents / (time.perf_counter() - t0)
+
+
 def run_reference_arm(args, rank):
-    """`--impl reference`: the reference's CPU algorithm (oracle port) on all host threads, rank 0 only."""
+    """`--impl reference`: the reference itself on all host threads, rank 0 only."""
     if rank != 0:
         return
+    if not os.path.isdir(os.path.join(ORACLE_REF, 'training')):
+        print(json.dumps(dict(impl='reference', unavailable='oracle/_ref is missing (tools/vendor_reference.py needs /root/reference)')), flush=True)
+        return
+    L = _load_plain_reference()
     res = args.cpu_res or args.res
     budget_s = 240.0
     t_start = time.perf_counter()
     vals, phases, done_warm, done = [], None, 0, 0
-    for i in range(args.warmup + args.steps):
-        v, ph = cpu_reference_iteration(res, args.cfg, args.cpu_batch, seed=i)
-        if i >= args.warmup or (time.perf_counter() - t_start) > budget_s * 0.5:
-            vals.append(v); phases = ph; done += 1
-        else:
-            done_warm += 1
-        if (time.perf_counter() - t_start) > budget_s and vals:
-            break
+    if args.workload == 'ga':
+        n_ind = 2
+        vals = [cpu_reference_ga(L, args, n_ind)]
+        done, phases = 1, {}
+        sample = f'{n_ind} individuals x {args.latents} latents at {args.res}x{args.res} {args.cfg}, reference G/D eval on the host cores'
+        batch_for_ms = n_ind * args.latents
+    else:
+        for i in range(args.warmup + args.steps):
+            v, ph = cpu_reference_iteration(L, args, args.cpu_batch, seed=i)
+            if i >= args.warmup or (time.perf_counter() - t_start) > budget_s * 0.5:
+                vals.append(v); phases = ph; done += 1
+            else:
+                done_warm += 1
+            if (time.perf_counter() - t_start) > budget_s and vals:
+                break
+        sample = (f'{done} timed + {done_warm} warm-up amortised iterations (Gmain+Dmain+Greg/4+Dreg/16 incl. Adam) at batch '
+                  f'{args.cpu_batch}, {res}x{res} {args.cfg} fp32, the unmodified reference (training/networks.py, training/loss.py on its '
+                  f'impl=ref operators), torch {torch.__version__} CPU, {torch.get_num_threads()} threads; wall budget {budget_s:.0f}s')
+        batch_for_ms = args.cpu_batch
     value = float(np.mean(vals))
-    sample = (f'{done} timed + {done_warm} warm-up amortised iterations (Gmain+Dmain+Greg/4+Dreg/16 incl. Adam) at batch '
-              f'{args.cpu_batch}, {res}x{res} {args.cfg} fp32, oracle port of impl=ref; wall budget {budget_s:.0f}s')
-    line = dict(metric=METRIC, value=value, unit=UNIT, impl='reference', n_gpus=args.gpus, steps=done, warmup=done_warm,
-                ms_per_step=1000.0 * args.cpu_batch / value, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
-                data='synthetic',
+    world = max(args.gpus, 1)
+    line = dict(metric=METRIC if args.workload != 'ga' else 'ga_population_fitness_images_per_sec', value=value, unit=UNIT, impl='reference',
+                n_gpus=args.gpus, steps=done, warmup=done_warm, ms_per_step=1000.0 * batch_for_ms / value, higher_is_better=True,
+                scaling=args.scaling, vs_baseline=None, dtype='f32', data='synthetic',
                 # the same workload as the GPU arm (its `config.workload`, `global_batch`); what was actually timed is `cpu_baseline.sample`
-                config=dict(workload=f'StyleGAN2 {args.cfg} (config-f) {args.res}x{args.res} G+D train iteration fp32, batch {args.batch}/GPU '
-                                     f'in rounds of {min(args.batch_gpu, args.batch)}', global_batch=args.batch * max(args.gpus, 1),
-                            parallelism=f'dp{max(args.gpus, 1)}', reference_sample=f'batch {args.cpu_batch} at {res}x{res} on the host cores, scaled per image'),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=os.cpu_count(), kind='port', sample=sample,
-                                  phase_seconds={k: round(v, 3) for k, v in phases.items()}),
+                config=dict(workload=workload_text(args, world), global_batch=args.batch * world, parallelism=f'dp{world}',
+                            reference_sample=f'batch {args.cpu_batch} at {res}x{res} on the host cores, scaled per image'),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=os.cpu_count(), kind='reference', sample=sample,
+                                  phase_seconds={k: round(v, 3) for k, v in (phases or {}).items()}),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_child(args):
+    """The cpu_baseline leg of the GPU arm: the reference arm as a child process (the parent has this build's operators installed
+    under the reference's module names, the child is a clean interpreter that never loads them)."""
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '1', '--warmup', '0', '--workload', args.workload,
+           '--cfg', args.cfg, '--res', str(args.res), '--cpu-res', str(args.cpu_res), '--cpu-batch', str(args.cpu_batch),
+           '--batch', str(args.batch), '--population', str(args.population), '--latents', str(args.latents)]
+    env = dict(os.environ, WORLD_SIZE='1', RANK='0', LOCAL_RANK='0', CUDA_VISIBLE_DEVICES='')
+    try:
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900, env=env)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith('{'):
+                d = json.loads(ln)
+                return d.get('cpu_baseline', d)
+        return dict(unavailable=(out.stderr or 'no output')[-300:])
+    except Exception as e:       # a failed baseline must not lose the GPU measurement
+        return dict(unavailable=str(e)[-300:])
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -192,8 +308,13 @@ def main():
         return
 
     import torch.distributed as dist
+    import gagan_b200
+    if not os.path.isdir(os.path.join(CHECKOUT, 'training')):
+        raise SystemExit('bench.py: baseline/_ref/DissimilarDomains is missing -- the bench drives the reference checkout on this build; '
+                         'run `python tools/vendor_reference.py` where /root/reference exists')
+    gagan_b200.install(CHECKOUT, fused_callers=not args.reference_forwards)
     from torch_utils import custom_ops
-    from training import training_loop
+    from gagan_b200.training import training_loop, ga_eval
 
     assert torch.cuda.is_available(), 'bench.py needs a B200; there is no CPU path (use --impl reference for the CPU arm)'
     torch.cuda.set_device(local_rank)
@@ -205,52 +326,82 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     custom_ops.verbosity = 'none'
-    custom_ops.conv_precision = dict(auto=custom_ops.PREC_AUTO, simt=custom_ops.PREC_FP32_SIMT, tf32x1=custom_ops.PREC_TF32X1,
-                                     tf32x3=custom_ops.PREC_TF32X3)[args.prec]
-
-    spec = training_loop.CONFIGS[args.cfg]
-    torch.manual_seed(0 * world + rank)                       # training_loop.py:204-205
-    G, D = training_loop.build_networks(args.res, args.cfg, device=dev)
-    step = training_loop.TrainingStep(G, D, batch_size=args.batch * world, batch_gpu=min(args.batch_gpu, args.batch), device=dev,
-                                      lrate=spec['lrate'], r1_gamma=spec['gamma'], ema_kimg=spec['ema'], rank=rank, num_gpus=world)
-    n_phases = len(step.phases)
-
-    # synthetic inputs: device-resident for `value`, pinned host uint8 + host latents for `e2e`
-    real_dev = torch.rand(args.batch, 3, args.res, args.res, device=dev) * 2 - 1      # training_loop.py:441 range
-    real_host = torch.randint(0, 256, (args.batch, 3, args.res, args.res), dtype=torch.uint8).pin_memory()
-    z_host = torch.randn(n_phases, args.batch, 512).pin_memory()
-    h2d_bytes = real_host.numel() + z_host.numel() * 4
+    PREC = dict(auto=custom_ops.PREC_AUTO, simt=custom_ops.PREC_FP32_SIMT, tf32x1=custom_ops.PREC_TF32X1, tf32x3=custom_ops.PREC_TF32X3)
+    custom_ops.conv_precision = PREC[args.prec]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    spec = training_loop.CONFIGS[args.cfg]
+    torch.manual_seed(0 * world + rank)                       # training_loop.py:204-205
+
+    if args.workload == 'ga':
+        G, D = training_loop.build_networks(args.res, args.cfg, device=dev, use_domain_modulation=True, domain_modulation_parametrization='additive')
+        pop = ga_eval.init_population(G, args.population, seed=0)
+        z_host = torch.randn(args.latents, 512, generator=torch.Generator().manual_seed(1)).pin_memory()
+        z_dev = z_host.to(dev)
+        units = args.population * args.latents               # images through G and D per step, whole job
+
+        def one_step(host_inputs):
+            z = z_host.to(dev, non_blocking=True) if host_inputs else z_dev
+            fit = ga_eval.evaluate_population(G, D, pop, z, rank=rank, world=world)
+            return fit.cpu() if host_inputs else fit
+        h2d_bytes, metric = z_host.numel() * 4 + pop.numel() * 4, 'ga_population_fitness_images_per_sec'
+    else:
+        extra, step_kw = {}, {}
+        if args.workload == 'ada':
+            extra = dict(use_domain_modulation=True, domain_modulation_parametrization=AFFINE_PLUS_PARAM,
+                         generator_requires_grad_parts=AFFINE_PLUS_PARTS)
+            step_kw = dict(g_parts=AFFINE_PLUS_PARTS, glrate=0.02, augment_kwargs=training_loop.AUGPIPE_BGC, ada_target=0.6, augment_p=0.0)
+        G, D = training_loop.build_networks(args.res, args.cfg, device=dev, **extra)
+        step = training_loop.TrainingStep(G, D, batch_size=args.batch * world, batch_gpu=min(args.batch_gpu, args.batch), device=dev,
+                                          lrate=spec['lrate'], r1_gamma=spec['gamma'], ema_kimg=spec['ema'], rank=rank, num_gpus=world, **step_kw)
+        n_phases = len(step.phases)
+        # synthetic inputs: device-resident for `value`, pinned host uint8 + host latents for `e2e`
+        n_real = args.batch if args.workload == 'train' else 10       # ada: a 10-shot target set cycled by the sampler
+        real_host_set = torch.randint(0, 256, (n_real, 3, args.res, args.res), dtype=torch.uint8)
+        real_host = real_host_set[torch.arange(args.batch) % n_real].contiguous().pin_memory()
+        real_dev = real_host.to(dev).to(torch.float32) / 127.5 - 1    # training_loop.py:441
+        z_host = torch.randn(n_phases, args.batch, 512).pin_memory()
+        units = args.batch * world
+        h2d_bytes, metric = real_host.numel() + z_host.numel() * 4, METRIC
+
+        def one_step(host_inputs):
+            if host_inputs:
+                real = real_host.to(dev, non_blocking=True).to(torch.float32) / 127.5 - 1
+                step.run(real, z_host.to(dev, non_blocking=True))
+                return step.read_stats()                  # the step's loss statistics -> host (syncs; all-reduce across ranks)
+            step.run(real_dev)
+            return None
+
     def timed(n_steps, host_inputs):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        step.cur_it = 0                       # Greg fires ceil(K/4) times, Dreg ceil(K/16) times: never under-counted
-        d2h = 0
+        if args.workload != 'ga':
+            step.cur_it = 0                       # Greg fires ceil(K/4) times, Dreg ceil(K/16) times: never under-counted
+        out = None
         e0.record()
         for _ in range(n_steps):
-            if host_inputs:
-                real = real_host.to(dev, non_blocking=True).to(torch.float32) / 127.5 - 1
-                zs = z_host.to(dev, non_blocking=True)
-                out = step.run(real, zs)
-                host_vals = torch.stack([v for v in out.values()]).cpu()      # the step's loss scalars -> host (syncs)
-                d2h = host_vals.numel() * 4
-            else:
-                step.run(real_dev)
+            out = one_step(host_inputs)
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), d2h
+        d2h = 0
+        if host_inputs and out is not None:
+            d2h = (out.numel() * 4) if isinstance(out, torch.Tensor) else 3 * 8 * len(out)     # training_stats moves 3 fp64 moments per name
+        return max_over_ranks(e0.elapsed_time(e1)), d2h
 
     for _ in range(max(args.warmup, 0)):                      # warm-up covers all four phases (cur_it = 0 fires both regs)
-        step.cur_it = 0
-        step.run(real_dev)
+        if args.workload != 'ga':
+            step.cur_it = 0
+        one_step(False)
     barrier()
 
     sampler = ClockSampler(local_rank)
@@ -264,9 +415,21 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, d2h_bytes = timed(args.steps, host_inputs=True)
 
-    imgs = args.batch * world * args.steps
-    value = imgs / (ms_total / 1000.0)
-    e2e_value = imgs / (ms_e2e / 1000.0)
+    fast = None
+    if not args.no_fast_mode and args.prec == 'auto' and args.workload == 'train':
+        custom_ops.conv_precision = custom_ops.PREC_TF32X1
+        k = min(args.steps, 4)
+        one_step(False)
+        ms_fast, _ = timed(k, host_inputs=False)
+        custom_ops.conv_precision = PREC[args.prec]
+        fast = dict(mode='tf32x1 (one TF32 product per MAC instead of hi*hi + hi*lo + lo*hi)', value=units * k / (ms_fast / 1000.0), unit=UNIT,
+                    steps=k, ms_per_step=ms_fast / k,
+                    parity='NOT fp32-faithful: network-level max-rel-err of the four loss-phase goldens and the config-size layers is '
+                           'recorded by tests/test_gpu_config_size.py::test_fast_mode_report -> profiles/r2_fast_mode_parity.txt; '
+                           'the headline stays the 3xTF32 mode')
+
+    value = units * args.steps / (ms_total / 1000.0)
+    e2e_value = units * args.steps / (ms_e2e / 1000.0)
 
     # roofline of the dominant kernel, from the per-launch CUDA events recorded inside the timed region: conv_tc_kernel, the
     # tcgen05 implicit-GEMM convolution that serves every forward and data-gradient contraction (by_kind lists the others)
@@ -281,8 +444,8 @@ def main():
     all_conv_ms = sum(v[2] for v in by_kind.values())
     tf32_peak = peaks['bf16_sustained'] / 2.0
     achieved = dom_flops / (dom_ms / 1000.0) / 1e12 if dom_ms > 0 else 0.0
-    # DRAM bytes per launch of the same kernel from the committed ncu --set full capture of this command (profiles/): bench.py cannot
-    # run a profiler itself, so the figure is read from the summary that tools/ncu_traffic.py wrote; null if there is none
+    # DRAM bytes per launch of the same kernel family from the committed ncu capture of this command (profiles/): bench.py cannot run
+    # a profiler itself, so the figure is read from the summary that tools/ncu_traffic.py wrote; null if there is none
     traffic, traffic_note = None, 'no ncu capture committed'
     tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
     if os.path.isfile(tpath):
@@ -309,26 +472,22 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cres = args.cpu_res or args.res
-        v, ph = cpu_reference_iteration(cres, args.cfg, args.cpu_batch)
-        cpu = dict(value=v, unit=UNIT, cores=os.cpu_count(), kind='port',
-                   sample=f'one amortised iteration (Gmain+Dmain+Greg/4+Dreg/16 incl. Adam) at batch {args.cpu_batch}, {cres}x{cres} '
-                          f'{args.cfg} fp32, oracle port of the reference impl=ref path, torch {torch.__version__} CPU, '
-                          f'{torch.get_num_threads()} threads',
-                   phase_seconds={k: round(x, 3) for k, x in ph.items()})
+        cpu = cpu_baseline_child(args)
 
-    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
-                data='synthetic',
-                config=dict(workload=f'StyleGAN2 {args.cfg} (config-f) {args.res}x{args.res} G+D train iteration fp32, batch {args.batch}/GPU '
-                                     f'in rounds of {min(args.batch_gpu, args.batch)}', global_batch=args.batch * world,
-                            parallelism=f'dp{world}', conv_precision=args.prec,
-                            peak_hbm_gb=round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1),
-                            l2_policy='inputs and activations (>1 GB per round) exceed the 126 MB L2; no explicit flush',
-                            reg_schedule='Greg every 4th, Dreg every 16th iteration, counter reset at the start of the timed region'),
+    cfg = dict(workload=workload_text(args, world), global_batch=args.batch * world, parallelism=f'dp{world}', conv_precision=args.prec,
+               callers=f'reference checkout (training/networks.py, training/loss.py) + gagan_b200.install(fused_callers={not args.reference_forwards})',
+               peak_hbm_gb=round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1),
+               l2_policy='inputs and activations (>1 GB per round) exceed the 126 MB L2; no explicit flush')
+    if args.workload != 'ga':
+        cfg['reg_schedule'] = 'Greg every 4th, Dreg every 16th iteration, counter reset at the start of the timed region'
+    else:
+        cfg['individuals_per_sec'] = args.population * args.steps / (ms_total / 1000.0)
+    line = dict(metric=metric, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms_total / args.steps, higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype='f32',
+                data='synthetic', config=cfg,
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=int(d2h_bytes),
                          ms_per_step=ms_e2e / args.steps),
-                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, clocks=clocks)
+                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, fast_mode=fast, clocks=clocks)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

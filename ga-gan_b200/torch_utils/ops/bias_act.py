@@ -15,20 +15,31 @@ import numpy as np
 import torch
 
 from .. import custom_ops
-from .. import misc
 
 # ----------------------------------------------------------------------------
 
+class _Act:
+    """One row of `activation_funcs`: attribute access (`.def_gain`, `.cuda_idx`, ...) as the callers expect."""
+    __slots__ = ('func', 'def_alpha', 'def_gain', 'cuda_idx', 'ref', 'has_2nd_grad')
+
+    def __init__(self, func, def_alpha, def_gain, cuda_idx, ref, has_2nd_grad):
+        self.func, self.def_alpha, self.def_gain = func, def_alpha, def_gain
+        self.cuda_idx, self.ref, self.has_2nd_grad = cuda_idx, ref, has_2nd_grad
+
+    def __getitem__(self, key):
+        return getattr(self, key)
+
+
 activation_funcs = {
-    'linear':   misc.EasyDict(func=lambda x, **_: x,                                          def_alpha=0,   def_gain=1,          cuda_idx=1, ref='',  has_2nd_grad=False),
-    'relu':     misc.EasyDict(func=lambda x, **_: torch.nn.functional.relu(x),                def_alpha=0,   def_gain=np.sqrt(2), cuda_idx=2, ref='y', has_2nd_grad=False),
-    'lrelu':    misc.EasyDict(func=lambda x, alpha, **_: torch.nn.functional.leaky_relu(x, alpha), def_alpha=0.2, def_gain=np.sqrt(2), cuda_idx=3, ref='y', has_2nd_grad=False),
-    'tanh':     misc.EasyDict(func=lambda x, **_: torch.tanh(x),                              def_alpha=0,   def_gain=1,          cuda_idx=4, ref='y', has_2nd_grad=True),
-    'sigmoid':  misc.EasyDict(func=lambda x, **_: torch.sigmoid(x),                           def_alpha=0,   def_gain=1,          cuda_idx=5, ref='y', has_2nd_grad=True),
-    'elu':      misc.EasyDict(func=lambda x, **_: torch.nn.functional.elu(x),                 def_alpha=0,   def_gain=1,          cuda_idx=6, ref='y', has_2nd_grad=True),
-    'selu':     misc.EasyDict(func=lambda x, **_: torch.nn.functional.selu(x),                def_alpha=0,   def_gain=1,          cuda_idx=7, ref='y', has_2nd_grad=True),
-    'softplus': misc.EasyDict(func=lambda x, **_: torch.nn.functional.softplus(x),            def_alpha=0,   def_gain=1,          cuda_idx=8, ref='y', has_2nd_grad=True),
-    'swish':    misc.EasyDict(func=lambda x, **_: torch.sigmoid(x) * x,                       def_alpha=0,   def_gain=np.sqrt(2), cuda_idx=9, ref='x', has_2nd_grad=True),
+    'linear':   _Act(func=lambda x, **_: x,                                          def_alpha=0,   def_gain=1,          cuda_idx=1, ref='',  has_2nd_grad=False),
+    'relu':     _Act(func=lambda x, **_: torch.nn.functional.relu(x),                def_alpha=0,   def_gain=np.sqrt(2), cuda_idx=2, ref='y', has_2nd_grad=False),
+    'lrelu':    _Act(func=lambda x, alpha, **_: torch.nn.functional.leaky_relu(x, alpha), def_alpha=0.2, def_gain=np.sqrt(2), cuda_idx=3, ref='y', has_2nd_grad=False),
+    'tanh':     _Act(func=lambda x, **_: torch.tanh(x),                              def_alpha=0,   def_gain=1,          cuda_idx=4, ref='y', has_2nd_grad=True),
+    'sigmoid':  _Act(func=lambda x, **_: torch.sigmoid(x),                           def_alpha=0,   def_gain=1,          cuda_idx=5, ref='y', has_2nd_grad=True),
+    'elu':      _Act(func=lambda x, **_: torch.nn.functional.elu(x),                 def_alpha=0,   def_gain=1,          cuda_idx=6, ref='y', has_2nd_grad=True),
+    'selu':     _Act(func=lambda x, **_: torch.nn.functional.selu(x),                def_alpha=0,   def_gain=1,          cuda_idx=7, ref='y', has_2nd_grad=True),
+    'softplus': _Act(func=lambda x, **_: torch.nn.functional.softplus(x),            def_alpha=0,   def_gain=1,          cuda_idx=8, ref='y', has_2nd_grad=True),
+    'swish':    _Act(func=lambda x, **_: torch.sigmoid(x) * x,                       def_alpha=0,   def_gain=np.sqrt(2), cuda_idx=9, ref='x', has_2nd_grad=True),
 }
 
 # ----------------------------------------------------------------------------

@@ -7,7 +7,7 @@ bit-for-bit against the oracle; `conv2d_resample()` executes the plan on this bu
 """
 import torch
 
-from .. import misc
+from ..._util import check_dims, scoped
 from . import conv2d_gradfix
 from . import upfirdn2d
 from .upfirdn2d import _parse_padding
@@ -16,7 +16,7 @@ from .upfirdn2d import _get_filter_size
 
 def _get_weight_shape(w):
     shape = [int(sz) for sz in w.shape]
-    misc.assert_shape(w, shape)
+    check_dims(w, shape, 'weight')
     return shape
 
 
@@ -157,7 +157,7 @@ def _fir_from_pm(z, f, padding, flip_filter, gain, valid_hw):
     return upfirdn2d.fir_from_pm(z, f, padding, flip_filter, gain, valid_hw)
 
 
-@misc.profiled_function
+@scoped
 def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False, in_scale=None,
                     out_scale=None):
     r"""2D convolution with optional up/downsampling; padding is applied once, up front.

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from .. import custom_ops
-from .. import misc
+from ..._util import check_dims
 
 # ----------------------------------------------------------------------------
 
@@ -55,7 +55,7 @@ def _get_filter_size(f):
     assert isinstance(f, torch.Tensor) and f.ndim in [1, 2]
     fw = int(f.shape[-1])
     fh = int(f.shape[0])
-    misc.assert_shape(f, [fh, fw][:f.ndim])
+    check_dims(f, [fh, fw][:f.ndim], 'filter')
     assert fw >= 1 and fh >= 1
     return fw, fh
 

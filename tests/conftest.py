@@ -3,9 +3,9 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, 'ga-gan_b200')):
-    if p not in sys.path:
-        sys.path.insert(0, p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+import tests.util  # noqa: E402,F401  (installs the drop-in: gagan_b200.install(baseline/_ref/DissimilarDomains))
 
 
 def pytest_configure(config):

@@ -1,19 +1,22 @@
-"""GPU: network-level parity.  The product modules (training/networks.py, training/loss.py) loaded with the
-golden weights must reproduce what the REFERENCE's own Generator / Discriminator / StyleGAN2Loss produced on CPU
-(tests/golden/networks.npz): eval and train forward, and parameter gradients after each of the four loss phases
-(Greg and Dreg are double-backward through every op)."""
+"""GPU: network-level parity of the DROP-IN.  The reference's OWN Generator / Discriminator / StyleGAN2Loss (the checkout in
+baseline/_ref, unmodified) run on this build's operators (gagan_b200.install) with the golden weights and must reproduce
+what the same classes produced on the reference's CPU impl='ref' operators (tests/golden/networks.npz): eval and train
+forward, and parameter gradients after each of the four loss phases (Greg and Dreg are double-backward through every op).
+Every test runs twice: with the reference's forwards untouched, and with this build's fused forwards laid over them."""
 import numpy as np
 import pytest
 import torch
 
-from tests.util import load_golden, t, assert_close, patched_randn, TOL
+from tests.util import load_golden, t, assert_close, patched_randn, TOL, reference_networks, quiet
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope='module')
-def nets(device):
-    from training import networks
+@pytest.fixture(scope='module', params=['fused_forwards', 'reference_forwards'])
+def nets(device, request):
+    import gagan_b200.training.networks as mine
+    networks = reference_networks()
+    mine.attach(networks, fused_callers=(request.param == 'fused_forwards'))
     g = load_golden('networks')
     cfg = {kv.split('=')[0]: int(kv.split('=')[1]) for kv in (str(m) for m in g['meta'])}
     G = networks.Generator(z_dim=cfg['z_dim'], c_dim=0, w_dim=cfg['w_dim'], img_resolution=cfg['res'], img_channels=3,
@@ -23,7 +26,8 @@ def nets(device):
                                channel_max=cfg['channel_max'], epilogue_kwargs=dict(mbstd_group_size=cfg['mbstd']))
     G.load_state_dict({k[2:]: t(v) for k, v in g.items() if k.startswith('G.')}, strict=False)
     D.load_state_dict({k[2:]: t(v) for k, v in g.items() if k.startswith('D.')}, strict=False)
-    return G.to(device), D.to(device), g, cfg
+    yield G.to(device), D.to(device), g, cfg
+    mine.attach(networks, fused_callers=True)
 
 
 def test_eval_forward(nets, device):
@@ -80,9 +84,10 @@ def test_loss_phase_parameter_gradients(nets, device, phase):
 
 def test_ga_population_fitness_eval_on_the_device(device):
     """BASELINE configs[3] at toy size: fitness of StyleSpace-offset individuals through the CUDA G/D (world = 1)."""
-    from training import networks, ga_eval
+    from gagan_b200.training import ga_eval
+    networks = reference_networks()
     torch.manual_seed(3)
-    G = networks.Generator(z_dim=32, c_dim=0, w_dim=32, img_resolution=32, img_channels=3, mapping_kwargs=dict(num_layers=2),
+    G = quiet(networks.Generator, z_dim=32, c_dim=0, w_dim=32, img_resolution=32, img_channels=3, mapping_kwargs=dict(num_layers=2),
                            synthesis_kwargs=dict(channel_base=512, channel_max=32, use_domain_modulation=True,
                                                  domain_modulation_parametrization='additive')).to(device)
     D = networks.Discriminator(c_dim=0, img_resolution=32, img_channels=3, channel_base=512, channel_max=32).to(device)
@@ -106,9 +111,10 @@ def test_ga_population_fitness_eval_on_the_device(device):
 def test_ga_population_eval_cuda_graph_replay_matches_eager(device):
     """Shards of >= 16 individuals are evaluated by replaying one captured CUDA graph (ga_eval.evaluate_population): the
     same kernels, so the fitness vector must equal the eager loop's bit for bit (up to atomics-free determinism)."""
-    from training import networks, ga_eval
+    from gagan_b200.training import ga_eval
+    networks = reference_networks()
     torch.manual_seed(4)
-    G = networks.Generator(z_dim=32, c_dim=0, w_dim=32, img_resolution=32, img_channels=3, mapping_kwargs=dict(num_layers=2),
+    G = quiet(networks.Generator, z_dim=32, c_dim=0, w_dim=32, img_resolution=32, img_channels=3, mapping_kwargs=dict(num_layers=2),
                            synthesis_kwargs=dict(channel_base=512, channel_max=32, use_domain_modulation=True,
                                                  domain_modulation_parametrization='additive')).to(device)
     D = networks.Discriminator(c_dim=0, img_resolution=32, img_channels=3, channel_base=512, channel_max=32).to(device)

@@ -20,7 +20,10 @@ def _meta(g):
 def ops(device):
     from torch_utils import custom_ops
     from torch_utils.ops import upfirdn2d, bias_act, conv2d_resample, conv2d_gradfix, fma
-    from training import networks
+    try:
+        from training import networks                 # the reference's module with this build's modulated_conv2d attached
+    except ImportError:
+        from gagan_b200.training import networks      # no checkout on this box: the function itself
     custom_ops.load_library()
     import types
     return types.SimpleNamespace(upfirdn2d=upfirdn2d, bias_act=bias_act, conv2d_resample=conv2d_resample,

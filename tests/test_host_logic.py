@@ -10,9 +10,10 @@ import torch
 from tests.util import ROOT, PKG
 from oracle import ops_ref as R
 
-from torch_utils import custom_ops
+from tests.util import CHECKOUT, HAVE_CHECKOUT, reference_networks, quiet
+
+from torch_utils import custom_ops                                                      # after install(): this build's modules
 from torch_utils.ops import upfirdn2d, bias_act, conv2d_resample, conv2d_gradfix, fma
-from training import networks
 
 
 def test_conv2d_resample_plan_bit_exact():
@@ -100,8 +101,37 @@ def test_fma_matches_oracle_on_cpu():
         assert torch.allclose(u, v, atol=1e-6)
 
 
-def test_network_state_dict_names_match_golden_weights():
+def test_install_binds_the_operator_modules_into_the_reference_checkout():
+    """The drop-in: after gagan_b200.install(checkout) the reference's own modules resolve their operators to this build,
+    nothing else of the checkout is shadowed, and its module tree is the reference's code (not a copy shipped here)."""
+    import sys
+    import gagan_b200
+    networks = reference_networks()
+    for name in gagan_b200.OPS:
+        mod = sys.modules['torch_utils.ops.' + name]
+        assert mod.__name__ == f'gagan_b200.torch_utils.ops.{name}', mod
+    assert sys.modules['torch_utils.custom_ops'].__name__ == 'gagan_b200.torch_utils.custom_ops'
+    for attr in ('conv2d_resample', 'upfirdn2d', 'bias_act', 'fma'):                     # networks.py:16-19
+        assert getattr(networks, attr).__name__.startswith('gagan_b200.'), attr
+    assert networks.modulated_conv2d.__module__ == 'gagan_b200.training.networks'
+    assert os.path.abspath(networks.__file__).startswith(CHECKOUT)
+    from training import loss, augment                                                    # loss.py:13, augment.py:14-16
+    assert loss.conv2d_gradfix.__name__.startswith('gagan_b200.') and augment.upfirdn2d.__name__.startswith('gagan_b200.')
+    assert augment.conv2d_gradfix.__name__.startswith('gagan_b200.')
+    from torch_utils import misc, persistence, training_stats                             # the checkout's own, not shadowed
+    for mod in (misc, persistence, training_stats, loss, augment):
+        assert os.path.abspath(mod.__file__).startswith(CHECKOUT), mod
+    # nothing under ga-gan_b200/ defines the reference's module tree or loss
+    for dirpath, _, files in os.walk(PKG):
+        for fn in files:
+            if fn.endswith('.py'):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert 'class Generator' not in src and 'class StyleGAN2Loss' not in src and 'class SynthesisBlock' not in src, fn
+
+
+def test_reference_networks_build_with_the_golden_state_dict_names():
     from tests.util import load_golden
+    networks = reference_networks()
     g = load_golden('networks')
     cfg = {kv.split('=')[0]: int(kv.split('=')[1]) for kv in (str(m) for m in g['meta'])}
     G = networks.Generator(z_dim=cfg['z_dim'], c_dim=0, w_dim=cfg['w_dim'], img_resolution=cfg['res'], img_channels=3,
@@ -113,12 +143,32 @@ def test_network_state_dict_names_match_golden_weights():
         sd = {k: v for k, v in net.state_dict().items() if not k.endswith('resample_filter')}
         gold = {k[2:]: v for k, v in g.items() if k.startswith(pre)}
         assert set(sd) == set(gold), (set(sd) ^ set(gold))
-        for k in sd:
-            assert tuple(sd[k].shape) == tuple(gold[k].shape), k
-    # parameter counts of the real configs: cfg-f 1024^2 G 30.37 M / D 29.01 M
+    # parameter counts of the real configs: cfg-f 1024^2 G 30.37 M
     Gf = networks.Generator(512, 0, 512, 1024, 3, mapping_kwargs=dict(num_layers=8), synthesis_kwargs=dict(channel_base=32768))
-    assert sum(p.numel() for p in Gf.parameters()) == 30370060
-    assert Gf.num_ws == 18
+    assert sum(p.numel() for p in Gf.parameters()) == 30370060 and Gf.num_ws == 18
+
+
+def _affine_plus_generator(networks):
+    return quiet(networks.Generator, z_dim=16, c_dim=0, w_dim=16, img_resolution=64, img_channels=3, mapping_kwargs=dict(num_layers=2),
+                 synthesis_kwargs=dict(channel_base=1024, channel_max=16, use_domain_modulation=True,
+                                       domain_modulation_parametrization='out_in_5_1,additive,affine_out_in_5_1',
+                                       generator_requires_grad_parts=['all']))
+
+
+def test_trainable_part_filter_matches_the_golden_selection():
+    """training_loop.select_parts == the reference's name_filters / set_requires_grad (training_loop.py:57-95); the golden
+    selections were produced by the reference function itself (tests/golden/make_parts_golden.py)."""
+    import json
+    from gagan_b200.training import training_loop
+    networks = reference_networks()
+    gold = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'requires_grad_parts.json')))
+    G = _affine_plus_generator(networks)
+    assert [n for n, _ in G.named_parameters()] == gold['parameter_names']
+    assert len(gold['specs']) >= 10
+    for spec, want in zip(gold['specs'], gold['selected']):
+        assert training_loop.select_parts(G, spec) == want, spec
+        training_loop.set_requires_grad(G, spec)
+        assert [n for n, p in G.named_parameters() if p.requires_grad] == want
 
 
 def test_phase_major_forms_of_the_stride2_layers_match_the_oracle():

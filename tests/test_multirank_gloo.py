@@ -80,7 +80,7 @@ def _free_port():
 
 
 def _run_step(rank, world, port, out_dir):
-    from training.training_loop import TrainingStep
+    from gagan_b200.training.training_loop import TrainingStep
     if world > 1:
         os.environ['MASTER_ADDR'] = '127.0.0.1'
         os.environ['MASTER_PORT'] = str(port)
@@ -137,7 +137,7 @@ def test_training_step_shards_by_minibatch_and_allreduces_once_per_phase():
 
 
 def _run_ga(rank, world, port, out_dir):
-    from training import ga_eval
+    from gagan_b200.training import ga_eval
     if world > 1:
         os.environ['MASTER_ADDR'] = '127.0.0.1'
         os.environ['MASTER_PORT'] = str(port)

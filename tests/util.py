@@ -8,9 +8,34 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, 'ga-gan_b200')
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
-for p in (ROOT, PKG):
-    if p not in sys.path:
-        sys.path.insert(0, p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# The drop-in under test: the reference checkout that travels with the repo (tools/vendor_reference.py -> baseline/_ref,
+# git-ignored, byte-identical to /root/reference) with this build's operators installed into it.  Without the checkout only
+# the operator modules are registered and every test that needs the reference's networks skips.
+CHECKOUT = os.path.join(ROOT, 'baseline', '_ref', 'DissimilarDomains')
+HAVE_CHECKOUT = os.path.isdir(os.path.join(CHECKOUT, 'training'))
+
+import gagan_b200  # noqa: E402
+
+gagan_b200.install(CHECKOUT if HAVE_CHECKOUT else None)
+
+
+def reference_networks():
+    """The reference's own `training.networks` module running on the library (skips if the checkout did not travel)."""
+    import pytest
+    if not HAVE_CHECKOUT:
+        pytest.skip('baseline/_ref/DissimilarDomains is absent (run tools/vendor_reference.py where /root/reference exists)')
+    import training.networks
+    return training.networks
+
+
+def quiet(fn, *args, **kwargs):
+    """Call `fn` with stdout swallowed (the reference prints one line per layer when it registers domain modulation)."""
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*args, **kwargs)
 
 TOL = 1e-3   # BASELINE.json north_star: max relative error 1e-3 vs the reference in fp32 / TF32 off
 
