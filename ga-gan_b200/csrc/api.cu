@@ -73,6 +73,8 @@ extern "C" GG_API int gg_conv2d_f32(const float* x, const float* w, float* y, in
                "conv2d: unknown precision mode %d", prec);
     cudaStream_t st = (cudaStream_t)stream;
     bool tc_ok = gg::conv2d_tc_eligible(N, I, H, W, O, KH, KW, OH, OW, stride, pad_y, pad_x, transposed);
+    // the TMA descriptor of x needs a 16-byte aligned base: an unaligned view falls back to the exact FFMA kernel under AUTO
+    if (prec == GG_PREC_AUTO && (reinterpret_cast<uintptr_t>(x) & 15) != 0) tc_ok = false;
     if ((prec == GG_PREC_TF32X1 || prec == GG_PREC_TF32X3) && !tc_ok) {
         gg::set_error("conv2d: shape N=%d I=%d H=%d W=%d O=%d k=%dx%d stride=%d transposed=%d is not served by the tcgen05 path",
                       N, I, H, W, O, KH, KW, stride, transposed);

@@ -24,6 +24,16 @@ inline int check_launch(const char* what) {
     return GG_OK;
 }
 
+// Per-device "done once" flag (function attributes such as the dynamic shared-memory opt-in belong to the device's context, and one
+// process may drive several GPUs).  Usage:  if (!done_on_this_device(flag)) { ...; mark_done_on_this_device(flag); }
+inline uint64_t current_device_bit() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return 1ull << (dev & 63);
+}
+inline bool done_on_this_device(const std::atomic<uint64_t>& flag) { return (flag.load(std::memory_order_acquire) & current_device_bit()) != 0; }
+inline void mark_done_on_this_device(std::atomic<uint64_t>& flag) { flag.fetch_or(current_device_bit(), std::memory_order_release); }
+
 #define GG_REQUIRE(cond, ...)            \
     do {                                 \
         if (!(cond)) {                   \

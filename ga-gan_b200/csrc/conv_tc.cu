@@ -527,10 +527,10 @@ int launch_conv_tc(const CUtensorMap& xmap, const TcP& p, cudaStream_t st) {
     const SmemLayout L = make_layout(p.boxW, p.boxH, p.rawW, NT);
     const size_t smem = L.total + 128;
     if (smem > 227 * 1024) { gg::set_error("conv2d(tc): shared-memory layout of %zu bytes does not fit", smem); return GG_EUNSUPPORTED; }
-    static std::atomic<int> attr_set{0};
-    if (!attr_set.load()) {
+    static std::atomic<uint64_t> attr_set{0};           // one bit per device: the opt-in belongs to the device's context
+    if (!gg::done_on_this_device(attr_set)) {
         GG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT, SUBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set.store(1);
+        gg::mark_done_on_this_device(attr_set);
     }
     const int grid = p.total_tiles < GG_NUM_SMS ? p.total_tiles : GG_NUM_SMS;
     conv_tc_kernel<NT, SUBS><<<grid, NUM_THREADS, smem, st>>>(xmap, p);
@@ -563,9 +563,7 @@ bool conv2d_tc_eligible(int N, int I, int H, int W, int O, int KH, int KW, int O
     if (W % 4 != 0) return false;                      // TMA global strides must be multiples of 16 bytes
     // small maps (4x4, 5x8 ...) also run here: one mostly empty 16x16 tile per image and n-tile still beats an FFMA kernel that
     // can only spread N*OH*OW <= 128 output pixels over a handful of CTAs while walking K = 9*512 sequentially.
-    static const int min_hw = [] { const char* e = getenv("GG_TC_MIN_HW"); return e ? atoi(e) : 1; }();   // debug: force small maps to FFMA
-    if (OW < min_hw || OH < min_hw) return false;
-    (void)H; (void)transposed;
+    (void)H; (void)OH; (void)OW; (void)transposed;
     return true;
 }
 
@@ -621,7 +619,7 @@ int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int
     if (total > 0x7fffffffLL) { cudaFreeAsync(wp, st); set_error("conv2d(tc): too many tiles"); return GG_EINVAL; }
     p.total_tiles = (int)total;
     p.boxW = boxW; p.boxH = boxH; p.rawW = rawW;
-    { const char* e = getenv("GG_CHUNK_TAPS"); const int v = e ? atoi(e) : CHUNK_TAPS; p.chunk_taps = v < 1 ? 1 : (v > 9 ? 9 : v); }
+    p.chunk_taps = CHUNK_TAPS;
     int rc;
     if (NT == 256) rc = launch_conv_tc<256, 1>(xmap, p, st);
     else if (NT == 128) rc = launch_conv_tc<128, 2>(xmap, p, st);

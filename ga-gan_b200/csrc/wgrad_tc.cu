@@ -51,7 +51,7 @@ struct WgP {
     int RB, rb_shift, nshift, zgroups, btiles, atiles;
     int RR, ustrips, rstrips, S;
     int total_units, units_per_cta, nprod, vecX, vecG;
-    int dbg;                    // GG_WG_DBG experiments (timing only, results are garbage): 1 = no MMAs, 2 = no global loads, 4 = no split / st.shared, 8 = no proxy fence
+    int dbg;                    // always 0 in the library (the role-ablation bits of the development builds: 1 = no MMAs, 2 = no global loads, 4 = no split / st.shared, 8 = no proxy fence)
 };
 
 struct Unit { int n, r0, rows, u0, b0, a0, kx0, ns, tile; };
@@ -391,10 +391,10 @@ template <int NTA>
 int launch_wgrad(const WgP& p, int grid, cudaStream_t st) {
     constexpr uint32_t LBO_B = NTA * 16;
     const size_t smem = GS * 2 * 4 * LBO_A + XS * 2 * 4 * LBO_B + 256 + 16 + 128;
-    static std::atomic<int> attr_set{0};
-    if (!attr_set.load()) {
+    static std::atomic<uint64_t> attr_set{0};           // one bit per device
+    if (!gg::done_on_this_device(attr_set)) {
         GG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<NTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set.store(1);
+        gg::mark_done_on_this_device(attr_set);
     }
     wgrad_tc_kernel<NTA><<<grid, WG_THREADS, smem, st>>>(p);
     return gg::check_launch("conv2d_wgrad(tc)");
@@ -423,9 +423,8 @@ int wgrad_tma(const float* a, const float* b, float* dw, int N, int A, int HA, i
 int wgrad_tc(const float* a, const float* b, float* dw, int N, int A, int HA, int WA, int B, int HB, int WB, int K, int /*KW*/,
              int pad_y, int pad_x, int flip_w, int out_layout, const float* a_scale, const float* b_scale, int nprod, int pm_dim,
              unsigned pm_dead, cudaStream_t st) {
-    { const char* e = getenv("GG_WG_LDG");      // development switch: force the global-load kernel below
-      if (!(e && atoi(e)) && wgrad_tma_eligible(a, b, WA, WB))
-          return wgrad_tma(a, b, dw, N, A, HA, WA, B, HB, WB, K, pad_y, pad_x, flip_w, out_layout, a_scale, b_scale, nprod, pm_dim, pm_dead, st); }
+    if (wgrad_tma_eligible(a, b, WA, WB))
+        return wgrad_tma(a, b, dw, N, A, HA, WA, B, HB, WB, K, pad_y, pad_x, flip_w, out_layout, a_scale, b_scale, nprod, pm_dim, pm_dead, st);
     WgP p{};
     p.X = a; p.G = b; p.dw = dw; p.xs = a_scale; p.gs = b_scale;
     p.N = N; p.A = A; p.HA = HA; p.WA = WA; p.B = B; p.HB = HB; p.WB = WB; p.K = K; p.pad_y = pad_y; p.pad_x = pad_x;
@@ -452,7 +451,7 @@ int wgrad_tc(const float* a, const float* b, float* dw, int N, int A, int HA, in
     parts = (S + p.units_per_cta - 1) / p.units_per_cta;
     const int grid = (int)(parts * ntiles);
     p.nprod = (nprod == GG_PREC_TF32X1) ? 1 : 3;
-    { const char* e = getenv("GG_WG_DBG"); p.dbg = e ? atoi(e) : 0; }
+    p.dbg = 0;
     p.vecX = ((reinterpret_cast<uintptr_t>(a) & 15) == 0 && WA % 4 == 0) ? 1 : 0;
     p.vecG = ((reinterpret_cast<uintptr_t>(b) & 15) == 0 && WB % 4 == 0) ? 1 : 0;
     GG_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)A * B * K * K, st));

@@ -438,10 +438,10 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
 template <int NTA>
 int launch_wgrad_tma(const CUtensorMap& xmap, const CUtensorMap& gmap, const WtP& p, int grid, cudaStream_t st) {
     const size_t smem = XS * 2 * 4 * (NTA * 16) + ST * (STG_G + NTA * ROW_B) + 512 + 16 + 128;
-    static std::atomic<int> attr_set{0};
-    if (!attr_set.load()) {
+    static std::atomic<uint64_t> attr_set{0};           // one bit per device
+    if (!gg::done_on_this_device(attr_set)) {
         GG_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<NTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set.store(1);
+        gg::mark_done_on_this_device(attr_set);
     }
     wgrad_tma_kernel<NTA><<<grid, THREADS, smem, st>>>(xmap, gmap, p);
     return gg::check_launch("conv2d_wgrad(tc)");

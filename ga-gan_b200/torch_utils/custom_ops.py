@@ -345,6 +345,12 @@ class _Plugin:
         if N != N2:
             raise RuntimeError('conv2d_wgrad: batch size mismatch')
         KH, KW = kernel_size
+        # per-sample channel scales: dense [N,A] / [N,B] fp32 on the operands' device (raw pointers go to the kernel)
+        for nm, sc, ch in (('a_scale', a_scale, A), ('b_scale', b_scale, B)):
+            if sc is not None and (tuple(sc.shape) != (N, ch) or sc.dtype != torch.float32 or sc.device != a.device):
+                raise RuntimeError(f'conv2d_wgrad: {nm} must be a float32 [{N},{ch}] tensor on {a.device}')
+        a_scale = a_scale.contiguous() if a_scale is not None else None
+        b_scale = b_scale.contiguous() if b_scale is not None else None
         shape = [A, B, KH, KW] if out_layout else [B, A, KH, KW]
         dw = torch.empty(shape, dtype=a.dtype, device=a.device)
         used = ctypes.c_int(0)

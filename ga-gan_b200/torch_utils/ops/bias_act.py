@@ -80,6 +80,11 @@ def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, 
         # `x.add_(noise)` / fma pass of the SynthesisLayer (networks.py:648-653)
         if dim != 1 or x.ndim != 4:
             raise RuntimeError('bias_act(noise=...) needs an NCHW tensor with dim == 1')
+        spec = activation_funcs[act]
+        if 'x' in spec.ref or spec.has_2nd_grad:
+            # these activations differentiate through the saved INPUT (swish: act'(x + b)): it must include the noise, so the
+            # add is made explicit and the regular path runs (lrelu / linear / relu, what the networks use, stay fused)
+            return _bias_act_cuda(dim=dim, act=act, alpha=alpha, gain=gain, clamp=clamp).apply(x + noise.to(x.dtype), b)
         return _bias_act_cuda(dim=dim, act=act, alpha=alpha, gain=gain, clamp=clamp).apply(x, b, noise)
     return _bias_act_cuda(dim=dim, act=act, alpha=alpha, gain=gain, clamp=clamp).apply(x, b)
 

@@ -126,3 +126,156 @@ def test_ga_population_eval_cuda_graph_replay_matches_eager(device):
     assert torch.isfinite(graph).all() and len({round(float(v), 5) for v in graph}) == 18
     assert float((graph - eager).abs().max()) <= 1e-6 * float(eager.abs().max())
     assert float((again - graph).abs().max()) <= 1e-6 * float(eager.abs().max())
+
+
+# ------------------------------------------------------------------------------------------------ Affine+ / AffineLight+ / StyleSpace
+PARAMETRIZATIONS = [
+    'out_in_additive',                      # Affine+ (DD/README.md:191-196): full [O,I,1,1] weight offsets
+    'out_in_5_1',                           # AffineLight+: rank-5 low-rank offsets, one term, multiplicative
+    'out_in_5_2_additive',                  # two rank-5 terms, additive
+    'out+in',                               # rank-1 sum form
+    'in_spatial_additive',                  # per-(input channel, tap) offsets
+    'multiplicative,out_in_10_dual',        # StyleSpace multiplicative offsets + dual low-rank weights
+    'additive,out_in_5_1_train_in',         # StyleSpace additive offsets + half-frozen low-rank weights
+    'additive_w_space,affine_out_in_5_1',   # W-space offsets + low-rank offsets of the affine layers
+]
+
+
+@pytest.mark.parametrize('param', PARAMETRIZATIONS)
+def test_domain_adaptation_parametrizations_match_the_live_reference(device, param):
+    """Every weight / style parameterization the reference trains (networks.py:24-579: weight_to_weight :535-579, w_to_s :474-532)
+    flows through this build's modulated_conv2d: image and ALL parameter gradients of a generator built with it must equal the
+    same reference class on its CPU impl='ref' operators."""
+    from oracle import live_ref
+    if not live_ref.available():
+        pytest.skip('oracle/_ref is absent')
+    L = live_ref.load()
+    networks = reference_networks()
+    kw = dict(z_dim=32, c_dim=0, w_dim=32, img_resolution=32, img_channels=3, mapping_kwargs=dict(num_layers=2),
+              synthesis_kwargs=dict(channel_base=512, channel_max=32, use_domain_modulation=True, domain_modulation_parametrization=param,
+                                    generator_requires_grad_parts=['all']))
+    torch.manual_seed(5)
+    G_cpu = quiet(L.networks.Generator, **kw).train()
+    with torch.no_grad():
+        for n, p in G_cpu.named_parameters():                 # offsets / biases / noise strengths start at zero: move them
+            if float(p.abs().max()) == 0:
+                p.copy_(torch.randn(p.shape) * 0.2)
+    G = quiet(networks.Generator, **kw).train()
+    missing = G.load_state_dict(G_cpu.state_dict())
+    assert not missing.missing_keys and not missing.unexpected_keys
+    G = G.to(device)
+    G.mapping.w_avg_beta = G_cpu.mapping.w_avg_beta = None
+    z = torch.randn(4, 32); c = torch.zeros(4, 0)
+    r = torch.randn(4, 3, 32, 32)
+    img_cpu = G_cpu(z, c, noise_mode='const')
+    (img_cpu * r).sum().backward()
+    img = G(z.to(device), c.to(device), noise_mode='const')
+    (img * r.to(device)).sum().backward()
+    assert_close(img, img_cpu, 2e-5, f'{param}: image')
+    cpu = dict(G_cpu.named_parameters())
+    checked = 0
+    for n, p in G.named_parameters():
+        want = cpu[n].grad
+        if want is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0, n
+            continue
+        if float(want.abs().max()) == 0:
+            assert float(p.grad.abs().max()) <= 1e-6, n
+            continue
+        assert_close(p.grad, want, 1e-4, f'{param}: d/d{n}')
+        checked += 1
+    assert checked > 30
+
+
+# ------------------------------------------------------------------------------------------------ a full training iteration
+def _cpu_iteration(L, G, D, real, zs, batch_gpu, lrate, gamma):
+    """One iteration of the upstream loop on the live reference (CPU): training_loop.py:293-318 (phases, lazy regularisation),
+    :459-512 (rounds, nan_to_num, Adam), with every phase firing (iteration 0)."""
+    import copy
+    G_ema = copy.deepcopy(G).eval()
+    loss = L.loss.StyleGAN2Loss(device=torch.device('cpu'), G_mapping=G.mapping, G_synthesis=G.synthesis, D=D, style_mixing_prob=0,
+                                r1_gamma=gamma, pl_weight=2)
+    opts = {}
+    for name, net, interval in (('G', G, 4), ('D', D, 16)):
+        r = interval / (interval + 1)
+        opts[name] = torch.optim.Adam(net.parameters(), lr=lrate * r, betas=(0.0 ** r, 0.99 ** r), eps=1e-8)
+    c = torch.zeros(real.shape[0], 0)
+    for (phase, net, interval), z in zip((('Gmain', G, 1), ('Greg', G, 4), ('Dmain', D, 1), ('Dreg', D, 16)), zs):
+        opt = opts[phase[0]]
+        opt.zero_grad(set_to_none=True)
+        net.requires_grad_(True)
+        rounds = list(zip(real.split(batch_gpu), c.split(batch_gpu), z.split(batch_gpu)))
+        for r_img, r_c, g_z in rounds:
+            loss.accumulate_gradients(phase=phase, real_img=r_img, real_c=r_c, gen_z=g_z, gen_c=r_c, sync=True, gain=interval)
+        net.requires_grad_(False)
+        for p in net.parameters():
+            if p.grad is not None:
+                torch.nan_to_num(p.grad, nan=0, posinf=1e5, neginf=-1e5, out=p.grad)
+        opt.step()
+    beta = 0.5 ** (real.shape[0] / 10000.0)
+    with torch.no_grad():
+        for p_ema, p in zip(G_ema.parameters(), G.parameters()):
+            p_ema.copy_(p.lerp(p_ema, beta))
+        for b_ema, b in zip(G_ema.buffers(), G.buffers()):
+            b_ema.copy_(b)
+    return G_ema, loss
+
+
+def test_full_training_iteration_matches_the_live_reference(device):
+    """TrainingStep.run (all four phases, two accumulation rounds, Adam, G_ema) on the library vs the same iteration of the live
+    reference on CPU: last-phase gradients, parameter UPDATES and G_ema.  Adam's first steps are sign-like (|update| ~ lr), so
+    updates are compared element-wise with a small allowance for gradients at the noise floor."""
+    from oracle import live_ref
+    if not live_ref.available():
+        pytest.skip('oracle/_ref is absent')
+    from gagan_b200.training.training_loop import TrainingStep
+    L = live_ref.load()
+    networks = reference_networks()
+    res, cb, cm, zd = 32, 512, 32, 32
+    kw_g = dict(z_dim=zd, c_dim=0, w_dim=zd, img_resolution=res, img_channels=3, mapping_kwargs=dict(num_layers=2),
+                synthesis_kwargs=dict(channel_base=cb, channel_max=cm))
+    kw_d = dict(c_dim=0, img_resolution=res, img_channels=3, channel_base=cb, channel_max=cm, epilogue_kwargs=dict(mbstd_group_size=2))
+    torch.manual_seed(9)
+    G_cpu, D_cpu = quiet(L.networks.Generator, **kw_g).train(), quiet(L.networks.Discriminator, **kw_d).train()
+    with torch.no_grad():
+        for p in list(G_cpu.parameters()) + list(D_cpu.parameters()):
+            if float(p.abs().max()) == 0:
+                p.copy_(torch.randn(p.shape) * 0.1)
+    G, D = quiet(networks.Generator, **kw_g), quiet(networks.Discriminator, **kw_d)
+    G.load_state_dict(G_cpu.state_dict()); D.load_state_dict(D_cpu.state_dict())
+    before = {('G.' + k): v.clone() for k, v in G_cpu.named_parameters()}
+    before.update({('D.' + k): v.clone() for k, v in D_cpu.named_parameters()})
+    lrate, gamma, batch, batch_gpu = 1e-3, 1.0, 4, 2
+    real = torch.rand(batch, 3, res, res) * 2 - 1
+    zs = torch.randn(4, batch, zd)
+    L.conv2d_gradfix.enabled = True
+    for net in (G_cpu, D_cpu):
+        net.requires_grad_(False)
+    with patched_randn(21):
+        G_ema_cpu, loss_cpu = _cpu_iteration(L, G_cpu, D_cpu, real, zs, batch_gpu, lrate, gamma)
+    step = TrainingStep(G, D, batch_size=batch, batch_gpu=batch_gpu, device=device, lrate=lrate, r1_gamma=gamma, ema_kimg=10.0,
+                        style_mixing_prob=0.0, pl_weight=2.0)
+    with patched_randn(21):
+        step.run(real.to(device), zs.to(device))
+    assert_close(step.loss.pl_mean, loss_cpu.pl_mean, 1e-4, 'pl_mean')
+    after_cpu = {('G.' + k): v for k, v in G_cpu.named_parameters()}
+    after_cpu.update({('D.' + k): v for k, v in D_cpu.named_parameters()})
+    after = {('G.' + k): v for k, v in step.G.named_parameters()}
+    after.update({('D.' + k): v for k, v in step.D.named_parameters()})
+    total = off = 0
+    for k, b in before.items():
+        d_cpu = (after_cpu[k].detach() - b)
+        d_gpu = (after[k].detach().cpu() - b)
+        assert float(d_cpu.abs().max()) > 0, f'{k} was not updated by the reference iteration'
+        scale = float(d_cpu.abs().max())
+        bad = ((d_gpu - d_cpu).abs() > 0.02 * scale)
+        total += bad.numel(); off += int(bad.sum())
+        g_cpu, g_gpu = after_cpu[k].grad, after[k].grad            # gradients of the last phase (Greg / Dreg)
+        if g_cpu is not None and float(g_cpu.abs().max()) > 0:
+            assert_close(g_gpu, g_cpu, 2e-4, f'last-phase gradient of {k}')
+    assert off <= 2e-3 * total, f'{off} of {total} parameter updates differ from the reference iteration'
+    for (k, a), b in zip(step.G_ema.named_parameters(), G_ema_cpu.parameters()):
+        assert_close(a, b, 1e-4, f'G_ema {k}')
+    stats = step.read_stats()
+    assert {'Loss/G/loss', 'Loss/D/loss', 'Loss/G/reg', 'Loss/D/reg'} <= set(stats)
+    print(f'full iteration: {off} of {total} parameter updates off by more than 2 % of the step size')

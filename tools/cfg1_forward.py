@@ -3,11 +3,13 @@
 (the reference's CPU-runnable case: 0.725 s per batch with impl='ref' on 8 cores)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, 'ga-gan_b200')):
-    sys.path.insert(0, p)
+sys.path.insert(0, ROOT)
+import gagan_b200  # noqa: E402
+_CHECKOUT = os.path.join(ROOT, 'baseline', '_ref', 'DissimilarDomains')
+gagan_b200.install(_CHECKOUT if os.path.isdir(_CHECKOUT) else None)   # the reference checkout on this build's operators
 import torch
 from torch_utils import custom_ops
-from training import training_loop
+from gagan_b200.training import training_loop
 custom_ops.verbosity = 'none'
 dev = torch.device('cuda:0')
 torch.backends.cuda.matmul.allow_tf32 = False

@@ -4,8 +4,10 @@ a 1024^2 layer -- sum over all pixels and channels of (conv output x per-pixel n
 SynthesisLayer -- computed from the tcgen05 conv, the exact FFMA conv and an fp64 CPU reference (development tool)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, 'ga-gan_b200')):
-    sys.path.insert(0, p)
+sys.path.insert(0, ROOT)
+import gagan_b200  # noqa: E402
+_CHECKOUT = os.path.join(ROOT, 'baseline', '_ref', 'DissimilarDomains')
+gagan_b200.install(_CHECKOUT if os.path.isdir(_CHECKOUT) else None)   # the reference checkout on this build's operators
 import numpy as np, torch
 from torch_utils import custom_ops
 dev = torch.device('cuda:0')

@@ -2,8 +2,10 @@
 """Run one conv configuration a few times (target of `ncu -k regex:conv_tc_kernel`)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, 'ga-gan_b200')):
-    sys.path.insert(0, p)
+sys.path.insert(0, ROOT)
+import gagan_b200  # noqa: E402
+_CHECKOUT = os.path.join(ROOT, 'baseline', '_ref', 'DissimilarDomains')
+gagan_b200.install(_CHECKOUT if os.path.isdir(_CHECKOUT) else None)   # the reference checkout on this build's operators
 import numpy as np
 import torch
 from torch_utils import custom_ops

@@ -11,8 +11,10 @@ import argparse
 import collections
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, 'ga-gan_b200')):
-    sys.path.insert(0, p)
+sys.path.insert(0, ROOT)
+import gagan_b200  # noqa: E402
+_CHECKOUT = os.path.join(ROOT, 'baseline', '_ref', 'DissimilarDomains')
+gagan_b200.install(_CHECKOUT if os.path.isdir(_CHECKOUT) else None)   # the reference checkout on this build's operators
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -29,7 +31,7 @@ def main():
     ap.add_argument('--main-only', action='store_true', help='profile an iteration without the lazy regularisation phases')
     args = ap.parse_args()
     from torch_utils import custom_ops
-    from training import training_loop
+    from gagan_b200.training import training_loop
     dev = torch.device('cuda:0')
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False

@@ -1,0 +1,13 @@
+#!/bin/bash
+# compute-sanitizer over the small-shape driver, one tool at a time; logs -> gpurun_out/r2_sanitizer_<tool>.log
+#   tools/sanitize.sh [tool ...]        (default: memcheck racecheck synccheck)
+cd "$(dirname "$0")/.." || exit 1
+mkdir -p gpurun_out
+TOOLS=${@:-memcheck racecheck synccheck}
+for tool in $TOOLS; do
+  log=gpurun_out/r2_sanitizer_${tool}.log
+  echo "== compute-sanitizer --tool $tool" | tee "$log"
+  timeout 900 compute-sanitizer --tool "$tool" --print-limit 20 python tools/sanitize_driver.py >> "$log" 2>&1
+  echo "exit code $?" | tee -a "$log"
+  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard|Invalid|sanitize_driver: done" "$log" | tail -8
+done

@@ -6,8 +6,10 @@ result bit for bit over many launches; the atomically flushed weight gradient to
 """
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, 'ga-gan_b200')):
-    sys.path.insert(0, p)
+sys.path.insert(0, ROOT)
+import gagan_b200  # noqa: E402
+_CHECKOUT = os.path.join(ROOT, 'baseline', '_ref', 'DissimilarDomains')
+gagan_b200.install(_CHECKOUT if os.path.isdir(_CHECKOUT) else None)   # the reference checkout on this build's operators
 import numpy as np, torch
 from torch_utils import custom_ops
 from torch_utils.ops import upfirdn2d, conv2d_resample as cr
