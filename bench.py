@@ -417,7 +417,7 @@ def main():
 
     fast = None
     if not args.no_fast_mode and args.prec == 'auto' and args.workload == 'train':
-        custom_ops.conv_precision = custom_ops.PREC_TF32X1
+        custom_ops.conv_precision = custom_ops.PREC_AUTO_FAST
         k = min(args.steps, 4)
         one_step(False)
         ms_fast, _ = timed(k, host_inputs=False)

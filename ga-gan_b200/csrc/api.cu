@@ -6,6 +6,7 @@ namespace gg {
 
 static thread_local char t_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+int g_march_enabled = 1;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -33,6 +34,10 @@ bool conv2d_tc_eligible(int N, int I, int H, int W, int O, int KH, int KW, int O
                         int transposed);
 int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int KH, int KW, int OH, int OW, int pad_y,
               int pad_x, int flip_w, int w_is_IO, const float* in_scale, const float* out_scale, int nprod, cudaStream_t st);
+// conv_march.cu (row-marching tcgen05 path for <= 64 output channels)
+bool conv2d_march_eligible(const float* x, int N, int I, int H, int W, int O, int KH, int KW, int OH, int OW, int stride, int pad_y, int pad_x);
+int conv2d_march(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int K, int OH, int OW, int pad_y, int pad_x,
+                 int flip_w, int w_is_IO, const float* in_scale, const float* out_scale, int nprod, cudaStream_t st);
 bool wgrad_tc_eligible(int N, int A, int HA, int WA, int B, int HB, int WB, int KH, int KW, int stride, int pad_y, int pad_x);
 int wgrad_tc(const float* a, const float* b, float* dw, int N, int A, int HA, int WA, int B, int HB, int WB, int KH, int KW,
              int pad_y, int pad_x, int flip_w, int out_layout, const float* a_scale, const float* b_scale, int nprod, int pm_dim,
@@ -43,6 +48,7 @@ int wgrad_tc(const float* a, const float* b, float* dw, int N, int A, int HA, in
 extern "C" GG_API const char* gg_last_error(void) { return gg::t_err; }
 extern "C" GG_API int gg_version(void) { return 100; }
 extern "C" GG_API int64_t gg_launch_count(void) { return gg::g_launches.load(); }
+extern "C" GG_API int gg_set_conv_kernel_family(int family) { const int old = gg::g_march_enabled; gg::g_march_enabled = (family != 0); return old; }
 
 extern "C" GG_API int gg_device_ok(void) {
     int dev = 0;
@@ -69,19 +75,21 @@ extern "C" GG_API int gg_conv2d_f32(const float* x, const float* w, float* y, in
         }
     }
     GG_REQUIRE((int64_t)N * I * H * W <= 0x7fffffffLL && (int64_t)N * O * OH * OW <= 0x7fffffffLL, "conv2d: tensor is too large");
-    GG_REQUIRE(prec == GG_PREC_AUTO || prec == GG_PREC_FP32_SIMT || prec == GG_PREC_TF32X1 || prec == GG_PREC_TF32X3,
+    GG_REQUIRE(prec == GG_PREC_AUTO || prec == GG_PREC_AUTO_FAST || prec == GG_PREC_FP32_SIMT || prec == GG_PREC_TF32X1 || prec == GG_PREC_TF32X3,
                "conv2d: unknown precision mode %d", prec);
     cudaStream_t st = (cudaStream_t)stream;
     bool tc_ok = gg::conv2d_tc_eligible(N, I, H, W, O, KH, KW, OH, OW, stride, pad_y, pad_x, transposed);
     // the TMA descriptor of x needs a 16-byte aligned base: an unaligned view falls back to the exact FFMA kernel under AUTO
-    if (prec == GG_PREC_AUTO && (reinterpret_cast<uintptr_t>(x) & 15) != 0) tc_ok = false;
+    const bool is_auto = (prec == GG_PREC_AUTO || prec == GG_PREC_AUTO_FAST);
+    const int auto_tc = (prec == GG_PREC_AUTO_FAST) ? GG_PREC_TF32X1 : GG_PREC_TF32X3;
+    if (is_auto && (reinterpret_cast<uintptr_t>(x) & 15) != 0) tc_ok = false;
     if ((prec == GG_PREC_TF32X1 || prec == GG_PREC_TF32X3) && !tc_ok) {
         gg::set_error("conv2d: shape N=%d I=%d H=%d W=%d O=%d k=%dx%d stride=%d transposed=%d is not served by the tcgen05 path",
                       N, I, H, W, O, KH, KW, stride, transposed);
         return GG_EUNSUPPORTED;
     }
     const bool thin_ok = N > 0 && gg::conv1x1_thin_eligible(x, y, N, I, H, W, O, KH, KW, OH, OW, stride, pad_y, pad_x);
-    int use = (prec == GG_PREC_AUTO) ? ((tc_ok && !thin_ok) ? GG_PREC_TF32X3 : GG_PREC_FP32_SIMT) : prec;
+    int use = is_auto ? ((tc_ok && !thin_ok) ? auto_tc : GG_PREC_FP32_SIMT) : prec;
     if (used_prec) *used_prec = use;
     if (use == GG_PREC_FP32_SIMT && thin_ok)
         return gg::conv1x1_thin(x, w, y, N, I, H, W, O, transposed, in_scale, out_scale, st);
@@ -90,6 +98,9 @@ extern "C" GG_API int gg_conv2d_f32(const float* x, const float* w, float* y, in
                                out_scale, st);
     // stride-1 conv_transpose2d == correlation with the flipped kernel and padding K-1-p; both are
     // handled inside the tensor-core path through its weight-packing step.
+    const int tpy = transposed ? KH - 1 - pad_y : pad_y, tpx = transposed ? KW - 1 - pad_x : pad_x;
+    if (gg::g_march_enabled && gg::conv2d_march_eligible(x, N, I, H, W, O, KH, KW, OH, OW, stride, tpy, tpx))
+        return gg::conv2d_march(x, w, y, N, I, H, W, O, KH, OH, OW, tpy, tpx, transposed ? !flip_w : flip_w, transposed, in_scale, out_scale, use, st);
     return gg::conv2d_tc(x, w, y, N, I, H, W, O, KH, KW, OH, OW, transposed ? KH - 1 - pad_y : pad_y, transposed ? KW - 1 - pad_x : pad_x,
                          transposed ? !flip_w : flip_w, transposed, in_scale, out_scale, use, st);
 }
@@ -110,7 +121,7 @@ extern "C" GG_API int gg_conv2d_wgrad_pm_f32(const float* a, const float* b, flo
     GG_REQUIRE(N >= 0 && A >= 1 && B >= 1 && HA >= 1 && WA >= 1 && HB >= 1 && WB >= 1 && KH >= 1 && KW >= 1, "conv2d_wgrad: bad shape");
     GG_REQUIRE(stride >= 1 && pad_y >= 0 && pad_x >= 0, "conv2d_wgrad: bad stride/padding");
     GG_REQUIRE((int64_t)N * A * HA * WA <= 0x7fffffffLL && (int64_t)N * B * HB * WB <= 0x7fffffffLL, "conv2d_wgrad: tensor is too large");
-    GG_REQUIRE(prec == GG_PREC_AUTO || prec == GG_PREC_FP32_SIMT || prec == GG_PREC_TF32X1 || prec == GG_PREC_TF32X3,
+    GG_REQUIRE(prec == GG_PREC_AUTO || prec == GG_PREC_AUTO_FAST || prec == GG_PREC_FP32_SIMT || prec == GG_PREC_TF32X1 || prec == GG_PREC_TF32X3,
                "conv2d_wgrad: unknown precision mode %d", prec);
     cudaStream_t st = (cudaStream_t)stream;
     bool tc_ok = gg::wgrad_tc_eligible(N, A, HA, WA, B, HB, WB, KH, KW, stride, pad_y, pad_x);
@@ -119,7 +130,8 @@ extern "C" GG_API int gg_conv2d_wgrad_pm_f32(const float* a, const float* b, flo
         return GG_EUNSUPPORTED;
     }
     const bool thin_ok = N > 0 && gg::wgrad1x1_thin_eligible(a, b, N, A, HA, WA, B, HB, WB, KH, KW, stride, pad_y, pad_x);
-    int use = (prec == GG_PREC_AUTO) ? ((tc_ok && !thin_ok) ? GG_PREC_TF32X3 : GG_PREC_FP32_SIMT) : prec;
+    const bool is_auto = (prec == GG_PREC_AUTO || prec == GG_PREC_AUTO_FAST);
+    int use = is_auto ? ((tc_ok && !thin_ok) ? (prec == GG_PREC_AUTO_FAST ? GG_PREC_TF32X1 : GG_PREC_TF32X3) : GG_PREC_FP32_SIMT) : prec;
     if (used_prec) *used_prec = use;
     if (use == GG_PREC_FP32_SIMT && thin_ok)
         return gg::wgrad1x1_thin(a, b, dw, N, A, HA, WA, B, out_layout, a_scale, b_scale, st);

@@ -507,21 +507,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-// The stream-ordered scratch comes from the device's default memory pool.  Its default release threshold of 0 hands the
-// memory back to the driver at every synchronisation, which makes the next cudaMallocAsync cost ~1 ms; keep it cached.
-void keep_pool_memory() {
-    static std::atomic<uint64_t> done{0};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
-    if (done.load() & (1ull << dev)) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
-    done.fetch_or(1ull << dev);
-}
-
 template <int NT, int SUBS>
 int launch_conv_tc(const CUtensorMap& xmap, const TcP& p, cudaStream_t st) {
     const SmemLayout L = make_layout(p.boxW, p.boxH, p.rawW, NT);
@@ -553,6 +538,21 @@ gg::EncodeTiledFn gg::get_encode_fn() {
 }
 
 namespace gg {
+
+// The stream-ordered scratch comes from the device's default memory pool.  Its default release threshold of 0 hands the
+// memory back to the driver at every synchronisation, which makes the next cudaMallocAsync cost ~1 ms; keep it cached.
+void keep_pool_memory() {
+    static std::atomic<uint64_t> done{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    if (done.load() & (1ull << dev)) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done.fetch_or(1ull << dev);
+}
 
 bool conv2d_tc_eligible(int N, int I, int H, int W, int O, int KH, int KW, int OH, int OW, int stride, int pad_y, int pad_x,
                         int transposed) {

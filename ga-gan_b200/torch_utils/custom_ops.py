@@ -38,7 +38,7 @@ _cached_plugins = dict()
 _lib = None
 _lib_lock = threading.Lock()
 
-PREC_FP32_SIMT, PREC_TF32X1, PREC_TF32X3, PREC_AUTO = 0, 1, 3, -1
+PREC_FP32_SIMT, PREC_TF32X1, PREC_TF32X3, PREC_AUTO, PREC_AUTO_FAST = 0, 1, 3, -1, -2
 conv_precision = PREC_AUTO   # module-level switch, like conv2d_gradfix.enabled
 conv_profile = None          # bench.py sets this to a list: (kind, flops, prec, start_event, end_event) per conv launch
 
@@ -64,6 +64,7 @@ _SIGNATURES = {
     'gg_version': (ctypes.c_int, []),
     'gg_device_ok': (ctypes.c_int, []),
     'gg_launch_count': (ctypes.c_int64, []),
+    'gg_set_conv_kernel_family': (ctypes.c_int, [ctypes.c_int]),
     'gg_bias_act_f32': (ctypes.c_int, [_c_float_p] * 7 + [ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
                                                           ctypes.c_float, ctypes.c_int64, ctypes.c_int, ctypes.c_int64,
                                                           ctypes.c_void_p]),
@@ -113,6 +114,11 @@ def load_library():
             fn.argtypes = argtypes
         _lib = lib
         return lib
+
+
+def set_conv_kernel_family(family):
+    """1 = row-marching kernel for the <= 64-channel 3x3 layers (default), 0 = the tile kernel for everything; returns the old value."""
+    return int(load_library().gg_set_conv_kernel_family(int(family)))
 
 
 def launch_count():

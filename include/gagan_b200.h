@@ -46,7 +46,8 @@ enum {
     GG_PREC_FP32_SIMT = 0, /* exact fp32 FFMA kernel (small / odd shapes, and the on-GPU cross-check) */
     GG_PREC_TF32X1 = 1,    /* tcgen05 kind::tf32, one product per MAC (fast mode, ~3e-4 per layer) */
     GG_PREC_TF32X3 = 3,    /* tcgen05 kind::tf32, hi/lo split, 3 products per MAC (~4e-7, the parity mode) */
-    GG_PREC_AUTO = -1      /* TF32X3 on tensor cores when the shape is eligible, else FP32_SIMT */
+    GG_PREC_AUTO = -1,     /* TF32X3 on tensor cores when the shape is eligible, else FP32_SIMT */
+    GG_PREC_AUTO_FAST = -2 /* like AUTO but TF32X1 on the tensor cores: the fast mode, NOT fp32-faithful (bench.py fast_mode) */
 };
 
 GG_API const char* gg_last_error(void);
@@ -164,6 +165,12 @@ GG_API int gg_chan_dot_f32(const float* a, const float* b, float* out, int64_t r
 
 /* Number of kernels this library has launched since load (all streams); bench.py reports the delta. */
 GG_API int64_t gg_launch_count(void);
+
+/* Which tcgen05 kernel family serves the 3x3 stride-1 layers with <= 64 output channels: 1 (default) = the row-marching kernel
+ * (conv_march.cu: filter rows in the MMA N dimension), 0 = the tile kernel that serves every other shape (conv_tc.cu).  Both
+ * compute the same fp32-faithful 3xTF32 result; the switch exists for A/B measurements (tools/microbench.py) and for the parity
+ * tests that run every shape through both.  Process-wide; returns the previous setting. */
+GG_API int gg_set_conv_kernel_family(int family);
 
 #ifdef __cplusplus
 }

@@ -129,11 +129,11 @@ def test_ga_population_eval_cuda_graph_replay_matches_eager(device):
 
 
 # ------------------------------------------------------------------------------------------------ Affine+ / AffineLight+ / StyleSpace
+# ('out+in' is not in the list: the reference's own weight_to_weight adds two python lists for it, networks.py:567, and raises)
 PARAMETRIZATIONS = [
     'out_in_additive',                      # Affine+ (DD/README.md:191-196): full [O,I,1,1] weight offsets
     'out_in_5_1',                           # AffineLight+: rank-5 low-rank offsets, one term, multiplicative
     'out_in_5_2_additive',                  # two rank-5 terms, additive
-    'out+in',                               # rank-1 sum form
     'in_spatial_additive',                  # per-(input channel, tap) offsets
     'multiplicative,out_in_10_dual',        # StyleSpace multiplicative offsets + dual low-rank weights
     'additive,out_in_5_1_train_in',         # StyleSpace additive offsets + half-frozen low-rank weights
@@ -272,7 +272,7 @@ def test_full_training_iteration_matches_the_live_reference(device):
         total += bad.numel(); off += int(bad.sum())
         g_cpu, g_gpu = after_cpu[k].grad, after[k].grad            # gradients of the last phase (Greg / Dreg)
         if g_cpu is not None and float(g_cpu.abs().max()) > 0:
-            assert_close(g_gpu, g_cpu, 2e-4, f'last-phase gradient of {k}')
+            assert_close(g_gpu, g_cpu, TOL, f'last-phase gradient of {k}')     # Greg / Dreg: double backward, see test_gpu_config_size (conditioning)
     assert off <= 2e-3 * total, f'{off} of {total} parameter updates differ from the reference iteration'
     for (k, a), b in zip(step.G_ema.named_parameters(), G_ema_cpu.parameters()):
         assert_close(a, b, 1e-4, f'G_ema {k}')

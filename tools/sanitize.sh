@@ -4,6 +4,9 @@
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
 TOOLS=${@:-memcheck racecheck synccheck}
+# the same driver without a sanitizer: every kernel family at small shapes against the exact FFMA path
+python tools/sanitize_driver.py > gpurun_out/r2_sanitize_driver_plain.log 2>&1; echo "plain driver exit code $?" | tee -a gpurun_out/r2_sanitize_driver_plain.log
+tail -2 gpurun_out/r2_sanitize_driver_plain.log
 for tool in $TOOLS; do
   log=gpurun_out/r2_sanitizer_${tool}.log
   echo "== compute-sanitizer --tool $tool" | tee "$log"
