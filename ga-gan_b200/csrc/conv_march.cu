@@ -35,7 +35,7 @@ constexpr int MK = 32;                    // input channels per K-block = one 12
 constexpr int SEG = 128;                  // pixels per segment = UMMA M
 constexpr int RAWW = SEG + 8;             // raw box width: up to 3 columns of alignment slack + K-1 halo, multiple of 4
 constexpr int CVT_PIX = SEG + 8;          // pixel rows of a converted buffer (whole 8-row swizzle atoms)
-constexpr int MW_STAGES = 4;
+constexpr int MW_STAGES = 6;             // ring stages; with <= 6 (16-channel group, kx) blocks the weights stay resident
 constexpr int M_PROD_WARPS = 4, M_CONS_WARPS = 8;
 constexpr int M_CONS_THREADS = M_CONS_WARPS * 32;
 constexpr int M_THREADS = (M_PROD_WARPS + M_CONS_WARPS) * 32;
@@ -49,7 +49,10 @@ struct MarchP {
     int num_kb;            // 32-channel K-blocks
     int num_g16;           // 16-channel groups (= weight stages per kx)
     int strips_x, bands, band_rows, total_units, nprod;
+    int resident;          // all num_g16*K weight stages fit the ring: loaded once per CTA, never recycled
 };
+
+__host__ __device__ constexpr int march_stages(int N) { return N > 128 ? 4 : MW_STAGES; }
 
 struct MLayout {
     uint32_t raw0, cvt0, w0, wbytes, scale, bars, tmem_slot, total;
@@ -64,7 +67,7 @@ __host__ __device__ inline MLayout make_mlayout(int N) {      // offsets from th
     L.cvt0 = off; off += 4 * CVT_BYTES;                        // first: swizzled buffers need 1024-byte alignment
     L.raw0 = off; off += 2 * RAW_BYTES;
     L.wbytes = (uint32_t)(2 * 4 * N * 16);
-    L.w0 = off; off += MW_STAGES * L.wbytes;
+    L.w0 = off; off += (uint32_t)march_stages(N) * L.wbytes;   // 4 x 24 KB (N = 192) or 6 x 12 KB (N = 96)
     L.scale = off; off += M_MAX_CH * 4;
     L.bars = off; off += 256;
     L.tmem_slot = off; off += 16;
@@ -122,6 +125,7 @@ __global__ void __launch_bounds__(M_THREADS, 1) conv_march_kernel(const __grid_c
     constexpr int N = K * NT;                       // accumulator columns of one set: (ky, o)
     constexpr uint32_t TMEM_COLS = (2 * N <= 256) ? 256 : 512;
     constexpr uint32_t w_bytes = (uint32_t)(2 * 4 * N * 16);
+    constexpr int STAGES = march_stages(N);
     extern __shared__ __align__(1024) uint8_t msmem_raw[];
     const uint32_t base = (smem_u32(msmem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = msmem_raw + (base - smem_u32(msmem_raw));
@@ -179,7 +183,13 @@ __global__ void __launch_bounds__(M_THREADS, 1) conv_march_kernel(const __grid_c
             if (elect_one()) {
                 uint32_t ws = 0, wph = 0;
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wp);
-                for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+                if (p.resident) {                                         // the whole weight image stays in shared memory
+                    for (int st = 0; st < p.num_g16 * K; ++st) {
+                        mbar_expect_tx(BAR_W_FULL(st), w_bytes);
+                        bulk_load(base + L.wst(st), src + (size_t)st * w_bytes, w_bytes, BAR_W_FULL(st));
+                    }
+                }
+                for (int u = blockIdx.x; !p.resident && u < p.total_units; u += gridDim.x) {
                     const Unit un = decode_unit(u, p);
                     for (int t = un.y0; t < un.y1 + K - 1; ++t) {
                         const int r = t - p.pad_y;
@@ -189,7 +199,7 @@ __global__ void __launch_bounds__(M_THREADS, 1) conv_march_kernel(const __grid_c
                                 mbar_wait(BAR_W_EMPTY(ws), wph ^ 1);
                                 mbar_expect_tx(BAR_W_FULL(ws), w_bytes);
                                 bulk_load(base + L.wst(ws), src + (size_t)(g * K + kx) * w_bytes, w_bytes, BAR_W_FULL(ws));
-                                if (++ws == MW_STAGES) { ws = 0; wph ^= 1; }
+                                if (++ws == STAGES) { ws = 0; wph ^= 1; }
                             }
                     }
                 }
@@ -197,6 +207,7 @@ __global__ void __launch_bounds__(M_THREADS, 1) conv_march_kernel(const __grid_c
         } else if (warp == 2) {
             if (elect_one()) {
                 uint32_t sc = 0, ws = 0, wph = 0, ac = 0;
+                bool w_ready = false;                                     // resident weights: waited for once
                 const uint32_t idesc = umma_idesc_tf32(128, N, 0, 0);
                 // A: SWIZZLE_128B K-major.  start>>4 | LBO (unused, 1) << 16 | SBO = 1024 B (8 pixel rows) << 32 | version 1 << 46 |
                 //    layout type 2 << 61.  base_offset (bits 49..51) stays 0 although the tap views start 128*kx bytes into a
@@ -225,7 +236,12 @@ __global__ void __launch_bounds__(M_THREADS, 1) conv_march_kernel(const __grid_c
                                 const uint32_t d = tmem_base + as * N;
                                 uint32_t accf = 0u;
                                 for (int kx = 0; kx < K; ++kx) {
-                                    mbar_wait(BAR_W_FULL(ws), wph);
+                                    if (p.resident) {
+                                        ws = (uint32_t)((kb * 2 + c16) * K + kx);
+                                        if (!w_ready) mbar_wait(BAR_W_FULL(ws), 0);
+                                    } else {
+                                        mbar_wait(BAR_W_FULL(ws), wph);
+                                    }
                                     tc_fence_after();
                                     const uint64_t b_hi0 = b_word + ((base + L.wst(ws)) >> 4), b_lo0 = b_hi0 + b_lo_off;
 #pragma unroll
@@ -238,14 +254,17 @@ __global__ void __launch_bounds__(M_THREADS, 1) conv_march_kernel(const __grid_c
                                         if (three) { umma_tf32(d, adh, b_lo0 + ks * b_ks, idesc, 1u); umma_tf32(d, adl, b_hi0 + ks * b_ks, idesc, 1u); }
                                         accf = 1u;
                                     }
-                                    umma_commit(BAR_W_EMPTY(ws));
-                                    if (++ws == MW_STAGES) { ws = 0; wph ^= 1; }
+                                    if (!p.resident) {
+                                        umma_commit(BAR_W_EMPTY(ws));
+                                        if (++ws == STAGES) { ws = 0; wph ^= 1; }
+                                    }
                                 }
                                 umma_commit(BAR_ACC_FULL(as));
                                 ++ac;
                             }
                             umma_commit(BAR_CVT_EMPTY(cs));
                             ++sc;
+                            if (kb == p.num_kb - 1) w_ready = true;        // every stage has been seen once
                         }
                     }
                 }
@@ -263,6 +282,10 @@ __global__ void __launch_bounds__(M_THREADS, 1) conv_march_kernel(const __grid_c
         for (int s = 0; s < K; ++s)
 #pragma unroll
             for (int j = 0; j < HN; ++j) acc[s][j] = 0.f;
+        float osc[HN];                                    // out_scale of this thread's channels for the current image
+#pragma unroll
+        for (int j = 0; j < HN; ++j) osc[j] = 1.f;
+        int osc_img = -1;
         float* sc_s = reinterpret_cast<float*>(gbase + L.scale);
         const size_t plane = (size_t)p.OH * p.OW;
         const float kcomp = rz_compensation(2 * K, p.nprod);
@@ -302,7 +325,6 @@ __global__ void __launch_bounds__(M_THREADS, 1) conv_march_kernel(const __grid_c
             const int n0 = hcol * HN;
             const bool ok = (y >= un.y0) && (y < un.y1) && (x < p.OW);
             float* yp = p.y + ((size_t)un.img * p.O + n0) * plane + (size_t)y * p.OW + x;
-            const float* os = p.out_scale ? p.out_scale + (size_t)un.img * p.O + n0 : nullptr;
             const int nvalid = ok ? min(HN, p.O - n0) : 0;
 #pragma unroll
             for (int pp = 0; pp < K; ++pp) {
@@ -311,9 +333,7 @@ __global__ void __launch_bounds__(M_THREADS, 1) conv_march_kernel(const __grid_c
 #pragma unroll
                     for (int j = 0; j < HN; ++j) {
                         if (j < nvalid) {
-                            float val = acc[slot][j];
-                            if (os) val *= __ldg(os + j);
-                            *yp = val;
+                            *yp = acc[slot][j] * osc[j];
                         }
                         yp += plane;
                         acc[slot][j] = 0.f;
@@ -340,6 +360,11 @@ __global__ void __launch_bounds__(M_THREADS, 1) conv_march_kernel(const __grid_c
             for (int s = 0; s < K; ++s)
 #pragma unroll
                 for (int j = 0; j < HN; ++j) acc[s][j] = 0.f;
+            if (p.out_scale && un.img != osc_img) {
+#pragma unroll
+                for (int j = 0; j < HN; ++j) osc[j] = (hcol * HN + j < p.O) ? __ldg(p.out_scale + (size_t)un.img * p.O + hcol * HN + j) : 0.f;
+                osc_img = un.img;
+            }
             if (p.in_scale && un.img != cur_img) {
                 mnamed_bar_sync(1, M_CONS_THREADS);
                 for (int i = ct; i < p.num_kb * MK; i += M_CONS_THREADS)
@@ -483,6 +508,7 @@ int conv2d_march(const float* x, const float* w, float* y, int N, int I, int H, 
     if (total > 0x7fffffffLL) { cudaFreeAsync(wp, st); set_error("conv2d(march): too many units"); return GG_EINVAL; }
     p.total_units = (int)total;
     p.nprod = (nprod == GG_PREC_TF32X1) ? 1 : 3;
+    p.resident = (num_g16 * K <= march_stages(Ncols)) ? 1 : 0;
     int rc;
     if (K == 3 && NT == 32) rc = launch_march<32, 3>(xmap, p, st);
     else if (K == 3 && NT == 64) rc = launch_march<64, 3>(xmap, p, st);
