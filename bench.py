@@ -407,11 +407,11 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    custom_ops.conv_profile = []
+    custom_ops.conv_profile = [] if args.workload != 'ga' else None     # (the GA evaluation replays CUDA graphs: no events inside a capture)
     launches0 = custom_ops.launch_count()
     ms_total, _ = timed(args.steps, host_inputs=False)
     launches = custom_ops.launch_count() - launches0
-    prof, custom_ops.conv_profile = custom_ops.conv_profile, None
+    prof, custom_ops.conv_profile = (custom_ops.conv_profile or []), None
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, d2h_bytes = timed(args.steps, host_inputs=True)
 
@@ -454,7 +454,7 @@ def main():
             traffic, traffic_note = tj['conv_tc_kernel']['dram_bytes_per_launch'], tj['conv_tc_kernel']['note']
         except Exception as e:      # a malformed summary must not break the bench line
             traffic_note = f'unreadable {tpath}: {e}'
-    roofline = dict(bound='tensor', achieved=achieved, peak=tf32_peak, unit='TFLOP/s', frac=achieved / tf32_peak, traffic=traffic,
+    roofline = dict(bound='tensor', achieved=(achieved if prof else None), peak=tf32_peak, unit='TFLOP/s', frac=(achieved / tf32_peak if prof else None), traffic=traffic,
                     traffic_note=traffic_note,
                     kernel='conv_tc_kernel (tcgen05 implicit-GEMM conv: forward + data gradient of every conv layer)',
                     launches=dom_launches, avg_launch_ms=(dom_ms / dom_launches if dom_launches else None),

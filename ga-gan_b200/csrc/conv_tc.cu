@@ -282,10 +282,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             const uint32_t a_ks = 2u * (uint32_t)npix;          // second K=8 step: two 4-channel chunks further (16-byte units)
             constexpr uint32_t b_ks = 2u * NT, b_lo_off = 4u * NT;
             const bool three = p.nprod == 3;
+            int live_nt = -1, live_total = 0;                   // live (K-block, tap) pairs of the current n-tile
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(t, p);
                 const uint32_t* mrow = p.mask + (size_t)tc.nt * p.num_kb;
+                if (tc.nt != live_nt) {
+                    live_total = 0;
+                    for (int kb = 0; kb < p.num_kb; ++kb) live_total += __popc(__ldg(mrow + kb));
+                    live_nt = tc.nt;
+                }
                 uint32_t m_next = __ldg(mrow);
+                // A chunk = up to chunk_taps live taps accumulated in one TMEM set.  It may SPAN K-blocks (the phase-major stride-2
+                // weights have K-blocks with one or two live taps: one drain per K-block made those layers drain-bound); it closes
+                // when it is full or with the last live tap of the tile.
+                uint32_t d = 0, accf = 0u;
+                int in_chunk = 0, left = live_total;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     const uint32_t m = m_next;
                     if (kb + 1 < p.num_kb) m_next = __ldg(mrow + kb + 1);
@@ -295,10 +306,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     tc_fence_after();
                     // sub-tile `sub` starts 8 pixels (8 x 16 bytes) to the right
                     const uint64_t a_hi0 = a_word + ((base + L.cvt(cs, 0)) >> 4) + 8u * sub, a_lo0 = a_word + ((base + L.cvt(cs, 1)) >> 4) + 8u * sub;
-                    uint32_t d = 0;
-                    uint32_t accf = 0u;                               // first MMA of a chunk overwrites the accumulator
                     uint32_t tap = 0;
-                    int in_chunk = 0, left = __popc(m);
                     for (int ky = 0; ky < p.K; ++ky) {
                         for (int kx = 0; kx < p.K; ++kx, ++tap) {
                             if (!((m >> tap) & 1u)) continue;
@@ -352,7 +360,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         uint32_t kbc = 0;
         bool pend = false, pend_last = false;
         uint32_t ac = 0, pend_ac = 0;                   // accumulator-chunk counter (same sequence as the MMA issuer's)
-        int pend_live = 0;                              // live taps of the pending K-block
+        int pend_n = 0, pend_size = 0;                  // chunks that closed inside the pending K-block, taps of the last of them
+        int open_taps = 0;                              // taps already in the chunk that is still open (chunks span K-blocks)
         TileCoord pend_tc{0, 0, 0, 0};
         const size_t plane = (size_t)p.OH * p.OW;
         int cvt_src[CVT_ITEMS];                         // conversion plan: source index in the raw box per (chunk, pixel) item
@@ -411,16 +420,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             if (lane == 0) mbar_arrive(BAR_ACC_EMPTY(s));
         };
 
-        auto drain = [&](uint32_t first_chunk, int live) {   // all chunks of one K-block, with the truncation compensation
-            for (int c = 0; live > 0; ++c, live -= p.chunk_taps)
-                drain_chunk(first_chunk + c, rz_compensation(2 * min(live, p.chunk_taps), p.nprod));
+        // the chunks that CLOSED inside one K-block: all full (chunk_taps taps) except possibly the last one of a tile
+        auto drain = [&](uint32_t first_chunk, int nclosed, int last_size) {
+            for (int c = 0; c < nclosed; ++c)
+                drain_chunk(first_chunk + c, rz_compensation(2 * (c == nclosed - 1 ? last_size : p.chunk_taps), p.nprod));
         };
 
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             const TileCoord tc = decode_tile(t, p);
             if (tc.nt != cur_nt) { M.load(p, tc.nt, lane); cur_nt = tc.nt; }
             if (M.last_kb < 0) {                        // the whole n-tile of weights is zero: the output tile is zero
-                if (pend) { drain(pend_ac, pend_live); if (pend_last) store_tile(pend_tc); pend = false; }
+                if (pend) { drain(pend_ac, pend_n, pend_size); if (pend_last) store_tile(pend_tc); pend = false; }
                 store_tile(tc);
                 continue;
             }
@@ -460,8 +470,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 float4* lo = reinterpret_cast<float4*>(gbase + L.cvt(s, 1));
                 // K-block j is converted and published FIRST, then the partial sums of K-block j-1 are drained: the tensor core goes
                 // from the MMAs of j-1 straight to those of j (other TMEM set) while the drain of j-1 runs next to them.
-                int pend_left = pend ? pend_live : 0;
-                uint32_t pend_chunk = pend_ac;
 #pragma unroll
                 for (int it = 0; it < CVT_ITEMS; ++it) {
                     const int plan = cvt_src[it], src = plan < 0 ? plan : (plan & 0xFFFFFF);
@@ -486,17 +494,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(BAR_CVT_FULL(s)); mbar_arrive(BAR_RAW_EMPTY(s)); }
                 if (pend) {
-                    for (; pend_left > 0; pend_left -= p.chunk_taps)
-                        drain_chunk(pend_chunk++, rz_compensation(2 * min(pend_left, p.chunk_taps), p.nprod));
+                    drain(pend_ac, pend_n, pend_size);
                     if (pend_last) store_tile(pend_tc);
                 }
                 pend = true; pend_last = (kb == M.last_kb); pend_tc = tc;
-                pend_ac = ac; pend_live = __popc(live);
-                ac += (pend_live + p.chunk_taps - 1) / p.chunk_taps;
+                pend_ac = ac;
+                {   // same chunk sequence as the issuer: full chunks close as they fill up, the remainder closes with the tile
+                    const int total = open_taps + __popc(live);
+                    pend_n = pend_last ? (total + p.chunk_taps - 1) / p.chunk_taps : total / p.chunk_taps;
+                    const int rem = total % p.chunk_taps;
+                    pend_size = (pend_last && rem != 0) ? rem : p.chunk_taps;
+                    open_taps = pend_last ? 0 : rem;
+                }
+                ac += pend_n;
                 ++kbc;
             }
         }
-        if (pend) { drain(pend_ac, pend_live); if (pend_last) store_tile(pend_tc); }
+        if (pend) { drain(pend_ac, pend_n, pend_size); if (pend_last) store_tile(pend_tc); }
         tc_fence_before();
     }
     __syncthreads();

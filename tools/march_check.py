@@ -38,9 +38,8 @@ for (N, I, O, H, W, pad, tr, flip, sc) in cases:
         idx = torch.nonzero(d > 1e-3 * y0.abs().max())
         print('   first bad (n,o,y,x):', idx[:5].tolist(), ' count', idx.shape[0], 'of', d.numel())
 print('BAD', bad)
-if len(sys.argv) > 1 and sys.argv[1] == 'quick':
-    sys.exit(0)
-for (N, I, O, R) in [(8, 32, 32, 1024), (8, 64, 64, 512), (32, 32, 32, 1024), (32, 64, 64, 512), (4, 64, 64, 256)]:
+QUICK = len(sys.argv) > 1 and sys.argv[1] == 'quick'
+for (N, I, O, R) in ([] if QUICK else [(8, 32, 32, 1024), (8, 64, 64, 512), (32, 32, 32, 1024), (32, 64, 64, 512), (4, 64, 64, 256)]):
     x = torch.randn(N, I, R, R, device=dev); w = torch.randn(O, I, 3, 3, device=dev) / np.sqrt(9 * I)
     a = torch.rand(N, I, device=dev) + 0.5; b = torch.rand(N, O, device=dev) + 0.5
     for fam in (1, 0):
@@ -56,4 +55,27 @@ for (N, I, O, R) in [(8, 32, 32, 1024), (8, 64, 64, 512), (32, 32, 32, 1024), (3
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 5
             print(f'N{N} {I}->{O} @{R}^2 family {"march" if fam else "tile "} scaled={scaled}: {ms:.3f} ms  {2.0 * N * O * I * 9 * R * R / ms / 1e9:.1f} TFLOP/s', flush=True)
+custom_ops.set_conv_kernel_family(1)
+
+# phase-major stride-2 layers (2x2 kernels with structurally dead taps) through conv2d_resample: K = 2 instantiations
+from torch_utils.ops import conv2d_resample as cr, upfirdn2d
+f = upfirdn2d.setup_filter([1, 3, 3, 1]).to(dev)
+print('--- conv2d_resample up / down (phase-major 2x2): forward + gradients, march vs FFMA')
+for (N, I, O, R, up, down) in [(2, 64, 32, 128, 2, 1), (2, 32, 64, 256, 1, 2), (1, 48, 24, 96, 2, 1), (2, 128, 64, 64, 2, 1), (2, 64, 128, 128, 1, 2)]:
+    x = torch.randn(N, I, R, R, device=dev, requires_grad=True); w = (torch.randn(O, I, 3, 3, device=dev) / np.sqrt(9 * I)).requires_grad_(True)
+    outs = []
+    for prec, fam in ((custom_ops.PREC_AUTO, 1), (custom_ops.PREC_AUTO, 0), (custom_ops.PREC_FP32_SIMT, 0)):
+        custom_ops.conv_precision = prec; custom_ops.set_conv_kernel_family(fam)
+        y = cr.conv2d_resample(x, w, f=f, up=up, down=down, padding=1, flip_weight=(up == 1))
+        if not outs:
+            dy = torch.randn_like(y)
+        outs.append([y.detach()] + list(torch.autograd.grad(y, [x, w], dy)))
+    custom_ops.conv_precision = custom_ops.PREC_AUTO; custom_ops.set_conv_kernel_family(1)
+    errs = [[float((a - b).abs().max() / b.abs().max()) for a, b in zip(o, outs[2])] for o in outs[:2]]
+    ok = max(errs[0]) < 2e-5
+    bad += (not ok)
+    print(f'{(N, I, O, R, up, down)}: march y/dx/dw ' + ' '.join(f'{e:.1e}' for e in errs[0]) + '   tile ' + ' '.join(f'{e:.1e}' for e in errs[1]) + ('  ok' if ok else '  MISMATCH'), flush=True)
+print('BAD', bad)
+if len(sys.argv) > 1 and sys.argv[1] == 'quick':
+    sys.exit(0)
 custom_ops.set_conv_kernel_family(1)
