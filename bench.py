@@ -65,6 +65,7 @@ def parse_args():
     ap.add_argument('--prec', default='auto', choices=['auto', 'simt', 'tf32x1', 'tf32x3'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-fast-mode', action='store_true')
+    ap.add_argument('--fused-epilogue', action='store_true', help='A/B: bias / noise / activation in the conv store loop instead of a separate bias_act launch')
     ap.add_argument('--reference-forwards', action='store_true', help="run the reference's forwards untouched (no fused callers)")
     ap.add_argument('--cpu-res', type=int, default=0, help='resolution of the CPU sample (0 = same as --res)')
     ap.add_argument('--cpu-batch', type=int, default=2)
@@ -328,6 +329,9 @@ def main():
     custom_ops.verbosity = 'none'
     PREC = dict(auto=custom_ops.PREC_AUTO, simt=custom_ops.PREC_FP32_SIMT, tf32x1=custom_ops.PREC_TF32X1, tf32x3=custom_ops.PREC_TF32X3)
     custom_ops.conv_precision = PREC[args.prec]
+    if args.fused_epilogue:
+        from torch_utils.ops import conv2d_gradfix
+        conv2d_gradfix.fuse_epilogue = True
 
     def barrier():
         if world > 1:

@@ -1,5 +1,5 @@
 // C-ABI glue of libgagan_b200.so: error state, argument validation and kernel-family dispatch.
-#include "common.cuh"
+#include "tc_common.cuh"
 #include <string.h>
 
 namespace gg {
@@ -33,11 +33,12 @@ int wgrad1x1_thin(const float* a, const float* b, float* dw, int N, int A, int H
 bool conv2d_tc_eligible(int N, int I, int H, int W, int O, int KH, int KW, int OH, int OW, int stride, int pad_y, int pad_x,
                         int transposed);
 int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int KH, int KW, int OH, int OW, int pad_y,
-              int pad_x, int flip_w, int w_is_IO, const float* in_scale, const float* out_scale, int nprod, cudaStream_t st);
+              int pad_x, int flip_w, int w_is_IO, const float* in_scale, const float* out_scale, int nprod, const ggtc::ConvEpilogue* epi,
+              cudaStream_t st);
 // conv_march.cu (row-marching tcgen05 path for <= 64 output channels)
 bool conv2d_march_eligible(const float* x, int N, int I, int H, int W, int O, int KH, int KW, int OH, int OW, int stride, int pad_y, int pad_x);
 int conv2d_march(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int K, int OH, int OW, int pad_y, int pad_x,
-                 int flip_w, int w_is_IO, const float* in_scale, const float* out_scale, int nprod, cudaStream_t st);
+                 int flip_w, int w_is_IO, const float* in_scale, const float* out_scale, int nprod, const ggtc::ConvEpilogue* epi, cudaStream_t st);
 bool wgrad_tc_eligible(int N, int A, int HA, int WA, int B, int HB, int WB, int KH, int KW, int stride, int pad_y, int pad_x);
 int wgrad_tc(const float* a, const float* b, float* dw, int N, int A, int HA, int WA, int B, int HB, int WB, int KH, int KW,
              int pad_y, int pad_x, int flip_w, int out_layout, const float* a_scale, const float* b_scale, int nprod, int pm_dim,
@@ -59,9 +60,13 @@ extern "C" GG_API int gg_device_ok(void) {
     return (major == 10 && minor == 0) ? 1 : 0;
 }
 
-extern "C" GG_API int gg_conv2d_f32(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int KH, int KW,
-                             int OH, int OW, int stride, int pad_y, int pad_x, int transposed, int flip_w,
-                             const float* in_scale, const float* out_scale, int prec, int* used_prec, gg_stream_t stream) {
+// `epi` (may be null): bias / noise / activation to apply to the result.  *epi_fused tells the caller whether the convolution kernel
+// did it in its epilogue; if not, the caller runs the bias_act kernel over y.
+static int conv2d_impl(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int KH, int KW,
+                       int OH, int OW, int stride, int pad_y, int pad_x, int transposed, int flip_w,
+                       const float* in_scale, const float* out_scale, int prec, int* used_prec, const ggtc::ConvEpilogue* epi,
+                       bool* epi_fused, gg_stream_t stream) {
+    if (epi_fused) *epi_fused = false;
     GG_REQUIRE(x && w && y, "conv2d: null pointer");
     GG_REQUIRE(N >= 0 && I >= 1 && H >= 1 && W >= 1 && O >= 1 && KH >= 1 && KW >= 1, "conv2d: bad shape");
     GG_REQUIRE(stride >= 1 && pad_y >= 0 && pad_x >= 0, "conv2d: bad stride/padding");
@@ -99,10 +104,39 @@ extern "C" GG_API int gg_conv2d_f32(const float* x, const float* w, float* y, in
     // stride-1 conv_transpose2d == correlation with the flipped kernel and padding K-1-p; both are
     // handled inside the tensor-core path through its weight-packing step.
     const int tpy = transposed ? KH - 1 - pad_y : pad_y, tpx = transposed ? KW - 1 - pad_x : pad_x;
+    const bool fuse = epi && epi->act >= 1 && epi->act <= 3;          // linear / relu / lrelu ride in the store loop of the tcgen05 kernels
+    if (epi_fused) *epi_fused = fuse;
     if (gg::g_march_enabled && gg::conv2d_march_eligible(x, N, I, H, W, O, KH, KW, OH, OW, stride, tpy, tpx))
-        return gg::conv2d_march(x, w, y, N, I, H, W, O, KH, OH, OW, tpy, tpx, transposed ? !flip_w : flip_w, transposed, in_scale, out_scale, use, st);
+        return gg::conv2d_march(x, w, y, N, I, H, W, O, KH, OH, OW, tpy, tpx, transposed ? !flip_w : flip_w, transposed, in_scale, out_scale, use,
+                                fuse ? epi : nullptr, st);
     return gg::conv2d_tc(x, w, y, N, I, H, W, O, KH, KW, OH, OW, transposed ? KH - 1 - pad_y : pad_y, transposed ? KW - 1 - pad_x : pad_x,
-                         transposed ? !flip_w : flip_w, transposed, in_scale, out_scale, use, st);
+                         transposed ? !flip_w : flip_w, transposed, in_scale, out_scale, use, fuse ? epi : nullptr, st);
+}
+
+extern "C" GG_API int gg_conv2d_f32(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int KH, int KW,
+                             int OH, int OW, int stride, int pad_y, int pad_x, int transposed, int flip_w,
+                             const float* in_scale, const float* out_scale, int prec, int* used_prec, gg_stream_t stream) {
+    return conv2d_impl(x, w, y, N, I, H, W, O, KH, KW, OH, OW, stride, pad_y, pad_x, transposed, flip_w, in_scale, out_scale, prec, used_prec,
+                       nullptr, nullptr, stream);
+}
+
+extern "C" GG_API int gg_conv2d_act_f32(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int KH, int KW,
+                                 int OH, int OW, int stride, int pad_y, int pad_x, int transposed, int flip_w,
+                                 const float* in_scale, const float* out_scale, const float* bias, const float* noise,
+                                 int64_t noise_batch_stride, int act, float alpha, float gain, float clamp, int prec, int* used_prec,
+                                 int* fused, gg_stream_t stream) {
+    GG_REQUIRE(act >= 1 && act <= 9, "conv2d_act: act must be the reference's cuda_idx 1..9");
+    GG_REQUIRE(noise == nullptr || noise_batch_stride == 0 || noise_batch_stride == (int64_t)OH * OW, "conv2d_act: noise must be [OH*OW] or [N, OH*OW]");
+    ggtc::ConvEpilogue epi{bias, noise, (long long)noise_batch_stride, act, alpha, gain, clamp};
+    bool did = false;
+    int rc = conv2d_impl(x, w, y, N, I, H, W, O, KH, KW, OH, OW, stride, pad_y, pad_x, transposed, flip_w, in_scale, out_scale, prec, used_prec,
+                         &epi, &did, stream);
+    if (fused) *fused = did ? 1 : 0;
+    if (rc != GG_OK || did || N == 0) return rc;
+    // the kernel family that served this shape (FFMA / thin 1x1) has no epilogue: the same arithmetic as a second launch, in place
+    if (noise == nullptr)
+        return gg_bias_act_f32(y, bias, nullptr, nullptr, nullptr, y, nullptr, 0, act, alpha, gain, clamp, (int64_t)N * O * OH * OW, O, (int64_t)OH * OW, stream);
+    return gg_bias_act_noise_f32(y, bias, noise, noise_batch_stride, y, act, alpha, gain, clamp, (int64_t)N * O * OH * OW, O, (int64_t)OH * OW, stream);
 }
 
 extern "C" GG_API int gg_conv2d_wgrad_f32(const float* a, const float* b, float* dw, int N, int A, int HA, int WA, int B, int HB, int WB,

@@ -50,6 +50,7 @@ struct MarchP {
     int num_g16;           // 16-channel groups (= weight stages per kx)
     int strips_x, bands, band_rows, total_units, nprod;
     int resident;          // all num_g16*K weight stages fit the ring: loaded once per CTA, never recycled
+    ConvEpilogue epi;      // fused bias / noise / activation (act == 0: none)
 };
 
 __host__ __device__ constexpr int march_stages(int N) { return N > 128 ? 4 : MW_STAGES; }
@@ -68,7 +69,7 @@ __host__ __device__ inline MLayout make_mlayout(int N) {      // offsets from th
     L.raw0 = off; off += 2 * RAW_BYTES;
     L.wbytes = (uint32_t)(2 * 4 * N * 16);
     L.w0 = off; off += (uint32_t)march_stages(N) * L.wbytes;   // 4 x 24 KB (N = 192) or 6 x 12 KB (N = 96)
-    L.scale = off; off += M_MAX_CH * 4;
+    L.scale = off; off += M_MAX_CH * 4 + 256;                  // in_scale of the image's channels, then the fused bias of <= 64 outputs
     L.bars = off; off += 256;
     L.tmem_slot = off; off += 16;
     L.total = off;
@@ -120,7 +121,7 @@ __device__ __forceinline__ Unit decode_unit(int u, const MarchP& p) {
 
 __device__ __forceinline__ void mnamed_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-template <int NT, int K>
+template <int NT, int K, bool EPI>
 __global__ void __launch_bounds__(M_THREADS, 1) conv_march_kernel(const __grid_constant__ CUtensorMap xmap, MarchP p) {
     constexpr int N = K * NT;                       // accumulator columns of one set: (ky, o)
     constexpr uint32_t TMEM_COLS = (2 * N <= 256) ? 256 : 512;
@@ -286,6 +287,17 @@ __global__ void __launch_bounds__(M_THREADS, 1) conv_march_kernel(const __grid_c
 #pragma unroll
         for (int j = 0; j < HN; ++j) osc[j] = 1.f;
         int osc_img = -1;
+        float* bsc = reinterpret_cast<float*>(gbase + L.scale) + M_MAX_CH + hcol * HN;   // EPI: the bias of this thread's channels (shared memory)
+        if (EPI) {
+            if (ct < NT) reinterpret_cast<float*>(gbase + L.scale)[M_MAX_CH + ct] = (p.epi.bias && ct < p.O) ? __ldg(p.epi.bias + ct) : 0.f;
+            mnamed_bar_sync(1, M_CONS_THREADS);
+        }
+        const EpilogueScalars epi_s = epilogue_scalars(p.epi);
+        auto fetch_nz = [&](const Unit& un, int y) -> float {     // the noise value of this thread's pixel in output row y
+            if (!EPI || p.epi.noise == nullptr) return 0.f;
+            const int x = un.x0 + q * 32 + lane;
+            return (y >= un.y0 && y < un.y1 && x < p.OW) ? __ldg(p.epi.noise + (size_t)un.img * p.epi.noise_bs + (size_t)y * p.OW + x) : 0.f;
+        };
         float* sc_s = reinterpret_cast<float*>(gbase + L.scale);
         const size_t plane = (size_t)p.OH * p.OW;
         const float kcomp = rz_compensation(2 * K, p.nprod);
@@ -320,12 +332,13 @@ __global__ void __launch_bounds__(M_THREADS, 1) conv_march_kernel(const __grid_c
             }
         };
         // the output row completed by the input row with phase ph: slot (ph + 1) mod K; stored, then cleared for row y + K
-        auto store_row = [&](const Unit& un, int y, int ph) {
+        auto store_row = [&](const Unit& un, int y, int ph, float row_nz) {
             const int x = un.x0 + q * 32 + lane;
             const int n0 = hcol * HN;
             const bool ok = (y >= un.y0) && (y < un.y1) && (x < p.OW);
             float* yp = p.y + ((size_t)un.img * p.O + n0) * plane + (size_t)y * p.OW + x;
             const int nvalid = ok ? min(HN, p.O - n0) : 0;
+            const float nz = EPI ? row_nz : 0.f;          // fetched when this row's input was converted (not here: critical path)
 #pragma unroll
             for (int pp = 0; pp < K; ++pp) {
                 if (ph == pp) {
@@ -333,7 +346,9 @@ __global__ void __launch_bounds__(M_THREADS, 1) conv_march_kernel(const __grid_c
 #pragma unroll
                     for (int j = 0; j < HN; ++j) {
                         if (j < nvalid) {
-                            *yp = acc[slot][j] * osc[j];
+                            float val = acc[slot][j] * osc[j];
+                            if (EPI) val = epilogue_apply(val, bsc[j] + nz, epi_s);
+                            *yp = val;
                         }
                         yp += plane;
                         acc[slot][j] = 0.f;
@@ -344,12 +359,12 @@ __global__ void __launch_bounds__(M_THREADS, 1) conv_march_kernel(const __grid_c
 
         // pending work of the previous step: its chunks are drained AFTER the next step has been converted and published
         bool pend = false, pend_last = false;
-        uint32_t pend_ac = 0; int pend_n = 0, pend_ph = 0, pend_y = 0;
+        uint32_t pend_ac = 0; int pend_n = 0, pend_ph = 0, pend_y = 0; float pend_nz = 0.f;
         Unit pend_un{0, 0, 0, 0};
         auto flush = [&]() {
             if (!pend) return;
             for (int c = 0; c < pend_n; ++c) drain_chunk(pend_ac + c, pend_ph);
-            if (pend_last) store_row(pend_un, pend_y, pend_ph);
+            if (pend_last) store_row(pend_un, pend_y, pend_ph, pend_nz);
             pend = false;
         };
 
@@ -380,7 +395,7 @@ __global__ void __launch_bounds__(M_THREADS, 1) conv_march_kernel(const __grid_c
                 const int y = t - (K - 1);                             // the output row this input row completes
                 if (r < 0 || r >= p.H) {                               // a row of zero padding: nothing to add, but row y is complete
                     flush();
-                    store_row(un, y, ph);
+                    store_row(un, y, ph, fetch_nz(un, y));
                     continue;
                 }
                 for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -416,9 +431,10 @@ __global__ void __launch_bounds__(M_THREADS, 1) conv_march_kernel(const __grid_c
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) { mbar_arrive(BAR_CVT_FULL(s)); mbar_arrive(BAR_RAW_EMPTY(s)); }
-                    flush();
                     const int n16 = min(2, p.num_g16 - 2 * kb);
-                    pend = true; pend_ac = ac; pend_n = n16; pend_ph = ph; pend_un = un; pend_y = y;
+                    const float nz_here = (kb == p.num_kb - 1) ? fetch_nz(un, y) : 0.f;   // issued before the drains below
+                    flush();
+                    pend = true; pend_ac = ac; pend_n = n16; pend_ph = ph; pend_un = un; pend_y = y; pend_nz = nz_here;
                     pend_last = (kb == p.num_kb - 1);
                     ac += n16;
                     ++sc;
@@ -435,18 +451,18 @@ __global__ void __launch_bounds__(M_THREADS, 1) conv_march_kernel(const __grid_c
     }
 }
 
-template <int NT, int K>
+template <int NT, int K, bool EPI>
 int launch_march(const CUtensorMap& xmap, const MarchP& p, cudaStream_t st) {
     const MLayout L = make_mlayout(K * NT);
     const size_t smem = L.total + 1024;
     if (smem > 227 * 1024) { gg::set_error("conv2d(march): shared-memory layout of %zu bytes does not fit", smem); return GG_EUNSUPPORTED; }
     static std::atomic<uint64_t> attr_set{0};
     if (!gg::done_on_this_device(attr_set)) {
-        GG_CUDA(cudaFuncSetAttribute(conv_march_kernel<NT, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        GG_CUDA(cudaFuncSetAttribute(conv_march_kernel<NT, K, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         gg::mark_done_on_this_device(attr_set);
     }
     const int grid = p.total_units < GG_NUM_SMS ? p.total_units : GG_NUM_SMS;
-    conv_march_kernel<NT, K><<<grid, M_THREADS, smem, st>>>(xmap, p);
+    conv_march_kernel<NT, K, EPI><<<grid, M_THREADS, smem, st>>>(xmap, p);
     return gg::check_launch("conv2d(march)");
 }
 
@@ -466,7 +482,7 @@ bool conv2d_march_eligible(const float* x, int N, int I, int H, int W, int O, in
 }
 
 int conv2d_march(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int K, int OH, int OW, int pad_y, int pad_x,
-                 int flip_w, int w_is_IO, const float* in_scale, const float* out_scale, int nprod, cudaStream_t st) {
+                 int flip_w, int w_is_IO, const float* in_scale, const float* out_scale, int nprod, const ConvEpilogue* epi, cudaStream_t st) {
     const int NT = O > 32 ? 64 : 32;
     const int Ncols = K * NT;
     const int num_g16 = (I + 15) / 16, num_kb = (I + MK - 1) / MK;
@@ -509,9 +525,11 @@ int conv2d_march(const float* x, const float* w, float* y, int N, int I, int H, 
     p.total_units = (int)total;
     p.nprod = (nprod == GG_PREC_TF32X1) ? 1 : 3;
     p.resident = (num_g16 * K <= march_stages(Ncols)) ? 1 : 0;
+    if (epi) p.epi = *epi;
     int rc;
-    if (K == 3 && NT == 32) rc = launch_march<32, 3>(xmap, p, st);
-    else if (K == 3 && NT == 64) rc = launch_march<64, 3>(xmap, p, st);
+    const bool e = p.epi.act != 0;      // the fused-epilogue instantiations are separate kernels
+    if (K == 3 && NT == 32) rc = e ? launch_march<32, 3, true>(xmap, p, st) : launch_march<32, 3, false>(xmap, p, st);
+    else if (K == 3 && NT == 64) rc = e ? launch_march<64, 3, true>(xmap, p, st) : launch_march<64, 3, false>(xmap, p, st);
     else { set_error("conv2d(march): unsupported configuration"); rc = GG_EUNSUPPORTED; }
     cudaFreeAsync(wp, st);
     return rc;

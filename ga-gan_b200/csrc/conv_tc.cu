@@ -111,6 +111,7 @@ struct TcP {
     int boxW, boxH;            // converted halo tile in pixels; boxW is its smem pixel pitch
     int chunk_taps;            // live taps accumulated in TMEM before the partial sum is drained (<= CHUNK_TAPS)
     int rawW;                  // width of the raw TMA box (>= boxW: the box must start on a 16-byte boundary in global memory)
+    ConvEpilogue epi;          // fused bias / noise / activation (act == 0: none)
 };
 
 struct SmemLayout {   // byte offsets from the 128-byte aligned dynamic smem base (arithmetic, so that stage indices stay in registers)
@@ -178,7 +179,7 @@ struct KbMasks {
     }
 };
 
-template <int NT, int SUBS>
+template <int NT, int SUBS, bool EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, TcP p) {
     constexpr int W_STAGES = w_stages_for(NT);
     constexpr int TILE_W = 8 * SUBS;
@@ -367,6 +368,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         int cvt_src[CVT_ITEMS];                         // conversion plan: source index in the raw box per (chunk, pixel) item
         int plan_dx = INT_MIN, plan_dy = INT_MIN;
 
+        const EpilogueScalars epi_s = epilogue_scalars(p.epi);
+        float tile_nz[SUBS], next_nz[SUBS];             // EPI: the noise value of this thread's output pixel(s), current / upcoming tile
+#pragma unroll
+        for (int sub = 0; sub < SUBS; ++sub) { tile_nz[sub] = 0.f; next_nz[sub] = 0.f; }
+        auto load_nz = [&](const TileCoord& tc, float (&dst)[SUBS]) {
+            if (!EPI || p.epi.noise == nullptr) return;
+            const int m = q * 32 + lane;
+            const int oy = tc.ty * TILE_H + (m >> 3);
+#pragma unroll
+            for (int sub = 0; sub < SUBS; ++sub) {
+                const int ox = tc.tx * TILE_W + 8 * sub + (m & 7);
+                dst[sub] = (oy < p.OH && ox < p.OW) ? __ldg(p.epi.noise + (size_t)tc.img * p.epi.noise_bs + (size_t)oy * p.OW + ox) : 0.f;
+            }
+        };
         auto store_tile = [&](const TileCoord& tc) {
             const int m = q * 32 + lane;                // accumulator row = pixel inside the 8x16 sub-tile
             const int r = m >> 3, c = m & 7;
@@ -379,11 +394,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 float* yp = p.y + ((size_t)tc.img * p.O + n0) * plane + (size_t)oy * p.OW + ox;
                 const float* os = p.out_scale ? p.out_scale + (size_t)tc.img * p.O + n0 : nullptr;
                 const int nvalid = pix_ok ? min(HN, p.O - n0) : 0;
+                const float nz = EPI ? tile_nz[sub] : 0.f;     // prefetched when the tile was opened (a global load in here would sit on the
+                                                                // consumers' critical path)
 #pragma unroll
                 for (int j = 0; j < HN; ++j) {
                     if (j < nvalid) {
                         float val = acc[sub][j];
                         if (os) val *= __ldg(os + j);
+                        if (EPI) val = epilogue_apply(val, (p.epi.bias ? __ldg(p.epi.bias + n0 + j) : 0.f) + nz, epi_s);
                         *yp = val;
                     }
                     yp += plane;                        // running pointer: one live address instead of HN
@@ -431,8 +449,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             if (tc.nt != cur_nt) { M.load(p, tc.nt, lane); cur_nt = tc.nt; }
             if (M.last_kb < 0) {                        // the whole n-tile of weights is zero: the output tile is zero
                 if (pend) { drain(pend_ac, pend_n, pend_size); if (pend_last) store_tile(pend_tc); pend = false; }
+                load_nz(tc, tile_nz);
                 store_tile(tc);
                 continue;
+            }
+            {   // EPI: fetch this tile's noise now; if the previous tile is still waiting for its store, keep its values until then
+                if (pend && pend_last) load_nz(tc, next_nz); else load_nz(tc, tile_nz);
             }
             if (p.in_scale && tc.img != cur_img) {      // stage this image's per-channel input scales (styles)
                 named_bar_sync(1, CONS_THREADS);
@@ -495,7 +517,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 if (lane == 0) { mbar_arrive(BAR_CVT_FULL(s)); mbar_arrive(BAR_RAW_EMPTY(s)); }
                 if (pend) {
                     drain(pend_ac, pend_n, pend_size);
-                    if (pend_last) store_tile(pend_tc);
+                    if (pend_last) {
+                        store_tile(pend_tc);
+                        if (EPI && (pend_tc.tx != tc.tx || pend_tc.ty != tc.ty || pend_tc.img != tc.img || pend_tc.nt != tc.nt)) {
+#pragma unroll
+                            for (int sub = 0; sub < SUBS; ++sub) tile_nz[sub] = next_nz[sub];
+                        }
+                    }
                 }
                 pend = true; pend_last = (kb == M.last_kb); pend_tc = tc;
                 pend_ac = ac;
@@ -521,18 +549,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-template <int NT, int SUBS>
+template <int NT, int SUBS, bool EPI>
 int launch_conv_tc(const CUtensorMap& xmap, const TcP& p, cudaStream_t st) {
     const SmemLayout L = make_layout(p.boxW, p.boxH, p.rawW, NT);
     const size_t smem = L.total + 128;
     if (smem > 227 * 1024) { gg::set_error("conv2d(tc): shared-memory layout of %zu bytes does not fit", smem); return GG_EUNSUPPORTED; }
     static std::atomic<uint64_t> attr_set{0};           // one bit per device: the opt-in belongs to the device's context
     if (!gg::done_on_this_device(attr_set)) {
-        GG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT, SUBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        GG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT, SUBS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         gg::mark_done_on_this_device(attr_set);
     }
     const int grid = p.total_tiles < GG_NUM_SMS ? p.total_tiles : GG_NUM_SMS;
-    conv_tc_kernel<NT, SUBS><<<grid, NUM_THREADS, smem, st>>>(xmap, p);
+    conv_tc_kernel<NT, SUBS, EPI><<<grid, NUM_THREADS, smem, st>>>(xmap, p);
     return gg::check_launch("conv2d(tc)");
 }
 
@@ -582,7 +610,8 @@ bool conv2d_tc_eligible(int N, int I, int H, int W, int O, int KH, int KW, int O
 }
 
 int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int K, int /*KW*/, int OH, int OW, int pad_y,
-              int pad_x, int flip_w, int w_is_IO, const float* in_scale, const float* out_scale, int nprod, cudaStream_t st) {
+              int pad_x, int flip_w, int w_is_IO, const float* in_scale, const float* out_scale, int nprod, const ConvEpilogue* epi,
+              cudaStream_t st) {
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) { set_error("conv2d(tc): x must be 16-byte aligned"); return GG_EINVAL; }
     const int NT = O > 128 ? 256 : (O > 64 ? 128 : (O > 32 ? 64 : 32));
     const int TILE_W = NT == 256 ? 8 : 16;
@@ -634,11 +663,13 @@ int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int
     p.total_tiles = (int)total;
     p.boxW = boxW; p.boxH = boxH; p.rawW = rawW;
     p.chunk_taps = CHUNK_TAPS;
+    if (epi) p.epi = *epi;             // (value-initialised otherwise: act == 0)
     int rc;
-    if (NT == 256) rc = launch_conv_tc<256, 1>(xmap, p, st);
-    else if (NT == 128) rc = launch_conv_tc<128, 2>(xmap, p, st);
-    else if (NT == 64) rc = launch_conv_tc<64, 2>(xmap, p, st);
-    else rc = launch_conv_tc<32, 2>(xmap, p, st);
+    const bool e = p.epi.act != 0;      // the fused-epilogue instantiations are separate kernels: the plain ones stay as they were
+    if (NT == 256) rc = e ? launch_conv_tc<256, 1, true>(xmap, p, st) : launch_conv_tc<256, 1, false>(xmap, p, st);
+    else if (NT == 128) rc = e ? launch_conv_tc<128, 2, true>(xmap, p, st) : launch_conv_tc<128, 2, false>(xmap, p, st);
+    else if (NT == 64) rc = e ? launch_conv_tc<64, 2, true>(xmap, p, st) : launch_conv_tc<64, 2, false>(xmap, p, st);
+    else rc = e ? launch_conv_tc<32, 2, true>(xmap, p, st) : launch_conv_tc<32, 2, false>(xmap, p, st);
     cudaFreeAsync(wp, st);
     return rc;
 }

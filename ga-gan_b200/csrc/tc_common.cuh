@@ -156,4 +156,33 @@ __device__ __forceinline__ float rz_compensation(int m, int nprod) {
     return 1.0f + 5.0e-8f * (float)nprod * 0.5f * (float)(m + 1);
 }
 
+
+// Optional fused epilogue of the convolution kernels: y = clamp(act(conv + (bias[o] + noise[pixel])) * gain), the bias_act pass
+// (torch_utils/ops/bias_act.py; reference kernel bias_act.cu:56-142) of the layers whose convolution is the LAST operator of
+// conv2d_resample.  act = 0: no epilogue; 1 linear, 2 relu, 3 lrelu (the reference's cuda_idx; same strict comparisons).
+struct ConvEpilogue {
+    const float* bias;          // [O] or null
+    const float* noise;         // [OH*OW] (noise_bs == 0) or [N, OH*OW] (noise_bs == OH*OW) or null
+    long long noise_bs;
+    int act;
+    float alpha, gain, clamp;   // clamp < 0: off
+};
+// The per-element work sits in the consumer warps' store loop, i.e. on the critical path of the small-K layers: keep it at
+// add, compare, select, multiply (+ the clamp only when there is one).  act(v) * gain == v * (v > 0 ? gain : gain * slope) with slope 1
+// (linear), 0 (relu) or alpha (lrelu); the product gain * alpha is rounded once instead of twice (<= 1 ulp from the two-step form).
+struct EpilogueScalars { float g_pos, g_neg, clamp; };
+__device__ __forceinline__ EpilogueScalars epilogue_scalars(const ConvEpilogue& e) {
+    EpilogueScalars s;
+    s.g_pos = e.gain;
+    s.g_neg = e.act == 1 ? e.gain : (e.act == 2 ? 0.f : e.gain * e.alpha);
+    s.clamp = e.clamp;
+    return s;
+}
+__device__ __forceinline__ float epilogue_apply(float v, float bias_plus_noise, const EpilogueScalars& s) {
+    v += bias_plus_noise;
+    v *= (v > 0.f) ? s.g_pos : s.g_neg;
+    if (s.clamp >= 0.f) v = (v > -s.clamp && v < s.clamp) ? v : (v >= 0.f) ? s.clamp : -s.clamp;
+    return v;
+}
+
 }  // namespace ggtc

@@ -76,6 +76,11 @@ _SIGNATURES = {
     'gg_chan_dot_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
     'gg_conv2d_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 14 + [_c_float_p, _c_float_p, ctypes.c_int,
                                                         ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
+    'gg_conv2d_act_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 14 + [_c_float_p] * 4 + [ctypes.c_int64, ctypes.c_int, ctypes.c_float,
+                                                            ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                                            ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
+    'gg_chan_dot_preact_f32': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_int64, _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int,
+                                                 ctypes.c_float, ctypes.c_float, ctypes.c_void_p]),
     'gg_conv2d_wgrad_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 14 + [_c_float_p, _c_float_p, ctypes.c_int,
                                                               ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
     'gg_conv2d_wgrad_pm_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 14 + [_c_float_p, _c_float_p, ctypes.c_int,
@@ -267,6 +272,25 @@ class _Plugin:
             _check(self._lib.gg_chan_dot_f32(_ptr(a), _ptr(b), _ptr(out), rows, a.numel() // max(rows, 1), _stream(a)), 'chan_dot')
         return out
 
+    # d out_scale of a convolution with a fused epilogue (include/gagan_b200.h: gg_chan_dot_preact_f32)
+    def chan_dot_preact(self, ds, y, bias, noise, act_idx, alpha, gain):
+        _require_cuda(ds, 'ds')
+        _require_cuda(y, 'y')
+        _check_device(ds)
+        if ds.shape != y.shape or ds.dim() != 4:
+            raise RuntimeError('chan_dot_preact: ds and y must have the same [N,C,H,W] shape')
+        ds = ds.contiguous(); y = y.contiguous()
+        N, C, H, W = ds.shape
+        nbs = 0
+        if noise is not None:
+            noise = noise.contiguous()
+            nbs = H * W if (noise.numel() == N * H * W and noise.ndim == 4) else 0
+        out = torch.empty([N, C], dtype=ds.dtype, device=ds.device)
+        with torch.cuda.device(ds.device):
+            _check(self._lib.gg_chan_dot_preact_f32(_ptr(ds), _ptr(y), _ptr(bias.contiguous() if bias is not None else None), _ptr(noise), nbs,
+                                                   _ptr(out), N, C, H * W, int(act_idx), float(alpha), float(gain), _stream(ds)), 'chan_dot_preact')
+        return out
+
     # 4x4 FIR at unit rate with a phase-major side (include/gagan_b200.h: gg_fir4_pm_f32)
     def fir4_pm(self, x, f, padx0, pady0, flip, gain, in_hw, out_hw, in_pm=None, out_pm=None):
         """x: plain [N,C,H,W] or, with in_pm=(pmH,pmW), phase-major [N,4C,pmH,pmW] whose valid logical extent is in_hw.
@@ -294,7 +318,9 @@ class _Plugin:
 
     # replaces torch.nn.functional.conv2d / conv_transpose2d (conv2d_gradfix.py:141-146), groups == 1
     def conv2d(self, x, w, stride=1, padding=(0, 0), transposed=False, output_padding=(0, 0), flip_w=False,
-               in_scale=None, out_scale=None, prec=None, out_hw=None, flop_scale=1.0):
+               in_scale=None, out_scale=None, prec=None, out_hw=None, flop_scale=1.0, epilogue=None):
+        """`epilogue=(bias, noise, act_idx, alpha, gain, clamp)`: the bias_act pass that follows the convolution, fused into the
+        kernel's store loop (include/gagan_b200.h: gg_conv2d_act_f32); bias [O] / noise [OH,OW] or [N,1,OH,OW] may be None."""
         _require_cuda(x, 'input')
         _require_cuda(w, 'weight')
         _check_device(x)
@@ -327,10 +353,30 @@ class _Plugin:
         used = ctypes.c_int(0)
         ev0 = _prof_begin(x)
         with torch.cuda.device(x.device):
-            _check(self._lib.gg_conv2d_f32(_ptr(x), _ptr(w), _ptr(y), N, I, H, W, O, KH, KW, OH, OW, int(stride), int(padding[0]),
-                                          int(padding[1]), 1 if transposed else 0, 1 if flip_w else 0, _ptr(in_scale),
-                                          _ptr(out_scale), int(conv_precision if prec is None else prec), ctypes.byref(used),
-                                          _stream(x)), 'conv2d')
+            if epilogue is None:
+                _check(self._lib.gg_conv2d_f32(_ptr(x), _ptr(w), _ptr(y), N, I, H, W, O, KH, KW, OH, OW, int(stride), int(padding[0]),
+                                              int(padding[1]), 1 if transposed else 0, 1 if flip_w else 0, _ptr(in_scale),
+                                              _ptr(out_scale), int(conv_precision if prec is None else prec), ctypes.byref(used),
+                                              _stream(x)), 'conv2d')
+            else:
+                bias, noise, act_idx, alpha, gain, clamp = epilogue
+                nbs = 0
+                if bias is not None:
+                    bias = bias.contiguous()
+                    if tuple(bias.shape) != (O,) or bias.dtype != torch.float32 or bias.device != x.device:
+                        raise RuntimeError(f'conv2d: the fused bias must be a float32 [{O}] tensor on {x.device}')
+                if noise is not None:
+                    noise = noise.contiguous()
+                    if noise.dtype != torch.float32 or noise.device != x.device or noise.numel() not in (OH * OW, N * OH * OW):
+                        raise RuntimeError('conv2d: the fused noise must be float32 [OH,OW] or [N,1,OH,OW] on the device of x')
+                    nbs = OH * OW if (noise.numel() == N * OH * OW and noise.ndim == 4) else 0
+                fused = ctypes.c_int(0)
+                _check(self._lib.gg_conv2d_act_f32(_ptr(x), _ptr(w), _ptr(y), N, I, H, W, O, KH, KW, OH, OW, int(stride), int(padding[0]),
+                                                  int(padding[1]), 1 if transposed else 0, 1 if flip_w else 0, _ptr(in_scale),
+                                                  _ptr(out_scale), _ptr(bias), _ptr(noise), nbs, int(act_idx), float(alpha), float(gain),
+                                                  float(clamp), int(conv_precision if prec is None else prec), ctypes.byref(used),
+                                                  ctypes.byref(fused), _stream(x)), 'conv2d')
+                self.last_conv_fused = fused.value
         self.last_conv_prec = used.value
         # algorithmic FLOPs: 2*N*O*I*kh*kw*Hout*Wout, transposed: *Hin*Win
         _prof_end(x, ev0, 'convT' if transposed else 'conv', flop_scale * 2.0 * N * O * I * KH * KW * (H * W if (transposed and stride != 1) else OH * OW), used.value)

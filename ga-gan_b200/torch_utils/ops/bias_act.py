@@ -212,6 +212,8 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
 
             return d_dy, d_x, d_b, d_y, None
 
+    BiasActCuda.Grad = BiasActCudaGrad          # the closed backward op, also used by the fused conv + bias_act Function (conv2d_gradfix)
+    BiasActCuda.is_identity = is_identity
     _bias_act_cuda_cache[key] = BiasActCuda
     return BiasActCuda
 

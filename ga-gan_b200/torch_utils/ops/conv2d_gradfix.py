@@ -125,16 +125,38 @@ def _run_wgrad(grad_output, input, weight_shape, transpose, stride, padding, gro
 _conv2d_s1_cache = dict()
 
 
-def conv2d_s1(x, w, padding=(0, 0), out_hw=None, io=False, flip=False, live=1.0, in_scale=None, out_scale=None, pm=None):
+FUSABLE_ACTS = ('linear', 'relu', 'lrelu')          # the activations the convolution kernels apply in their store loop
+fuse_epilogue = False                               # module switch.  Measured on the 1024^2 step: neutral (47.2 vs 47.3 img/s) -- the activation
+                                                    # arithmetic lands in the consumer warps' store loop, the critical path of the small-K layers, and
+                                                    # costs what the separate HBM-speed bias_act pass cost; it saves one activation tensor per layer
+
+
+def conv2d_s1(x, w, padding=(0, 0), out_hw=None, io=False, flip=False, live=1.0, in_scale=None, out_scale=None, pm=None, epilogue=None):
     """`in_scale [N,I]` / `out_scale [N,O]`: per-sample channel scales folded into the kernel's operand conversion and
     epilogue -- y = out_scale * conv(in_scale * x, w) -- i.e. the style modulation / demodulation of modulated_conv2d
-    (networks.py:642,648-651) without their full-tensor multiply passes."""
+    (networks.py:642,648-651) without their full-tensor multiply passes.
+
+    `epilogue = dict(bias, noise, act, alpha, gain, clamp)`: additionally y = bias_act(y + noise, bias, act, alpha, gain, clamp)
+    inside the same kernel launch (see _conv_act_s1)."""
     _check_input(x)
     kh, kw = int(w.shape[2]), int(w.shape[3])
     padding = _tuple_of_ints(padding, 2)
     if out_hw is None:
         out_hw = (x.shape[2] + 2 * padding[0] - kh + 1, x.shape[3] + 2 * padding[1] - kw + 1)
     key = (tuple(w.shape), padding, (int(out_hw[0]), int(out_hw[1])), bool(io), bool(flip), float(live), (tuple(pm) if pm else None))
+    if epilogue is not None:
+        from . import bias_act as _ba
+        act = epilogue.get('act', 'linear')
+        spec = _ba.activation_funcs[act]
+        alpha = float(epilogue['alpha'] if epilogue.get('alpha') is not None else spec.def_alpha)
+        gain = float(epilogue['gain'] if epilogue.get('gain') is not None else spec.def_gain)
+        clamp = float(epilogue['clamp'] if epilogue.get('clamp') is not None else -1)
+        bias, noise = epilogue.get('bias'), epilogue.get('noise')
+        if act in FUSABLE_ACTS and fuse_scales is not False and fuse_epilogue:
+            fn = _conv_act_s1(*key, in_scale is not None, out_scale is not None, act, alpha, gain, clamp)
+            return fn.apply(x, w, in_scale, out_scale, bias, noise)
+        y = conv2d_s1(x, w, padding=padding, out_hw=out_hw, io=io, flip=flip, live=live, in_scale=in_scale, out_scale=out_scale, pm=pm)
+        return _ba.bias_act(y, bias, act=act, alpha=alpha, gain=gain, clamp=(clamp if clamp >= 0 else None), noise=noise)
     if in_scale is None and out_scale is None:
         return _conv2d_s1(*key).apply(x, w)
     if fuse_scales is False:            # debug switch: explicit multiply passes around the unscaled kernel
@@ -216,6 +238,107 @@ def _scaled_conv2d_s1(weight_shape, padding, out_hw, io, flip, live, pm, has_a, 
 
     _scaled_conv2d_s1_cache[key] = ScaledConvS1
     return ScaledConvS1
+
+
+_conv_act_s1_cache = dict()
+
+
+def _conv_act_s1(weight_shape, padding, out_hw, io, flip, live, pm, has_a, has_b, act, alpha, gain, clamp):
+    """y = clamp(act(b * conv(a * x, w) + noise + bias) * gain) as ONE kernel launch (gg_conv2d_act_f32): the SynthesisLayer /
+    Conv2dLayer pattern `bias_act(modulated_conv2d(...))` (networks.py:904-921, 752-760) when the convolution is the layer's last
+    operator.  Backward = the bias_act gradient kernel on the saved OUTPUT (lrelu / relu / linear need nothing else), then the
+    ScaledConvS1 gradients; the pre-activation tensor is never stored -- the one place that needs it, the gradient of the output
+    scale b, reconstructs it from y (gg_chan_dot_preact_f32).  Closed under double differentiation: with grad mode on inside
+    backward every partial derivative is spelled out with differentiable ops over the closed primitives."""
+    key = (weight_shape, padding, out_hw, io, flip, live, pm, has_a, has_b, act, alpha, gain, clamp)
+    if key in _conv_act_s1_cache:
+        return _conv_act_s1_cache[key]
+    from . import bias_act as _ba
+    _ba._init()                         # the backward below calls the bias_act gradient kernel directly
+    spec = _ba.activation_funcs[act]
+    BA = _ba._bias_act_cuda(dim=1, act=act, alpha=alpha, gain=gain, clamp=(clamp if clamp >= 0 else None))
+    kh, kw = weight_shape[2], weight_shape[3]
+    dpad = (kh - 1 - padding[0], kw - 1 - padding[1])
+    invertible = clamp < 0 and gain != 0 and (act == 'linear' or (act == 'lrelu' and alpha != 0))
+
+    def kernel(x, w, a, b, pad, hw, io_, flip_, epi=None):
+        if not io_:
+            return _plugin.conv2d(x, w, stride=1, padding=pad, transposed=False, flip_w=flip_, out_hw=hw, flop_scale=live,
+                                  in_scale=a, out_scale=b, epilogue=epi)
+        return _plugin.conv2d(x, w, stride=1, padding=(kh - 1 - pad[0], kw - 1 - pad[1]), transposed=True, flip_w=(not flip_),
+                              out_hw=hw, flop_scale=live, in_scale=a, out_scale=b, epilogue=epi)
+
+    def unbroadcast_noise(ds, shape):
+        dn = ds.sum(dim=1, keepdim=True)
+        if len(shape) == 2:
+            dn = dn.sum(dim=[0, 1])
+        return dn.reshape(shape)
+
+    class ConvActS1(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, w, a, b, bias, noise):
+            assert tuple(w.shape) == weight_shape
+            a_ = a.contiguous() if a is not None else None
+            b_ = b.contiguous() if b is not None else None
+            y = kernel(x, w, a_, b_, padding, out_hw, io, flip,
+                       epi=(bias, noise.to(x.dtype) if noise is not None else None, spec.cuda_idx, alpha, gain, clamp))
+            ctx.save_for_backward(x, w, a, b, bias, noise, y)
+            return y
+
+        @staticmethod
+        def backward(ctx, dy):
+            x, w, a, b, bias, noise, y = ctx.saved_tensors
+            need = ctx.needs_input_grad
+            null = torch.empty([0], dtype=dy.dtype, device=dy.device)
+            dy = dy.contiguous()
+            # 1. through bias / noise / activation: the closed bias_act gradient op (for these activations it only reads y)
+            want_db = bool(bias is not None and need[4])
+            if BA.is_identity:
+                ds = dy
+                dbias = ds.sum([0, 2, 3]) if want_db else None
+            else:
+                ds, dbias = BA.Grad.apply(dy, null, null, y, want_db)
+                if not want_db:
+                    dbias = None
+            dnoise = unbroadcast_noise(ds, noise.shape) if (noise is not None and need[5]) else None
+            dx = dw = da = db = None
+            # 2. through the scaled convolution (same algebra as ScaledConvS1.backward with dy := ds)
+            if torch.is_grad_enabled():
+                conv = _conv2d_s1(weight_shape, padding, out_hw, io, flip, live, pm)
+                conv_t = _conv2d_s1(weight_shape, dpad, (x.shape[2], x.shape[3]), not io, not flip, live, pm)
+                xa = x * a[:, :, None, None] if a is not None else x
+                dsb = ds * b[:, :, None, None] if b is not None else ds
+                if need[0] or (a is not None and need[2]):
+                    u = conv_t.apply(dsb, w)
+                    if need[0]:
+                        dx = u * a[:, :, None, None] if a is not None else u
+                    if a is not None and need[2]:
+                        da = (x * u).sum([2, 3])
+                if need[1] and not weight_gradients_disabled:
+                    dw = conv.Wgrad.apply(dsb, xa)
+                if b is not None and need[3]:
+                    db = (ds * conv.apply(xa, w)).sum([2, 3])
+                return dx, dw, da, db, dbias, dnoise
+            ds = ds.contiguous()
+            if need[0] or (a is not None and need[2]):
+                dx = kernel(ds, w, b, a, dpad, (x.shape[2], x.shape[3]), not io, not flip)
+                if a is not None and need[2]:
+                    da = _plugin.chan_dot(x, dx) / torch.where(a == 0, torch.ones_like(a), a)
+                if not need[0]:
+                    dx = None
+            if need[1] and not weight_gradients_disabled:
+                dw = _plugin.conv2d_wgrad(x, ds, (kh, kw), stride=1, padding=padding, flip_w=flip, out_layout=(1 if io else 0),
+                                          flop_scale=live, a_scale=a, b_scale=b, pm=pm)
+            if b is not None and need[3]:
+                # d/db[n,o] = sum_p ds * conv(a*x, w) = sum_p ds * (pre - bias - noise) / b,   pre = act^-1(y / gain)
+                if invertible and (y.shape[2] * y.shape[3]) % 4 == 0:
+                    db = _plugin.chan_dot_preact(ds, y, bias, noise, spec.cuda_idx, alpha, gain) / torch.where(b == 0, torch.ones_like(b), b)
+                else:                       # relu / clamped outputs cannot be inverted: one more (unscaled) convolution instead
+                    db = _plugin.chan_dot(ds, kernel(x, w, a, None, padding, out_hw, io, flip))
+            return dx, dw, da, db, dbias, dnoise
+
+    _conv_act_s1_cache[key] = ConvActS1
+    return ConvActS1
 
 
 def _conv2d_s1(weight_shape, padding, out_hw, io, flip, live=1.0, pm=None):

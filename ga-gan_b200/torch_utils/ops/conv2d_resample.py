@@ -85,7 +85,7 @@ def _round_up(v, m):
     return (v + m - 1) // m * m
 
 
-def down2_phase_major(x, w, f, fir_pad, flip_weight, flip_filter, conv_s1, fir_to_pm):
+def down2_phase_major(x, w, f, fir_pad, flip_weight, flip_filter, conv_s1, fir_to_pm, epilogue=None):
     """conv2d_resample.py:119-122 (FIR, then stride-2 conv) with the conv in phase-major form.
     `conv_s1(x, w, padding, out_hw, live)` and `fir_to_pm(x, f, padding, flip_filter, gain, ys, xs)` are injected (the CPU
     algebra test passes torch stand-ins); on the device the FIR writes the phase-major tensor directly."""
@@ -97,6 +97,8 @@ def down2_phase_major(x, w, f, fir_pad, flip_weight, flip_filter, conv_s1, fir_t
     if not flip_weight:
         w = w.flip([2, 3])
     xs = fir_to_pm(x, f, fir_pad, flip_filter, 1, oh + 1, _round_up(ow + 1, 4))   # width % 4: TMA row pitch must be 16-byte aligned
+    if epilogue is not None:           # the convolution is this layer's last operator: bias / activation ride in its store loop
+        return conv_s1(xs, phase_major_weight_down(w), (0, 0), (oh, ow), _pm_live('down', kh, kw), epilogue=epilogue)
     return conv_s1(xs, phase_major_weight_down(w), (0, 0), (oh, ow), _pm_live('down', kh, kw))
 
 
@@ -144,9 +146,18 @@ def plan(w_shape, f, up, down, padding):
     return dict(branch='generic', fir_pad=[px0, px1, py0, py1])
 
 
-def _conv_s1(x, w, padding, out_hw, live, in_scale=None, out_scale=None):
+def _conv_s1(x, w, padding, out_hw, live, in_scale=None, out_scale=None, epilogue=None):
     return conv2d_gradfix.conv2d_s1(x, w, padding=padding, out_hw=out_hw, live=float(live), in_scale=in_scale, out_scale=out_scale,
-                                    pm=getattr(live, 'pm', None))
+                                    pm=getattr(live, 'pm', None), epilogue=epilogue)
+
+
+def _bias_act_after(y, epilogue):
+    """The unfused form of `epilogue` (branches whose last operator is not the convolution)."""
+    from . import bias_act
+    if epilogue is None:
+        return y
+    return bias_act.bias_act(y, epilogue.get('bias'), act=epilogue.get('act', 'linear'), alpha=epilogue.get('alpha'), gain=epilogue.get('gain'),
+                             clamp=epilogue.get('clamp'), noise=epilogue.get('noise'))
 
 
 def _fir_to_pm(x, f, padding, flip_filter, gain, ys, xs):
@@ -159,12 +170,30 @@ def _fir_from_pm(z, f, padding, flip_filter, gain, valid_hw):
 
 @scoped
 def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False, in_scale=None,
-                    out_scale=None):
+                    out_scale=None, epilogue=None):
     r"""2D convolution with optional up/downsampling; padding is applied once, up front.
 
     x `[N, I, H, W]`, w `[O, I//groups, kh, kw]`, f from `upfirdn2d.setup_filter()` or None.
     `flip_weight=True` = correlation (what `F.conv2d` does), False = convolution.
+
+    Extensions over the reference signature (all optional): `in_scale [N,I]` / `out_scale [N,O]` = the modulation / demodulation
+    factors of modulated_conv2d, and `epilogue = dict(bias, noise, act, alpha, gain, clamp)` = the `bias_act(y + noise, bias, ...)`
+    call that follows the layer: the result is bias_act(conv2d_resample(...)), computed inside the convolution kernel where the
+    convolution is the last operator of the branch and by the bias_act kernel otherwise.
     """
+    if epilogue is not None:
+        fusable = (groups == 1) and epilogue.get('act', 'linear') in conv2d_gradfix.FUSABLE_ACTS
+        _, _, kh_, kw_ = _get_weight_shape(w)
+        pl_ = plan(w.shape, f, up, down, padding)
+        if fusable and pl_['branch'] == 'plain' and pl_['conv_pad'][0] <= kh_ - 1 and pl_['conv_pad'][1] <= kw_ - 1 \
+                and isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32:
+            return conv2d_gradfix.conv2d_s1(x, w, padding=pl_['conv_pad'], flip=(not flip_weight), in_scale=in_scale, out_scale=out_scale,
+                                            epilogue=epilogue)
+        if fusable and pl_['branch'] == 'down' and down == 2 and kh_ <= 4 and kw_ <= 4 and in_scale is None and out_scale is None:
+            return down2_phase_major(x, w, f, pl_['fir_pad'], flip_weight, flip_filter, _conv_s1, _fir_to_pm, epilogue=epilogue)
+        return _bias_act_after(conv2d_resample(x, w, f=f, up=up, down=down, padding=padding, groups=groups, flip_weight=flip_weight,
+                                               flip_filter=flip_filter, in_scale=in_scale, out_scale=out_scale), epilogue)
+
     assert isinstance(x, torch.Tensor) and (x.ndim == 4)
     assert isinstance(w, torch.Tensor) and (w.ndim == 4) and (w.dtype == x.dtype)
     assert f is None or (isinstance(f, torch.Tensor) and f.ndim in [1, 2] and f.dtype == torch.float32)

@@ -36,6 +36,7 @@ def modulated_conv2d(
         demodulate=True,        # Apply weight demodulation?
         flip_weight=True,       # False = convolution, True = correlation (matches F.conv2d).
         fused_modconv=True,     # Accepted for API compatibility; see below.
+        epilogue=None,          # Extension: dict(bias, act, alpha, gain, clamp) -> bias_act(result, ...) inside the same kernels.
 ):
     """y[n,o] = dcoef[n,o] * sum_i conv(styles[n,i] * x[n,i], weight[o,i]) (+ noise).
 
@@ -60,6 +61,10 @@ def modulated_conv2d(
         wsq = weight.square().sum(dim=[2, 3])                                  # [O, I]
         dcoefs = (styles.square() @ wsq.t() + 1e-8).rsqrt()                    # [N, O]
 
+    if epilogue is not None:            # bias_act(conv + noise, bias, ...): noise and bias join the activation (one pass fewer, or none)
+        epilogue = dict(epilogue, noise=noise)
+        return conv2d_resample.conv2d_resample(x=x, w=weight.to(x.dtype), f=resample_filter, up=up, down=down, padding=padding,
+                                               flip_weight=flip_weight, in_scale=styles.to(x.dtype), out_scale=dcoefs, epilogue=epilogue)
     x = conv2d_resample.conv2d_resample(x=x, w=weight.to(x.dtype), f=resample_filter, up=up, down=down, padding=padding,
                                         flip_weight=flip_weight, in_scale=styles.to(x.dtype), out_scale=dcoefs)
     if noise is not None:
@@ -81,11 +86,12 @@ def _synthesis_layer_forward(ref):
             noise = torch.randn([x.shape[0], 1, self.resolution, self.resolution], device=x.device) * self.noise_strength
         elif self.use_noise and noise_mode == 'const':
             noise = self.noise_const * self.noise_strength
-        # conv (+ FIR) with styles / dcoefs inside the kernel; the noise joins the bias inside the activation kernel
-        x = ref.modulated_conv2d(x=x, weight=weight, styles=styles, noise=None, up=self.up, padding=self.padding,
-                                 resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
+        # styles / dcoefs ride inside the convolution kernel; noise + bias + activation ride in its store loop when the convolution
+        # is the layer's last operator (up == 1) and in ONE bias_act launch behind the FIR otherwise
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
-        return bias_act.bias_act(x, self.bias.to(x.dtype), act=self.activation, gain=self.act_gain * gain, clamp=clamp, noise=noise)
+        return modulated_conv2d(x=x, weight=weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
+                                resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv,
+                                epilogue=dict(bias=self.bias.to(x.dtype), act=self.activation, gain=self.act_gain * gain, clamp=clamp))
     return forward
 
 
@@ -96,6 +102,14 @@ def _conv2d_layer_forward(ref, original):
             w = self.weight * (self.weight_gain * self.act_gain * gain)
             return conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, up=self.up, down=self.down,
                                                    padding=self.padding, flip_weight=(self.up == 1))
+        if x.is_cuda and x.dtype == torch.float32:
+            # bias + activation in the store loop of the convolution kernel (plain and down-sampling layers), else one bias_act launch
+            w = self.weight * self.weight_gain
+            clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
+            return conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, up=self.up, down=self.down,
+                                                   padding=self.padding, flip_weight=(self.up == 1),
+                                                   epilogue=dict(bias=(self.bias.to(x.dtype) if self.bias is not None else None),
+                                                                 act=self.activation, gain=self.act_gain * gain, clamp=clamp))
         return original(self, x, gain=gain)
     return forward
 

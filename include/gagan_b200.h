@@ -163,6 +163,26 @@ GG_API int gg_conv2d_wgrad_pm_f32(const float* a, const float* b, float* dw, int
  * (training/networks.py:642,648-651 and their autograd reductions).  out is overwritten. */
 GG_API int gg_chan_dot_f32(const float* a, const float* b, float* out, int64_t rows, int64_t P, gg_stream_t stream);
 
+/* gg_conv2d_f32 with the bias_act pass that follows it in the networks fused into the kernel's store loop:
+ *     y = clamp(act(out_scale * conv(in_scale * x, w) + bias[o] + noise[pixel]) * gain)
+ * i.e. `bias_act.bias_act(modulated_conv2d(..., noise=noise), b, act=..., gain=..., clamp=...)` of SynthesisLayer.forward
+ * (training/networks.py:904-921) and `bias_act(conv2d_resample(...), b, ...)` of Conv2dLayer.forward (:752-760) as ONE launch
+ * when the convolution is the last operator of the layer.  `bias` [O], `noise` ([OH*OW] with noise_batch_stride 0, or [N, OH*OW]
+ * with noise_batch_stride OH*OW) may be NULL; act = the reference's cuda_idx.  linear / relu / lrelu are fused by the tcgen05
+ * kernels (*fused = 1); for every other activation or kernel family the same result is produced by a second launch of the
+ * bias_act kernel in place (*fused = 0).  stride-1 semantics and all other arguments as gg_conv2d_f32. */
+GG_API int gg_conv2d_act_f32(const float* x, const float* w, float* y, int N, int I, int H, int W, int O, int KH, int KW,
+                      int OH, int OW, int stride, int pad_y, int pad_x, int transposed, int flip_w,
+                      const float* in_scale, const float* out_scale, const float* bias, const float* noise,
+                      int64_t noise_batch_stride, int act, float alpha, float gain, float clamp, int prec, int* used_prec,
+                      int* fused, gg_stream_t stream);
+
+/* out[n,c] = sum_p ds[n,c,p] * (pre(y[n,c,p]) - bias[c] - noise[n,p]) with pre() the inverse of y = act(.) * gain (linear, or lrelu
+ * with alpha != 0): the gradient of the [N,C] output scale (demodulation coefficients) of gg_conv2d_act_f32, whose pre-activation
+ * tensor is never materialised.  ds, y: [N,C,P] dense, 16-byte aligned, P % 4 == 0. */
+GG_API int gg_chan_dot_preact_f32(const float* ds, const float* y, const float* bias, const float* noise, int64_t noise_batch_stride,
+                           float* out, int N, int C, int64_t P, int act, float alpha, float gain, gg_stream_t stream);
+
 /* Number of kernels this library has launched since load (all streams); bench.py reports the delta. */
 GG_API int64_t gg_launch_count(void);
 

@@ -622,3 +622,60 @@ def test_wgrad_phase_major_hint_skips_only_dead_taps(ops, device, kind, N, I, O,
         assert (float((dead != 0).float().mean()) < 1.0) == skips   # something was skipped (when a tile lies inside a phase pair) ...
         tol = 1e-6 * float(full.abs().max())                     # (atomic flush order differs between two launches)
         assert bool(((dead == 0) | ((dead - full[~mask]).abs() <= tol)).all())  # ... and what was not skipped is the plain result
+
+
+# ------------------------------------------------------------------------------------------------ conv + bias_act in one kernel
+@pytest.mark.parametrize('case', [
+    # (N, I, O, R, up, down, k, act, modulated, noise)
+    (2, 32, 32, 64, 1, 1, 3, 'lrelu', True, 'random'),     # G conv1 on the marching kernel
+    (2, 64, 48, 32, 1, 1, 3, 'lrelu', True, 'const'),      # tile kernel, ragged output channels
+    (2, 512, 512, 8, 1, 1, 3, 'lrelu', False, None),       # D conv0, N = 256 tiles
+    (2, 32, 64, 64, 1, 2, 3, 'lrelu', False, None),        # D conv1: the phase-major 2x2 conv is the last operator
+    (2, 64, 32, 16, 2, 1, 3, 'lrelu', True, 'random'),     # G conv0: the FIR is last -> one bias_act launch behind it
+    (2, 3, 32, 64, 1, 1, 1, 'lrelu', False, None),         # fromRGB: thin kernel + in-place bias_act
+    (2, 16, 16, 32, 1, 1, 3, 'linear', False, None),
+    (2, 16, 16, 32, 1, 1, 3, 'relu', True, 'const'),       # not invertible: d dcoef takes the extra convolution
+    (2, 16, 16, 32, 1, 1, 3, 'tanh', False, None),         # not fusable: conv kernel + bias_act kernel
+])
+def test_fused_conv_bias_act_matches_the_unfused_pair(ops, device, case):
+    """conv2d_resample(..., epilogue=...) / modulated_conv2d(..., epilogue=...) == bias_act(conv(...) + noise, bias, ...) computed by
+    the two separate ops: forward, first-order gradients of every input, and a second-order gradient (the closure R1 / path length
+    regularisation need)."""
+    N, I, O, Rr, up, down, k, act, mod, noise_kind = case
+    ops.conv2d_gradfix.fuse_epilogue = True                  # (off by default: measured neutral on the 1024^2 step)
+    g = torch.Generator().manual_seed(Rr + I + O)
+    x = torch.randn(N, I, Rr, Rr, generator=g); w = torch.randn(O, I, k, k, generator=g) / np.sqrt(I * k * k)
+    b = torch.randn(O, generator=g) * 0.3; s = torch.randn(N, I, generator=g) * 0.5 + 1.0
+    Ro = Rr * up // down
+    noise = None if noise_kind is None else (torch.randn(Ro, Ro, generator=g) if noise_kind == 'const' else torch.randn(N, 1, Ro, Ro, generator=g)) * 0.3
+    dy = torch.randn(N, O, Ro, Ro, generator=g)
+    f = ops.upfirdn2d.setup_filter([1, 3, 3, 1]).to(device)
+    modconv = ops.networks.modulated_conv2d if hasattr(ops.networks, 'modulated_conv2d') else None
+    gain, clamp = (0.7, None) if act != 'relu' else (1.3, 2.0)
+
+    def run(fused):
+        ts = dict(x=x, w=w, b=b, s=s)
+        if noise is not None:
+            ts['noise'] = noise
+        ts = {n: t.to(device).requires_grad_(True) for n, t in ts.items()}
+        epi = dict(bias=ts['b'], act=act, gain=gain, clamp=clamp)
+        if mod:
+            kw = dict(x=ts['x'], weight=ts['w'], styles=ts['s'], noise=ts.get('noise'), up=up, padding=k // 2, resample_filter=f, flip_weight=(up == 1))
+            y = modconv(**kw, epilogue=epi) if fused else ops.bias_act.bias_act(modconv(**kw), ts['b'], act=act, gain=gain, clamp=clamp)
+        else:
+            kw = dict(x=ts['x'], w=ts['w'], f=f, up=up, down=down, padding=k // 2, flip_weight=(up == 1))
+            y = ops.conv2d_resample.conv2d_resample(**kw, epilogue=epi) if fused else \
+                ops.bias_act.bias_act(ops.conv2d_resample.conv2d_resample(**kw), ts['b'], act=act, gain=gain, clamp=clamp)
+        names = [n for n in ts if mod or n != 's']
+        g1 = torch.autograd.grad(y, [ts[n] for n in names], dy.to(device), create_graph=True)
+        g2 = torch.autograd.grad(sum(t.square().sum() for t in g1), [ts['x'], ts['w']], allow_unused=True)
+        return [y.detach()] + [t.detach() for t in g1] + [t.detach() for t in g2 if t is not None], ['y'] + ['d' + n for n in names] + ['ddx', 'ddw']
+
+    try:
+        got, names = run(True)
+    finally:
+        ops.conv2d_gradfix.fuse_epilogue = False
+    want, _ = run(False)
+    assert len(got) == len(want)
+    for n, a_, b_ in zip(names, got, want):
+        assert_close(a_, b_, 2e-5, f'{case}: {n}')
