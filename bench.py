@@ -65,6 +65,8 @@ def parse_args():
     ap.add_argument('--prec', default='auto', choices=['auto', 'simt', 'tf32x1', 'tf32x3'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-fast-mode', action='store_true')
+    ap.add_argument('--sync-debug', action='store_true', help='debug: synchronise after every library call and name the call that faulted')
+    ap.add_argument('--conv-family', type=int, default=1, help='A/B: 0 = the tile kernel serves every tcgen05 convolution (no marching kernel)')
     ap.add_argument('--fused-epilogue', action='store_true', help='A/B: bias / noise / activation in the conv store loop instead of a separate bias_act launch')
     ap.add_argument('--reference-forwards', action='store_true', help="run the reference's forwards untouched (no fused callers)")
     ap.add_argument('--cpu-res', type=int, default=0, help='resolution of the CPU sample (0 = same as --res)')
@@ -329,6 +331,23 @@ def main():
     custom_ops.verbosity = 'none'
     PREC = dict(auto=custom_ops.PREC_AUTO, simt=custom_ops.PREC_FP32_SIMT, tf32x1=custom_ops.PREC_TF32X1, tf32x3=custom_ops.PREC_TF32X3)
     custom_ops.conv_precision = PREC[args.prec]
+    custom_ops.set_conv_kernel_family(args.conv_family)
+    if args.sync_debug:
+        plug = custom_ops.get_plugin('conv2d_plugin')
+        for name in ('conv2d', 'conv2d_wgrad', 'bias_act', 'bias_act_noise', 'upfirdn2d', 'fir4_pm', 'chan_dot'):
+            def wrap(orig, name=name):
+                def fn(*a, **kw):
+                    out = orig(*a, **kw)
+                    try:
+                        torch.cuda.current_stream().synchronize()
+                    except Exception as e:
+                        shapes = [tuple(t.shape) for t in a if isinstance(t, torch.Tensor)]
+                        print(f'[rank {rank}] {custom_ops.watchdog_report()}', file=sys.stderr, flush=True)
+                        print(f'[rank {rank}] FAULT after {name} {shapes} { {k: (tuple(v.shape) if isinstance(v, torch.Tensor) else v) for k, v in kw.items()} }: {e}', file=sys.stderr, flush=True)
+                        raise
+                    return out
+                return fn
+            setattr(plug, name, wrap(getattr(plug, name)))
     if args.fused_epilogue:
         from torch_utils.ops import conv2d_gradfix
         conv2d_gradfix.fuse_epilogue = True
@@ -498,4 +517,16 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    try:
+        main()
+    except BaseException as e:
+        if not isinstance(e, SystemExit):
+            try:                                   # readable even after the CUDA context faulted (host-mapped record)
+                import gagan_b200  # noqa: F401
+                from gagan_b200.torch_utils import custom_ops as _co
+                rep = _co.watchdog_report()
+                if rep:
+                    print(f'[rank {os.environ.get("RANK", "0")}] {rep}', file=sys.stderr, flush=True)
+            except Exception:
+                pass
+        raise

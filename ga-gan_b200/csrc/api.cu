@@ -8,6 +8,23 @@ static thread_local char t_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 int g_march_enabled = 1;
 
+// 64 bytes of host-mapped, portable pinned memory: the wait-loop watchdog of the tcgen05 kernels writes its record here before it
+// traps, so the cause of a faulted context can still be read (tc_common.cuh)
+unsigned long long* watchdog_host_record() {
+    static std::atomic<unsigned long long*> rec{nullptr};
+    static std::atomic<int> tried{0};
+    if (tried.exchange(1) == 0) {
+        void* h = nullptr;
+        if (cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess && h != nullptr) {
+            memset(h, 0, 64);
+            rec.store(static_cast<unsigned long long*>(h));
+        } else {
+            (void)cudaGetLastError();
+        }
+    }
+    return rec.load();
+}
+
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -49,6 +66,17 @@ int wgrad_tc(const float* a, const float* b, float* dw, int N, int A, int HA, in
 extern "C" GG_API const char* gg_last_error(void) { return gg::t_err; }
 extern "C" GG_API int gg_version(void) { return 100; }
 extern "C" GG_API int64_t gg_launch_count(void) { return gg::g_launches.load(); }
+extern "C" GG_API int gg_watchdog_report(char* buf, int len) {
+    unsigned long long* r = gg::watchdog_host_record();
+    if (buf == nullptr || len <= 0) return 0;
+    buf[0] = 0;
+    if (r == nullptr || r[0] != 0x57415443484447ull) return 0;
+    static const char* const names[] = {"?", "conv_tc_kernel", "conv_march_kernel", "wgrad_tc_kernel", "wgrad_tma_kernel"};
+    const unsigned long long tag = r[1] < 5 ? r[1] : 0;
+    snprintf(buf, (size_t)len, "watchdog: %s CTA %llu thread %llu waited %.2f G cycles on the mbarrier at shared address 0x%llx", names[tag],
+             r[2] >> 32, r[2] & 0xffffffffull, (double)r[4] * 1e-9, r[3]);
+    return 1;
+}
 extern "C" GG_API int gg_set_conv_kernel_family(int family) { const int old = gg::g_march_enabled; gg::g_march_enabled = (family != 0); return old; }
 
 extern "C" GG_API int gg_device_ok(void) {

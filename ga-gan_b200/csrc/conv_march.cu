@@ -24,6 +24,7 @@
 //                ping-pong, the consumer warps drain each chunk into fp32 registers (round to nearest, expected-value
 //                compensation of the truncation, tc_common.cuh) while the tensor core works on the next chunk.
 // Warp roles     w0 TMA(x)  w1 TMA(weights)  w2 MMA issue + TMEM alloc  (w3 idle)  w4..w11 convert + drain + store.
+#define GG_TU_TAG 2
 #include "tc_common.cuh"
 #include <limits.h>
 
@@ -462,6 +463,7 @@ int launch_march(const CUtensorMap& xmap, const MarchP& p, cudaStream_t st) {
         gg::mark_done_on_this_device(attr_set);
     }
     const int grid = p.total_units < GG_NUM_SMS ? p.total_units : GG_NUM_SMS;
+    wd_arm();
     conv_march_kernel<NT, K, EPI><<<grid, M_THREADS, smem, st>>>(xmap, p);
     return gg::check_launch("conv2d(march)");
 }

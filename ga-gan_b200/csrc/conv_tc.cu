@@ -27,6 +27,7 @@
 //                tensor core works on the next K-block / the next tile.  The epilogue (x out_scale) runs from registers.
 // Warp roles     w0 TMA(x)  w1 TMA(weights)  w2 MMA issue + TMEM alloc  (w3 idle)  w4..w11 convert + drain + epilogue;
 //                setmaxnreg moves registers from the producer warpgroup to the two consumer warpgroups (128 accumulators/thread).
+#define GG_TU_TAG 1
 #include "tc_common.cuh"
 #include <stdlib.h>
 #include <limits.h>
@@ -560,6 +561,7 @@ int launch_conv_tc(const CUtensorMap& xmap, const TcP& p, cudaStream_t st) {
         gg::mark_done_on_this_device(attr_set);
     }
     const int grid = p.total_tiles < GG_NUM_SMS ? p.total_tiles : GG_NUM_SMS;
+    wd_arm();
     conv_tc_kernel<NT, SUBS, EPI><<<grid, NUM_THREADS, smem, st>>>(xmap, p);
     return gg::check_launch("conv2d(tc)");
 }

@@ -9,6 +9,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_fn();
+unsigned long long* watchdog_host_record();          // api.cu: 64 bytes of host-mapped memory, zeroed (nullptr if unavailable)
 }  // namespace gg
 
 namespace ggtc {
@@ -26,13 +27,30 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Watchdog shared by the wait loops: off the fast path (the clock is read once per 1024 polls -- reading it around every wait
-// was a visible share of the single-thread issue loops), ~4 s of SM clocks, then a fault instead of a hung GPU.  A watchdog
-// expiry shows up as "illegal memory access" (null store), distinguishable from a hardware fault.
+// was a visible share of the single-thread issue loops), ~4 s of SM clocks, then a trap instead of a hung GPU.  Before it traps
+// the thread leaves a record in HOST-mapped memory (it survives the faulted context): which kernel family, which barrier (its
+// shared-memory address), which CTA / thread, how long it waited.  gg_watchdog_report() formats it; the Python host appends it
+// to the error it raises.  Every translation unit has its own copy of the pointer (no relocatable device code) and sets it
+// with wd_arm() before its first launch on a device.
+#ifndef GG_TU_TAG
+#define GG_TU_TAG 0
+#endif
+static __device__ unsigned long long* gg_wd_ptr = nullptr;
 __device__ __forceinline__ void mbar_watchdog(uint32_t it, long long& t0, uint32_t bar) {
     if ((it & 1023u) != 1023u) return;
     const long long now = clock64();
     if (t0 == 0) t0 = now;
-    else if (now - t0 > 8000000000LL) { *reinterpret_cast<volatile int*>(8) = (int)bar; __trap(); }
+    else if (now - t0 > 8000000000LL) {
+        unsigned long long* r = gg_wd_ptr;
+        if (r != nullptr && atomicCAS(r, 0ull, 0x57415443484447ull) == 0ull) {       // first expiry wins ("WATCHDG")
+            r[1] = (unsigned long long)GG_TU_TAG;
+            r[2] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
+            r[3] = bar;
+            r[4] = (unsigned long long)(now - t0);
+            __threadfence_system();
+        }
+        __trap();
+    }
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     long long t0 = 0;
@@ -183,6 +201,16 @@ __device__ __forceinline__ float epilogue_apply(float v, float bias_plus_noise, 
     v *= (v > 0.f) ? s.g_pos : s.g_neg;
     if (s.clamp >= 0.f) v = (v > -s.clamp && v < s.clamp) ? v : (v >= 0.f) ? s.clamp : -s.clamp;
     return v;
+}
+
+
+// host: point this translation unit's watchdog at the host-mapped record (once per device)
+static inline void wd_arm() {
+    static std::atomic<uint64_t> armed{0};
+    if (gg::done_on_this_device(armed)) return;
+    unsigned long long* rec = gg::watchdog_host_record();
+    if (rec != nullptr) cudaMemcpyToSymbol(gg_wd_ptr, &rec, sizeof(rec));
+    gg::mark_done_on_this_device(armed);
 }
 
 }  // namespace ggtc

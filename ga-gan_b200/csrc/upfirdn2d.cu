@@ -646,14 +646,18 @@ extern "C" GG_API int gg_upfirdn2d_f32(const float* x, const float* f, float* y,
     Params p{x, f, y, N, C, inH, inW, fH, fW, upx, upy, downx, downy, padx0, pady0, flip, gain, outH, outW};
     cudaStream_t st = (cudaStream_t)stream;
 
-    const bool f4 = (fH == 4 && fW == 4) && upx == upy && downx == downy && outW >= 48;
-    if (f4 && upx == 1 && downx == 1) {   // unit rate: the register-streaming kernel (also serves the phase-major layouts)
+    // 4x4 filter, isotropic factors.  The marching kernels serve every size from 8 output columns up (column groups of neighbouring
+    // strips / planes fill the warps of narrow images; the cfg 5 sweep had the generic kernel at half the speed of the reference's
+    // SIMT plugin on the 16^2 and 32^2 maps); the shared-memory tile kernels below them want >= 48 columns.
+    const bool f4m = (fH == 4 && fW == 4) && upx == upy && downx == downy && outW >= 8;
+    const bool f4 = f4m && outW >= 48;
+    if (f4m && upx == 1 && downx == 1) {   // unit rate: the register-streaming kernel (also serves the phase-major layouts)
         StreamP sp{x, f, y, N, C, inH, inW, padx0, pady0, flip, gain, outH, outW, 0, 0, 0, 0, 0, 0, 0};
         if (stream_ok(sp, false)) return launch_stream<0>(sp, st);
-        return launch_tile<1, 1, 0, 4, 4>(p, st);
+        if (f4) return launch_tile<1, 1, 0, 4, 4>(p, st);
     }
     // true 2x resampling: the marching kernels need 16-byte aligned input rows, 0 <= pad0 <= 3 and (up2) no pad0 beyond the filter reach
-    const bool march_ok = f4 && padx0 >= 0 && padx0 <= 3 && pady0 >= 0 && pady0 <= 3 && inW % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    const bool march_ok = f4m && padx0 >= 0 && padx0 <= 3 && pady0 >= 0 && pady0 <= 3 && inW % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     if (march_ok && upx == 1 && downx == 2) {
         Res2P rp{x, f, y, N * C, inH, inW, padx0, pady0, flip, gain, outH, outW, 0, 0, 0};
         return launch_resample2<false>(rp, st);

@@ -22,6 +22,7 @@
 //               (<= 16 rows x 2 steps x 3 products); two TMEM sets ping-pong and the converter warps drain every finished
 //               strip into fp32 REGISTERS (round-to-nearest).  A tile's partial sum leaves the CTA once, with fp32 atomics
 //               into the zero-initialised dw (a handful of partials per tile: one per CTA that worked on it).
+#define GG_TU_TAG 3
 #include "tc_common.cuh"
 #include <stdlib.h>
 
@@ -396,6 +397,7 @@ int launch_wgrad(const WgP& p, int grid, cudaStream_t st) {
         GG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<NTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gg::mark_done_on_this_device(attr_set);
     }
+    wd_arm();
     wgrad_tc_kernel<NTA><<<grid, WG_THREADS, smem, st>>>(p);
     return gg::check_launch("conv2d_wgrad(tc)");
 }

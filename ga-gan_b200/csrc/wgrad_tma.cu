@@ -25,6 +25,7 @@
 //
 // Requirements (checked by wgrad_tma_eligible, otherwise wgrad_tc.cu's kernel runs): 16-byte aligned base pointers and row
 // pitches (WA % 4 == 0, WB % 4 == 0) -- the TMA global-stride rule.
+#define GG_TU_TAG 4
 #include "tc_common.cuh"
 #include <stdlib.h>
 #include <limits.h>
@@ -443,6 +444,7 @@ int launch_wgrad_tma(const CUtensorMap& xmap, const CUtensorMap& gmap, const WtP
         GG_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<NTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gg::mark_done_on_this_device(attr_set);
     }
+    wd_arm();
     wgrad_tma_kernel<NTA><<<grid, THREADS, smem, st>>>(xmap, gmap, p);
     return gg::check_launch("conv2d_wgrad(tc)");
 }

@@ -65,6 +65,7 @@ _SIGNATURES = {
     'gg_device_ok': (ctypes.c_int, []),
     'gg_launch_count': (ctypes.c_int64, []),
     'gg_set_conv_kernel_family': (ctypes.c_int, [ctypes.c_int]),
+    'gg_watchdog_report': (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     'gg_bias_act_f32': (ctypes.c_int, [_c_float_p] * 7 + [ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
                                                           ctypes.c_float, ctypes.c_int64, ctypes.c_int, ctypes.c_int64,
                                                           ctypes.c_void_p]),
@@ -124,6 +125,12 @@ def load_library():
 def set_conv_kernel_family(family):
     """1 = row-marching kernel for the <= 64-channel 3x3 layers (default), 0 = the tile kernel for everything; returns the old value."""
     return int(load_library().gg_set_conv_kernel_family(int(family)))
+
+
+def watchdog_report():
+    """One line describing the first mbarrier-wait watchdog expiry of this process ('' if none): readable even after the CUDA context faulted."""
+    buf = ctypes.create_string_buffer(256)
+    return buf.value.decode() if load_library().gg_watchdog_report(buf, 256) else ''
 
 
 def launch_count():

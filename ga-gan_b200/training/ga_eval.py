@@ -75,6 +75,9 @@ def default_fitness(G, D, ws, c):
     return D(img, c).mean()
 
 
+_graph_cache = dict()       # (id(G), id(D), fitness_fn, ws shape, device) -> (graph, static_ws, static_c, static_out)
+
+
 @torch.no_grad()
 def evaluate_population(G, D, population, z, c=None, rank=0, world=1, fitness_fn=None, cuda_graph=True):
     """Fitness [P] of every individual, identical on all ranks.
@@ -83,10 +86,11 @@ def evaluate_population(G, D, population, z, c=None, rank=0, world=1, fitness_fn
     z: the shared latent batch [B, z_dim] on this rank's device.  `fitness_fn(G, D, ws, c)` defaults to the mean logit.
 
     One individual is ~130 library launches plus a few hundred small torch ops for ~10 ms of device work at 256^2, partly
-    launch-bound from Python.  With `cuda_graph=True` (CUDA only, shards of >= 16 individuals) the evaluation of ONE individual is
-    captured into a CUDA graph after an eager warm-up and replayed for every other individual -- only the offsets (device
-    tensors, updated in place between replays) change.  The same kernels run either way and the results are identical
-    (measured: 82 -> 97 individuals/s at 256^2 paper256, batch 8, one B200; tools/ga_bench.py).
+    launch-bound from Python.  With `cuda_graph=True` (CUDA only) the evaluation of ONE individual is captured into a CUDA graph
+    after an eager warm-up and replayed for every other individual -- only the offsets (device tensors, updated in place between
+    replays) change -- and the captured graph is kept for the next call with the same networks and latent shape (the next
+    generation), so its ~0.1 s capture is paid once.  The same kernels run either way and the results are identical (measured:
+    82 -> 97 individuals/s at 256^2 paper256, batch 8, one B200; tools/ga_bench.py).
     """
     fitness_fn = fitness_fn or default_fitness
     device = z.device
@@ -98,16 +102,23 @@ def evaluate_population(G, D, population, z, c=None, rank=0, world=1, fitness_fn
     mine = shard_indices(population.shape[0], rank, world)
     local = []
     graph = static_out = None
-    if cuda_graph and device.type == 'cuda' and len(mine) >= 16:      # capturing costs ~0.1 s: only worth it for a long shard
-        load_individual(G, population[mine[0]])
-        side = torch.cuda.Stream(device)                  # warm-up on a side stream, as graph capture requires
-        side.wait_stream(torch.cuda.current_stream(device))
-        with torch.cuda.stream(side):
-            fitness_fn(G, D, ws, c)                       # plugin / attribute / allocator initialisation happens here, not in the capture
-        torch.cuda.current_stream(device).wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            static_out = fitness_fn(G, D, ws, c)
+    if cuda_graph and device.type == 'cuda' and len(mine) >= 2:
+        key = (id(G), id(D), fitness_fn, tuple(ws.shape), tuple(c.shape), str(device))
+        entry = _graph_cache.get(key)
+        if entry is None:
+            static_ws, static_c = ws.clone(), c.clone()
+            load_individual(G, population[mine[0]])
+            side = torch.cuda.Stream(device)              # warm-up on a side stream, as graph capture requires
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                fitness_fn(G, D, static_ws, static_c)     # plugin / attribute / allocator initialisation happens here, not in the capture
+            torch.cuda.current_stream(device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = fitness_fn(G, D, static_ws, static_c)
+            entry = _graph_cache[key] = (graph, static_ws, static_c, static_out)
+        graph, static_ws, static_c, static_out = entry
+        static_ws.copy_(ws); static_c.copy_(c)
     for i in mine:
         load_individual(G, population[i])
         if graph is not None:

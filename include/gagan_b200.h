@@ -186,6 +186,11 @@ GG_API int gg_chan_dot_preact_f32(const float* ds, const float* y, const float* 
 /* Number of kernels this library has launched since load (all streams); bench.py reports the delta. */
 GG_API int64_t gg_launch_count(void);
 
+/* The tcgen05 kernels bound every mbarrier wait (~4 s of SM clocks); on expiry the waiting thread records what it was waiting for in
+ * host-mapped memory and traps (the launch fails with a CUDA error instead of hanging the GPU).  Writes a one-line description of the
+ * first expiry of this process into buf and returns 1, or returns 0 if no watchdog has fired. */
+GG_API int gg_watchdog_report(char* buf, int len);
+
 /* Which tcgen05 kernel family serves the 3x3 stride-1 layers with <= 64 output channels: 1 (default) = the row-marching kernel
  * (conv_march.cu: filter rows in the MMA N dimension), 0 = the tile kernel that serves every other shape (conv_tc.cu).  Both
  * compute the same fp32-faithful 3xTF32 result; the switch exists for A/B measurements (tools/microbench.py) and for the parity

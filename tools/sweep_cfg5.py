@@ -172,13 +172,19 @@ def main():
                 ref_f = (lambda: L.networks.modulated_conv2d(x=xi, weight=w, styles=si, fused_modconv=False, **kw)) if L else None
                 with torch.no_grad():
                     point(name + ' fwd', r, n, ours_f, ref_f, flops=fl)
-                yo = ours_f(); dyo = torch.randn_like(yo)
-                yr = ref_f() if L else None
-                point(name + ' dgrad', r, n, lambda: torch.autograd.grad(yo, xi, dyo, retain_graph=True),
-                      (lambda: torch.autograd.grad(yr, xi, dyo, retain_graph=True)) if L else None, flops=fl)
-                point(name + ' wgrad', r, n, lambda: torch.autograd.grad(yo, w, dyo, retain_graph=True),
-                      (lambda: torch.autograd.grad(yr, w, dyo, retain_graph=True)) if L else None, flops=fl)
-                del yo, yr, dyo, xi, w
+                # one graph per gradient: only the tensor in question requires grad, so both sides compute exactly that gradient
+                dyo = None
+                for what, tx, tw in (('dgrad', True, False), ('wgrad', False, True)):
+                    xi.requires_grad_(tx); w.requires_grad_(tw)
+                    yo = ours_f()
+                    if dyo is None:
+                        dyo = torch.randn_like(yo)
+                    yr = ref_f() if L else None
+                    tgt = xi if tx else w
+                    point(f'{name} {what}', r, n, lambda: torch.autograd.grad(yo, tgt, dyo, retain_graph=True),
+                          (lambda: torch.autograd.grad(yr, tgt, dyo, retain_graph=True)) if L else None, flops=fl)
+                    del yo, yr
+                del dyo, xi, w
             del x
             torch.cuda.empty_cache()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
