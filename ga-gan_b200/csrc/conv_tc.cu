@@ -615,7 +615,22 @@ int conv2d_tc(const float* x, const float* w, float* y, int N, int I, int H, int
               int pad_x, int flip_w, int w_is_IO, const float* in_scale, const float* out_scale, int nprod, const ConvEpilogue* epi,
               cudaStream_t st) {
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) { set_error("conv2d(tc): x must be 16-byte aligned"); return GG_EINVAL; }
-    const int NT = O > 128 ? 256 : (O > 64 ? 128 : (O > 32 ? 64 : 32));
+    int NT = O > 128 ? 256 : (O > 64 ? 128 : (O > 32 ? 64 : 32));
+    {
+        // Small problems (the 4^2 .. 32^2 maps, small batches) do not fill one wave of CTAs with the widest n-tile, and the K loop of a
+        // single CTA is then the whole cost of the launch.  Model: cost = waves * (M sub-tiles per CTA) * max(NT, 64) -- an MMA takes
+        // ~NT cycles but never less than the 64 it needs to fetch its 128 A rows -- and take the cheapest n-tile (ties: the widest).
+        auto cost = [&](int nt) {
+            const int tw = nt == 256 ? 8 : 16;
+            const int64_t ctas = (int64_t)((OW + tw - 1) / tw) * ((OH + TILE_H - 1) / TILE_H) * N * ((O + nt - 1) / nt);
+            const int64_t waves = (ctas + GG_NUM_SMS - 1) / GG_NUM_SMS;
+            return waves * (nt == 256 ? 1 : 2) * (nt > 64 ? nt : 64);
+        };
+        int best = NT;
+        for (int nt = NT / 2; nt >= 32; nt /= 2)
+            if (cost(nt) < cost(best)) best = nt;
+        if (cost(NT) <= 4 * 256) NT = best;      // only launches of a few waves: large ones stay on the widest tile (weights fetched once)
+    }
     const int TILE_W = NT == 256 ? 8 : 16;
     const int n_tiles = (O + NT - 1) / NT;
     const int num_kb = (I + KB_CH - 1) / KB_CH;

@@ -213,6 +213,7 @@ struct StreamP {
     int outH, outW;                             // logical (valid) output extent
     int ipH, ipW, opH, opW;                     // phase-major plane sizes (LAYOUT 1 / 2)
     int RS, ncg, nst;                           // rows per strip, 8-column groups per row, strips per plane
+    int vec_in;                                 // plain input rows are 16-byte aligned (width % 4 == 0): 128-bit loads, else scalar
 };
 
 template <int LAYOUT, int PX0, bool SEP>
@@ -240,7 +241,7 @@ __device__ __forceinline__ void fir_march(const StreamP& p, const float (&K)[4][
                 if (b == 0 && PX0 == 0) continue;                // left halo not needed
                 if (b == 3 && PX0 == 3) continue;                // right halo not needed
                 const int cb = x0 - 4 + 4 * b;
-                if (row_ok && cb >= 0 && cb + 3 < p.inW) {
+                if (p.vec_in && row_ok && cb >= 0 && cb + 3 < p.inW) {
                     const float4 v = __ldg(reinterpret_cast<const float4*>(rowp - 4 + 4 * b));
                     buf[4 * b] = v.x; buf[4 * b + 1] = v.y; buf[4 * b + 2] = v.z; buf[4 * b + 3] = v.w;
                 } else {
@@ -409,6 +410,7 @@ template <int LAYOUT, int PX0>
 int launch_stream2(StreamP p, cudaStream_t st) {
     const int fullW = LAYOUT == 2 ? 2 * p.opW : p.outW, fullH = LAYOUT == 2 ? 2 * p.opH : p.outH;
     p.RS = fullH >= 128 ? 32 : (fullH >= 32 ? 16 : 8);
+    p.vec_in = (LAYOUT != 1 && p.inW % 4 == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0) ? 1 : 0;
     p.ncg = (fullW + 7) / 8;
     p.nst = (fullH + p.RS - 1) / p.RS;
     const long long threads = (long long)p.ncg * p.nst * p.N * p.C;
@@ -620,10 +622,11 @@ int launch_resample2(Res2P p, cudaStream_t st) {
     return gg::check_launch("upfirdn2d(fir_resample2)");
 }
 
-// 128-bit row loads need 16-byte aligned rows; padx0 must be one of the four instantiations
+// padx0 must be one of the four instantiations; phase-major input rows must be 16-byte aligned (plain rows that are not take the
+// scalar loads of fir_march: the odd-width maps behind an up-sampling convolution, 17^2 .. 1025^2)
 bool stream_ok(const StreamP& p, bool in_pm) {
-    const int pitch = in_pm ? p.ipW : p.inW;
-    return p.padx0 >= 0 && p.padx0 <= 3 && pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0;
+    if (p.padx0 < 0 || p.padx0 > 3) return false;
+    return !in_pm || (p.ipW % 4 == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
 }
 
 }  // namespace
@@ -652,7 +655,7 @@ extern "C" GG_API int gg_upfirdn2d_f32(const float* x, const float* f, float* y,
     const bool f4m = (fH == 4 && fW == 4) && upx == upy && downx == downy && outW >= 8;
     const bool f4 = f4m && outW >= 48;
     if (f4m && upx == 1 && downx == 1) {   // unit rate: the register-streaming kernel (also serves the phase-major layouts)
-        StreamP sp{x, f, y, N, C, inH, inW, padx0, pady0, flip, gain, outH, outW, 0, 0, 0, 0, 0, 0, 0};
+        StreamP sp{x, f, y, N, C, inH, inW, padx0, pady0, flip, gain, outH, outW, 0, 0, 0, 0, 0, 0, 0, 0};
         if (stream_ok(sp, false)) return launch_stream<0>(sp, st);
         if (f4) return launch_tile<1, 1, 0, 4, 4>(p, st);
     }
@@ -692,9 +695,9 @@ extern "C" GG_API int gg_fir4_pm_f32(const float* x, const float* f, float* y, i
     GG_REQUIRE((int64_t)N * C * (in_pm ? 4LL * in_pmH * in_pmW : (int64_t)inH * inW) <= 0x7fffffffLL &&
                (int64_t)N * C * (out_pm ? 4LL * out_pmH * out_pmW : (int64_t)outH * outW) <= 0x7fffffffLL, "fir4_pm: tensor is too large");
     if (N == 0) return GG_OK;
-    StreamP p{x, f, y, N, C, inH, inW, padx0, pady0, flip, gain, outH, outW, in_pmH, in_pmW, out_pmH, out_pmW, 0, 0, 0};
+    StreamP p{x, f, y, N, C, inH, inW, padx0, pady0, flip, gain, outH, outW, in_pmH, in_pmW, out_pmH, out_pmW, 0, 0, 0, 0};
     cudaStream_t st = (cudaStream_t)stream;
-    GG_REQUIRE(stream_ok(p, in_pm != 0), "fir4_pm: needs 0 <= padx0 <= 3 and 16-byte aligned input rows (width %% 4 == 0)");
+    GG_REQUIRE(stream_ok(p, in_pm != 0), "fir4_pm: needs 0 <= padx0 <= 3 and, for a phase-major input, 16-byte aligned rows (width %% 4 == 0)");
     if (in_pm) return launch_stream<1>(p, st);
     if (out_pm) return launch_stream<2>(p, st);
     return launch_stream<0>(p, st);

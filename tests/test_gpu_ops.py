@@ -55,6 +55,10 @@ def test_upfirdn2d_golden(ops, device):
     ('up2_oddpad', (1, 2, 50, 70), 2, 1, [1, 2, 3, 0]), ('down2', (2, 3, 128, 128), 1, 2, [1, 1, 1, 1]),
     ('down2_ragged', (1, 2, 101, 131), 1, 2, [1, 1, 1, 1]), ('filt_crop', (1, 2, 90, 140), 1, 1, [-3, 2, -1, 4]),
     ('up2_bwd_of_down2', (1, 2, 64, 64), 2, 1, [2, 2, 2, 2]),
+    # odd widths (rows that are not 16-byte multiples) behind an up-sampling convolution: the scalar-load side of the marching kernel
+    ('filt_p1_17', (3, 5, 17, 17), 1, 1, [1, 1, 1, 1]), ('filt_p1_33', (2, 7, 33, 33), 1, 1, [1, 1, 1, 1]),
+    ('filt_p1_65', (2, 3, 65, 65), 1, 1, [1, 1, 1, 1]), ('filt_odd_ragged', (1, 3, 19, 45), 1, 1, [3, 0, 2, 1]),
+    ('filt_p1_9', (2, 4, 9, 9), 1, 1, [1, 1, 1, 1]),
 ])
 def test_upfirdn2d_tiled_vs_oracle(ops, device, case):
     name, shape, up, down, pad = case
