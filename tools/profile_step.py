@@ -21,6 +21,40 @@ import torch  # noqa: E402
 from torch.profiler import profile, ProfilerActivity  # noqa: E402
 
 
+def profile_ga(args):
+    from torch_utils import custom_ops
+    from gagan_b200.training import training_loop, ga_eval
+    dev = torch.device('cuda:0')
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    custom_ops.verbosity = 'none'
+    torch.manual_seed(0)
+    G, D = training_loop.build_networks(256, 'paper256', device=dev, use_domain_modulation=True, domain_modulation_parametrization='additive')
+    pop = ga_eval.init_population(G, 4, seed=0)
+    z = torch.randn(8, 512, generator=torch.Generator().manual_seed(1)).to(dev)
+    for _ in range(2):
+        ga_eval.evaluate_population(G, D, pop, z, cuda_graph=False)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        ga_eval.evaluate_population(G, D, pop, z, cuda_graph=False)
+        torch.cuda.synchronize()
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for ev in prof.events():
+        if ev.device_type == torch.autograd.DeviceType.CUDA:
+            name = ev.name.replace('(anonymous namespace)::', '').replace('void ', '')
+            agg[name[:110]][0] += 1
+            agg[name[:110]][1] += ev.device_time if hasattr(ev, 'device_time') else ev.cuda_time
+    total = sum(v[1] for v in agg.values())
+    lines = [f'GA fitness evaluation, 4 individuals x 8 latents at 256^2 (paper256): {total / 1000:.2f} ms of kernel time in {sum(v[0] for v in agg.values())} launches']
+    for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+        lines.append(f'{us / 1000:10.3f} ms {100 * us / total:5.1f}%  {n:6d}x  {name}')
+    text = '\n'.join(lines)
+    print(text)
+    if args.out:
+        os.makedirs(os.path.dirname(args.out) or '.', exist_ok=True)
+        open(args.out, 'w').write(text + '\n')
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--res', type=int, default=1024)
@@ -29,7 +63,10 @@ def main():
     ap.add_argument('--batch-gpu', type=int, default=4)
     ap.add_argument('--out', default='')
     ap.add_argument('--main-only', action='store_true', help='profile an iteration without the lazy regularisation phases')
+    ap.add_argument('--ga', action='store_true', help='profile the GA population fitness evaluation (BASELINE configs[3]) instead: paper256, 4 individuals x 8 latents')
     args = ap.parse_args()
+    if args.ga:
+        return profile_ga(args)
     from torch_utils import custom_ops
     from gagan_b200.training import training_loop
     dev = torch.device('cuda:0')

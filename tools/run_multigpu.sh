@@ -5,11 +5,13 @@ N=${1:-2}
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
-python -m pytest tests/test_gpu_multigpu.py -m gpu -q -s > gpurun_out/r2_n${N}_pytest.log 2>&1; echo "pytest multigpu rc=$?"; grep -E "DDP|passed|failed|skipped" gpurun_out/r2_n${N}_pytest.log | tail -3
+if [ "${ONLY_TRAIN:-0}" != "1" ]; then python -m pytest tests/test_gpu_multigpu.py -m gpu -q -s > gpurun_out/r2_n${N}_pytest.log 2>&1; echo "pytest multigpu rc=$?"; grep -E "DDP|passed|failed|skipped" gpurun_out/r2_n${N}_pytest.log | tail -3; fi
 if [ "${SKIP_WEAK:-0}" != "1" ]; then $TR bench.py --gpus $N --steps 8 --warmup 3 --no-fast-mode > gpurun_out/r2_n${N}_train_weak.json 2> gpurun_out/r2_n${N}_train_weak.err; echo "weak rc=$?"; fi
 $TR bench.py --gpus $N --global-batch 32 --steps 8 --warmup 3 --no-fast-mode > gpurun_out/r2_n${N}_train_strong.json 2> gpurun_out/r2_n${N}_train_strong.err; echo "strong rc=$?"
+if [ "${ONLY_TRAIN:-0}" != "1" ]; then
 $TR bench.py --gpus $N --workload ada --steps 8 --warmup 3 > gpurun_out/r2_n${N}_ada.json 2> gpurun_out/r2_n${N}_ada.err; echo "ada rc=$?"
 $TR bench.py --gpus $N --workload ga --steps 4 --warmup 2 > gpurun_out/r2_n${N}_ga.json 2> gpurun_out/r2_n${N}_ga.err; echo "ga rc=$?"
+fi
 for f in train_weak train_strong ada ga; do python - <<PY
 import json
 try:
