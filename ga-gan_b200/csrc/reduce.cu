@@ -150,3 +150,80 @@ extern "C" GG_API int gg_chan_dot_f32(const float* a, const float* b, float* out
     }
     return GG_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// y[r, p] = s[r] * x[r, p]: a per-(sample, channel) scale broadcast over the pixels of its plane.  The second-order gradients of
+// modulated_conv2d (path-length regularisation) need g[n,c] * t[n,c,:,:] as a tensor in two places per layer; torch's broadcasting
+// multiply takes its non-vectorised kernel for that stride pattern.  Flat grid-stride over 128-bit groups; the row of a group is one
+// integer division (P % 4 == 0, so a group never straddles two rows).
+namespace {
+__global__ void __launch_bounds__(256) scale_rows_vec4(const float4* __restrict__ x, const float* __restrict__ s, float4* __restrict__ y,
+                                                       int64_t total4, int64_t P4) {
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total4; i += stride) {
+        const float f = __ldg(s + i / P4);
+        const float4 v = __ldg(x + i);
+        y[i] = make_float4(f * v.x, f * v.y, f * v.z, f * v.w);
+    }
+}
+__global__ void __launch_bounds__(256) scale_rows_scalar(const float* __restrict__ x, const float* __restrict__ s, float* __restrict__ y,
+                                                         int64_t total, int64_t P) {
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) y[i] = __ldg(s + i / P) * __ldg(x + i);
+}
+}  // namespace
+
+extern "C" GG_API int gg_scale_rows_f32(const float* x, const float* s, float* y, int64_t rows, int64_t P, gg_stream_t stream) {
+    GG_REQUIRE(x && s && y, "scale_rows: null pointer");
+    GG_REQUIRE(rows >= 0 && P >= 0 && (rows == 0 || P <= 0x7fffffffLL * 4 / rows), "scale_rows: tensor is too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t total = rows * P;
+    if (total == 0) return GG_OK;
+    const bool vec = P % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    const int64_t work = vec ? total / 4 : total;
+    int64_t blocks = (work + 255) / 256;
+    if (blocks > (int64_t)GG_NUM_SMS * 16) blocks = (int64_t)GG_NUM_SMS * 16;
+    if (vec) scale_rows_vec4<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(x), s, reinterpret_cast<float4*>(y), total / 4, P / 4);
+    else scale_rows_scalar<<<(unsigned)blocks, 256, 0, st>>>(x, s, y, total, P);
+    return gg::check_launch("scale_rows");
+}
+
+// y[r, p] = s1[r] * x1[r, p] + s2[r] * x2[r, p]: the two gradient contributions that meet in front of a convolution in the second-order
+// pass (a * gg_dx + g_da * x), combined in one pass so that ONE convolution / weight-gradient launch serves both.
+namespace {
+__global__ void __launch_bounds__(256) axpby_rows_vec4(const float4* __restrict__ x1, const float* __restrict__ s1, const float4* __restrict__ x2,
+                                                       const float* __restrict__ s2, float4* __restrict__ y, int64_t total4, int64_t P4) {
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total4; i += stride) {
+        const int64_t r = i / P4;
+        const float f1 = __ldg(s1 + r), f2 = __ldg(s2 + r);
+        const float4 u = __ldg(x1 + i), v = __ldg(x2 + i);
+        y[i] = make_float4(fmaf(f1, u.x, f2 * v.x), fmaf(f1, u.y, f2 * v.y), fmaf(f1, u.z, f2 * v.z), fmaf(f1, u.w, f2 * v.w));
+    }
+}
+__global__ void __launch_bounds__(256) axpby_rows_scalar(const float* __restrict__ x1, const float* __restrict__ s1, const float* __restrict__ x2,
+                                                         const float* __restrict__ s2, float* __restrict__ y, int64_t total, int64_t P) {
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) {
+        const int64_t r = i / P;
+        y[i] = fmaf(__ldg(s1 + r), __ldg(x1 + i), __ldg(s2 + r) * __ldg(x2 + i));
+    }
+}
+}  // namespace
+
+extern "C" GG_API int gg_axpby_rows_f32(const float* x1, const float* s1, const float* x2, const float* s2, float* y, int64_t rows, int64_t P,
+                                        gg_stream_t stream) {
+    GG_REQUIRE(x1 && s1 && x2 && s2 && y, "axpby_rows: null pointer");
+    GG_REQUIRE(rows >= 0 && P >= 0 && (rows == 0 || P <= 0x7fffffffLL * 4 / rows), "axpby_rows: tensor is too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t total = rows * P;
+    if (total == 0) return GG_OK;
+    const bool vec = P % 4 == 0 && ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(x2) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    const int64_t work = vec ? total / 4 : total;
+    int64_t blocks = (work + 255) / 256;
+    if (blocks > (int64_t)GG_NUM_SMS * 16) blocks = (int64_t)GG_NUM_SMS * 16;
+    if (vec) axpby_rows_vec4<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(x1), s1, reinterpret_cast<const float4*>(x2), s2,
+                                                              reinterpret_cast<float4*>(y), total / 4, P / 4);
+    else axpby_rows_scalar<<<(unsigned)blocks, 256, 0, st>>>(x1, s1, x2, s2, y, total, P);
+    return gg::check_launch("axpby_rows");
+}

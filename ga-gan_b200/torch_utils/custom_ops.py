@@ -75,6 +75,8 @@ _SIGNATURES = {
                                                            ctypes.c_void_p]),
     'gg_fir4_pm_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 7 + [ctypes.c_float] + [ctypes.c_int] * 8 + [ctypes.c_void_p]),
     'gg_chan_dot_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
+    'gg_scale_rows_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
+    'gg_axpby_rows_f32': (ctypes.c_int, [_c_float_p] * 5 + [ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
     'gg_conv2d_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 14 + [_c_float_p, _c_float_p, ctypes.c_int,
                                                         ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
     'gg_conv2d_act_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 14 + [_c_float_p] * 4 + [ctypes.c_int64, ctypes.c_int, ctypes.c_float,
@@ -278,6 +280,35 @@ class _Plugin:
         with torch.cuda.device(a.device):
             _check(self._lib.gg_chan_dot_f32(_ptr(a), _ptr(b), _ptr(out), rows, a.numel() // max(rows, 1), _stream(a)), 'chan_dot')
         return out
+
+    # y[n,c,:,:] = s[n,c] * x[n,c,:,:] (include/gagan_b200.h: gg_scale_rows_f32)
+    def scale_rows(self, x, s):
+        _require_cuda(x, 'x')
+        _require_cuda(s, 's')
+        _check_device(x)
+        if x.dim() < 2 or tuple(s.shape) != tuple(x.shape[:2]) or s.device != x.device:
+            raise RuntimeError('scale_rows: x must be [N,C,...] and s [N,C] on the same device')
+        x = x.contiguous(); s = s.contiguous()
+        rows = x.shape[0] * x.shape[1]
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _check(self._lib.gg_scale_rows_f32(_ptr(x), _ptr(s), _ptr(y), rows, x.numel() // max(rows, 1), _stream(x)), 'scale_rows')
+        return y
+
+    # y[n,c,:,:] = s1[n,c] * x1[n,c,:,:] + s2[n,c] * x2[n,c,:,:] (include/gagan_b200.h: gg_axpby_rows_f32)
+    def axpby_rows(self, x1, s1, x2, s2):
+        for nm, t in (('x1', x1), ('s1', s1), ('x2', x2), ('s2', s2)):
+            _require_cuda(t, nm)
+        _check_device(x1)
+        if x1.shape != x2.shape or x1.dim() < 2 or tuple(s1.shape) != tuple(x1.shape[:2]) or s1.shape != s2.shape:
+            raise RuntimeError('axpby_rows: x1, x2 must be [N,C,...] of one shape and s1, s2 [N,C]')
+        x1 = x1.contiguous(); x2 = x2.contiguous(); s1 = s1.contiguous(); s2 = s2.contiguous()
+        rows = x1.shape[0] * x1.shape[1]
+        y = torch.empty_like(x1)
+        with torch.cuda.device(x1.device):
+            _check(self._lib.gg_axpby_rows_f32(_ptr(x1), _ptr(s1), _ptr(x2), _ptr(s2), _ptr(y), rows, x1.numel() // max(rows, 1), _stream(x1)),
+                   'axpby_rows')
+        return y
 
     # d out_scale of a convolution with a fused epilogue (include/gagan_b200.h: gg_chan_dot_preact_f32)
     def chan_dot_preact(self, ds, y, bias, noise, act_idx, alpha, gain):

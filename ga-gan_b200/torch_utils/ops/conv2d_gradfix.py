@@ -166,15 +166,59 @@ def conv2d_s1(x, w, padding=(0, 0), out_hw=None, io=False, flip=False, live=1.0,
 
 
 fuse_scales = True
+closed_scaled_backward = True       # gradients of gradients of the scaled convolution stay on the fused kernels (below); False = the
+                                    # round-1 formulation that spells the partial derivatives out with broadcast multiplies (A/B switch)
 _scaled_conv2d_s1_cache = dict()
 
 
+class _ChanDot(torch.autograd.Function):
+    """out[n,c] = sum_p p[n,c,:] * q[n,c,:] (gg_chan_dot_f32: one pass over both operands, no product tensor).  Its backward is
+    two broadcast multiplies written with torch ops, so the node is differentiable to any order."""
+    @staticmethod
+    def forward(ctx, p, q):
+        ctx.save_for_backward(p, q)
+        return _plugin.chan_dot(p, q)
+
+    @staticmethod
+    def backward(ctx, g):
+        p, q = ctx.saved_tensors
+        g = g[:, :, None, None]
+        return (g * q if ctx.needs_input_grad[0] else None), (g * p if ctx.needs_input_grad[1] else None)
+
+
+def _safe(s):
+    return torch.where(s == 0, torch.ones_like(s), s)
+
+
 def _scaled_conv2d_s1(weight_shape, padding, out_hw, io, flip, live, pm, has_a, has_b):
+    """y = b * conv(a * x, w) with the per-sample scales inside the kernels, differentiable twice ON THE FUSED KERNELS.
+
+    Returned object: `.apply(x, w, a, b)` and `.Wgrad` (the differentiable weight gradient).  Autograd sees two nodes,
+
+        yh = Core(x, w, a, b0)       b0 = b.detach(): one launch, y-hat = b0 * conv(a * x, w)
+        y  = OutScale(yh, b)         no launch (y is yh): carries the dependence on b,  d/db = sum_p dy * yh / b0
+
+    so that the demodulation-coefficient gradient d/db is a function of the graph node yh and of nothing else.  In the second-order
+    pass (path-length regularisation, loss.py:96-109) the gradient that d/db sends back therefore arrives at Core TOGETHER with
+    everything else that flows into yh, and one data-gradient + one weight-gradient launch serve both -- what the reference gets from
+    autograd by keeping the unscaled convolution output as a node of its own (networks.py:646-651).  Every first-order partial is a node
+    with EXPLICIT derivatives:
+
+        Core.backward (create_graph)   (dx, da) = DxDa(dy, w, a, x; b0),  dw = ScaledWgradS1(dy, x, a, b0)
+        DxDa.backward                  the two incoming gradients are combined in one pass (a * gg_dx + g_da * x), then one forward
+                                       convolution (-> d/d dy) and one weight gradient; da does not depend on a, so nothing flows there
+        OutScale.backward              g_yh = dy (identity; its b-dependence is the node RatioScale), g_b = DemodDot(dy, yh; b0)
+
+    Writing d/da and d/db as quotients (chan_dot(x, dx) / a, chan_dot(dy, y) / b) and letting autograd differentiate those instead
+    produces the missing a- / b-dependence as the difference of two large terms: 1.6e-3 on a second-order style gradient (measured).
+    (Re-running the forward and calling autograd.grad on it would be wrong as well: out_scale = dcoefs is itself a function of
+    in_scale = styles, and the total derivative would count that path twice.)"""
     key = (weight_shape, padding, out_hw, io, flip, live, pm, has_a, has_b)
     if key in _scaled_conv2d_s1_cache:
         return _scaled_conv2d_s1_cache[key]
     kh, kw = weight_shape[2], weight_shape[3]
     dpad = (kh - 1 - padding[0], kw - 1 - padding[1])
+    wg_kw = dict(stride=1, padding=padding, flip_w=flip, out_layout=(1 if io else 0), flop_scale=live, pm=pm)
 
     def kernel(x, w, a, b, pad, hw, io_, flip_):
         if not io_:
@@ -183,58 +227,217 @@ def _scaled_conv2d_s1(weight_shape, padding, out_hw, io, flip, live, pm, has_a, 
         return _plugin.conv2d(x, w, stride=1, padding=(kh - 1 - pad[0], kw - 1 - pad[1]), transposed=True, flip_w=(not flip_),
                               out_hw=hw, flop_scale=live, in_scale=a, out_scale=b)
 
-    class ScaledConvS1(torch.autograd.Function):
+    def hw_of(t):
+        return (int(t.shape[2]), int(t.shape[3]))
+
+    def unscaled_or_scaled(pad, hw, io_, flip_, t, w_, s_in):
+        # conv_{pad,hw,io_,flip_}(s_in * t, w_) as a differentiable node (the spelled-out routes below)
+        if s_in is None:
+            return _conv2d_s1(weight_shape, pad, hw, io_, flip_, live, pm).apply(t, w_)
+        return _scaled_conv2d_s1(weight_shape, pad, hw, io_, flip_, live, pm, True, False).apply(t, w_, s_in, None)
+
+    def partial_grads(expr_fn, inputs, need, g):
+        # third and higher order: differentiate the spelled-out expression with autograd
+        with torch.enable_grad():
+            expr = expr_fn()
+            idx = [i for i, t in enumerate(inputs) if need[i] and t is not None and t.requires_grad]
+            got = torch.autograd.grad(expr, [inputs[i] for i in idx], g, create_graph=True, allow_unused=True) if idx else ()
+        out = [None] * len(inputs)
+        for i, v in zip(idx, got):
+            out[i] = v
+        return out
+
+    class Core(torch.autograd.Function):
         @staticmethod
-        def forward(ctx, x, w, a, b):
+        def forward(ctx, x, w, a, b0):
             assert tuple(w.shape) == weight_shape
             a_ = a.contiguous() if a is not None else None
-            b_ = b.contiguous() if b is not None else None
-            y = kernel(x, w, a_, b_, padding, out_hw, io, flip)
-            ctx.save_for_backward(x, w, a, b, y if b is not None else None)
-            return y
+            b_ = b0.contiguous() if b0 is not None else None
+            ctx.save_for_backward(x, w, a, b0)
+            return kernel(x, w, a_, b_, padding, out_hw, io, flip)
 
         @staticmethod
         def backward(ctx, dy):
-            x, w, a, b, y = ctx.saved_tensors
+            x, w, a, b0 = ctx.saved_tensors
+            need = ctx.needs_input_grad
+            dx = dw = da = None
+            want_da = a is not None and need[2]
+            if torch.is_grad_enabled() and closed_scaled_backward:
+                if need[0] or want_da:
+                    dx, da = DxDa.apply(dy, w, a, x, b0)
+                    if not need[0]:
+                        dx = None
+                    if not want_da:
+                        da = None
+                if need[1] and not weight_gradients_disabled:
+                    dw = ScaledWgradS1.apply(dy, x, a, b0)
+                return dx, dw, da, None
             if torch.is_grad_enabled():
-                # A gradient of this gradient was requested (path-length / R1 regularisation): spell the four PARTIAL derivatives
-                # out with differentiable ops and the closed, unscaled primitives so that autograd can differentiate them again.
-                # (Re-running the forward and calling autograd.grad on it would be wrong: out_scale = dcoefs is itself a function
-                # of in_scale = styles, and the total derivative would count that path twice.)
+                # closed_scaled_backward = False: the round-1 formulation -- the partial derivatives spelled out with broadcast multiplies
+                # around the closed, unscaled primitives
                 conv = _conv2d_s1(weight_shape, padding, out_hw, io, flip, live, pm)
-                conv_t = _conv2d_s1(weight_shape, dpad, (x.shape[2], x.shape[3]), not io, not flip, live, pm)
+                conv_t = _conv2d_s1(weight_shape, dpad, hw_of(x), not io, not flip, live, pm)
                 xa = x * a[:, :, None, None] if a is not None else x
-                dyb = dy * b[:, :, None, None] if b is not None else dy
-                dx = dw = da = db = None
-                if ctx.needs_input_grad[0] or (a is not None and ctx.needs_input_grad[2]):
+                dyb = dy * b0[:, :, None, None] if b0 is not None else dy
+                if need[0] or want_da:
                     u = conv_t.apply(dyb, w)
-                    if ctx.needs_input_grad[0]:
+                    if need[0]:
                         dx = u * a[:, :, None, None] if a is not None else u
-                    if a is not None and ctx.needs_input_grad[2]:
+                    if want_da:
                         da = (x * u).sum([2, 3])
-                if ctx.needs_input_grad[1] and not weight_gradients_disabled:
+                if need[1] and not weight_gradients_disabled:
                     dw = conv.Wgrad.apply(dyb, xa)
-                if b is not None and ctx.needs_input_grad[3]:
-                    db = (dy * conv.apply(xa, w)).sum([2, 3])
-                return dx, dw, da, db
-            dx = dw = da = db = None
+                return dx, dw, da, None
             dy = dy.contiguous()
-            need_dx = ctx.needs_input_grad[0] or (a is not None and ctx.needs_input_grad[2])
-            if need_dx:
+            if need[0] or want_da:
                 # d/dx = a * convT(b * dy): the same kernel with the scales swapped
-                dx = kernel(dy, w, b, a, dpad, (x.shape[2], x.shape[3]), not io, not flip)
-                if a is not None and ctx.needs_input_grad[2]:
+                dx = kernel(dy, w, b0, a, dpad, hw_of(x), not io, not flip)
+                if want_da:
                     # d/da[n,i] = sum_p x * convT(b*dy) = sum_p x * dx / a      (a == 0 has measure zero; its gradient reads as 0)
-                    da = _plugin.chan_dot(x, dx) / torch.where(a == 0, torch.ones_like(a), a)
-                if not ctx.needs_input_grad[0]:
+                    da = _plugin.chan_dot(x, dx) / _safe(a)
+                if not need[0]:
                     dx = None
-            if ctx.needs_input_grad[1] and not weight_gradients_disabled:
-                dw = _plugin.conv2d_wgrad(x, dy, (kh, kw), stride=1, padding=padding, flip_w=flip, out_layout=(1 if io else 0),
-                                          flop_scale=live, a_scale=a, b_scale=b, pm=pm)
-            if b is not None and ctx.needs_input_grad[3]:
-                # d/db[n,o] = sum_p dy * conv(a*x, w) = sum_p dy * y / b
-                db = _plugin.chan_dot(dy, y) / torch.where(b == 0, torch.ones_like(b), b)
-            return dx, dw, da, db
+            if need[1] and not weight_gradients_disabled:
+                dw = _plugin.conv2d_wgrad(x, dy, (kh, kw), a_scale=a, b_scale=b0, **wg_kw)
+            return dx, dw, da, None
+
+    class DxDa(torch.autograd.Function):
+        """(dx, da) = (a * u, sum_p x * u),  u = convT(b0 * dy, w): the data and style gradients of Core as ONE node."""
+        @staticmethod
+        def forward(ctx, dy, w, a, x, b0):
+            ctx.set_materialize_grads(False)
+            dy = dy.contiguous()
+            dxf = kernel(dy, w, b0, a, dpad, hw_of(x), not io, not flip)
+            da = _plugin.chan_dot(x, dxf) / _safe(a) if a is not None else None
+            ctx.save_for_backward(dy, w, a, x, b0, dxf)
+            return dxf, da
+
+        @staticmethod
+        def backward(ctx, gg, g):
+            dy, w, a, x, b0, dxf = ctx.saved_tensors
+            need = ctx.needs_input_grad
+            if gg is None and g is None:
+                return None, None, None, None, None
+            if torch.is_grad_enabled():
+                def expr():
+                    u = unscaled_or_scaled(dpad, hw_of(x), not io, not flip, dy, w, b0)
+                    e = 0.0
+                    if gg is not None:
+                        e = e + (gg * (u * a[:, :, None, None] if a is not None else u)).sum()
+                    if g is not None:
+                        e = e + (g * (x * u).sum([2, 3])).sum()
+                    return e
+                g_dy, g_w, g_a, g_x = partial_grads(expr, [dy, w, a, x], need, None)
+                return g_dy, g_w, g_a, g_x, None
+            g_dy = g_w = g_a = g_x = None
+            # e = the gradient that arrives at u, as a conv INPUT:  a * gg (through dx)  +  g * x (through da)
+            if gg is not None:
+                gg = gg.contiguous()
+            if g is not None:
+                g = g.contiguous()
+            e, e_scale = None, None
+            if gg is not None and g is not None:
+                e = _plugin.axpby_rows(gg, a, x, g)
+            elif gg is not None:
+                e, e_scale = gg, a                                   # (a may be None: plain)
+            else:
+                e, e_scale = x, g
+            if need[0]:
+                g_dy = kernel(e, w, e_scale, b0, padding, hw_of(dy), io, flip)          # b0 * conv(e, w)
+            if need[1] and not weight_gradients_disabled:
+                g_w = _plugin.conv2d_wgrad(e, dy, (kh, kw), a_scale=e_scale, b_scale=b0, **wg_kw)
+            if a is not None and need[2] and gg is not None:
+                g_a = _plugin.chan_dot(gg, dxf) / _safe(a)          # sum_p gg * u      (da itself does not depend on a)
+            if need[3] and g is not None:
+                g_x = _plugin.scale_rows(dxf, g / _safe(a))         # g * u
+            return g_dy, g_w, g_a, g_x, None
+
+    class OutScale(torch.autograd.Function):
+        """y = yh * (b / b0): numerically yh itself (no launch); the node that owns the dependence on the output scale b."""
+        @staticmethod
+        def forward(ctx, yh, b):
+            ctx.save_for_backward(yh, b)
+            return yh.view_as(yh)
+
+        @staticmethod
+        def backward(ctx, dy):
+            yh, b = ctx.saved_tensors
+            need = ctx.needs_input_grad
+            if torch.is_grad_enabled():
+                b0 = b.detach()
+                return (RatioScale.apply(dy, b, b0) if need[0] else None), (DemodDot.apply(dy, yh, b0) if need[1] else None)
+            return (dy if need[0] else None), (_plugin.chan_dot(dy, yh) / _safe(b) if need[1] else None)
+
+    class RatioScale(torch.autograd.Function):
+        """g_yh = dy * (b / b0): numerically dy itself (no launch); d/db = sum_p gg * dy / b0."""
+        @staticmethod
+        def forward(ctx, dy, b, b0):
+            ctx.save_for_backward(dy, b0)
+            return dy.view_as(dy)
+
+        @staticmethod
+        def backward(ctx, gg):
+            dy, b0 = ctx.saved_tensors
+            need = ctx.needs_input_grad
+            if torch.is_grad_enabled():
+                return (gg if need[0] else None), ((gg * dy).sum([2, 3]) / _safe(b0) if need[1] else None), None
+            return (gg if need[0] else None), (_plugin.chan_dot(gg, dy) / _safe(b0) if need[1] else None), None
+
+    class DemodDot(torch.autograd.Function):
+        """db[n,o] = sum_p dy * yh / b0 = sum_p dy * conv(a * x, w): a function of the nodes dy and yh only."""
+        @staticmethod
+        def forward(ctx, dy, yh, b0):
+            ctx.save_for_backward(dy, yh, b0)
+            return _plugin.chan_dot(dy, yh) / _safe(b0)
+
+        @staticmethod
+        def backward(ctx, g):
+            dy, yh, b0 = ctx.saved_tensors
+            need = ctx.needs_input_grad
+            s = g / _safe(b0)
+            if torch.is_grad_enabled():
+                s4 = s[:, :, None, None]
+                return (s4 * yh if need[0] else None), (s4 * dy if need[1] else None), None
+            return (_plugin.scale_rows(yh, s) if need[0] else None), (_plugin.scale_rows(dy, s) if need[1] else None), None
+
+    class ScaledWgradS1(torch.autograd.Function):
+        """dw = wgrad(a * x, b * dy) with the scales inside the kernel; gradients w.r.t. (dy, x, a, b) for an incoming ggw are the two
+        scaled convolutions with ggw as the weight, and their channel dots (dw is bilinear in (a x, b dy): genuine dependences)."""
+        @staticmethod
+        def forward(ctx, dy, x, a, b):
+            ctx.save_for_backward(dy, x, a, b)
+            return _plugin.conv2d_wgrad(x, dy.contiguous(), (kh, kw), a_scale=(a.contiguous() if a is not None else None),
+                                        b_scale=(b.contiguous() if b is not None else None), **wg_kw)
+
+        @staticmethod
+        def backward(ctx, ggw):
+            dy, x, a, b = ctx.saved_tensors
+            need = ctx.needs_input_grad
+            g_dy = g_x = g_a = g_b = None
+            if need[0] or (b is not None and need[3]):
+                F = _scaled_conv2d_s1(weight_shape, padding, hw_of(dy), io, flip, live, pm, a is not None, b is not None)
+                t = F.apply(x, ggw, a, b)                           # b * conv(a * x, ggw)
+                if need[0]:
+                    g_dy = t
+                if b is not None and need[3]:
+                    g_b = _ChanDot.apply(dy, t) / _safe(b)
+            if need[1] or (a is not None and need[2]):
+                T = _scaled_conv2d_s1(weight_shape, dpad, hw_of(x), not io, not flip, live, pm, b is not None, a is not None)
+                t = T.apply(dy, ggw, b, a)                          # a * convT(b * dy, ggw)
+                if need[1]:
+                    g_x = t
+                if a is not None and need[2]:
+                    g_a = _ChanDot.apply(x, t) / _safe(a)
+            return g_dy, g_x, g_a, g_b
+
+    class ScaledConvS1:
+        Wgrad = ScaledWgradS1
+
+        @staticmethod
+        def apply(x, w, a, b):
+            if b is None:
+                return Core.apply(x, w, a, None)
+            return OutScale.apply(Core.apply(x, w, a, b.detach()), b)
 
     _scaled_conv2d_s1_cache[key] = ScaledConvS1
     return ScaledConvS1

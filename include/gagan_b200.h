@@ -183,6 +183,16 @@ GG_API int gg_conv2d_act_f32(const float* x, const float* w, float* y, int N, in
 GG_API int gg_chan_dot_preact_f32(const float* ds, const float* y, const float* bias, const float* noise, int64_t noise_batch_stride,
                            float* out, int N, int C, int64_t P, int act, float alpha, float gain, gg_stream_t stream);
 
+/* y[r,p] = s[r] * x[r,p] for `rows` rows of P contiguous floats (row = one (sample, channel) plane): the per-sample channel scale as a
+ * tensor, needed by the SECOND-order gradients of modulated_conv2d (training/loss.py:96-109 path-length regularisation: the gradient of
+ * a style / demodulation gradient w.r.t. the activations).  x and y may alias. */
+GG_API int gg_scale_rows_f32(const float* x, const float* s, float* y, int64_t rows, int64_t P, gg_stream_t stream);
+
+/* y[r,p] = s1[r] * x1[r,p] + s2[r] * x2[r,p]: two such scaled tensors summed in one pass -- the two gradient contributions that meet in
+ * front of a convolution in the second-order pass (through d/dx and through the style gradient d/da), so that one launch serves both. */
+GG_API int gg_axpby_rows_f32(const float* x1, const float* s1, const float* x2, const float* s2, float* y, int64_t rows, int64_t P,
+                      gg_stream_t stream);
+
 /* Number of kernels this library has launched since load (all streams); bench.py reports the delta. */
 GG_API int64_t gg_launch_count(void);
 

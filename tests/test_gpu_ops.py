@@ -354,11 +354,13 @@ def test_scaled_conv_first_and_second_order_gradients(ops, device, k, pad):
     a = torch.randn(N, I, generator=g) + 1.5; b = torch.rand(N, O, generator=g) + 0.5
     r = torch.randn(N, O, H + 2 * pad - k + 1, H + 2 * pad - k + 1, generator=g)
 
-    def run(conv, x, w, a, b, r):
+    def run(conv, x, w, a, b, r, full=False):
         ts = [t_.clone().requires_grad_(True) for t_ in (x, w, a, b)]
         y = conv(*ts)
         first = torch.autograd.grad((y * r).sum(), ts, create_graph=True)
         pen = first[2].square().sum() + first[0].square().mean()          # depends on d/da and d/dx
+        if full:                                                          # ... and on d/db and d/dw: every second-order node
+            pen = pen + 0.5 * first[3].square().sum() + 3.0 * first[1].square().sum()
         second = torch.autograd.grad(pen, ts, allow_unused=True)
         return y, first, second
 
@@ -371,6 +373,30 @@ def test_scaled_conv_first_and_second_order_gradients(ops, device, k, pad):
         assert_close(g1, r1, 5e-5, 'd' + name)
     for name, g2, r2 in zip('xwab', got[2], ref[2]):
         assert_close(g2, r2, 2e-4, 'second-order d' + name)
+    ref_conv = lambda x_, w_, a_, b_: torch.nn.functional.conv2d(x_ * a_[:, :, None, None], w_, padding=pad) * b_[:, :, None, None]
+    my_conv = lambda x_, w_, a_, b_: ops.conv2d_gradfix.conv2d_s1(x_, w_, padding=(pad, pad), in_scale=a_, out_scale=b_)
+    ref_full, got_full = run(ref_conv, x, w, a, b, r, full=True), run(my_conv, *dev, full=True)
+    for name, g2, r2 in zip('xwab', got_full[2], ref_full[2]):
+        assert_close(g2, r2, 2e-4, 'second-order (all four first-order gradients in the penalty) d' + name)
+    # the round-1 formulation of the second-order path (broadcast multiplies around the unscaled primitives) gives the same numbers
+    ops.conv2d_gradfix.closed_scaled_backward = False
+    try:
+        old_full = run(my_conv, *dev, full=True)
+    finally:
+        ops.conv2d_gradfix.closed_scaled_backward = True
+    for name, g2, r2 in zip('xwab', old_full[2], ref_full[2]):
+        assert_close(g2, r2, 2e-4, 'second-order, spelled-out formulation, d' + name)
+    # only one scale present (ToRGB: styles without demodulation)
+    for has_a, has_b in ((True, False), (False, True)):
+        rc = lambda x_, w_, a_, b_: (torch.nn.functional.conv2d(x_ * a_[:, :, None, None] if has_a else x_, w_, padding=pad)
+                                     * (b_[:, :, None, None] if has_b else 1.0)) + 0.0 * (a_.sum() + b_.sum())
+        mc = lambda x_, w_, a_, b_: ops.conv2d_gradfix.conv2d_s1(x_, w_, padding=(pad, pad), in_scale=(a_ if has_a else None),
+                                                                 out_scale=(b_ if has_b else None)) + 0.0 * (a_.sum() + b_.sum())
+        r1, g1 = run(rc, x, w, a, b, r, full=True), run(mc, *dev, full=True)
+        for name, gg, rr, like in zip('xwab', g1[2], r1[2], (x, w, a, b)):
+            gg = torch.zeros_like(like) if gg is None else gg           # (the absent scale: no second-order gradient on either side)
+            rr = torch.zeros_like(like) if rr is None else rr
+            assert_close(gg, rr, 2e-4, f'second-order with has_a={has_a} has_b={has_b} d' + name)
     # plain first-order backward (no create_graph) takes the fused kernels
     ts = [t_.clone().requires_grad_(True) for t_ in dev[:4]]
     y = ops.conv2d_gradfix.conv2d_s1(ts[0], ts[1], padding=(pad, pad), in_scale=ts[2], out_scale=ts[3])

@@ -128,6 +128,26 @@ def main():
              f'{total / 1000:.1f} ms of kernel time in {sum(v[0] for v in agg.values())} launches; wall clock of the same iteration without the profiler {wall_ms:.1f} ms']
     for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
         lines.append(f'{us / 1000:10.2f} ms {100 * us / total:5.1f}%  {n:6d}x  {name}')
+    # where does the GPU wait for the host?  gaps between consecutive kernels on the timeline, attributed to the kernel that follows
+    evs = sorted([(ev.time_range.start, ev.time_range.end, ev.name) for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA],
+                 key=lambda t: t[0])
+    gaps = collections.defaultdict(lambda: [0, 0.0])
+    idle, busy_end = 0.0, None
+    big = []
+    for st, en, name in evs:
+        if busy_end is not None and st > busy_end:
+            g = st - busy_end
+            idle += g
+            if g > 15:
+                key = name.replace('(anonymous namespace)::', '').replace('void ', '')[:70]
+                gaps[key][0] += 1; gaps[key][1] += g
+                big.append((g, key))
+        busy_end = en if busy_end is None else max(busy_end, en)
+    span = evs[-1][1] - evs[0][0]
+    lines.append(f'timeline: first kernel start -> last kernel end {span / 1000:.1f} ms, of which no kernel is running for {idle / 1000:.1f} ms; gaps > 15 us by the kernel that ends them:')
+    for key, (n, us) in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:14]:
+        lines.append(f'{us / 1000:10.2f} ms  {n:5d}x  before {key}')
+    lines.append('largest single gaps (us): ' + ', '.join(f'{g:.0f} [{k[:40]}]' for g, k in sorted(big, reverse=True)[:8]))
     text = '\n'.join(lines)
     print(text)
     if args.out:
