@@ -68,6 +68,8 @@ def parse_args():
     ap.add_argument('--sync-debug', action='store_true', help='debug: synchronise after every library call and name the call that faulted')
     ap.add_argument('--conv-family', type=int, default=1, help='A/B: 0 = the tile kernel serves every tcgen05 convolution (no marching kernel)')
     ap.add_argument('--fused-epilogue', action='store_true', help='A/B: bias / noise / activation in the conv store loop instead of a separate bias_act launch')
+    ap.add_argument('--spelled-out-second-order', action='store_true',
+                    help='A/B: the round-1 second-order path of the scaled convolution (broadcast multiplies around the unscaled kernels)')
     ap.add_argument('--reference-forwards', action='store_true', help="run the reference's forwards untouched (no fused callers)")
     ap.add_argument('--cpu-res', type=int, default=0, help='resolution of the CPU sample (0 = same as --res)')
     ap.add_argument('--cpu-batch', type=int, default=2)
@@ -351,6 +353,9 @@ def main():
     if args.fused_epilogue:
         from torch_utils.ops import conv2d_gradfix
         conv2d_gradfix.fuse_epilogue = True
+    if args.spelled_out_second_order:
+        from torch_utils.ops import conv2d_gradfix
+        conv2d_gradfix.closed_scaled_backward = False
 
     def barrier():
         if world > 1:

@@ -70,11 +70,14 @@ extern "C" GG_API int gg_watchdog_report(char* buf, int len) {
     unsigned long long* r = gg::watchdog_host_record();
     if (buf == nullptr || len <= 0) return 0;
     buf[0] = 0;
-    if (r == nullptr || r[0] != 0x57415443484447ull) return 0;
+    if (r == nullptr) return 0;
+    // layout written by mbar_watchdog (tc_common.cuh), 32-bit words: [0] = 0x5744 << 16 | kernel family, [2] = CTA, [3] = thread, [4] = barrier
+    const volatile unsigned int* w = reinterpret_cast<const volatile unsigned int*>(r);
+    if ((w[0] >> 16) != 0x5744u) return 0;
     static const char* const names[] = {"?", "conv_tc_kernel", "conv_march_kernel", "wgrad_tc_kernel", "wgrad_tma_kernel"};
-    const unsigned long long tag = r[1] < 5 ? r[1] : 0;
-    snprintf(buf, (size_t)len, "watchdog: %s CTA %llu thread %llu waited %.2f G cycles on the mbarrier at shared address 0x%llx", names[tag],
-             r[2] >> 32, r[2] & 0xffffffffull, (double)r[4] * 1e-9, r[3]);
+    const unsigned tag = (w[0] & 0xffffu) < 5 ? (w[0] & 0xffffu) : 0;
+    snprintf(buf, (size_t)len, "watchdog: %s CTA %u thread %u waited more than 8 G cycles on the mbarrier at shared address 0x%x", names[tag],
+             w[2], w[3], w[4]);
     return 1;
 }
 extern "C" GG_API int gg_set_conv_kernel_family(int family) { const int old = gg::g_march_enabled; gg::g_march_enabled = (family != 0); return old; }

@@ -237,3 +237,29 @@ def test_phase_major_dead_tap_mask_is_the_zero_pattern_of_the_weight(kind, k):
         n_dead += is_dead
     if k == 3:
         assert n_dead == 7 and abs(float(live) - 9.0 / 16.0) < 1e-12    # 9 of the 16 (phase, tap) blocks are live
+
+
+def test_tcgen05_kernels_keep_their_registers():
+    """The consumer warps of the tcgen05 kernels run at the 168-register cap that setmaxnreg gives them; a few bytes of spill stack in
+    those loops cost 11 % of the in-step convolution throughput once (round 2: a fatter watchdog expiry path inlined at every mbarrier
+    wait).  Every default instantiation must have a zero stack frame (the fused-epilogue <128,2> one is the known exception, off by
+    default).  Reads the objects `make` left in csrc/build with cuobjdump: no GPU needed."""
+    import shutil
+    import subprocess
+    build = os.path.join(PKG, 'csrc', 'build')
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    objs = [os.path.join(build, n + '.o') for n in ('conv_tc', 'conv_march', 'wgrad_tma', 'wgrad_tc')]
+    if not os.path.isfile(cuobjdump) or not all(os.path.isfile(o) for o in objs):
+        pytest.skip('cuobjdump or the object files are not available (run __graft_entry__.build() first)')
+    seen = 0
+    for obj in objs:
+        out = subprocess.run([cuobjdump, '--dump-resource-usage', obj], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
+        for name, regs, stack in re.findall(r'Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)', out):
+            if not re.search(r'conv_tc_kernel|conv_march_kernel|wgrad_tma_kernel|wgrad_tc_kernel', name):
+                continue
+            seen += 1
+            assert int(regs) <= 168, (name, regs)
+            if 'conv_tc_kernelILi128ELi2ELb1' in name:
+                continue
+            assert int(stack) == 0, f'{name} has a {stack}-byte stack frame: something in its loops spills'
+    assert seen >= 12, seen
