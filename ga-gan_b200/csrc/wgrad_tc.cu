@@ -130,7 +130,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
             constexpr uint32_t a_ks = 2 * (LBO_A >> 4), b_ks = 2 * (LBO_B >> 4);
             // The issue loop is scalar code of ONE thread: it is kept to a few dozen instructions per image row (ring positions
             // are masks / shifts of running counters), otherwise it -- not the tensor core -- sets the pace.
-            uint32_t gq = 0, xq = 0, sc = 0;        // running G-row, X-row and strip counters (ring positions)
+            // A converter group owns the tasks of one parity of the global task position (= X-ring position) and its own half of the
+            // G slots (slot = group + 2 * (its G-row count % (GS/2))): every EMPTY barrier has one waiting group, which meets the uses
+            // of a slot in program order (see wgrad_tma.cu for what happened when ownership flipped between the groups).
+            uint32_t gn0 = 0u, gn1 = 0u;            // G rows converted so far by group 0 / 1
+            uint32_t xq = 0, sc = 0;                // running X-row (= task) and strip counters
             const uint32_t g0_16 = (base + OFF_G) >> 4, x0_16 = (base + OFF_X) >> 4;
             const int per_tile_strips = p.ustrips;  // strip index -> row strip: (strip / ustrips) % rstrips
             for (int unit = unit_beg; unit < unit_end; ++unit) {
@@ -142,8 +146,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
                 const uint32_t d0 = tmem_base + buf * ACC_STRIDE;
                 for (int j = 0; j < K - 1; ++j) mbar_wait_spin(BAR_X_FULL((xq + j) & (XS - 1)), ((xq + j) / XS) & 1);
                 for (int i = 0; i < rows; ++i) {
-                    const uint32_t gslot = gq & (GS - 1), xlast = xq + K - 1;
-                    mbar_wait_spin(BAR_G_FULL(gslot), (gq / GS) & 1);
+                    const uint32_t xlast = xq + K - 1;
+                    const uint32_t og = xlast & 1u, gcount = og ? gn1 : gn0;                 // the group that converted this row's task
+                    const uint32_t gslot = og + 2u * (gcount % (GS / 2));
+                    mbar_wait_spin(BAR_G_FULL(gslot), (gcount / (GS / 2)) & 1);
                     mbar_wait_spin(BAR_X_FULL(xlast & (XS - 1)), (xlast / XS) & 1);          // X rows i .. i+K-2 were waited for earlier
                     tc_fence_after();
                     const uint64_t g_hi = a_word + (g0_16 + gslot * (G_SLOT >> 4)), g_lo = g_hi + (G_HALF >> 4);
@@ -167,7 +173,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
                     }
                     umma_commit(BAR_G_EMPTY(gslot));
                     umma_commit(BAR_X_EMPTY(xq & (XS - 1)));                           // X row i is not needed by later G rows
-                    ++gq; ++xq;
+                    gn0 += og ^ 1u; gn1 += og; ++xq;
                 }
                 for (int j = 0; j < K - 1; ++j) umma_commit(BAR_X_EMPTY((xq + j) & (XS - 1)));   // the strip's bottom halo rows
                 xq += K - 1;
@@ -281,10 +287,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
             *reinterpret_cast<float4*>(hi_addr + half_bytes) = l;
         };
         auto store_task = [&](const Cursor& t, const Regs& r) {
-            const uint32_t xslot = t.xc % XS, gslot = t.gc % GS;
+            const uint32_t xslot = t.xc % XS, gslot = (uint32_t)grp + 2u * (t.gc % (GS / 2));    // t.gc counts THIS GROUP's G rows
             const bool has_g = t.j >= K - 1;
             mbar_wait_spin(BAR_X_EMPTY(xslot), ((t.xc / XS) & 1) ^ 1);
-            if (has_g) mbar_wait_spin(BAR_G_EMPTY(gslot), ((t.gc / GS) & 1) ^ 1);
+            if (has_g) mbar_wait_spin(BAR_G_EMPTY(gslot), ((t.gc / (GS / 2)) & 1) ^ 1);
             uint8_t* xb = gbase + OFF_X + xslot * X_SLOT;
 #pragma unroll
             for (int k = 0; k < XI; ++k) {
@@ -361,22 +367,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgP p) {
         // Group g converts the local tasks j = g, g+2, ... of every unit; the ring positions follow from per-unit bases, so the
         // per-task bookkeeping is three adds.  The loads of task j+2 are issued right after task j has been published.
         Cursor C;
-        uint32_t xbase = 0, gbase = 0;                   // ring positions of the unit's first X row / G row
+        uint32_t xbase = 0, gn = 0;                      // ring position of the unit's first X row (= task); G rows this group has converted
         for (int unit = unit_beg; unit < unit_end; ++unit) {
             C.unit = unit;
             plan_unit(C);
             const int ntask = C.ntask;
             Regs R;
-            C.j = grp;
+            const int j0 = (int)((xbase ^ (uint32_t)grp) & 1u);       // the tasks whose GLOBAL position has this group's parity
+            C.j = j0;
             if (C.j < ntask) load_task(C, R);
-            for (int j = grp; j < ntask; j += 2) {
-                C.j = j; C.xc = xbase + (uint32_t)j; C.gc = gbase + (uint32_t)(j - (K - 1));
+            for (int j = j0; j < ntask; j += 2) {
+                C.j = j; C.xc = xbase + (uint32_t)j; C.gc = gn;
                 store_task(C, R);
+                if (j >= K - 1) ++gn;
                 C.j = j + 2;
                 if (C.j < ntask) load_task(C, R);
             }
             end_of_unit(unit, ntask - (K - 1));
-            xbase += (uint32_t)ntask; gbase += (uint32_t)(ntask - (K - 1));
+            xbase += (uint32_t)ntask;
         }
         if (pend) { drain(pend_sc, pend_rows); flush(decode_unit(pend_unit, p, NTA)); }
         tc_fence_before();

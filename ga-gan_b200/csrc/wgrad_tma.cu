@@ -181,7 +181,15 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
             const bool all_live = T.ky_live == (1u << K) - 1u;
             const uint64_t b_word = ((uint64_t)(8u | (1u << 14)) << 32) | ((uint64_t)(LBO_B >> 4) << 16);   // SBO 128 B, LBO
             constexpr uint32_t b_ks = 2 * (LBO_B >> 4);
-            uint32_t gq = 0, xq = 0, sc = 0;        // running G-row, X-row and strip counters (ring positions)
+            // Ring positions.  A converter GROUP owns the tasks of one parity of the global task position (= X-ring position), and
+            // with them: the X slots of that parity, and its own half of the G slots (slot = group + 2 * (its G-row count % (GS/2))).
+            // Every EMPTY barrier therefore has ONE waiting group, which meets the uses of a slot in program order.  (With the tasks
+            // dealt out by their index INSIDE a strip, slot ownership flipped between the groups whenever a strip had an odd number
+            // of tasks (K = 2) or of rows (HB = 16 n + 1): a group could then wait for release #u-1 of a slot before release #u-2 had
+            // happened, which an mbarrier parity wait cannot tell apart from success -- overwritten operands, and with the barrier
+            // over-arrived, launch failures.  Rare at 3 MMAs per product, immediate at 1.)
+            uint32_t gn0 = 0u, gn1 = 0u;            // G rows converted so far by group 0 / 1 (scalars: an indexed array would live on the stack)
+            uint32_t xq = 0, sc = 0;                // running X-row (= task) and strip counters
             const uint32_t x0_16 = (base + OFF_X) >> 4;
             const bool three = p.nprod == 3;
             for (int strip = strip_beg; strip < strip_end; ++strip) {
@@ -192,8 +200,11 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
                 const uint32_t d0 = tmem_base + buf * ACC_STRIDE;
                 for (int j = 0; j < K - 1; ++j) mbar_wait_spin(BAR_X_FULL((xq + j) & (XS - 1)), ((xq + j) / XS) & 1);
                 for (int i = 0; i < rows; ++i) {
-                    const uint32_t gslot = gq & (GS - 1), xlast = xq + K - 1, xfirst = xq & (XS - 1);
-                    mbar_wait_spin(BAR_G_FULL(gslot), (gq / GS) & 1);
+                    const uint32_t xlast = xq + K - 1, xfirst = xq & (XS - 1);
+                    const uint32_t og = xlast & 1u;                                          // the group that converted this row's task
+                    const uint32_t gcount = og ? gn1 : gn0;
+                    const uint32_t gslot = og + 2u * (gcount % (GS / 2));
+                    mbar_wait_spin(BAR_G_FULL(gslot), (gcount / (GS / 2)) & 1);
                     mbar_wait_spin(BAR_X_FULL(xlast & (XS - 1)), (xlast / XS) & 1);          // X rows i .. i+K-2 were waited for earlier
                     tc_fence_after();
                     const uint32_t g_hi = tmem_base + TM_G + gslot * 32, g_lo = g_hi + 16;   // columns: 16 pixels hi, 16 pixels lo
@@ -219,7 +230,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
                     }
                     umma_commit(BAR_G_EMPTY(gslot));
                     umma_commit(BAR_X_EMPTY(xfirst));                                  // X row i is not needed by later G rows
-                    ++gq; ++xq;
+                    gn0 += og ^ 1u; gn1 += og; ++xq;
                 }
                 for (int j = 0; j < K - 1; ++j) umma_commit(BAR_X_EMPTY((xq + j) & (XS - 1)));   // the strip's bottom halo rows
                 xq += K - 1;
@@ -342,7 +353,8 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
             }
         };
 
-        uint32_t sc = 0, tbase = 0, xbase = 0, gq0 = 0;   // strip counter; staging / X-ring / G-slot positions of the strip's first task
+        uint32_t sc = 0, tbase = 0, xbase = 0;             // strip counter; staging / X-ring positions of the strip's first task
+        uint32_t gn = 0;                                   // G rows this GROUP has converted (its own half of the G-slot ring)
         bool pend = false;
         int pend_rows = 0;
         uint32_t pend_sc = 0;
@@ -359,11 +371,11 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
                 const int bc = T.b0 + g_b;
                 gsc = (p.gs && bc < p.B) ? __ldg(p.gs + (size_t)s.n * p.B + bc) : 1.f;
             }
-            for (int j = grp; j < ntask; j += 2) {
+            for (int j = (int)((tbase ^ (uint32_t)grp) & 1u); j < ntask; j += 2) {     // the tasks whose GLOBAL position has this group's parity
                 const uint32_t tcn = tbase + (uint32_t)j, slot = tcn % ST;
                 const uint32_t xc = xbase + (uint32_t)j, xslot = xc & (XS - 1);
                 const bool has_g = j >= K - 1;
-                const uint32_t gc = gq0 + (uint32_t)(j - (K - 1)), gslot = gc & (GS - 1);
+                const uint32_t gslot = (uint32_t)grp + 2u * (gn % (GS / 2)), gphase = (gn / (GS / 2)) & 1u;
                 mbar_wait_block(BAR_STG_FULL(slot), (tcn / ST) & 1);
                 const uint8_t* stg = gbase + OFF_STG + slot * STG_SLOT;
                 float4 xv[XI];
@@ -405,7 +417,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
                         split_tf32(g[e] * gs_, h, l);
                         hi[e] = __float_as_uint(h); lo[e] = __float_as_uint(l);
                     }
-                    mbar_wait_block(BAR_G_EMPTY(gslot), ((gc / GS) & 1) ^ 1);
+                    mbar_wait_block(BAR_G_EMPTY(gslot), gphase ^ 1u);
                     tc_fence_after();
                     tmem_st16(g_taddr + gslot * 32, hi);
                     tmem_st16(g_taddr + gslot * 32 + 16, lo);
@@ -419,12 +431,13 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
                     mbar_arrive(BAR_X_FULL(xslot));
                     if (has_g) mbar_arrive(BAR_G_FULL(gslot));
                 }
+                if (has_g) ++gn;
             }
             // both groups drain their half of the accumulator columns of the strip that finished one strip earlier
             if (pend) drain(pend_sc, pend_rows);
             pend = true; pend_rows = s.rows; pend_sc = sc;
             ++sc;
-            tbase += (uint32_t)ntask; xbase += (uint32_t)ntask; gq0 += (uint32_t)s.rows;
+            tbase += (uint32_t)ntask; xbase += (uint32_t)ntask;
         }
         if (pend) { drain(pend_sc, pend_rows); flush(); }
         tc_fence_before();

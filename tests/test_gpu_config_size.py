@@ -265,6 +265,43 @@ def test_repeat_equality_of_the_layer_that_failed_once(ops, device):
     assert bad == [0, 0, 0], f'mismatching repetitions (forward, data gradient, weight gradient): {bad}'
 
 
+@pytest.mark.parametrize('form', ['up', 'down'])
+def test_weight_gradient_ring_ownership_regression(ops, device, form):
+    """The bug behind the rare `unspecified launch failure`s of rounds 1 and 2 (and the one failure of the layer above): the two
+    converter groups of the weight-gradient kernels dealt the row tasks out by their index INSIDE a strip, so whenever a strip had an
+    odd number of tasks (2x2 taps) or rows (heights 16 n + 1: the phase-major up-sampling layers) the ownership of the operand ring
+    slots flipped between the groups, and a group could wait for release #u-1 of a slot before release #u-2 had happened -- which an
+    mbarrier parity wait reports as success.  Overwritten operands, over-arrived barriers; rare with three MMAs per product, immediate
+    with one.  The one-product mode is therefore the sensitive probe: 12 launches of the two 2x2 forms at the sizes that failed must
+    agree with each other to 2e-6 and with the 3xTF32 result to the tf32 rounding level."""
+    co = ops.custom_ops
+    plugin = co.get_plugin('conv2d_plugin')
+    cr = ops.conv2d_resample
+    g = torch.Generator(device=device).manual_seed(3)
+    n = 8
+    if form == 'up':
+        a = torch.randn(n, 64, 512, 512, device=device, generator=g); b = torch.randn(n, 128, 513, 516, device=device, generator=g)
+        kw = dict(padding=(1, 1), pm=cr._pm_live('up', 3, 3).pm, flip_w=True, out_layout=1)
+    else:
+        a = torch.randn(n, 128, 513, 516, device=device, generator=g); b = torch.randn(n, 64, 512, 512, device=device, generator=g)
+        kw = dict(padding=(0, 0), pm=cr._pm_live('down', 3, 3).pm)
+    ref = plugin.conv2d_wgrad(a, b, (2, 2), prec=co.PREC_AUTO, **kw)
+    assert plugin.last_wgrad_prec == co.PREC_TF32X3
+    scale = float(ref.abs().max())
+    first = None
+    for rep in range(12):
+        dw = plugin.conv2d_wgrad(a, b, (2, 2), prec=co.PREC_AUTO_FAST, **kw)
+        if rep % 2 == 0:
+            torch.cuda.synchronize()                        # both launch patterns: isolated and back to back
+        first = dw if first is None else first
+        assert float((dw - first).abs().max()) <= 2e-6 * scale, f'{form}: launch {rep} differs from the first one'
+        assert float((dw - ref).abs().max()) <= 2e-3 * scale, f'{form}: launch {rep} is off the 3xTF32 result'
+    for rep in range(12):                                   # and the fp32-faithful mode stays put as well
+        dw = plugin.conv2d_wgrad(a, b, (2, 2), prec=co.PREC_AUTO, **kw)
+        assert float((dw - ref).abs().max()) <= 2e-6 * scale
+    torch.cuda.synchronize()
+
+
 # ------------------------------------------------------------------------------------------------ fma on the device
 def test_fma_forward_and_broadcast_gradients_on_the_device(ops, device):
     g = torch.Generator().manual_seed(1)
