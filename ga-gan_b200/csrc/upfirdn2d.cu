@@ -214,15 +214,28 @@ struct StreamP {
     int ipH, ipW, opH, opW;                     // phase-major plane sizes (LAYOUT 1 / 2)
     int RS, ncg, nst;                           // rows per strip, 8-column groups per row, strips per plane
     int vec_in;                                 // plain input rows are 16-byte aligned (width % 4 == 0): 128-bit loads, else scalar
+    int vec_out;                                // plain output rows are 16-byte aligned: 128-bit stores
 };
 
-template <int LAYOUT, int PX0, bool SEP>
+// STG (plain -> plain only): rows that are not 16-byte multiples (the reference-shaped (2r+1)^2 maps) are exchanged through a
+// per-warp shared-memory buffer so that every global access of the warp is one contiguous 128-byte segment: the warp loads its
+// 288-column window of an input row with nine coalesced instructions and hands each lane its 16 columns, and the eight outputs per
+// lane are written back as eight coalesced row segments (through per-lane row pointers, so the lanes of a warp may sit on different
+// rows).  Every lane runs RS + 3 steps whatever its strip (full-mask __syncwarp); for the input window the launch also pads the
+// column groups of a row to a multiple of 32, so that a warp's lanes share one row.
+struct StageBuf { float* v; float** ptr; int* nv; };           // per warp: 288 floats, 32 row pointers, 32 valid counts
+
+template <int LAYOUT, int PX0, bool SEP, bool STG>
 __device__ __forceinline__ void fir_march(const StreamP& p, const float (&K)[4][4], const float (&fx)[4], const float (&fy)[4],
-                                          int x0, int y0, int n, int c) {
+                                          int x0, int y0, int n, int c, const StageBuf sb) {
     constexpr bool IN_PM = LAYOUT == 1, OUT_PM = LAYOUT == 2;
+    static_assert(!STG || LAYOUT == 0, "the staged row exchange serves the plain -> plain layout");
+    const int lane = threadIdx.x & 31;
+    const bool raw_rows = STG && !p.vec_in;                     // rows travel as the warp's coalesced window (slots 0..8 of the row buffer)
     const int fullH = OUT_PM ? 2 * p.opH : p.outH;
     const int nrows = min(p.RS, fullH - y0);
-    const int nt = nrows + 3;                                   // input rows this strip touches
+    const int nt = (STG ? p.RS : nrows) + 3;                    // input rows this strip touches (STG: the same count in every lane of a warp,
+                                                                // whatever strip it works on -- rows beyond the image load zeros and store nothing)
     const int rbase = y0 - p.pady0;                             // logical input row of step 0
     const int pitch = IN_PM ? p.ipW : p.inW;
     const size_t iplane = IN_PM ? (size_t)p.ipH * p.ipW : (size_t)p.inH * p.inW;
@@ -233,7 +246,16 @@ __device__ __forceinline__ void fir_march(const StreamP& p, const float (&K)[4][
     auto load_row = [&](int rr, float (&in)[11]) {
         const int r = rbase + rr;
         const bool row_ok = (unsigned)r < (unsigned)p.inH;
-        if (!IN_PM) {
+        if (STG && raw_rows) {
+            const float* roww = xin + (size_t)(row_ok ? r : 0) * pitch;
+            const int w0 = x0 - 8 * lane - 4;                    // first column of the warp's window
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                const int col = w0 + 32 * i + lane;
+                in[i] = (row_ok && col >= 0 && col < p.inW) ? __ldg(roww + col) : 0.f;
+            }
+            in[9] = 0.f; in[10] = 0.f;
+        } else if (!IN_PM) {
             const float* rowp = xin + (size_t)(row_ok ? r : 0) * pitch + x0;
             float buf[16];                                       // columns x0-4 .. x0+11
 #pragma unroll
@@ -304,6 +326,19 @@ __device__ __forceinline__ void fir_march(const StreamP& p, const float (&K)[4][
             float* base = yout + (size_t)((y & 1) * 2) * p.C * oplane + (size_t)(y >> 1) * p.opW + (x0 >> 1);
             *reinterpret_cast<float4*>(base) = make_float4(v[0], v[2], v[4], v[6]);
             *reinterpret_cast<float4*>(base + (size_t)p.C * oplane) = make_float4(v[1], v[3], v[5], v[7]);
+        } else if (STG && !p.vec_out) {
+            const int nv = y < p.outH ? min(8, max(0, p.outW - x0)) : 0;
+            *reinterpret_cast<float4*>(sb.v + 8 * lane) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(sb.v + 8 * lane + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            sb.ptr[lane] = yout + (size_t)y * p.outW + x0;       // (only dereferenced for the nv valid columns)
+            sb.nv[lane] = nv;
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int e = 32 * t + lane, src = e >> 3, k = e & 7;
+                if (k < sb.nv[src]) sb.ptr[src][k] = sb.v[e];
+            }
+            __syncwarp();
         } else {
             if (y >= p.outH) return;
             float* dst = yout + (size_t)y * p.outW + x0;
@@ -352,26 +387,52 @@ __device__ __forceinline__ void fir_march(const StreamP& p, const float (&K)[4][
         if (rr >= 3) store_row(y0 + rr - 3, o);
     };
 
+    // a row buffer holds either the lane's 11 columns or (raw_rows) the lane's 9 elements of the warp's window: exchange first
+    auto consume = [&](int rr, const float (&buf)[11]) {
+        if (STG && raw_rows) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) sb.v[32 * i + lane] = buf[i];
+            __syncwarp();
+            float w16[16];                                       // window columns 8 lane .. 8 lane + 15 = image columns x0 - 4 .. x0 + 11
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(sb.v + 8 * lane + 4 * q4);
+                w16[4 * q4] = t4.x; w16[4 * q4 + 1] = t4.y; w16[4 * q4 + 2] = t4.z; w16[4 * q4 + 3] = t4.w;
+            }
+            __syncwarp();
+            float in[11];
+#pragma unroll
+            for (int j = 0; j < 11; ++j) in[j] = w16[4 - PX0 + j];
+            step(rr, in);
+        } else {
+            step(rr, buf);
+        }
+    };
     float r0[11], r1[11], r2[11];
     load_row(0, r0);
     load_row(1, r1);
     for (int rr = 0; rr < nt; rr += 3) {
         if (rr + 2 < nt) load_row(rr + 2, r2);
-        step(rr, r0);
+        consume(rr, r0);
         if (rr + 1 < nt) {
             if (rr + 3 < nt) load_row(rr + 3, r0);
-            step(rr + 1, r1);
+            consume(rr + 1, r1);
         }
         if (rr + 2 < nt) {
             if (rr + 4 < nt) load_row(rr + 4, r1);
-            step(rr + 2, r2);
+            consume(rr + 2, r2);
         }
     }
 }
 
-template <int LAYOUT, int PX0>
+template <int LAYOUT, int PX0, bool STG>
 __global__ void __launch_bounds__(128, 4) fir_stream(StreamP p) {
     __shared__ float sK[16];
+    __shared__ __align__(16) float s_stage[STG ? 4 * 288 : 1];
+    __shared__ float* s_ptr[STG ? 128 : 1];
+    __shared__ int s_nv[STG ? 128 : 1];
+    const int warp_ = threadIdx.x >> 5;
+    const StageBuf sb{s_stage + (STG ? warp_ * 288 : 0), s_ptr + (STG ? warp_ * 32 : 0), s_nv + (STG ? warp_ * 32 : 0)};
     if (threadIdx.x < 16) {
         int ky = threadIdx.x >> 2, kx = threadIdx.x & 3;
         int sy = p.flip ? ky : 3 - ky, sx = p.flip ? kx : 3 - kx;
@@ -400,10 +461,14 @@ __global__ void __launch_bounds__(128, 4) fir_stream(StreamP p) {
     const long long r = id / p.ncg;
     const int st = (int)(r % p.nst);
     const long long nc = r / p.nst;
-    if (nc >= (long long)p.N * p.C) return;
-    const int n = (int)(nc / p.C), c = (int)(nc - (long long)n * p.C);
-    if (separable) fir_march<LAYOUT, PX0, true>(p, K, fx, fy, cg * 8, st * p.RS, n, c);
-    else fir_march<LAYOUT, PX0, false>(p, K, fx, fy, cg * 8, st * p.RS, n, c);
+    const bool past_end = nc >= (long long)p.N * p.C;
+    if (!STG && past_end) return;
+    // STG: the lanes of the grid's last warp that have no work stay for the warp-wide exchanges, parked on a column beyond both images
+    // (every load is out of range and reads as zero, every store has zero valid columns)
+    const int n = past_end ? 0 : (int)(nc / p.C), c = past_end ? 0 : (int)(nc - (long long)n * p.C);
+    const int x0 = past_end ? ((max(p.inW, p.outW) + 31) / 8 * 8 + 64) : cg * 8;
+    if (separable) fir_march<LAYOUT, PX0, true, STG>(p, K, fx, fy, x0, st * p.RS, n, c, sb);
+    else fir_march<LAYOUT, PX0, false, STG>(p, K, fx, fy, x0, st * p.RS, n, c, sb);
 }
 
 template <int LAYOUT, int PX0>
@@ -411,12 +476,26 @@ int launch_stream2(StreamP p, cudaStream_t st) {
     const int fullW = LAYOUT == 2 ? 2 * p.opW : p.outW, fullH = LAYOUT == 2 ? 2 * p.opH : p.outH;
     p.RS = fullH >= 128 ? 32 : (fullH >= 32 ? 16 : 8);
     p.vec_in = (LAYOUT != 1 && p.inW % 4 == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0) ? 1 : 0;
+    p.vec_out = (LAYOUT == 2 || (p.outW % 4 == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0)) ? 1 : 0;
     p.ncg = (fullW + 7) / 8;
     p.nst = (fullH + p.RS - 1) / p.RS;
+    // plain -> plain with unaligned rows on either side, wide enough that padding the column groups to whole warps is cheap
+    // (measured, N = 8: the input window pays from 257 columns on -- 57 -> 69 % of the HBM peak, 67 -> 79 % at 1025 --, the output
+    // exchange from 513 on -- 51 -> 55 %, 60 % at 1025 -- and costs a little at 257)
+    const bool staged = LAYOUT == 0 && ((!p.vec_in && fullW >= 96) || (!p.vec_out && fullW >= 384));
+    // the coalesced input window needs the lanes of a warp on ONE row (column groups padded to whole warps); the output exchange works
+    // lane by lane and needs no padding
+    if (staged && !p.vec_in) p.ncg = (p.ncg + 31) / 32 * 32;
     const long long threads = (long long)p.ncg * p.nst * p.N * p.C;
     const long long blocks = (threads + 127) / 128;
     if (blocks > 0x7fffffffLL) { gg::set_error("upfirdn2d: grid too large"); return GG_EINVAL; }
-    fir_stream<LAYOUT, PX0><<<(unsigned)blocks, 128, 0, st>>>(p);
+    if constexpr (LAYOUT == 0) {
+        if (staged) {
+            fir_stream<0, PX0, true><<<(unsigned)blocks, 128, 0, st>>>(p);
+            return gg::check_launch("upfirdn2d(fir_stream, staged rows)");
+        }
+    }
+    fir_stream<LAYOUT, PX0, false><<<(unsigned)blocks, 128, 0, st>>>(p);
     return gg::check_launch("upfirdn2d(fir_stream)");
 }
 
@@ -655,7 +734,7 @@ extern "C" GG_API int gg_upfirdn2d_f32(const float* x, const float* f, float* y,
     const bool f4m = (fH == 4 && fW == 4) && upx == upy && downx == downy && outW >= 8;
     const bool f4 = f4m && outW >= 48;
     if (f4m && upx == 1 && downx == 1) {   // unit rate: the register-streaming kernel (also serves the phase-major layouts)
-        StreamP sp{x, f, y, N, C, inH, inW, padx0, pady0, flip, gain, outH, outW, 0, 0, 0, 0, 0, 0, 0, 0};
+        StreamP sp{x, f, y, N, C, inH, inW, padx0, pady0, flip, gain, outH, outW, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         if (stream_ok(sp, false)) return launch_stream<0>(sp, st);
         if (f4) return launch_tile<1, 1, 0, 4, 4>(p, st);
     }
@@ -695,7 +774,7 @@ extern "C" GG_API int gg_fir4_pm_f32(const float* x, const float* f, float* y, i
     GG_REQUIRE((int64_t)N * C * (in_pm ? 4LL * in_pmH * in_pmW : (int64_t)inH * inW) <= 0x7fffffffLL &&
                (int64_t)N * C * (out_pm ? 4LL * out_pmH * out_pmW : (int64_t)outH * outW) <= 0x7fffffffLL, "fir4_pm: tensor is too large");
     if (N == 0) return GG_OK;
-    StreamP p{x, f, y, N, C, inH, inW, padx0, pady0, flip, gain, outH, outW, in_pmH, in_pmW, out_pmH, out_pmW, 0, 0, 0, 0};
+    StreamP p{x, f, y, N, C, inH, inW, padx0, pady0, flip, gain, outH, outW, in_pmH, in_pmW, out_pmH, out_pmW, 0, 0, 0, 0, 0};
     cudaStream_t st = (cudaStream_t)stream;
     GG_REQUIRE(stream_ok(p, in_pm != 0), "fir4_pm: needs 0 <= padx0 <= 3 and, for a phase-major input, 16-byte aligned rows (width %% 4 == 0)");
     if (in_pm) return launch_stream<1>(p, st);
