@@ -480,9 +480,11 @@ int launch_stream2(StreamP p, cudaStream_t st) {
     p.ncg = (fullW + 7) / 8;
     p.nst = (fullH + p.RS - 1) / p.RS;
     // plain -> plain with unaligned rows on either side, wide enough that padding the column groups to whole warps is cheap
-    // (measured, N = 8: the input window pays from 257 columns on -- 57 -> 69 % of the HBM peak, 67 -> 79 % at 1025 --, the output
+    // (measured: the input window pays from 257 columns on -- 57 -> 69 % of the HBM peak at N = 8, 67 -> 79 % at 1025 --, the output
     // exchange from 513 on -- 51 -> 55 %, 60 % at 1025 -- and costs a little at 257)
-    const bool staged = LAYOUT == 0 && ((!p.vec_in && fullW >= 96) || (!p.vec_out && fullW >= 384));
+    // Below 256 output columns a row has fewer than 32 column groups and the padding idles up to half of every warp (129 -> 128
+    // columns: 63 -> 43 %): those stay on the per-lane scalar loads.
+    const bool staged = LAYOUT == 0 && ((!p.vec_in && fullW >= 256) || (!p.vec_out && fullW >= 384));
     // the coalesced input window needs the lanes of a warp on ONE row (column groups padded to whole warps); the output exchange works
     // lane by lane and needs no padding
     if (staged && !p.vec_in) p.ncg = (p.ncg + 31) / 32 * 32;
