@@ -263,3 +263,50 @@ def test_tcgen05_kernels_keep_their_registers():
                 continue
             assert int(stack) == 0, f'{name} has a {stack}-byte stack frame: something in its loops spills'
     assert seen >= 12, seen
+
+
+@pytest.mark.parametrize('K,rows_per_strip', [(2, [16] * 5), (2, [16, 16, 1, 16, 16, 1]), (3, [16] * 4), (3, [16, 16, 1, 16, 7]), (1, [16, 3, 16])])
+def test_weight_gradient_ring_indexing_keeps_one_owner_per_slot(K, rows_per_strip):
+    """Model of the ring arithmetic of wgrad_tma.cu / wgrad_tc.cu (the converter groups and the MMA issuer derive slot and mbarrier
+    phase from running counters): every X slot and every G slot must be filled by ONE converter group for the whole kernel, each group
+    must meet the uses of its slots in order, and the issuer must look for every row where its converter put it.  The round-1 / round-2
+    kernels dealt tasks out by their index inside a strip; with an odd number of tasks (K = 2) or rows (16 n + 1) per strip slot
+    ownership flipped between the groups, a parity wait could pass one release early, and launches failed now and then."""
+    XS, GS = 8, 4
+    conv = {0: [], 1: []}                                   # per group: (kind, slot, use) in program order
+    x_owner, g_owner = {}, {}
+    tbase, gn = 0, [0, 0]
+    g_of_row = []                                           # converter view: (slot, phase) of every G row in image order
+    for rows in rows_per_strip:
+        ntask = rows + K - 1
+        placed = {}
+        for grp in (0, 1):
+            for j in range((tbase ^ grp) & 1, ntask, 2):
+                pos = tbase + j
+                xslot = pos % XS
+                assert x_owner.setdefault(xslot, grp) == grp, 'an X slot changed hands'
+                conv[grp].append(('x', xslot, pos // XS))
+                if j >= K - 1:
+                    gslot, phase = grp + 2 * (gn[grp] % (GS // 2)), (gn[grp] // (GS // 2)) & 1
+                    assert g_owner.setdefault(gslot, grp) == grp, 'a G slot changed hands'
+                    conv[grp].append(('g', gslot, gn[grp] // (GS // 2)))
+                    placed[j - (K - 1)] = (gslot, phase)
+                    gn[grp] += 1
+        g_of_row += [placed[i] for i in range(rows)]
+        tbase += ntask
+    # a group's uses of one slot come in order 0, 1, 2, ... (so "release #u-1" is always awaited after "release #u-2" was seen)
+    for grp, seq in conv.items():
+        last = {}
+        for kind, slot, use in seq:
+            assert use == last.get((kind, slot), -1) + 1, (grp, kind, slot, use)
+            last[(kind, slot)] = use
+    # the issuer: one row at a time, group = parity of the row's task position, per-group counters
+    xq, cnt, seen = 0, [0, 0], []
+    for rows in rows_per_strip:
+        for _ in range(rows):
+            og = (xq + K - 1) & 1
+            seen.append((og + 2 * (cnt[og] % (GS // 2)), (cnt[og] // (GS // 2)) & 1))
+            cnt[og] += 1
+            xq += 1
+        xq += K - 1
+    assert seen == g_of_row
