@@ -90,7 +90,7 @@ def evaluate_population(G, D, population, z, c=None, rank=0, world=1, fitness_fn
     after an eager warm-up and replayed for every other individual -- only the offsets (device tensors, updated in place between
     replays) change -- and the captured graph is kept for the next call with the same networks and latent shape (the next
     generation), so its ~0.1 s capture is paid once.  The same kernels run either way and the results are identical (measured:
-    82 -> 97 individuals/s at 256^2 paper256, batch 8, one B200; tools/ga_bench.py).
+    82 -> 97 individuals/s at 256^2 paper256, batch 8, one B200; `bench.py --workload ga`).
     """
     fitness_fn = fitness_fn or default_fitness
     device = z.device
