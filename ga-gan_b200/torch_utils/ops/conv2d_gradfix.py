@@ -236,12 +236,16 @@ def _scaled_conv2d_s1(weight_shape, padding, out_hw, io, flip, live, pm, has_a, 
             return _conv2d_s1(weight_shape, pad, hw, io_, flip_, live, pm).apply(t, w_)
         return _scaled_conv2d_s1(weight_shape, pad, hw, io_, flip_, live, pm, True, False).apply(t, w_, s_in, None)
 
-    def partial_grads(expr_fn, inputs, need, g):
-        # third and higher order: differentiate the spelled-out expression with autograd
+    def partial_grads(outputs_fn, grad_outputs, inputs, need):
+        # third and higher order: the vector-Jacobian product of the spelled-out expressions, by autograd.  The incoming gradients go in
+        # as `grad_outputs` (cotangents), NOT as factors of a scalar: they depend on the inputs themselves through this very node, and
+        # differentiating a scalar that contains them would count that path again (3x on a squared-gradient penalty).
         with torch.enable_grad():
-            expr = expr_fn()
+            outs = outputs_fn()
+            pairs = [(o, go) for o, go in zip(outs, grad_outputs) if go is not None]
             idx = [i for i, t in enumerate(inputs) if need[i] and t is not None and t.requires_grad]
-            got = torch.autograd.grad(expr, [inputs[i] for i in idx], g, create_graph=True, allow_unused=True) if idx else ()
+            got = torch.autograd.grad([o for o, _ in pairs], [inputs[i] for i in idx], [go for _, go in pairs],
+                                      create_graph=True, allow_unused=True) if (idx and pairs) else ()
         out = [None] * len(inputs)
         for i, v in zip(idx, got):
             out[i] = v
@@ -319,15 +323,10 @@ def _scaled_conv2d_s1(weight_shape, padding, out_hw, io, flip, live, pm, has_a, 
             if gg is None and g is None:
                 return None, None, None, None, None
             if torch.is_grad_enabled():
-                def expr():
+                def outputs():
                     u = unscaled_or_scaled(dpad, hw_of(x), not io, not flip, dy, w, b0)
-                    e = 0.0
-                    if gg is not None:
-                        e = e + (gg * (u * a[:, :, None, None] if a is not None else u)).sum()
-                    if g is not None:
-                        e = e + (g * (x * u).sum([2, 3])).sum()
-                    return e
-                g_dy, g_w, g_a, g_x = partial_grads(expr, [dy, w, a, x], need, None)
+                    return [u * a[:, :, None, None] if a is not None else u, (x * u).sum([2, 3])]
+                g_dy, g_w, g_a, g_x = partial_grads(outputs, [gg, g], [dy, w, a, x], need)
                 return g_dy, g_w, g_a, g_x, None
             g_dy = g_w = g_a = g_x = None
             # e = the gradient that arrives at u, as a conv INPUT:  a * gg (through dx)  +  g * x (through da)

@@ -1,0 +1,56 @@
+"""A torch (CPU, any dtype) stand-in for the conv2d_plugin object, for testing the AUTOGRAD ALGEBRA of
+ga-gan_b200/torch_utils/ops/conv2d_gradfix.py without a GPU: same call signatures and semantics as custom_ops._Plugin
+(include/gagan_b200.h: gg_conv2d_f32 with stride-1 free-extent outputs, gg_conv2d_wgrad_f32, gg_chan_dot_f32, gg_scale_rows_f32,
+gg_axpby_rows_f32), written with plain torch ops.  Test infrastructure only: nothing in the product imports it."""
+import torch
+import torch.nn.functional as F
+
+
+def _bc(s):
+    return s[:, :, None, None]
+
+
+class FakePlugin:
+    last_conv_prec = 0
+    last_wgrad_prec = 0
+
+    def conv2d(self, x, w, stride=1, padding=(0, 0), transposed=False, output_padding=(0, 0), flip_w=False, in_scale=None, out_scale=None,
+               prec=None, out_hw=None, flop_scale=1.0, epilogue=None):
+        assert stride == 1 and epilogue is None
+        kh, kw = int(w.shape[2]), int(w.shape[3])
+        if transposed:                       # conv_transpose2d(x, w[I,O], padding=p) == correlation with w^T flipped, padding k-1-p
+            v, fl, py, px = w.transpose(0, 1), not flip_w, kh - 1 - padding[0], kw - 1 - padding[1]
+        else:
+            v, fl, py, px = w, flip_w, padding[0], padding[1]
+        if fl:
+            v = v.flip([2, 3])
+        xs = x * _bc(in_scale) if in_scale is not None else x
+        H, W = int(x.shape[2]), int(x.shape[3])
+        OH, OW = (int(out_hw[0]), int(out_hw[1])) if out_hw is not None else (H + 2 * py - kh + 1, W + 2 * px - kw + 1)
+        pb, pr = OH + kh - 1 - py - H, OW + kw - 1 - px - W          # rows / columns of zeros (or cropping, if negative) below / right
+        y = F.conv2d(F.pad(xs, (px, pr, py, pb)), v)
+        assert tuple(y.shape[2:]) == (OH, OW)
+        return y * _bc(out_scale) if out_scale is not None else y
+
+    def conv2d_wgrad(self, a, b, kernel_size, stride=1, padding=(0, 0), flip_w=False, out_layout=0, a_scale=None, b_scale=None, prec=None,
+                     flop_scale=1.0, pm=None):
+        assert stride == 1
+        kh, kw = kernel_size
+        a_s = a * _bc(a_scale) if a_scale is not None else a
+        b_s = b * _bc(b_scale) if b_scale is not None else b
+        HA, WA, HB, WB = int(a.shape[2]), int(a.shape[3]), int(b.shape[2]), int(b.shape[3])
+        ap = F.pad(a_s, (padding[1], WB + kw - 1 - padding[1] - WA, padding[0], HB + kh - 1 - padding[0] - HA))
+        dw = torch.stack([torch.stack([torch.einsum('noyx,niyx->oi', b_s, ap[:, :, ky:ky + HB, kx:kx + WB]) for kx in range(kw)], dim=-1)
+                          for ky in range(kh)], dim=-2)              # [B, A, kh, kw]
+        if flip_w:
+            dw = dw.flip([2, 3])
+        return dw.transpose(0, 1).contiguous() if out_layout else dw
+
+    def chan_dot(self, a, b):
+        return (a * b).flatten(2).sum(-1)
+
+    def scale_rows(self, x, s):
+        return x * _bc(s)
+
+    def axpby_rows(self, x1, s1, x2, s2):
+        return x1 * _bc(s1) + x2 * _bc(s2)

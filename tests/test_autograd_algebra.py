@@ -1,0 +1,95 @@
+"""CPU tests of the autograd algebra of conv2d_gradfix (first, second and third order) with the kernels replaced by a torch stand-in
+(tests/fake_plugin.py) in fp64: every node's backward formula is checked against autograd over the plain torch expression
+y = b * conv(a * x, w).  The kernels themselves are tested on the GPU (test_gpu_ops.py); this file pins the calculus."""
+import itertools
+import numpy as np
+import pytest
+import torch
+
+import tests.util  # noqa: F401  (installs the operator modules)
+from tests.fake_plugin import FakePlugin
+from torch_utils.ops import conv2d_gradfix as cg
+
+
+@pytest.fixture()
+def fake_plugin():
+    old = cg._plugin
+    cg._plugin = FakePlugin()
+    yield cg._plugin
+    cg._plugin = old
+
+
+def _ref(x, w, a, b, pad, io, flip):
+    v = w.transpose(0, 1) if io else w
+    if flip:
+        v = v.flip([2, 3])
+    xs = x * a[:, :, None, None] if a is not None else x
+    y = torch.nn.functional.conv2d(xs, v, padding=pad)
+    return y * b[:, :, None, None] if b is not None else y
+
+
+def _mine(x, w, a, b, pad, io, flip):
+    kh, kw = int(w.shape[2]), int(w.shape[3])
+    out_hw = (int(x.shape[2]) + 2 * pad - kh + 1, int(x.shape[3]) + 2 * pad - kw + 1)
+    if a is None and b is None:
+        return cg._conv2d_s1(tuple(w.shape), (pad, pad), out_hw, io, flip).apply(x, w)
+    return cg._scaled_conv2d_s1(tuple(w.shape), (pad, pad), out_hw, io, flip, 1.0, None, a is not None, b is not None).apply(x, w, a, b)
+
+
+def _orders(conv, x, w, a, b, r, which, closed=True):
+    cg.closed_scaled_backward = closed
+    try:
+        ts = [t.clone().requires_grad_(True) if t is not None else None for t in (x, w, a, b)]
+        live = [t for t in ts if t is not None]
+        y = conv(*ts)
+        first = torch.autograd.grad((y * r).sum(), live, create_graph=True)
+        pen = sum(first[i].square().sum() * (1.0 + 0.3 * i) for i in which if i < len(first))
+        second = torch.autograd.grad(pen, live, create_graph=True, allow_unused=True)
+        pen2 = sum(s.square().sum() for s in second if s is not None)
+        third = torch.autograd.grad(pen2, live, allow_unused=True, retain_graph=True)
+        second_plain = torch.autograd.grad(pen, live, allow_unused=True)          # the non-create_graph route (fused nodes)
+        return y, first, second, third, second_plain
+    finally:
+        cg.closed_scaled_backward = True
+
+
+def _close(u, v, tol, what):
+    if u is None or v is None:
+        assert (u is None or float(u.abs().max()) == 0) and (v is None or float(v.abs().max()) == 0), what + ': one side has no gradient'
+        return
+    err = float((u - v).abs().max()) / max(float(v.abs().max()), 1e-300)
+    assert err <= tol, f'{what}: max-rel-err {err:.3e}'
+
+
+@pytest.mark.parametrize('k,pad,io,flip', [(3, 1, False, False), (3, 1, True, True), (2, 1, False, True), (1, 0, False, False), (2, 0, True, False)])
+@pytest.mark.parametrize('scales', ['ab', 'a', 'b'])
+def test_scaled_conv_calculus_up_to_third_order(fake_plugin, k, pad, io, flip, scales):
+    g = torch.Generator().manual_seed(5 + k)
+    N, I, O, H = 2, 4, 3, 6
+    x = torch.randn(N, I, H, H, generator=g, dtype=torch.float64)
+    w = torch.randn(*((I, O) if io else (O, I)), k, k, generator=g, dtype=torch.float64) / np.sqrt(I * k * k)
+    a = (torch.randn(N, I, generator=g, dtype=torch.float64) + 1.5) if 'a' in scales else None
+    b = (torch.rand(N, O, generator=g, dtype=torch.float64) + 0.5) if 'b' in scales else None
+    r = torch.randn(N, O, H + 2 * pad - k + 1, H + 2 * pad - k + 1, generator=g, dtype=torch.float64)
+    n_in = 2 + len(scales)
+    for which in [[0], [1], list(range(n_in))] + ([[2]] if n_in > 2 else []) + ([[3]] if n_in > 3 else []):
+        want = _orders(lambda *t: _ref(*t, pad, io, flip), x, w, a, b, r, which)
+        for closed in (True, False):
+            got = _orders(lambda *t: _mine(*t, pad, io, flip), x, w, a, b, r, which, closed=closed)
+            tag = f'k{k} pad{pad} io{io} flip{flip} scales={scales} penalty on {which} closed={closed}'
+            _close(got[0], want[0], 1e-12, tag + ' y')
+            for lvl, name in ((1, 'first'), (2, 'second (create_graph)'), (3, 'third'), (4, 'second')):
+                for c, u, v in zip('xwab'[:2] + scales, got[lvl], want[lvl]):
+                    _close(u, v, 1e-9, f'{tag}: {name} d{c}')
+
+
+def test_unscaled_conv_calculus_up_to_third_order(fake_plugin):
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 3, 5, 5, generator=g, dtype=torch.float64); w = torch.randn(4, 3, 3, 3, generator=g, dtype=torch.float64) * 0.3
+    r = torch.randn(2, 4, 5, 5, generator=g, dtype=torch.float64)
+    for which in ([0], [1], [0, 1]):
+        want = _orders(lambda *t: _ref(*t, 1, False, False), x, w, None, None, r, which)
+        got = _orders(lambda *t: _mine(*t, 1, False, False), x, w, None, None, r, which)
+        for lvl in (1, 2, 3, 4):
+            for c, u, v in zip('xw', got[lvl], want[lvl]):
+                _close(u, v, 1e-9, f'unscaled, penalty on {which}, level {lvl}, d{c}')

@@ -405,6 +405,31 @@ def test_scaled_conv_first_and_second_order_gradients(ops, device, k, pad):
         assert_close(g1, r1, 5e-5, 'fused d' + name)
 
 
+def test_scaled_conv_third_order_gradients_fall_back_to_autograd(ops, device):
+    # the explicit second-order nodes of the scaled convolution (DxDa, DemodDot, RatioScale) hand higher orders to autograd over the
+    # spelled-out expression: gradient of a gradient of a gradient against torch on the CPU
+    g = torch.Generator().manual_seed(77)
+    N, I, O, H, k, pad = 2, 6, 5, 7, 3, 1
+    x = torch.randn(N, I, H, H, generator=g); w = torch.randn(O, I, k, k, generator=g) / np.sqrt(I * k * k)
+    a = torch.randn(N, I, generator=g) + 1.5; b = torch.rand(N, O, generator=g) + 0.5
+    r = torch.randn(N, O, H, H, generator=g)
+
+    def third(conv, x, w, a, b, r):
+        ts = [t_.clone().requires_grad_(True) for t_ in (x, w, a, b)]
+        y = conv(*ts)
+        first = torch.autograd.grad((y * r).sum(), ts, create_graph=True)
+        pen = first[2].square().sum() + first[0].square().mean() + first[3].square().sum()
+        second = torch.autograd.grad(pen, ts, create_graph=True)
+        pen2 = sum(s_.square().sum() for s_ in second)
+        return torch.autograd.grad(pen2, ts, allow_unused=True)
+
+    ref = third(lambda x_, w_, a_, b_: torch.nn.functional.conv2d(x_ * a_[:, :, None, None], w_, padding=pad) * b_[:, :, None, None], x, w, a, b, r)
+    got = third(lambda x_, w_, a_, b_: ops.conv2d_gradfix.conv2d_s1(x_, w_, padding=(pad, pad), in_scale=a_, out_scale=b_),
+                *[t_.to(device) for t_ in (x, w, a, b, r)])
+    for name, g3, r3 in zip('xwab', got, ref):
+        assert_close(g3, r3, 1e-3, 'third-order d' + name)
+
+
 def test_conv2d_double_backward_closure(ops, device):
     # R1-style: gradient of ||d y / d x||^2 w.r.t. the weight goes conv -> dgrad -> (wgrad of dgrad)
     g = torch.Generator().manual_seed(4)
