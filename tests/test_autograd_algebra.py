@@ -93,3 +93,38 @@ def test_unscaled_conv_calculus_up_to_third_order(fake_plugin):
         for lvl in (1, 2, 3, 4):
             for c, u, v in zip('xw', got[lvl], want[lvl]):
                 _close(u, v, 1e-9, f'unscaled, penalty on {which}, level {lvl}, d{c}')
+
+
+@pytest.mark.parametrize('k,demodulate', [(3, True), (1, False), (3, False)])
+def test_modulated_conv2d_against_the_live_reference_on_cpu(fake_plugin, monkeypatch, k, demodulate):
+    """The PRODUCT's modulated_conv2d (styles and demodulation coefficients as in-kernel scales, dcoefs as a small GEMM) against the
+    reference's own modulated_conv2d (networks.py:591-668, non-fused and fused form) in fp32 on the CPU (the product serves fp32 only), kernels replaced by the torch
+    stand-in: output, gradients w.r.t. x / weight / styles, and the path-length style second-order gradient.  Here the output scale
+    is itself a function of the input scale (dcoefs = rsqrt(styles^2 @ wsq)), so this is the check that no path is counted twice."""
+    from oracle import live_ref
+    if not live_ref.available():
+        pytest.skip('oracle/_ref is absent')
+    L = live_ref.load()
+    from gagan_b200.training import networks as mine
+    monkeypatch.setattr(cg, '_check_input', lambda t: None)           # (the device check; the stand-in runs on CPU tensors)
+    g = torch.Generator().manual_seed(31 + k)
+    N, I, O, H = 3, 5, 4, 6
+    x = torch.randn(N, I, H, H, generator=g, dtype=torch.float32)
+    w = torch.randn(O, I, k, k, generator=g, dtype=torch.float32)
+    s = torch.randn(N, I, generator=g, dtype=torch.float32) * 0.5 + 1
+    noise = torch.randn(N, 1, H, H, generator=g, dtype=torch.float32) * 0.1
+    r = torch.randn(N, O, H, H, generator=g, dtype=torch.float32)
+
+    def run(fn, **extra):
+        ts = [t.clone().requires_grad_(True) for t in (x, w, s)]
+        y = fn(x=ts[0], weight=ts[1], styles=ts[2], noise=noise, up=1, padding=k // 2, demodulate=demodulate, flip_weight=True, **extra)
+        first = torch.autograd.grad((y * r).sum(), ts, create_graph=True)
+        pen = first[2].square().sum() + first[0].square().mean()
+        second = torch.autograd.grad(pen, ts, allow_unused=True)
+        return [y] + list(first) + list(second)
+
+    mine_out = run(mine.modulated_conv2d.__wrapped__ if hasattr(mine.modulated_conv2d, '__wrapped__') else mine.modulated_conv2d)
+    for fused in (False, True):
+        want = run(L.networks.modulated_conv2d, fused_modconv=fused)
+        for name, u, v in zip(('y', 'dx', 'dw', 'ds', 'ddx', 'ddw', 'dds'), mine_out, want):
+            _close(u, v, 2e-4 if name.startswith('dd') else 2e-5, f'k{k} demodulate={demodulate} reference fused_modconv={fused}: {name}')
