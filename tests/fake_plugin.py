@@ -54,3 +54,56 @@ class FakePlugin:
 
     def axpby_rows(self, x1, s1, x2, s2):
         return x1 * _bc(s1) + x2 * _bc(s2)
+
+    # ---- upfirdn2d_plugin / fir4_pm (include/gagan_b200.h: gg_upfirdn2d_f32, gg_fir4_pm_f32)
+
+    @staticmethod
+    def _pad_crop(u, x0, x1, y0, y1):
+        u = F.pad(u, (max(x0, 0), max(x1, 0), max(y0, 0), max(y1, 0)))
+        return u[:, :, max(-y0, 0): u.shape[2] - max(-y1, 0), max(-x0, 0): u.shape[3] - max(-x1, 0)]
+
+    @staticmethod
+    def _fir(u, f, flip, gain):
+        ff = (f * gain).to(u.dtype)
+        if not flip:
+            ff = ff.flip([0, 1])
+        N, C, H, W = u.shape
+        return F.conv2d(u.reshape(N * C, 1, H, W), ff[None, None]).reshape(N, C, H - ff.shape[0] + 1, W - ff.shape[1] + 1)
+
+    def upfirdn2d(self, x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain):
+        N, C, H, W = x.shape
+        u = F.pad(x.reshape(N, C, H, 1, W, 1), (0, upx - 1, 0, 0, 0, upy - 1)).reshape(N, C, H * upy, W * upx)
+        y = self._fir(self._pad_crop(u, padx0, padx1, pady0, pady1), f, flip, gain)
+        return y[:, :, ::downy, ::downx].contiguous()
+
+    def fir4_pm(self, x, f, padx0, pady0, flip, gain, in_hw, out_hw, in_pm=None, out_pm=None):
+        from torch_utils.ops import upfirdn2d as U
+        t = U.depth_to_space(x)[:, :, :in_hw[0], :in_hw[1]] if in_pm is not None else x
+        H, W = int(in_hw[0]), int(in_hw[1])
+        y = self._fir(self._pad_crop(t, padx0, out_hw[1] + 3 - W - padx0, pady0, out_hw[0] + 3 - H - pady0), f, flip, gain)
+        assert tuple(y.shape[2:]) == (int(out_hw[0]), int(out_hw[1]))
+        return U.space_to_depth(y, out_pm[0], out_pm[1]).contiguous() if out_pm is not None else y.contiguous()
+
+    # ---- bias_act_plugin (include/gagan_b200.h: gg_bias_act_f32 incl. the fused bias gradient, gg_bias_act_noise_f32)
+    _ACTS = {1: 'linear', 2: 'relu', 3: 'lrelu', 4: 'tanh', 5: 'sigmoid', 6: 'elu', 7: 'selu', 8: 'softplus', 9: 'swish'}
+
+    def bias_act(self, x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp, dbias=None):
+        from oracle import ops_ref as R                     # (tests may use the oracle; the product never does)
+        name = self._ACTS[int(act)]
+        shape = [-1 if i == dim else 1 for i in range(x.ndim)]
+        bb = b.reshape(shape) if b.numel() else None
+        if grad == 0:
+            return R.bias_act(x, b if b.numel() else None, dim=dim, act=name, alpha=alpha, gain=gain, clamp=(clamp if clamp >= 0 else None))
+        xr = None
+        if xref.numel():
+            xr = xref + bb if bb is not None else xref       # bias_act.cu: the bias joins xref when grad > 0
+        y = R.bias_act_grad_formula(grad, name, x, xr, yref if yref.numel() else torch.zeros_like(x), dy if dy.numel() else None,
+                                    alpha, gain, clamp)
+        if dbias is not None:
+            dbias += y.sum([i for i in range(x.ndim) if i != dim])
+        return y
+
+    def bias_act_noise(self, x, b, noise, act, alpha, gain, clamp):
+        null = torch.empty([0], dtype=x.dtype)
+        n = noise.reshape(1, 1, *noise.shape) if noise.ndim == 2 else noise
+        return self.bias_act(x + n, b, null, null, null, 0, 1, act, alpha, gain, clamp)

@@ -128,3 +128,82 @@ def test_modulated_conv2d_against_the_live_reference_on_cpu(fake_plugin, monkeyp
         want = run(L.networks.modulated_conv2d, fused_modconv=fused)
         for name, u, v in zip(('y', 'dx', 'dw', 'ds', 'ddx', 'ddw', 'dds'), mine_out, want):
             _close(u, v, 2e-4 if name.startswith('dd') else 2e-5, f'k{k} demodulate={demodulate} reference fused_modconv={fused}: {name}')
+
+
+@pytest.mark.parametrize('case', [
+    # name, I, O, R, up, down, k, flip_weight  -- every branch of conv2d_resample the networks take
+    ('G conv0 up', 6, 5, 8, 2, 1, 3, False), ('D conv1 down', 5, 6, 16, 1, 2, 3, True), ('D skip down 1x1', 5, 4, 16, 1, 2, 1, True),
+    ('plain 3x3', 4, 4, 8, 1, 1, 3, True), ('ToRGB 1x1', 6, 3, 8, 1, 1, 1, True), ('G conv0 up, wide', 4, 4, 16, 2, 1, 3, False),
+])
+def test_conv2d_resample_against_the_live_reference_on_cpu(fake_plugin, monkeypatch, case):
+    """The product's conv2d_resample (stride-2 layers as stride-1 convolutions over phase-major tensors, FIRs fused with the re-layout,
+    every node an autograd Function of this build) against the reference's conv2d_resample (conv2d_resample.py:59-156) on the CPU,
+    kernels replaced by the torch stand-in: output, gradients, and the R1-style second-order gradient."""
+    from oracle import live_ref
+    if not live_ref.available():
+        pytest.skip('oracle/_ref is absent')
+    L = live_ref.load()
+    from torch_utils.ops import conv2d_resample as CR, upfirdn2d as U
+    name, I, O, R, up, down, k, flip_weight = case
+    monkeypatch.setattr(cg, '_check_input', lambda t: None)
+    monkeypatch.setattr(U, '_plugin', fake_plugin)
+    monkeypatch.setattr(U, 'upfirdn2d', lambda x, f, up=1, down=1, padding=0, flip_filter=False, gain=1, impl='cuda':
+                        U._upfirdn2d_cuda(up=up, down=down, padding=padding, flip_filter=flip_filter, gain=gain).apply(x, f))
+    g = torch.Generator().manual_seed(sum(map(ord, name)) % 997)
+    x = torch.randn(2, I, R, R, generator=g); w = torch.randn(O, I, k, k, generator=g) / np.sqrt(I * k * k)
+    f = U.setup_filter([1, 3, 3, 1])
+    kw = dict(f=f, up=up, down=down, padding=k // 2, flip_weight=flip_weight)
+
+    def run(fn):
+        ts = [t.clone().requires_grad_(True) for t in (x, w)]
+        y = fn(ts[0], ts[1], **kw)
+        gen = torch.Generator().manual_seed(3)
+        first = torch.autograd.grad((y * torch.randn(y.shape, generator=gen)).sum(), ts, create_graph=True)
+        second = torch.autograd.grad(first[0].square().sum() + first[1].square().sum(), ts)
+        return [y] + list(first) + list(second)
+
+    got, want = run(CR.conv2d_resample.__wrapped__ if hasattr(CR.conv2d_resample, '__wrapped__') else CR.conv2d_resample), run(L.conv2d_resample.conv2d_resample)
+    for nm, u, v in zip(('y', 'dx', 'dw', 'ddx', 'ddw'), got, want):
+        assert u.shape == v.shape, (name, nm, u.shape, v.shape)
+        _close(u, v, 2e-4 if nm.startswith('dd') else 2e-5, f'{name}: {nm}')
+
+
+@pytest.mark.parametrize('act', ['linear', 'relu', 'lrelu', 'tanh', 'sigmoid', 'elu', 'selu', 'softplus', 'swish'])
+@pytest.mark.parametrize('clamp', [None, 0.7])
+def test_bias_act_autograd_against_the_live_reference_on_cpu(fake_plugin, monkeypatch, act, clamp):
+    """bias_act.py's autograd Functions (forward, the closed gradient op with the fused bias reduction, its second-order backward, the
+    noise extension) against the reference's bias_act (bias_act.py:36-88, impl='ref' on CPU), kernels replaced by the stand-in that
+    evaluates the native kernel's formulas (bias_act.cu:40-142 as restated in oracle/ops_ref.py)."""
+    from oracle import live_ref
+    if not live_ref.available():
+        pytest.skip('oracle/_ref is absent')
+    L = live_ref.load()
+    from torch_utils.ops import bias_act as BA
+    monkeypatch.setattr(BA, '_plugin', fake_plugin)
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(3, 5, 4, 6, generator=g); b = torch.randn(5, generator=g) * 0.5
+    r = torch.randn(3, 5, 4, 6, generator=g)
+    spec = BA.activation_funcs[act]
+
+    def run(fn):
+        ts = [t.clone().requires_grad_(True) for t in (x, b)]
+        y = fn(ts[0], ts[1])
+        first = torch.autograd.grad((y * r).sum(), ts, create_graph=True)
+        pen = first[0].square().sum() + 2.0 * first[1].square().sum()
+        second = torch.autograd.grad(pen, ts, allow_unused=True) if pen.requires_grad else (None, None)     # (linear: constant gradients)
+        return [y] + list(first) + list(second)
+
+    mine = BA._bias_act_cuda(dim=1, act=act, alpha=None, gain=None, clamp=clamp)
+    got = run(lambda x_, b_: mine.apply(x_, b_))
+    want = run(lambda x_, b_: L.bias_act.bias_act(x_, b_, act=act, clamp=clamp, impl='ref'))
+    for nm, u, v in zip(('y', 'dx', 'db', 'ddx', 'ddb'), got, want):
+        _close(u, v, 5e-5, f'{act} clamp={clamp}: {nm}')
+    # the noise extension == an explicit add in front of the reference op
+    noise = torch.randn(3, 1, 4, 6, generator=g) * 0.3
+    if 'x' in spec.ref or spec.has_2nd_grad:
+        got_n = run(lambda x_, b_: mine.apply(x_ + noise, b_))
+    else:
+        got_n = run(lambda x_, b_: mine.apply(x_, b_, noise))
+    want_n = run(lambda x_, b_: L.bias_act.bias_act(x_ + noise, b_, act=act, clamp=clamp, impl='ref'))
+    for nm, u, v in zip(('y', 'dx', 'db', 'ddx', 'ddb'), got_n, want_n):
+        _close(u, v, 5e-5, f'{act} clamp={clamp} with noise: {nm}')
