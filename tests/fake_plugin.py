@@ -74,7 +74,7 @@ class FakePlugin:
         N, C, H, W = x.shape
         u = F.pad(x.reshape(N, C, H, 1, W, 1), (0, upx - 1, 0, 0, 0, upy - 1)).reshape(N, C, H * upy, W * upx)
         y = self._fir(self._pad_crop(u, padx0, padx1, pady0, pady1), f, flip, gain)
-        return y[:, :, ::downy, ::downx].contiguous()
+        return y[:, :, ::downy, ::downx].clone()            # (a fresh tensor, like the kernel's output: callers modify it in place)
 
     def fir4_pm(self, x, f, padx0, pady0, flip, gain, in_hw, out_hw, in_pm=None, out_pm=None):
         from torch_utils.ops import upfirdn2d as U
@@ -82,7 +82,7 @@ class FakePlugin:
         H, W = int(in_hw[0]), int(in_hw[1])
         y = self._fir(self._pad_crop(t, padx0, out_hw[1] + 3 - W - padx0, pady0, out_hw[0] + 3 - H - pady0), f, flip, gain)
         assert tuple(y.shape[2:]) == (int(out_hw[0]), int(out_hw[1]))
-        return U.space_to_depth(y, out_pm[0], out_pm[1]).contiguous() if out_pm is not None else y.contiguous()
+        return (U.space_to_depth(y, out_pm[0], out_pm[1]) if out_pm is not None else y).clone()
 
     # ---- bias_act_plugin (include/gagan_b200.h: gg_bias_act_f32 incl. the fused bias gradient, gg_bias_act_noise_f32)
     _ACTS = {1: 'linear', 2: 'relu', 3: 'lrelu', 4: 'tanh', 5: 'sigmoid', 6: 'elu', 7: 'selu', 8: 'softplus', 9: 'swish'}

@@ -207,3 +207,77 @@ def test_bias_act_autograd_against_the_live_reference_on_cpu(fake_plugin, monkey
     want_n = run(lambda x_, b_: L.bias_act.bias_act(x_ + noise, b_, act=act, clamp=clamp, impl='ref'))
     for nm, u, v in zip(('y', 'dx', 'db', 'ddx', 'ddb'), got_n, want_n):
         _close(u, v, 5e-5, f'{act} clamp={clamp} with noise: {nm}')
+
+
+@pytest.mark.parametrize('fused_callers', [True, False])
+def test_reference_networks_on_the_host_layer_with_stand_in_kernels(fake_plugin, monkeypatch, fused_callers):
+    """End to end on the CPU: the reference's OWN Generator / Discriminator (from the installed checkout) run on this build's host
+    layer -- install(), the fused forwards, modulated_conv2d, conv2d_resample with the phase-major stride-2 forms, upfirdn2d, bias_act
+    -- with every kernel replaced by the torch stand-in, against the live reference on its impl='ref' ops: image, logits, and the
+    gradients of a non-saturating G loss and of an R1 penalty."""
+    from oracle import live_ref
+    if not live_ref.available() or not tests.util.HAVE_CHECKOUT:
+        pytest.skip('the reference checkouts are absent')
+    L = live_ref.load()
+    from torch_utils import custom_ops
+    from torch_utils.ops import bias_act as BA, upfirdn2d as U
+    networks = tests.util.reference_networks()
+    from gagan_b200.training import networks as host_networks
+    host_networks.attach(networks, fused_callers=fused_callers)          # with False the reference's own layer forwards run untouched
+    for name in ('bias_act_plugin', 'upfirdn2d_plugin', 'conv2d_plugin'):
+        monkeypatch.setitem(custom_ops._cached_plugins, name, fake_plugin)
+    monkeypatch.setattr(BA, '_plugin', fake_plugin); monkeypatch.setattr(U, '_plugin', fake_plugin)
+    monkeypatch.setattr(cg, '_check_input', lambda t: None)
+    monkeypatch.setattr(U, 'upfirdn2d', lambda x, f, up=1, down=1, padding=0, flip_filter=False, gain=1, impl='cuda':
+                        U._upfirdn2d_cuda(up=up, down=down, padding=padding, flip_filter=flip_filter, gain=gain).apply(x, f))
+
+    def cpu_bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, impl='cuda', noise=None):
+        fn = BA._bias_act_cuda(dim=dim, act=act, alpha=alpha, gain=gain, clamp=clamp)
+        if noise is None:
+            return fn.apply(x, b)
+        spec = BA.activation_funcs[act]
+        return fn.apply(x + noise.to(x.dtype), b) if ('x' in spec.ref or spec.has_2nd_grad) else fn.apply(x, b, noise)
+    monkeypatch.setattr(BA, 'bias_act', cpu_bias_act)
+
+    kw_g = dict(z_dim=16, c_dim=0, w_dim=16, img_resolution=16, img_channels=3, mapping_kwargs=dict(num_layers=2),
+                synthesis_kwargs=dict(channel_base=256, channel_max=16))
+    kw_d = dict(c_dim=0, img_resolution=16, img_channels=3, channel_base=256, channel_max=16, epilogue_kwargs=dict(mbstd_group_size=2))
+    torch.manual_seed(4)
+    G_ref, D_ref = tests.util.quiet(L.networks.Generator, **kw_g).train(), tests.util.quiet(L.networks.Discriminator, **kw_d).train()
+    with torch.no_grad():
+        for p_ in list(G_ref.parameters()) + list(D_ref.parameters()):
+            if float(p_.abs().max()) == 0:
+                p_.copy_(torch.randn(p_.shape) * 0.1)
+    G, D = tests.util.quiet(networks.Generator, **kw_g).train(), tests.util.quiet(networks.Discriminator, **kw_d).train()
+    G.load_state_dict(G_ref.state_dict()); D.load_state_dict(D_ref.state_dict())
+    z = torch.randn(4, 16, generator=torch.Generator().manual_seed(2)); c = torch.zeros(4, 0)
+    real = torch.rand(4, 3, 16, 16, generator=torch.Generator().manual_seed(3)) * 2 - 1
+
+    def run(Gn, Dn):
+        for p_ in list(Gn.parameters()) + list(Dn.parameters()):
+            p_.grad = None
+        img = Gn(z, c, noise_mode='const')
+        logits = Dn(img, c)
+        torch.nn.functional.softplus(-logits).mean().backward()
+        g_grads = {k: p_.grad.clone() for k, p_ in Gn.named_parameters() if p_.grad is not None}
+        x = real.clone().requires_grad_(True)                       # R1: gradient of a gradient through D
+        r1, = torch.autograd.grad(Dn(x, c).sum(), x, create_graph=True)
+        for p_ in Dn.parameters():
+            p_.grad = None
+        r1.square().sum([1, 2, 3]).mean().backward()
+        d_grads = {k: p_.grad.clone() for k, p_ in Dn.named_parameters() if p_.grad is not None}
+        return img.detach(), logits.detach(), g_grads, d_grads
+
+    try:
+        img, logits, gg, dg = run(G, D)
+    finally:
+        host_networks.attach(networks, fused_callers=True)
+    img_r, logits_r, gg_r, dg_r = run(G_ref, D_ref)
+    _close(img, img_r, 2e-5, 'image'); _close(logits, logits_r, 2e-5, 'logits')
+    assert set(gg) == set(gg_r) and set(dg) == set(dg_r)
+    for k in gg_r:
+        if float(gg_r[k].abs().max()) > 0:
+            _close(gg[k], gg_r[k], 2e-4, 'G gradient ' + k)
+    for k in dg_r:
+        if float(dg_r[k].abs().max()) > 0:
+            _close(dg[k], dg_r[k], 1e-3, 'R1 gradient ' + k)
