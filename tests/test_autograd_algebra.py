@@ -209,21 +209,12 @@ def test_bias_act_autograd_against_the_live_reference_on_cpu(fake_plugin, monkey
         _close(u, v, 5e-5, f'{act} clamp={clamp} with noise: {nm}')
 
 
-@pytest.mark.parametrize('fused_callers', [True, False])
-def test_reference_networks_on_the_host_layer_with_stand_in_kernels(fake_plugin, monkeypatch, fused_callers):
-    """End to end on the CPU: the reference's OWN Generator / Discriminator (from the installed checkout) run on this build's host
-    layer -- install(), the fused forwards, modulated_conv2d, conv2d_resample with the phase-major stride-2 forms, upfirdn2d, bias_act
-    -- with every kernel replaced by the torch stand-in, against the live reference on its impl='ref' ops: image, logits, and the
-    gradients of a non-saturating G loss and of an R1 penalty."""
-    from oracle import live_ref
-    if not live_ref.available() or not tests.util.HAVE_CHECKOUT:
-        pytest.skip('the reference checkouts are absent')
-    L = live_ref.load()
+@pytest.fixture()
+def host_layer_on_cpu(fake_plugin, monkeypatch):
+    """Everything the operator modules need to run on CPU tensors: the stand-in behind all three plugin names, and the three device
+    checks of the public entry points taken out (they exist so that the PRODUCT never computes on the CPU; here that is the point)."""
     from torch_utils import custom_ops
     from torch_utils.ops import bias_act as BA, upfirdn2d as U
-    networks = tests.util.reference_networks()
-    from gagan_b200.training import networks as host_networks
-    host_networks.attach(networks, fused_callers=fused_callers)          # with False the reference's own layer forwards run untouched
     for name in ('bias_act_plugin', 'upfirdn2d_plugin', 'conv2d_plugin'):
         monkeypatch.setitem(custom_ops._cached_plugins, name, fake_plugin)
     monkeypatch.setattr(BA, '_plugin', fake_plugin); monkeypatch.setattr(U, '_plugin', fake_plugin)
@@ -238,6 +229,22 @@ def test_reference_networks_on_the_host_layer_with_stand_in_kernels(fake_plugin,
         spec = BA.activation_funcs[act]
         return fn.apply(x + noise.to(x.dtype), b) if ('x' in spec.ref or spec.has_2nd_grad) else fn.apply(x, b, noise)
     monkeypatch.setattr(BA, 'bias_act', cpu_bias_act)
+    return fake_plugin
+
+
+@pytest.mark.parametrize('fused_callers', [True, False])
+def test_reference_networks_on_the_host_layer_with_stand_in_kernels(host_layer_on_cpu, fused_callers):
+    """End to end on the CPU: the reference's OWN Generator / Discriminator (from the installed checkout) run on this build's host
+    layer -- install(), the fused forwards, modulated_conv2d, conv2d_resample with the phase-major stride-2 forms, upfirdn2d, bias_act
+    -- with every kernel replaced by the torch stand-in, against the live reference on its impl='ref' ops: image, logits, and the
+    gradients of a non-saturating G loss and of an R1 penalty."""
+    from oracle import live_ref
+    if not live_ref.available() or not tests.util.HAVE_CHECKOUT:
+        pytest.skip('the reference checkouts are absent')
+    L = live_ref.load()
+    networks = tests.util.reference_networks()
+    from gagan_b200.training import networks as host_networks
+    host_networks.attach(networks, fused_callers=fused_callers)          # with False the reference's own layer forwards run untouched
 
     kw_g = dict(z_dim=16, c_dim=0, w_dim=16, img_resolution=16, img_channels=3, mapping_kwargs=dict(num_layers=2),
                 synthesis_kwargs=dict(channel_base=256, channel_max=16))
@@ -281,3 +288,58 @@ def test_reference_networks_on_the_host_layer_with_stand_in_kernels(fake_plugin,
     for k in dg_r:
         if float(dg_r[k].abs().max()) > 0:
             _close(dg[k], dg_r[k], 1e-3, 'R1 gradient ' + k)
+
+
+def test_training_step_on_cpu_matches_the_reference_iteration(host_layer_on_cpu):
+    """The training-step driver (ga-gan_b200/training/training_loop.py::TrainingStep: four loss phases with lazy-regularisation gains,
+    two accumulation rounds, nan_to_num, Adam with the lazy-reg corrected betas, G_ema) on the host layer with stand-in kernels, against
+    the same iteration of the live reference (training_loop.py:293-318, 459-512): parameter updates, last-phase gradients, G_ema, pl_mean.
+    The GPU twin of this test is test_gpu_networks.py::test_full_training_iteration_matches_the_live_reference."""
+    from oracle import live_ref
+    if not live_ref.available() or not tests.util.HAVE_CHECKOUT:
+        pytest.skip('the reference checkouts are absent')
+    from tests.test_gpu_networks import _cpu_iteration
+    from gagan_b200.training.training_loop import TrainingStep
+    L = live_ref.load()
+    networks = tests.util.reference_networks()
+    res, zd = 16, 16
+    kw_g = dict(z_dim=zd, c_dim=0, w_dim=zd, img_resolution=res, img_channels=3, mapping_kwargs=dict(num_layers=2),
+                synthesis_kwargs=dict(channel_base=256, channel_max=16))
+    kw_d = dict(c_dim=0, img_resolution=res, img_channels=3, channel_base=256, channel_max=16, epilogue_kwargs=dict(mbstd_group_size=2))
+    torch.manual_seed(9)
+    G_cpu, D_cpu = tests.util.quiet(L.networks.Generator, **kw_g).train(), tests.util.quiet(L.networks.Discriminator, **kw_d).train()
+    with torch.no_grad():
+        for p_ in list(G_cpu.parameters()) + list(D_cpu.parameters()):
+            if float(p_.abs().max()) == 0:
+                p_.copy_(torch.randn(p_.shape) * 0.1)
+    G, D = tests.util.quiet(networks.Generator, **kw_g), tests.util.quiet(networks.Discriminator, **kw_d)
+    G.load_state_dict(G_cpu.state_dict()); D.load_state_dict(D_cpu.state_dict())
+    before = {('G.' + k): v.clone() for k, v in G_cpu.named_parameters()}
+    before.update({('D.' + k): v.clone() for k, v in D_cpu.named_parameters()})
+    lrate, gamma, batch, batch_gpu = 1e-3, 1.0, 4, 2
+    real = torch.rand(batch, 3, res, res) * 2 - 1
+    zs = torch.randn(4, batch, zd)
+    L.conv2d_gradfix.enabled = True
+    for net in (G_cpu, D_cpu):
+        net.requires_grad_(False)
+    with tests.util.patched_randn(21):
+        G_ema_cpu, loss_cpu = _cpu_iteration(L, G_cpu, D_cpu, real, zs, batch_gpu, lrate, gamma)
+    step = TrainingStep(G, D, batch_size=batch, batch_gpu=batch_gpu, device=torch.device('cpu'), lrate=lrate, r1_gamma=gamma, ema_kimg=10.0,
+                        style_mixing_prob=0.0, pl_weight=2.0)
+    with tests.util.patched_randn(21):
+        step.run(real, zs)
+    _close(step.loss.pl_mean, loss_cpu.pl_mean, 1e-4, 'pl_mean')
+    after_ref = {('G.' + k): v for k, v in G_cpu.named_parameters()}
+    after_ref.update({('D.' + k): v for k, v in D_cpu.named_parameters()})
+    after = {('G.' + k): v for k, v in step.G.named_parameters()}
+    after.update({('D.' + k): v for k, v in step.D.named_parameters()})
+    total = off = 0
+    for k, b0 in before.items():
+        d_ref, d_got = after_ref[k].detach() - b0, after[k].detach() - b0
+        assert float(d_ref.abs().max()) > 0, f'{k} was not updated by the reference iteration'
+        bad = (d_got - d_ref).abs() > 0.02 * float(d_ref.abs().max())
+        total += bad.numel(); off += int(bad.sum())
+    assert off <= 2e-3 * total, f'{off} of {total} parameter updates differ from the reference iteration'
+    for (k, a_), b_ in zip(step.G_ema.named_parameters(), G_ema_cpu.parameters()):
+        _close(a_, b_, 1e-4, 'G_ema ' + k)
+    assert {'Loss/G/loss', 'Loss/D/loss', 'Loss/G/reg', 'Loss/D/reg'} <= set(step.read_stats())
