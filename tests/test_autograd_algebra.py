@@ -343,3 +343,35 @@ def test_training_step_on_cpu_matches_the_reference_iteration(host_layer_on_cpu)
     for (k, a_), b_ in zip(step.G_ema.named_parameters(), G_ema_cpu.parameters()):
         _close(a_, b_, 1e-4, 'G_ema ' + k)
     assert {'Loss/G/loss', 'Loss/D/loss', 'Loss/G/reg', 'Loss/D/reg'} <= set(step.read_stats())
+
+
+def _augment_pair(L, device, p=1.0, res=32):
+    """The installed checkout's AugmentPipe (this build's operators) and the live reference's (impl='ref' ops), config 'bgc'."""
+    import importlib
+    from gagan_b200.training.training_loop import AUGPIPE_BGC
+    augment = importlib.import_module('training.augment')
+    mine, ref = augment.AugmentPipe(**AUGPIPE_BGC).to(device).train().requires_grad_(False), L.augment.AugmentPipe(**AUGPIPE_BGC).train().requires_grad_(False)
+    mine.p.copy_(torch.as_tensor(p)); ref.p.copy_(torch.as_tensor(p))
+    imgs = torch.rand(4, 3, res, res, generator=torch.Generator().manual_seed(6)) * 2 - 1
+    return mine, ref, imgs
+
+
+def test_ada_augment_pipe_on_the_host_layer_with_stand_in_kernels(host_layer_on_cpu):
+    """The reference's ADA AugmentPipe (augment.py:121-531: geometric transforms through the separable 12-tap sym6 up / down-sampling
+    with upfirdn2d, grid_sample, colour transforms) from the installed checkout, i.e. on this build's upfirdn2d module, against the
+    live reference with the same random draws: images and the gradient w.r.t. the input images."""
+    from oracle import live_ref
+    if not live_ref.available() or not tests.util.HAVE_CHECKOUT:
+        pytest.skip('the reference checkouts are absent')
+    L = live_ref.load()
+    L.grid_sample_gradfix.enabled = True
+    mine, ref, imgs = _augment_pair(L, torch.device('cpu'))
+    outs = []
+    for pipe in (mine, ref):
+        x = imgs.clone().requires_grad_(True)
+        with tests.util.patched_rand(17):
+            y = pipe(x)
+        gx, = torch.autograd.grad((y * torch.linspace(-1, 1, y.numel()).reshape(y.shape)).sum(), x)
+        outs.append((y.detach(), gx))
+    _close(outs[0][0], outs[1][0], 2e-5, 'augmented images')
+    _close(outs[0][1], outs[1][1], 2e-5, 'gradient w.r.t. the input images')

@@ -283,3 +283,26 @@ def test_full_training_iteration_matches_the_live_reference(device):
     stats = step.read_stats()
     assert {'Loss/G/loss', 'Loss/D/loss', 'Loss/G/reg', 'Loss/D/reg'} <= set(stats)
     print(f'full iteration: {off} of {total} parameter updates off by more than 2 % of the step size')
+
+
+def test_ada_augment_pipe_matches_the_live_reference(device):
+    """BASELINE configs[2]: the reference's ADA AugmentPipe ('bgc', augment.py:121-531) from the installed checkout -- its separable
+    12-tap sym6 up / down-sampling and its negative paddings run on this build's upfirdn2d kernels -- against the live reference on the
+    CPU with the same random draws (p = 1: every transform fires): augmented images and the gradient w.r.t. the input images."""
+    from oracle import live_ref
+    from tests.util import patched_rand
+    from tests.test_autograd_algebra import _augment_pair
+    if not live_ref.available():
+        pytest.skip('oracle/_ref is absent')
+    L = live_ref.load()
+    L.grid_sample_gradfix.enabled = True
+    mine, ref, imgs = _augment_pair(L, device, res=64)
+    outs = []
+    for pipe, dev_ in ((mine, device), (ref, torch.device('cpu'))):
+        x = imgs.clone().to(dev_).requires_grad_(True)
+        with patched_rand(17):
+            y = pipe(x)
+        gx, = torch.autograd.grad((y * torch.linspace(-1, 1, y.numel()).reshape(y.shape).to(dev_)).sum(), x)
+        outs.append((y.detach().cpu(), gx.cpu()))
+    assert_close(outs[0][0], outs[1][0], 1e-4, 'augmented images')
+    assert_close(outs[0][1], outs[1][1], 1e-4, 'gradient w.r.t. the input images')

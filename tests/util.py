@@ -91,3 +91,23 @@ def patched_randn(seed):
         yield
     finally:
         torch.randn, torch.randn_like = orig_randn, orig_like
+
+
+@contextlib.contextmanager
+def patched_rand(seed):
+    """patched_randn plus torch.rand through the same seeded CPU generator (the ADA pipe draws its apply / skip masks, flips and
+    angles with torch.rand on the device)."""
+    orig_rand = torch.rand
+    with patched_randn(seed):
+        g = torch.Generator().manual_seed(seed + 1)
+
+        def rand(*size, device=None, dtype=None, generator=None, **_):
+            if len(size) == 1 and isinstance(size[0], (list, tuple, torch.Size)):
+                size = tuple(size[0])
+            out = orig_rand(tuple(int(s_) for s_ in size), generator=g, dtype=dtype or torch.float32)
+            return out.to(device) if device is not None else out
+        torch.rand = rand
+        try:
+            yield
+        finally:
+            torch.rand = orig_rand
