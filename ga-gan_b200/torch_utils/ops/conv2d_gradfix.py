@@ -212,7 +212,11 @@ def _scaled_conv2d_s1(weight_shape, padding, out_hw, io, flip, live, pm, has_a, 
     Writing d/da and d/db as quotients (chan_dot(x, dx) / a, chan_dot(dy, y) / b) and letting autograd differentiate those instead
     produces the missing a- / b-dependence as the difference of two large terms: 1.6e-3 on a second-order style gradient (measured).
     (Re-running the forward and calling autograd.grad on it would be wrong as well: out_scale = dcoefs is itself a function of
-    in_scale = styles, and the total derivative would count that path twice.)"""
+    in_scale = styles, and the total derivative would count that path twice.)
+
+    Third and higher orders: the second-order nodes hand over to autograd over the spelled-out expression (`partial_grads`).  The whole
+    calculus is pinned on the CPU against autograd over y = b * conv(a * x, w) in fp64, up to third order, with the kernels replaced by
+    a torch stand-in (tests/test_autograd_algebra.py), and on the GPU by tests/test_gpu_ops.py."""
     key = (weight_shape, padding, out_hw, io, flip, live, pm, has_a, has_b)
     if key in _scaled_conv2d_s1_cache:
         return _scaled_conv2d_s1_cache[key]
