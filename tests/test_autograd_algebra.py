@@ -375,3 +375,55 @@ def test_ada_augment_pipe_on_the_host_layer_with_stand_in_kernels(host_layer_on_
         outs.append((y.detach(), gx))
     _close(outs[0][0], outs[1][0], 2e-5, 'augmented images')
     _close(outs[0][1], outs[1][1], 2e-5, 'gradient w.r.t. the input images')
+
+
+def _parametrizations():
+    from tests.test_gpu_networks import PARAMETRIZATIONS
+    return PARAMETRIZATIONS
+
+
+@pytest.mark.parametrize('param', _parametrizations())
+def test_domain_adaptation_parametrizations_on_the_host_layer_with_stand_in_kernels(host_layer_on_cpu, param):
+    """CPU twin of test_gpu_networks.py::test_domain_adaptation_parametrizations_match_the_live_reference: every Affine+ / AffineLight+ /
+    StyleSpace parameterization of the reference's generator through this build's modulated_conv2d, image and all parameter gradients."""
+    from tests.test_gpu_networks import test_domain_adaptation_parametrizations_match_the_live_reference as body
+    if not tests.util.HAVE_CHECKOUT:
+        pytest.skip('baseline/_ref/DissimilarDomains is absent')
+    body(torch.device('cpu'), param)
+
+
+@pytest.fixture(params=['fused_forwards', 'reference_forwards'])
+def nets_on_cpu(host_layer_on_cpu, request):
+    """The golden generator / discriminator of tests/golden/networks.npz (outputs of the reference itself) built from the installed
+    checkout on CPU tensors -- the same construction as the GPU fixture of test_gpu_networks.py."""
+    if not tests.util.HAVE_CHECKOUT:
+        pytest.skip('baseline/_ref/DissimilarDomains is absent')
+    import gagan_b200.training.networks as mine
+    from tests.util import load_golden, t
+    networks = tests.util.reference_networks()
+    mine.attach(networks, fused_callers=(request.param == 'fused_forwards'))
+    g = load_golden('networks')
+    cfg = {kv.split('=')[0]: int(kv.split('=')[1]) for kv in (str(m) for m in g['meta'])}
+    G = networks.Generator(z_dim=cfg['z_dim'], c_dim=0, w_dim=cfg['w_dim'], img_resolution=cfg['res'], img_channels=3,
+                           mapping_kwargs=dict(num_layers=cfg['num_layers']),
+                           synthesis_kwargs=dict(channel_base=cfg['channel_base'], channel_max=cfg['channel_max']))
+    D = networks.Discriminator(c_dim=0, img_resolution=cfg['res'], img_channels=3, channel_base=cfg['channel_base'],
+                               channel_max=cfg['channel_max'], epilogue_kwargs=dict(mbstd_group_size=cfg['mbstd']))
+    G.load_state_dict({k[2:]: t(v) for k, v in g.items() if k.startswith('G.')}, strict=False)
+    D.load_state_dict({k[2:]: t(v) for k, v in g.items() if k.startswith('D.')}, strict=False)
+    yield G, D, g, cfg
+    mine.attach(networks, fused_callers=True)
+
+
+def test_golden_forwards_on_the_host_layer_with_stand_in_kernels(nets_on_cpu):
+    from tests import test_gpu_networks as gpu_tests
+    gpu_tests.test_eval_forward(nets_on_cpu, torch.device('cpu'))
+    gpu_tests.test_train_forward_random_noise(nets_on_cpu, torch.device('cpu'))
+
+
+@pytest.mark.parametrize('phase', ['Gmain', 'Greg', 'Dmain', 'Dreg'])
+def test_golden_loss_phases_on_the_host_layer_with_stand_in_kernels(nets_on_cpu, phase):
+    """The four loss phases of the reference's own StyleGAN2Loss (loss.py:59-133, incl. the double-backward regularisers) on the host
+    layer with stand-in kernels, against the golden parameter gradients the reference itself produced."""
+    from tests import test_gpu_networks as gpu_tests
+    gpu_tests.test_loss_phase_parameter_gradients(nets_on_cpu, torch.device('cpu'), phase)
