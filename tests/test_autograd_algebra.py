@@ -427,3 +427,11 @@ def test_golden_loss_phases_on_the_host_layer_with_stand_in_kernels(nets_on_cpu,
     layer with stand-in kernels, against the golden parameter gradients the reference itself produced."""
     from tests import test_gpu_networks as gpu_tests
     gpu_tests.test_loss_phase_parameter_gradients(nets_on_cpu, torch.device('cpu'), phase)
+
+
+def test_ga_population_fitness_on_the_host_layer_with_stand_in_kernels(host_layer_on_cpu):
+    """CPU twin of test_gpu_networks.py::test_ga_population_fitness_eval_on_the_device (BASELINE configs[3] at toy size; eager path)."""
+    if not tests.util.HAVE_CHECKOUT:
+        pytest.skip('baseline/_ref/DissimilarDomains is absent')
+    from tests import test_gpu_networks as gpu_tests
+    gpu_tests.test_ga_population_fitness_eval_on_the_device(torch.device('cpu'))
