@@ -734,3 +734,16 @@ def test_fused_conv_bias_act_matches_the_unfused_pair(ops, device, case):
     assert len(got) == len(want)
     for n, a_, b_ in zip(names, got, want):
         assert_close(a_, b_, 2e-5, f'{case}: {n}')
+
+
+@pytest.mark.parametrize('case', [
+    # name, shape, pad -- unit-rate filters on rows that are not 16-byte multiples, wide enough for the shared-memory row exchange of
+    # fir_stream (coalesced input window from 256 output columns, coalesced output segments from 384).  The same code path ran the
+    # 129^2 and 77x203 cases above while the thresholds stood at 96 columns during development; these are its shipped sizes.
+    ('filt_p1_257', (1, 2, 257, 257), [1, 1, 1, 1]), ('filt_p2_384', (1, 2, 384, 384), [2, 2, 2, 2]),
+    ('filt_both_odd_wide', (1, 1, 301, 515), [1, 1, 1, 1]), ('filt_p1_1025', (1, 1, 70, 1025), [1, 1, 2, 0]),
+], ids=lambda c: c[0])
+def test_upfirdn2d_wide_unaligned_rows_vs_oracle(ops, device, case):
+    name, shape, pad = case
+    test_upfirdn2d_tiled_vs_oracle(ops, device, (name, shape, 1, 1, pad))
+
