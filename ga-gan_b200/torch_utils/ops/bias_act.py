@@ -7,14 +7,16 @@ structure (`BiasActCuda` :181-214, `BiasActCudaGrad` :217-245), over the C-ABI k
 
   * the bias gradient is produced by the SAME kernel launch as dx (warp-shuffle reduction +
     atomics) instead of a second full-tensor `dx.sum(...)` pass (reference :211-212, :243);
-  * fp32 only; `impl='cuda'` on a non-CUDA tensor or with a missing library raises -- there is no
-    fallback; `impl='ref'` is not part of the product (the restatement lives in oracle/, which only
-    tests and the CPU-baseline leg of bench.py may import).
+  * fp32 kernels; float16 tensors are served with fp32 arithmetic and a float16 result
+    (`_util.fp16_storage`); `impl='cuda'` on a non-CUDA tensor or with a missing library raises --
+    there is no fallback; `impl='ref'` is not part of the product (the restatement lives in
+    oracle/, which only tests and the CPU-baseline leg of bench.py may import).
 """
 import numpy as np
 import torch
 
 from .. import custom_ops
+from ..._util import fp16_storage
 
 # ----------------------------------------------------------------------------
 
@@ -62,19 +64,24 @@ def _null_like(x):
 
 # ----------------------------------------------------------------------------
 
+def _check_input(x):
+    if x.device.type != 'cuda':
+        raise RuntimeError('bias_act: the B200 build has no CPU path; x must be a CUDA tensor')
+    _init()
+
+
+@fp16_storage('x')
 def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, impl='cuda', noise=None):
     r"""Fused bias and activation function: `clamp(act(x + b) * gain)`.
 
     Args / semantics identical to the reference (bias_act.py:88-122).  Supports first and second
-    order gradients, not third.
+    order gradients, not third.  float16 tensors: fp32 arithmetic, float16 result (`_util.fp16_storage`).
     """
     assert isinstance(x, torch.Tensor)
     assert impl in ['ref', 'cuda']
     if impl != 'cuda':
         raise RuntimeError("bias_act: impl='ref' is not shipped in the B200 build (see oracle/ops_ref.py for the CPU restatement)")
-    if x.device.type != 'cuda':
-        raise RuntimeError('bias_act: the B200 build has no CPU path; x must be a CUDA tensor')
-    _init()
+    _check_input(x)
     if noise is not None:
         # extension: per-pixel noise ([H,W] or [N,1,H,W]) added before the activation inside the same kernel -- the
         # `x.add_(noise)` / fma pass of the SynthesisLayer (networks.py:648-653)

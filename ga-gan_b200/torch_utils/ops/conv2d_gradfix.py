@@ -17,6 +17,7 @@ import contextlib
 import torch
 
 from .. import custom_ops
+from ..._util import fp16_storage
 
 # pylint: disable=redefined-builtin
 
@@ -59,6 +60,7 @@ def _is_s1(weight, stride, padding, dilation, groups, output_padding=0):
             and _tuple_of_ints(output_padding, 2) == (0, 0) and pad[0] <= k[0] - 1 and pad[1] <= k[1] - 1)
 
 
+@fp16_storage('input')
 def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
     _check_input(input)
     if _is_s1(weight, stride, padding, dilation, groups):
@@ -68,6 +70,7 @@ def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
                            dilation=dilation, groups=groups).apply(input, weight, bias)
 
 
+@fp16_storage('input')
 def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_padding=0, groups=1, dilation=1):
     _check_input(input)
     if _is_s1(weight, stride, padding, dilation, groups, output_padding):

@@ -7,7 +7,7 @@ bit-for-bit against the oracle; `conv2d_resample()` executes the plan on this bu
 """
 import torch
 
-from ..._util import check_dims, scoped
+from ..._util import check_dims, scoped, fp16_storage
 from . import conv2d_gradfix
 from . import upfirdn2d
 from .upfirdn2d import _parse_padding
@@ -169,6 +169,7 @@ def _fir_from_pm(z, f, padding, flip_filter, gain, valid_hw):
 
 
 @scoped
+@fp16_storage('x')
 def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False, in_scale=None,
                     out_scale=None, epilogue=None):
     r"""2D convolution with optional up/downsampling; padding is applied once, up front.

@@ -6,13 +6,13 @@ helpers that `conv2d_resample` imports (`_parse_padding` :53-62, `_get_filter_si
 `_parse_scaling` :43-50) and the same autograd structure (`Upfirdn2dCuda` :237-283: the backward
 of upfirdn2d is upfirdn2d with up<->down swapped, mirrored padding and the flipped filter, so
 gradients of any order stay inside this one op).  The body is the C-ABI kernel family
-`gg_upfirdn2d_f32` (include/gagan_b200.h); fp32 only; no `impl='ref'` and no CPU fallback.
+`gg_upfirdn2d_f32` (include/gagan_b200.h); fp32 kernels (float16 images: `_util.fp16_storage`); no `impl='ref'`, no CPU fallback.
 """
 import numpy as np
 import torch
 
 from .. import custom_ops
-from ..._util import check_dims
+from ..._util import check_dims, fp16_storage
 
 # ----------------------------------------------------------------------------
 
@@ -93,19 +93,25 @@ def setup_filter(f, device=torch.device('cpu'), normalize=True, flip_filter=Fals
 
 # ----------------------------------------------------------------------------
 
+def _check_input(x):
+    if x.device.type != 'cuda':
+        raise RuntimeError('upfirdn2d: the B200 build has no CPU path; x must be a CUDA tensor')
+    _init()
+
+
+@fp16_storage('x')
 def upfirdn2d(x, f, up=1, down=1, padding=0, flip_filter=False, gain=1, impl='cuda'):
     r"""Pad, upsample, filter, and downsample a batch of 2D images (upfirdn2d.py:130-174).
 
     1. zero-stuff by `up`; 2. pad (negative = crop) by `padding`; 3. convolve with `f`
     (`flip_filter=True` = correlate); 4. keep every `down`-th pixel.  Gradients of arbitrary order.
+    float16 images: fp32 arithmetic, float16 result (`_util.fp16_storage`).
     """
     assert isinstance(x, torch.Tensor)
     assert impl in ['ref', 'cuda']
     if impl != 'cuda':
         raise RuntimeError("upfirdn2d: impl='ref' is not shipped in the B200 build (see oracle/ops_ref.py)")
-    if x.device.type != 'cuda':
-        raise RuntimeError('upfirdn2d: the B200 build has no CPU path; x must be a CUDA tensor')
-    _init()
+    _check_input(x)
     return _upfirdn2d_cuda(up=up, down=down, padding=padding, flip_filter=flip_filter, gain=gain).apply(x, f)
 
 

@@ -13,9 +13,10 @@ of :24-579); `gagan_b200.install()` imports them from the user's checkout and ca
     without it the first 4x4 block raises AttributeError on `None.ndim`) by letting `misc.assert_shape` and
     `upfirdn2d.upsample2d` pass `None` through -- the reference file itself is not edited.
 """
+import numpy as np
 import torch
 
-from .._util import check_dims, scoped
+from .._util import check_dims, scoped, to_f32
 from ..torch_utils.ops import conv2d_resample
 from ..torch_utils.ops import bias_act
 from ..torch_utils.ops import upfirdn2d
@@ -52,9 +53,21 @@ def modulated_conv2d(
     out_channels, in_channels, kh, kw = (int(v) for v in weight.shape)
     check_dims(x, [batch_size, in_channels, None, None], 'modulated_conv2d: x')
     check_dims(styles, [batch_size, in_channels], 'modulated_conv2d: styles')
-    if x.dtype != torch.float32:
-        raise RuntimeError('modulated_conv2d: this build serves the fp32 path only')
     _ = fused_modconv
+    if x.dtype == torch.float16:
+        # Mixed precision (`num_fp16_res`, networks.py:994,1031-1035): float16 activations in, float16 out, fp32 (3xTF32) arithmetic
+        # in between -- the kernels are fp32 (`_util.fp16_storage`).  The reference pre-normalises weight and styles so that its
+        # fp16 products cannot overflow (:621-627); that cannot happen here, but the same two divisions are applied so that the
+        # 1e-8 inside the demodulation acts on the scale it has in the reference.
+        if demodulate:
+            weight = weight * (1 / np.sqrt(in_channels * kh * kw) / weight.norm(float('inf'), dim=[1, 2, 3], keepdim=True))
+            styles = styles / styles.norm(float('inf'), dim=1, keepdim=True)
+        y = modulated_conv2d(x=x.float(), weight=weight.float(), styles=styles.float(), noise=to_f32(noise), up=up, down=down,
+                             padding=padding, resample_filter=resample_filter, demodulate=demodulate, flip_weight=flip_weight,
+                             epilogue=to_f32(epilogue))
+        return y.to(torch.float16)
+    if x.dtype != torch.float32:
+        raise RuntimeError('modulated_conv2d: this build serves float32 and float16 tensors')
 
     dcoefs = None
     if demodulate:

@@ -16,7 +16,12 @@ class FakePlugin:
 
     def conv2d(self, x, w, stride=1, padding=(0, 0), transposed=False, output_padding=(0, 0), flip_w=False, in_scale=None, out_scale=None,
                prec=None, out_hw=None, flop_scale=1.0, epilogue=None):
-        assert stride == 1 and epilogue is None
+        assert epilogue is None
+        if stride != 1:                      # the generic strided route (conv2d_gradfix._conv2d_gradfix): no scales, no free extents
+            assert in_scale is None and out_scale is None and out_hw is None
+            v = w.flip([2, 3]) if flip_w else w
+            return F.conv_transpose2d(x, v, stride=stride, padding=padding, output_padding=output_padding) if transposed \
+                else F.conv2d(x, v, stride=stride, padding=padding)
         kh, kw = int(w.shape[2]), int(w.shape[3])
         if transposed:                       # conv_transpose2d(x, w[I,O], padding=p) == correlation with w^T flipped, padding k-1-p
             v, fl, py, px = w.transpose(0, 1), not flip_w, kh - 1 - padding[0], kw - 1 - padding[1]

@@ -212,23 +212,16 @@ def test_bias_act_autograd_against_the_live_reference_on_cpu(fake_plugin, monkey
 @pytest.fixture()
 def host_layer_on_cpu(fake_plugin, monkeypatch):
     """Everything the operator modules need to run on CPU tensors: the stand-in behind all three plugin names, and the three device
-    checks of the public entry points taken out (they exist so that the PRODUCT never computes on the CPU; here that is the point)."""
+    checks of the public entry points taken out.  The public functions themselves (argument parsing, fp16 entry, autograd) are the
+    product's."""
     from torch_utils import custom_ops
     from torch_utils.ops import bias_act as BA, upfirdn2d as U
     for name in ('bias_act_plugin', 'upfirdn2d_plugin', 'conv2d_plugin'):
         monkeypatch.setitem(custom_ops._cached_plugins, name, fake_plugin)
     monkeypatch.setattr(BA, '_plugin', fake_plugin); monkeypatch.setattr(U, '_plugin', fake_plugin)
-    monkeypatch.setattr(cg, '_check_input', lambda t: None)
-    monkeypatch.setattr(U, 'upfirdn2d', lambda x, f, up=1, down=1, padding=0, flip_filter=False, gain=1, impl='cuda':
-                        U._upfirdn2d_cuda(up=up, down=down, padding=padding, flip_filter=flip_filter, gain=gain).apply(x, f))
-
-    def cpu_bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, impl='cuda', noise=None):
-        fn = BA._bias_act_cuda(dim=dim, act=act, alpha=alpha, gain=gain, clamp=clamp)
-        if noise is None:
-            return fn.apply(x, b)
-        spec = BA.activation_funcs[act]
-        return fn.apply(x + noise.to(x.dtype), b) if ('x' in spec.ref or spec.has_2nd_grad) else fn.apply(x, b, noise)
-    monkeypatch.setattr(BA, 'bias_act', cpu_bias_act)
+    # the device checks of the public entry points exist so that the PRODUCT never computes on the CPU; here that is the point
+    for mod in (cg, U, BA):
+        monkeypatch.setattr(mod, '_check_input', lambda t: None)
     return fake_plugin
 
 
@@ -435,3 +428,144 @@ def test_ga_population_fitness_on_the_host_layer_with_stand_in_kernels(host_laye
         pytest.skip('baseline/_ref/DissimilarDomains is absent')
     from tests import test_gpu_networks as gpu_tests
     gpu_tests.test_ga_population_fitness_eval_on_the_device(torch.device('cpu'))
+
+
+# ----------------------------------------------------------------------------
+# Mixed precision: float16 tensors at the operator boundaries, fp32 arithmetic inside.
+
+HALF_ULP = 2.0 ** -11          # one rounding to float16, relative to the element; the bounds below are relative to max|reference|
+
+
+def _half_like_reference(L):
+    f = L.upfirdn2d.setup_filter([1, 3, 3, 1])
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 6, 12, 12, generator=g).half()
+    w = (torch.randn(5, 6, 3, 3, generator=g) * 0.2)
+    s = torch.randn(2, 6, generator=g) * 0.5 + 1
+    b = (torch.randn(5, generator=g) * 0.3)
+    return f, x, w, s, b
+
+
+def test_float16_operators_round_once_at_their_boundary(host_layer_on_cpu):
+    """Every public operator accepts float16 tensors (also channels_last ones), returns float16, sends float16 gradients back, and its
+    result is the reference's fp32 result on the same (float16-valued) inputs rounded to float16 ONCE: within 2^-11 of max|y| (plus
+    fp32 noise), where the reference's own fp16 evaluation (bias_act.py:127-157, upfirdn2d.py:179-219, conv2d_resample.py:59-154 on
+    torch's CPU half kernels) rounds after every elementary step."""
+    from oracle import live_ref
+    if not live_ref.available():
+        pytest.skip('oracle/_ref is absent')
+    L = live_ref.load()
+    from torch_utils.ops import bias_act as BA, upfirdn2d as U, conv2d_resample as CR
+    f, x, w, s, b = _half_like_reference(L)
+    xc = x.to(memory_format=torch.channels_last)
+    bound = HALF_ULP + 2e-5
+
+    cases = {
+        'bias_act lrelu clamp': (lambda t: BA.bias_act(t, b[:1].repeat(6).half(), act='lrelu', clamp=0.8),
+                                 lambda t: L.bias_act.bias_act(t, b[:1].repeat(6).half().float(), act='lrelu', clamp=0.8, impl='ref')),
+        'bias_act linear gain': (lambda t: BA.bias_act(t, None, act='linear', gain=0.5),
+                                 lambda t: L.bias_act.bias_act(t, None, act='linear', gain=0.5, impl='ref')),
+        'upfirdn2d up2': (lambda t: U.upsample2d(t, f), lambda t: L.upfirdn2d.upsample2d(t, f, impl='ref')),
+        'upfirdn2d down2': (lambda t: U.downsample2d(t, f), lambda t: L.upfirdn2d.downsample2d(t, f, impl='ref')),
+        'conv2d_resample plain': (lambda t: CR.conv2d_resample(t, w.half(), padding=1), lambda t: L.conv2d_resample.conv2d_resample(t, w.half().float(), padding=1)),
+        'conv2d_resample up2': (lambda t: CR.conv2d_resample(x=t, w=w.half(), f=f, up=2, padding=1, flip_weight=False),
+                                lambda t: L.conv2d_resample.conv2d_resample(x=t, w=w.half().float(), f=f, up=2, padding=1, flip_weight=False)),
+        'conv2d_resample down2': (lambda t: CR.conv2d_resample(x=t, w=w.half(), f=f, down=2, padding=1),
+                                  lambda t: L.conv2d_resample.conv2d_resample(x=t, w=w.half().float(), f=f, down=2, padding=1)),
+        'conv2d': (lambda t: cg.conv2d(t, w.half(), padding=1), lambda t: torch.nn.functional.conv2d(t, w.half().float(), padding=1)),
+        'conv_transpose2d': (lambda t: cg.conv_transpose2d(input=t, weight=w.half().transpose(0, 1), padding=1),
+                             lambda t: torch.nn.functional.conv_transpose2d(t, w.half().float().transpose(0, 1), padding=1)),
+    }
+    for name, (mine, ref) in cases.items():
+        for xin in (x, xc):
+            t16 = xin.clone().requires_grad_(True)
+            y = mine(t16)
+            assert y.dtype == torch.float16, name
+            t32 = x.float().requires_grad_(True)
+            y32 = ref(t32)
+            assert y.shape == y32.shape, name
+            _close(y.float(), y32.detach(), bound, name)
+            r = torch.randn(y32.shape, generator=torch.Generator().manual_seed(5)).half()
+            gx, = torch.autograd.grad(y, t16, r)
+            gx32, = torch.autograd.grad(y32, t32, r.float())
+            assert gx.dtype == torch.float16, name
+            _close(gx.float(), gx32, bound, name + ': dx')
+
+
+@pytest.mark.parametrize('demodulate,up', [(True, 1), (True, 2), (False, 1)])
+def test_float16_modulated_conv2d_against_the_live_reference(host_layer_on_cpu, demodulate, up):
+    """modulated_conv2d on float16 activations (networks.py:591-668 with the fp16 pre-normalisation of :621-627): float16 in and out,
+    and no further from the reference's fp32 result than ONE float16 rounding -- while the reference's own float16 evaluation (both
+    formulations) sits several roundings away."""
+    from oracle import live_ref
+    if not live_ref.available():
+        pytest.skip('oracle/_ref is absent')
+    L = live_ref.load()
+    import training.networks as N
+    f, x, w, s, b = _half_like_reference(L)
+    kw = dict(up=up, padding=1, resample_filter=f, demodulate=demodulate, flip_weight=(up == 1))
+    noise = torch.randn(12 * up, 12 * up, generator=torch.Generator().manual_seed(3)) * 0.1
+    ws = [t.clone().requires_grad_(True) for t in (w, s)]
+    y = N.modulated_conv2d(x=x, weight=ws[0], styles=ws[1], noise=noise, **kw)
+    assert y.dtype == torch.float16
+    wr = [t.clone().requires_grad_(True) for t in (w, s)]
+    y32 = L.networks.modulated_conv2d(x=x.float(), weight=wr[0], styles=wr[1], noise=noise, fused_modconv=False, **kw)
+    y16 = L.networks.modulated_conv2d(x=x, weight=w, styles=s, noise=noise, fused_modconv=False, **kw)
+    e_mine, e_ref16 = tests.util.max_rel_err(y.float(), y32), tests.util.max_rel_err(y16.float(), y32)
+    assert e_mine <= HALF_ULP + 2e-5, (e_mine, e_ref16)
+    r = torch.randn(y32.shape, generator=torch.Generator().manual_seed(6)).half()
+    g = torch.autograd.grad(y, ws, r)
+    g32 = torch.autograd.grad(y32, wr, r.float())
+    for nm, u, v in zip(('dweight', 'dstyles'), g, g32):
+        assert u.dtype == torch.float32                      # parameters stay fp32 (networks.py:897: weight.to(x.dtype) inside the op)
+        _close(u, v, 2e-3, f'fp16 modulated_conv2d {nm}')     # the incoming gradient is float16-valued; the rounding of y does not enter
+
+
+@pytest.mark.parametrize('fused_callers', [True, False])
+def test_mixed_precision_networks_on_the_host_layer(host_layer_on_cpu, fused_callers):
+    """The reference's default configuration is mixed precision (`num_fp16_res=4`, `conv_clamp=256`, train.py:267-268,425-429): its own
+    Generator / Discriminator built that way run on this build's host layer, and land CLOSER to the reference's fp32 evaluation
+    (`force_fp32=True`) than the reference's own fp16 evaluation does: image, logits and every parameter gradient of a G loss."""
+    from oracle import live_ref
+    if not live_ref.available() or not tests.util.HAVE_CHECKOUT:
+        pytest.skip('the reference checkouts are absent')
+    L = live_ref.load()
+    networks = tests.util.reference_networks()
+    from gagan_b200.training import networks as host_networks
+    host_networks.attach(networks, fused_callers=fused_callers)
+    kw_g = dict(z_dim=16, c_dim=0, w_dim=16, img_resolution=32, img_channels=3, mapping_kwargs=dict(num_layers=2),
+                synthesis_kwargs=dict(channel_base=512, channel_max=16, num_fp16_res=2, conv_clamp=256))
+    kw_d = dict(c_dim=0, img_resolution=32, img_channels=3, channel_base=512, channel_max=16, num_fp16_res=2, conv_clamp=256,
+                epilogue_kwargs=dict(mbstd_group_size=2))
+    torch.manual_seed(4)
+    G_ref, D_ref = tests.util.quiet(L.networks.Generator, **kw_g).train(), tests.util.quiet(L.networks.Discriminator, **kw_d).train()
+    with torch.no_grad():
+        for p_ in list(G_ref.parameters()) + list(D_ref.parameters()):
+            if float(p_.abs().max()) == 0:
+                p_.copy_(torch.randn(p_.shape) * 0.1)
+    G, D = tests.util.quiet(networks.Generator, **kw_g).train(), tests.util.quiet(networks.Discriminator, **kw_d).train()
+    G.load_state_dict(G_ref.state_dict()); D.load_state_dict(D_ref.state_dict())
+    z = torch.randn(4, 16, generator=torch.Generator().manual_seed(2)); c = torch.zeros(4, 0)
+
+    def run(Gn, Dn, **kw):
+        for p_ in list(Gn.parameters()) + list(Dn.parameters()):
+            p_.grad = None
+        img = Gn(z, c, noise_mode='const', **kw)
+        logits = Dn(img, c, **kw)
+        torch.nn.functional.softplus(-logits).mean().backward()
+        return img.detach(), logits.detach(), {k: p_.grad.clone() for k, p_ in Gn.named_parameters() if p_.grad is not None}
+
+    try:
+        mine = run(G, D)
+    finally:
+        host_networks.attach(networks, fused_callers=True)
+    ref16, ref32 = run(G_ref, D_ref), run(G_ref, D_ref, force_fp32=True)
+    err = tests.util.max_rel_err
+    assert mine[0].dtype == torch.float32 and set(mine[2]) == set(ref32[2])
+    for i, nm in ((0, 'image'), (1, 'logits')):
+        e_mine, e_ref16 = err(mine[i], ref32[i]), err(ref16[i], ref32[i])
+        assert e_mine <= 1.25 * e_ref16 + 1e-4, (nm, e_mine, e_ref16)        # measured: 0.9e-3 / 1.2e-3 against 1.8e-3 (image)
+        assert err(mine[i], ref16[i]) <= 3 * e_ref16 + 1e-4, nm
+    live = [k for k in ref32[2] if float(ref32[2][k].abs().max()) > 0]
+    worst_mine, worst_ref16 = max(err(mine[2][k], ref32[2][k]) for k in live), max(err(ref16[2][k], ref32[2][k]) for k in live)
+    assert worst_mine <= 1.25 * worst_ref16, (worst_mine, worst_ref16)        # measured: 0.08 / 0.09 against 0.105 (fp16 gradients, no loss scaling)

@@ -130,7 +130,7 @@ def test_upfirdn2d_errors(ops, device):
     with pytest.raises(RuntimeError, match='at least 1x1'):
         ops.upfirdn2d.upfirdn2d(x, f, padding=0)          # 2 - 4 + 1 < 1
     with pytest.raises(RuntimeError, match='fp32'):
-        ops.upfirdn2d.upfirdn2d(x.half(), f)
+        ops.upfirdn2d.upfirdn2d(x.double(), f, padding=1)          # float64 is not served (float16 is: test_gpu_mixed_precision.py)
 
 
 # ------------------------------------------------------------------------------------------------ bias_act
@@ -734,6 +734,129 @@ def test_fused_conv_bias_act_matches_the_unfused_pair(ops, device, case):
     assert len(got) == len(want)
     for n, a_, b_ in zip(names, got, want):
         assert_close(a_, b_, 2e-5, f'{case}: {n}')
+
+
+# ------------------------------------------------------------------------------------------------ mixed precision (row f4)
+HALF_ULP = 2.0 ** -11          # one rounding to float16
+
+
+def test_float16_operators_round_once_at_their_boundary(ops, device):
+    """float16 tensors (plain and channels_last, as the reference's `num_fp16_res` blocks hand them over: networks.py:1031-1035) through
+    every public operator: float16 out, float16 gradients back, and the value is the fp32 oracle's result on the same float16-valued
+    inputs rounded to float16 once (2^-11 of max|y| plus fp32 noise).  CPU twin: tests/test_autograd_algebra.py."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 6, 20, 20, generator=g).half()
+    w = (torch.randn(5, 6, 3, 3, generator=g) * 0.2).half()
+    b = (torch.randn(6, generator=g) * 0.3).half()
+    f = R.setup_filter([1, 3, 3, 1])
+    fd = f.to(device)
+    bound = HALF_ULP + 2e-5
+    o = ops
+    cases = {
+        'bias_act lrelu clamp': (lambda t: o.bias_act.bias_act(t, b.to(device), act='lrelu', clamp=0.8),
+                                 lambda t: R.bias_act(t, b.float(), act='lrelu', clamp=0.8)),
+        'bias_act linear gain': (lambda t: o.bias_act.bias_act(t, None, act='linear', gain=0.5), lambda t: R.bias_act(t, None, act='linear', gain=0.5)),
+        'upsample2d': (lambda t: o.upfirdn2d.upsample2d(t, fd), lambda t: R.upsample2d(t, f)),
+        'downsample2d': (lambda t: o.upfirdn2d.downsample2d(t, fd), lambda t: R.downsample2d(t, f)),
+        'conv2d_resample plain': (lambda t: o.conv2d_resample.conv2d_resample(t, w.to(device), padding=1), lambda t: R.conv2d_resample(t, w.float(), padding=1)),
+        'conv2d_resample up2': (lambda t: o.conv2d_resample.conv2d_resample(x=t, w=w.to(device), f=fd, up=2, padding=1, flip_weight=False),
+                                lambda t: R.conv2d_resample(x=t, w=w.float(), f=f, up=2, padding=1, flip_weight=False)),
+        'conv2d_resample down2': (lambda t: o.conv2d_resample.conv2d_resample(x=t, w=w.to(device), f=fd, down=2, padding=1),
+                                  lambda t: R.conv2d_resample(x=t, w=w.float(), f=f, down=2, padding=1)),
+        'conv2d stride 2': (lambda t: o.conv2d_gradfix.conv2d(t, w.to(device), stride=2, padding=1),
+                            lambda t: torch.nn.functional.conv2d(t, w.float(), stride=2, padding=1)),
+        'conv_transpose2d stride 2': (lambda t: o.conv2d_gradfix.conv_transpose2d(input=t, weight=w.to(device).transpose(0, 1), stride=2),
+                                      lambda t: torch.nn.functional.conv_transpose2d(t, w.float().transpose(0, 1), stride=2)),
+    }
+    for name, (mine, ref) in cases.items():
+        t32 = x.float().requires_grad_(True)
+        y32 = ref(t32)
+        r = torch.randn(y32.shape, generator=torch.Generator().manual_seed(5)).half()
+        gx32, = torch.autograd.grad(y32, t32, r.float())
+        for fmt in (torch.contiguous_format, torch.channels_last):
+            t16 = x.to(device).to(memory_format=fmt).requires_grad_(True)
+            y = mine(t16)
+            assert y.dtype == torch.float16 and y.shape == y32.shape, name
+            assert_close(y.float(), y32, bound, name)
+            gx, = torch.autograd.grad(y, t16, r.to(device))
+            assert gx.dtype == torch.float16, name
+            assert_close(gx.float(), gx32, bound, name + ': dx')
+    with pytest.raises(RuntimeError):
+        o.bias_act.bias_act(x.to(device).double(), None)          # float64 is not served
+
+
+@pytest.mark.parametrize('demodulate,up,fused', [(True, 1, False), (True, 2, False), (False, 1, False), (True, 1, True)])
+def test_float16_modulated_conv2d_vs_oracle(ops, device, demodulate, up, fused):
+    """modulated_conv2d on float16 activations (networks.py:591-668 incl. the fp16 pre-normalisation :621-627), without and with the
+    fused bias / noise / activation epilogue the fused SynthesisLayer forward hands it: one float16 rounding away from the fp32 oracle."""
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(2, 16, 24, 24, generator=g).half()
+    w = torch.randn(8, 16, 3, 3, generator=g) * 0.2
+    s = torch.randn(2, 16, generator=g) * 0.5 + 1
+    b = (torch.randn(8, generator=g) * 0.3).half().float()          # float16-valued: the layer hands `bias.to(x.dtype)` over
+    noise = torch.randn(24 * up, 24 * up, generator=g) * 0.1
+    f = R.setup_filter([1, 3, 3, 1])
+    kw = dict(up=up, padding=1, demodulate=demodulate, flip_weight=(up == 1))
+    wr, sr = w.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    y32 = R.modulated_conv2d(x.float(), wr, sr, noise=noise, resample_filter=f, fused_modconv=False, **kw)
+    if fused:
+        y32 = R.bias_act(y32, b, act='lrelu', clamp=256.0)
+    wd, sd = w.to(device).requires_grad_(True), s.to(device).requires_grad_(True)
+    epi = dict(epilogue=dict(bias=b.to(device).half(), act='lrelu', gain=None, clamp=256.0)) if fused else {}
+    y = ops.networks.modulated_conv2d(x=x.to(device), weight=wd, styles=sd, noise=noise.to(device), resample_filter=f.to(device), **kw, **epi)
+    assert y.dtype == torch.float16
+    assert_close(y.float(), y32, HALF_ULP + 2e-5, 'y')
+    r = torch.randn(y32.shape, generator=torch.Generator().manual_seed(6)).half()
+    got = torch.autograd.grad(y, [wd, sd], r.to(device))
+    want = torch.autograd.grad(y32, [wr, sr], r.float())
+    for nm, u, v in zip(('dweight', 'dstyles'), got, want):
+        assert u.dtype == torch.float32
+        assert_close(u, v, 1e-4, nm)           # the rounding of y does not enter: both sides differentiate the unrounded fp32 expression
+
+
+def test_mixed_precision_networks_vs_the_live_reference(device):
+    """The reference's default configuration (`num_fp16_res`, `conv_clamp=256`; train.py:267-268,425-429): its own Generator and
+    Discriminator built that way, on the library, are closer to the reference's fp32 evaluation (`force_fp32=True`, CPU) than the
+    reference's own float16 evaluation is: image, logits, every generator gradient of a non-saturating loss."""
+    from oracle import live_ref
+    from tests.util import reference_networks, quiet, max_rel_err
+    if not live_ref.available():
+        pytest.skip('oracle/_ref is absent')
+    L = live_ref.load()
+    networks = reference_networks()
+    kw_g = dict(z_dim=32, c_dim=0, w_dim=32, img_resolution=64, img_channels=3, mapping_kwargs=dict(num_layers=2),
+                synthesis_kwargs=dict(channel_base=1024, channel_max=32, num_fp16_res=3, conv_clamp=256))
+    kw_d = dict(c_dim=0, img_resolution=64, img_channels=3, channel_base=1024, channel_max=32, num_fp16_res=3, conv_clamp=256,
+                epilogue_kwargs=dict(mbstd_group_size=2))
+    torch.manual_seed(4)
+    G_ref, D_ref = quiet(L.networks.Generator, **kw_g).train(), quiet(L.networks.Discriminator, **kw_d).train()
+    with torch.no_grad():
+        for p_ in list(G_ref.parameters()) + list(D_ref.parameters()):
+            if float(p_.abs().max()) == 0:
+                p_.copy_(torch.randn(p_.shape) * 0.1)
+    G, D = quiet(networks.Generator, **kw_g).train(), quiet(networks.Discriminator, **kw_d).train()
+    G.load_state_dict(G_ref.state_dict()); D.load_state_dict(D_ref.state_dict())
+    G, D = G.to(device), D.to(device)
+    z = torch.randn(4, 32, generator=torch.Generator().manual_seed(2)); c = torch.zeros(4, 0)
+
+    def run(Gn, Dn, dev, **kw):
+        for p_ in list(Gn.parameters()) + list(Dn.parameters()):
+            p_.grad = None
+        img = Gn(z.to(dev), c.to(dev), noise_mode='const', **kw)
+        logits = Dn(img, c.to(dev), **kw)
+        torch.nn.functional.softplus(-logits).mean().backward()
+        return img.detach().cpu(), logits.detach().cpu(), {k: p_.grad.cpu() for k, p_ in Gn.named_parameters() if p_.grad is not None}
+
+    mine = run(G, D, device)
+    ref16, ref32 = run(G_ref, D_ref, 'cpu'), run(G_ref, D_ref, 'cpu', force_fp32=True)
+    assert mine[0].dtype == torch.float32 and set(mine[2]) == set(ref32[2])
+    for i, nm in ((0, 'image'), (1, 'logits')):
+        e_mine, e_ref16 = max_rel_err(mine[i], ref32[i]), max_rel_err(ref16[i], ref32[i])
+        assert e_mine <= 1.5 * e_ref16 + 2e-4, (nm, e_mine, e_ref16)
+    live = [k for k in ref32[2] if float(ref32[2][k].abs().max()) > 0]
+    worst_mine = max(max_rel_err(mine[2][k], ref32[2][k]) for k in live)
+    worst_ref16 = max(max_rel_err(ref16[2][k], ref32[2][k]) for k in live)
+    assert worst_mine <= 1.5 * worst_ref16 + 1e-3, (worst_mine, worst_ref16)
 
 
 @pytest.mark.parametrize('case', [
