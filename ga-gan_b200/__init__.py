@@ -104,5 +104,14 @@ def install(reference_root=None, fused_callers=True):
     return ref_networks
 
 
+def install_rosinality(model_module, fused_layers=True):
+    """Bind this build's operators into a rosinality-style StyleGAN2 module -- GA-GAN's second code base,
+    SimilarDomains/gan_models/StyleGAN2/model.py (`ModulatedConv2d` :176-275, `op.upfirdn2d`, `op.fused_leaky_relu`); see
+    rosinality.py.  (`SimilarDomains/gan_models/StyleGAN2/nvidia.py` needs nothing of its own: it imports `torch_utils.ops.*`
+    by module path, :16-21, which `install()` already serves.)"""
+    from .rosinality import install_rosinality as bind
+    return bind(model_module, fused_layers=fused_layers)
+
+
 def installed():
     return dict(_state)

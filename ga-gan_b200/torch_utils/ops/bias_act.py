@@ -67,6 +67,8 @@ def _null_like(x):
 def _check_input(x):
     if x.device.type != 'cuda':
         raise RuntimeError('bias_act: the B200 build has no CPU path; x must be a CUDA tensor')
+    if x.dtype != torch.float32:                        # (float16 never arrives here: fp16_storage)
+        raise RuntimeError('bias_act: this build serves fp32 kernels (float16 tensors through them); other dtypes are out of scope')
     _init()
 
 
@@ -122,8 +124,6 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
     class BiasActCuda(torch.autograd.Function):
         @staticmethod
         def forward(ctx, x, b, noise=None):  # pylint: disable=arguments-differ
-            if x.dtype != torch.float32:
-                raise RuntimeError('bias_act: this build serves fp32 only')
             ctx.memory_format = torch.channels_last if x.ndim > 2 and x.stride()[1] == 1 else torch.contiguous_format
             ctx.noise_shape = tuple(noise.shape) if noise is not None else None
             if noise is not None:
@@ -163,9 +163,9 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
                 return dx, db
             dn = None
             if want_dn:                                   # the noise enters like a bias that varies per pixel instead of per channel
-                dn = dx.sum(dim=1, keepdim=True)
-                if len(ctx.noise_shape) == 2:
-                    dn = dn.sum(dim=[0, 1])
+                dn = dx.sum(dim=1, keepdim=True)          # [N,1,H,W]
+                if int(np.prod(ctx.noise_shape)) != dn.numel():   # one plane shared by the batch: [H,W] or [1,1,H,W]
+                    dn = dn.sum(dim=0)
                 dn = dn.reshape(ctx.noise_shape)
             return (dx if ctx.needs_input_grad[0] else None), db, dn
 

@@ -14,6 +14,7 @@ Unlike the reference (:61-81) the custom op is not limited to torch 1.7-1.9 and 
 CUDA tensors; `enabled` is kept for API compatibility.  CPU tensors raise: there is no fallback.
 """
 import contextlib
+import numpy as np
 import torch
 
 from .. import custom_ops
@@ -478,9 +479,9 @@ def _conv_act_s1(weight_shape, padding, out_hw, io, flip, live, pm, has_a, has_b
                               out_hw=hw, flop_scale=live, in_scale=a, out_scale=b, epilogue=epi)
 
     def unbroadcast_noise(ds, shape):
-        dn = ds.sum(dim=1, keepdim=True)
-        if len(shape) == 2:
-            dn = dn.sum(dim=[0, 1])
+        dn = ds.sum(dim=1, keepdim=True)                    # [N,1,H,W]
+        if int(np.prod(shape)) != dn.numel():               # one plane shared by the batch: [H,W] or [1,1,H,W]
+            dn = dn.sum(dim=0)
         return dn.reshape(shape)
 
     class ConvActS1(torch.autograd.Function):

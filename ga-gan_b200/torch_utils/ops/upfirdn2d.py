@@ -96,6 +96,8 @@ def setup_filter(f, device=torch.device('cpu'), normalize=True, flip_filter=Fals
 def _check_input(x):
     if x.device.type != 'cuda':
         raise RuntimeError('upfirdn2d: the B200 build has no CPU path; x must be a CUDA tensor')
+    if x.dtype != torch.float32:                        # (float16 never arrives here: fp16_storage)
+        raise RuntimeError('upfirdn2d: this build serves fp32 kernels (float16 images through them); other dtypes are out of scope')
     _init()
 
 
@@ -134,8 +136,6 @@ def _upfirdn2d_cuda(up=1, down=1, padding=0, flip_filter=False, gain=1):
         @staticmethod
         def forward(ctx, x, f):  # pylint: disable=arguments-differ
             assert isinstance(x, torch.Tensor) and x.ndim == 4
-            if x.dtype != torch.float32:
-                raise RuntimeError('upfirdn2d: this build serves fp32 only')
             if f is None:
                 f = torch.ones([1, 1], dtype=torch.float32, device=x.device)
             assert isinstance(f, torch.Tensor) and f.ndim in [1, 2]
@@ -206,7 +206,7 @@ def _fused_fir_ok(f, px0, plain_w, pm_w):
 
 
 def fir_to_pm(x, f, padding, flip_filter, gain, ys, xs):
-    _init()
+    _check_input(x)
     px0, px1, py0, py1 = _parse_padding(padding)
     if not _fused_fir_ok(f, px0, int(x.shape[3]), int(xs)):      # odd widths / other filters: the same result from the unfused ops
         return space_to_depth(upfirdn2d(x, f, padding=padding, flip_filter=flip_filter, gain=gain), ys, xs)
@@ -215,7 +215,7 @@ def fir_to_pm(x, f, padding, flip_filter, gain, ys, xs):
 
 
 def fir_from_pm(z, f, padding, flip_filter, gain, valid_hw):
-    _init()
+    _check_input(z)
     px0, px1, py0, py1 = _parse_padding(padding)
     vh, vw = int(valid_hw[0]), int(valid_hw[1])
     fw, fh = _get_filter_size(f)
@@ -237,8 +237,6 @@ def _fir_pm(to_pm, px0, py0, flip, gain, in_hw, out_hw, pm_hw):
     class FirPM(torch.autograd.Function):
         @staticmethod
         def forward(ctx, x, f):
-            if x.dtype != torch.float32:
-                raise RuntimeError('upfirdn2d: this build serves fp32 only')
             ctx.save_for_backward(f)
             if to_pm:
                 return _plugin.fir4_pm(x, f, px0, py0, flip, gain, in_hw, out_hw, out_pm=pm_hw)

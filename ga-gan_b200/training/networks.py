@@ -66,8 +66,6 @@ def modulated_conv2d(
                              padding=padding, resample_filter=resample_filter, demodulate=demodulate, flip_weight=flip_weight,
                              epilogue=to_f32(epilogue))
         return y.to(torch.float16)
-    if x.dtype != torch.float32:
-        raise RuntimeError('modulated_conv2d: this build serves float32 and float16 tensors')
 
     dcoefs = None
     if demodulate:

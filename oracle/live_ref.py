@@ -72,3 +72,34 @@ def load():
         sys.modules.update(saved)
     _cache = ns
     return ns
+
+
+SD_ROOT = os.path.join(ROOT, 'oracle', '_ref', 'SimilarDomains')
+_sd_cache = None
+
+
+def rosinality_available():
+    return os.path.isfile(os.path.join(SD_ROOT, 'gan_models', 'StyleGAN2', 'model.py'))
+
+
+def load_rosinality():
+    """The reference's second StyleGAN2 implementation (SimilarDomains/gan_models/StyleGAN2/model.py with the torch-native op/ files
+    its op/__init__.py:1-6 selects), unmodified, as a private module object: nothing stays in `sys.modules`, so the copy of the same
+    file that a test binds the product into (gagan_b200.install_rosinality) is a different object."""
+    global _sd_cache
+    if _sd_cache is not None:
+        return _sd_cache
+    if not rosinality_available():
+        raise RuntimeError(f'{SD_ROOT} is missing: run tools/vendor_reference.py where /root/reference exists')
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k.split('.')[0] == 'gan_models'}
+    sys.path.insert(0, SD_ROOT)
+    try:
+        mod = importlib.import_module('gan_models.StyleGAN2.model')
+        assert os.path.abspath(mod.__file__).startswith(SD_ROOT), mod.__file__
+    finally:
+        sys.path.remove(SD_ROOT)
+        for k in [k for k in sys.modules if k.split('.')[0] == 'gan_models']:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    _sd_cache = mod
+    return mod

@@ -39,14 +39,18 @@ class FakePlugin:
 
     def conv2d_wgrad(self, a, b, kernel_size, stride=1, padding=(0, 0), flip_w=False, out_layout=0, a_scale=None, b_scale=None, prec=None,
                      flop_scale=1.0, pm=None):
-        assert stride == 1
         kh, kw = kernel_size
+        s_ = int(stride)
         a_s = a * _bc(a_scale) if a_scale is not None else a
         b_s = b * _bc(b_scale) if b_scale is not None else b
         HA, WA, HB, WB = int(a.shape[2]), int(a.shape[3]), int(b.shape[2]), int(b.shape[3])
-        ap = F.pad(a_s, (padding[1], WB + kw - 1 - padding[1] - WA, padding[0], HB + kh - 1 - padding[0] - HA))
-        dw = torch.stack([torch.stack([torch.einsum('noyx,niyx->oi', b_s, ap[:, :, ky:ky + HB, kx:kx + WB]) for kx in range(kw)], dim=-1)
-                          for ky in range(kh)], dim=-2)              # [B, A, kh, kw]
+        # dw[o,i,ky,kx] = sum b[n,o,oy,ox] * a[n,i, oy*stride - pad + ky, ox*stride - pad + kx]   (include/gagan_b200.h)
+        need_h, need_w = (HB - 1) * s_ + kh, (WB - 1) * s_ + kw
+        ap = F.pad(a_s, (padding[1], max(need_w - padding[1] - WA, 0), padding[0], max(need_h - padding[0] - HA, 0)))
+        if s_ == 1:
+            ap = F.pad(a_s, (padding[1], WB + kw - 1 - padding[1] - WA, padding[0], HB + kh - 1 - padding[0] - HA))
+        dw = torch.stack([torch.stack([torch.einsum('noyx,niyx->oi', b_s, ap[:, :, ky:ky + (HB - 1) * s_ + 1:s_, kx:kx + (WB - 1) * s_ + 1:s_])
+                                       for kx in range(kw)], dim=-1) for ky in range(kh)], dim=-2)              # [B, A, kh, kw]
         if flip_w:
             dw = dw.flip([2, 3])
         return dw.transpose(0, 1).contiguous() if out_layout else dw

@@ -859,6 +859,63 @@ def test_mixed_precision_networks_vs_the_live_reference(device):
     assert worst_mine <= 1.5 * worst_ref16 + 1e-3, (worst_mine, worst_ref16)
 
 
+# ------------------------------------------------------------------------------------------------ rosinality adapter (row f4)
+@pytest.mark.parametrize('fused_layers', [True, False])
+def test_rosinality_networks_vs_the_unmodified_module(device, fused_layers):
+    """GA-GAN's second StyleGAN2 code base (SimilarDomains/gan_models/StyleGAN2/model.py) bound to the library by
+    gagan_b200.install_rosinality, against the same file unmodified on the CPU (its torch-native ops): image from W and from S codes,
+    logits, generator and R1 gradients.  These networks are 512 channels wide at every size, so in fp32 an occasional leaky-ReLU
+    argument changes sign between two correct implementations and moves a few gradient entries by ~1e-2 of the maximum (measured on
+    the CPU: the reference's fp32 run against its own fp64 run shows the same; the exact comparison is the fp64 CPU twin in
+    tests/test_autograd_algebra.py).  Hence: image / logits within 2e-5, 90 % of the gradient tensors within 5e-4, all within 5e-2."""
+    from oracle import live_ref
+    from tests.util import rosinality_model, max_rel_err
+    if not live_ref.rosinality_available():
+        pytest.skip('oracle/_ref/SimilarDomains is absent')
+    ref = live_ref.load_rosinality()
+    mine = rosinality_model(fused_layers=fused_layers)
+    size, style_dim = 16, 32
+    torch.manual_seed(7)
+    G_ref, D_ref = ref.Generator(size, style_dim, 2, channel_multiplier=1), ref.Discriminator(size, channel_multiplier=1)
+    with torch.no_grad():
+        for p_ in list(G_ref.parameters()) + list(D_ref.parameters()):
+            if float(p_.abs().max()) == 0:
+                p_.copy_(torch.randn(p_.shape) * 0.1)
+    G, D = mine.Generator(size, style_dim, 2, channel_multiplier=1), mine.Discriminator(size, channel_multiplier=1)
+    G.load_state_dict(G_ref.state_dict()); D.load_state_dict(D_ref.state_dict())
+    G, D = G.to(device), D.to(device)
+    z = torch.randn(2, style_dim, generator=torch.Generator().manual_seed(2))
+    real = torch.rand(2, 3, size, size, generator=torch.Generator().manual_seed(3)) * 2 - 1
+    noises = [torch.randn(1, 1, 2 ** (2 + (i + 1) // 2), 2 ** (2 + (i + 1) // 2), generator=torch.Generator().manual_seed(10 + i)) for i in range(G_ref.num_layers)]
+
+    def run(Gn, Dn, dev):
+        for p_ in list(Gn.parameters()) + list(Dn.parameters()):
+            p_.grad = None
+        nz = [n.to(dev) for n in noises]
+        img, _ = Gn([z.to(dev)], noise=nz)
+        logits = Dn(img)
+        torch.nn.functional.softplus(-logits).mean().backward()
+        g_grads = {k: p_.grad.cpu() for k, p_ in Gn.named_parameters() if p_.grad is not None}
+        x = real.to(dev).requires_grad_(True)
+        r1, = torch.autograd.grad(Dn(x).sum(), x, create_graph=True)
+        for p_ in Dn.parameters():
+            p_.grad = None
+        r1.square().sum([1, 2, 3]).mean().backward()
+        d_grads = {k: p_.grad.cpu() for k, p_ in Dn.named_parameters() if p_.grad is not None}
+        with torch.no_grad():
+            img_s = Gn(Gn.get_s_code([Gn.style(z.to(dev))], input_is_latent=True), is_s_code=True, noise=nz)[0]
+        return img.detach().cpu(), logits.detach().cpu(), g_grads, d_grads, img_s.cpu()
+
+    img, logits, gg, dg, img_s = run(G, D, device)
+    img_r, logits_r, gg_r, dg_r, img_s_r = run(G_ref, D_ref, 'cpu')
+    assert_close(img, img_r, 2e-5, 'image'); assert_close(logits, logits_r, 2e-5, 'logits'); assert_close(img_s, img_s_r, 2e-5, 'image from S codes')
+    assert set(gg) == set(gg_r) and set(dg) == set(dg_r)
+    for nm, got, want in (('G', gg, gg_r), ('R1', dg, dg_r)):
+        errs = sorted((max_rel_err(got[k], want[k]), k) for k in want if float(want[k].abs().max()) > 0)
+        assert errs[-1][0] <= 5e-2, (nm, errs[-3:])
+        assert errs[int(0.9 * (len(errs) - 1))][0] <= 5e-4, (nm, errs[int(0.9 * (len(errs) - 1))], errs[-3:])
+
+
 @pytest.mark.parametrize('case', [
     # name, shape, pad -- unit-rate filters on rows that are not 16-byte multiples, wide enough for the shared-memory row exchange of
     # fir_stream (coalesced input window from 256 output columns, coalesced output segments from 384).  The same code path ran the

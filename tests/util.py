@@ -31,6 +31,22 @@ def reference_networks():
     return training.networks
 
 
+SD_CHECKOUT = os.path.join(ROOT, 'baseline', '_ref', 'SimilarDomains')
+
+
+def rosinality_model(fused_layers=True):
+    """SimilarDomains/gan_models/StyleGAN2/model.py from the checkout that travels with the repo, with this build bound into it
+    (gagan_b200.install_rosinality); skips if the file did not travel."""
+    import pytest
+    if not os.path.isfile(os.path.join(SD_CHECKOUT, 'gan_models', 'StyleGAN2', 'model.py')):
+        pytest.skip('baseline/_ref/SimilarDomains is absent (run tools/vendor_reference.py where /root/reference exists)')
+    if SD_CHECKOUT not in sys.path:
+        sys.path.insert(0, SD_CHECKOUT)
+    import importlib
+    model = importlib.import_module('gan_models.StyleGAN2.model')
+    return gagan_b200.install_rosinality(model, fused_layers=fused_layers)
+
+
 def quiet(fn, *args, **kwargs):
     """Call `fn` with stdout swallowed (the reference prints one line per layer when it registers domain modulation)."""
     import io

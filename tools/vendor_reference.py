@@ -15,8 +15,10 @@ travel to the GPU box with the repo snapshot exactly like the built .so does.
     oracle/_ref/DissimilarDomains/     the oracle's private copy: imported under private module names by
                                        oracle/live_ref.py as the CPU `impl='ref'` ground truth of the parity tests.
 
-Only the packages the hot path's callers import are taken (SURVEY.md section 8: torch_utils, training, dnnlib);
-CLI, metrics, dataset tooling, SimilarDomains and GA are out of scope and stay where they are.
+Only the packages the hot path's callers import are taken (torch_utils, training, dnnlib), plus -- for
+row f4, the rosinality adapter -- the five files of SimilarDomains' second StyleGAN2 implementation that hold its hot path
+(gan_models/StyleGAN2/{model,nvidia}.py and the torch-native op/ files that op/__init__.py selects); CLI, metrics, dataset
+tooling, the rest of SimilarDomains and GA are out of scope and stay where they are.
 """
 import os
 import sys
@@ -27,6 +29,8 @@ import argparse
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PACKAGES = ('torch_utils', 'training', 'dnnlib')
 TARGETS = (os.path.join('baseline', '_ref'), os.path.join('oracle', '_ref'))
+SD_FILES = ('gan_models/__init__.py', 'gan_models/StyleGAN2/model.py', 'gan_models/StyleGAN2/nvidia.py', 'gan_models/StyleGAN2/op/__init__.py',
+            'gan_models/StyleGAN2/op/upfirdn2d_torch_native.py', 'gan_models/StyleGAN2/op/fused_act_torch_native.py')
 
 
 def tree_digest(path):
@@ -65,6 +69,14 @@ def vendor(reference='/root/reference', verbose=True):
                     'Git-ignored; not product source.\n')
             for pkg in PACKAGES:
                 f.write(f'{pkg} sha256 {tree_digest(os.path.join(dst_root, pkg))}\n')
+        sd_src, sd_dst = os.path.join(reference, 'SimilarDomains'), os.path.join(ROOT, target, 'SimilarDomains')
+        for rel in SD_FILES:
+            src, dst = os.path.join(sd_src, rel), os.path.join(sd_dst, rel)
+            if not os.path.isfile(src):
+                continue
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            if not os.path.isfile(dst) or open(src, 'rb').read() != open(dst, 'rb').read():
+                shutil.copy2(src, dst)
         if verbose:
             print(f'vendor_reference: {dst_root} up to date')
     return True
