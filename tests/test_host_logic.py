@@ -129,6 +129,28 @@ def test_install_binds_the_operator_modules_into_the_reference_checkout():
                 assert 'class Generator' not in src and 'class StyleGAN2Loss' not in src and 'class SynthesisBlock' not in src, fn
 
 
+def test_similar_domains_consumers_bind_to_this_build():
+    """The second consumer of the module-path boundary: SimilarDomains/gan_models/StyleGAN2/nvidia.py imports `torch_utils.ops.*`
+    (nvidia.py:16-21) and needs nothing beyond install(); the rosinality module of the same tree is bound by install_rosinality."""
+    import importlib
+    import gagan_b200
+    from tests.util import SD_CHECKOUT, rosinality_model
+    reference_networks()
+    model = rosinality_model()
+    nvidia = importlib.import_module('gan_models.StyleGAN2.nvidia')
+    assert os.path.abspath(nvidia.__file__).startswith(SD_CHECKOUT)
+    for attr in ('conv2d_resample', 'upfirdn2d', 'bias_act', 'fma'):
+        assert getattr(nvidia, attr).__name__.startswith('gagan_b200.'), attr
+    assert model.upfirdn2d.__module__ == 'gagan_b200.rosinality' and model.ModulatedConv2d.forward.__module__ == 'gagan_b200.rosinality'
+    st = model._gagan_b200_rosinality
+    gagan_b200.install_rosinality(model, fused_layers=False)                 # the module's own layer code on the replaced pieces
+    assert model.StyledConv.forward is st['styled_conv_forward'] and model.ConvLayer.forward is st['conv_layer_forward']
+    gagan_b200.install_rosinality(model, fused_layers=True)
+    assert model.StyledConv.forward.__module__ == 'gagan_b200.rosinality'
+    with pytest.raises(RuntimeError):                                        # no CPU path behind the adapter either
+        model.Upsample([1, 3, 3, 1])(torch.zeros(1, 1, 4, 4))
+
+
 def test_reference_networks_build_with_the_golden_state_dict_names():
     from tests.util import load_golden
     networks = reference_networks()
