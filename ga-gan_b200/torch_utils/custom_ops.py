@@ -76,6 +76,7 @@ _SIGNATURES = {
     'gg_fir4_pm_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 7 + [ctypes.c_float] + [ctypes.c_int] * 8 + [ctypes.c_void_p]),
     'gg_chan_dot_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
     'gg_scale_rows_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
+    'gg_fma_rows_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int64, _c_float_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
     'gg_axpby_rows_f32': (ctypes.c_int, [_c_float_p] * 5 + [ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
     'gg_conv2d_f32': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 14 + [_c_float_p, _c_float_p, ctypes.c_int,
                                                         ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
@@ -293,6 +294,26 @@ class _Plugin:
         y = torch.empty_like(x)
         with torch.cuda.device(x.device):
             _check(self._lib.gg_scale_rows_f32(_ptr(x), _ptr(s), _ptr(y), rows, x.numel() // max(rows, 1), _stream(x)), 'scale_rows')
+        return y
+
+    # y[n,c,:,:] = s[n,c] * x[n,c,:,:] + z[n or 0,:,:] (include/gagan_b200.h: gg_fma_rows_f32); z is [H,W], [1,1,H,W] or [N,1,H,W]
+    def fma_rows(self, x, s, z):
+        for nm, t in (('x', x), ('s', s), ('z', z)):
+            _require_cuda(t, nm)
+        _check_device(x)
+        if x.dim() != 4 or tuple(s.shape) != tuple(x.shape[:2]) or s.device != x.device or z.device != x.device:
+            raise RuntimeError('fma_rows: x must be [N,C,H,W], s [N,C], on one device')
+        N, C, H, W = x.shape
+        if z.numel() == H * W:
+            zbs = 0
+        elif z.numel() == N * H * W:
+            zbs = H * W
+        else:
+            raise RuntimeError('fma_rows: z must be [H,W], [1,1,H,W] or [N,1,H,W]')
+        x = x.contiguous(); s = s.contiguous(); z = z.contiguous()
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _check(self._lib.gg_fma_rows_f32(_ptr(x), _ptr(s), _ptr(z), zbs, _ptr(y), N * C, C, H * W, _stream(x)), 'fma_rows')
         return y
 
     # y[n,c,:,:] = s1[n,c] * x1[n,c,:,:] + s2[n,c] * x2[n,c,:,:] (include/gagan_b200.h: gg_axpby_rows_f32)

@@ -188,6 +188,12 @@ GG_API int gg_chan_dot_preact_f32(const float* ds, const float* y, const float* 
  * a style / demodulation gradient w.r.t. the activations).  x and y may alias. */
 GG_API int gg_scale_rows_f32(const float* x, const float* s, float* y, int64_t rows, int64_t P, gg_stream_t stream);
 
+/* y[r,p] = s[r] * x[r,p] + z[(r / C) * z_batch_stride + p]  (rows = N*C planes of P contiguous floats): replaces the torch.addcmul
+ * behind torch_utils/ops/fma.py:15-16,23 for the one shape the reference calls it with (training/networks.py:648:
+ * fma(x [N,O,H,W], dcoefs [N,O,1,1], noise [N,1,H,W] or [H,W])).  z_batch_stride is 0 (one plane for the batch) or P. */
+GG_API int gg_fma_rows_f32(const float* x, const float* s, const float* z, int64_t z_batch_stride, float* y, int64_t rows, int64_t C,
+                           int64_t P, gg_stream_t stream);
+
 /* y[r,p] = s1[r] * x1[r,p] + s2[r] * x2[r,p]: two such scaled tensors summed in one pass -- the two gradient contributions that meet in
  * front of a convolution in the second-order pass (through d/dx and through the style gradient d/da), so that one launch serves both. */
 GG_API int gg_axpby_rows_f32(const float* x1, const float* s1, const float* x2, const float* s2, float* y, int64_t rows, int64_t P,

@@ -61,6 +61,10 @@ class FakePlugin:
     def scale_rows(self, x, s):
         return x * _bc(s)
 
+    def fma_rows(self, x, s, z):
+        N, C, H, W = x.shape
+        return x * _bc(s) + (z.reshape(1, 1, H, W) if z.numel() == H * W else z.reshape(N, 1, H, W))
+
     def axpby_rows(self, x1, s1, x2, s2):
         return x1 * _bc(s1) + x2 * _bc(s2)
 

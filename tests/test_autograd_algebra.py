@@ -687,3 +687,35 @@ def test_rosinality_adapter_pieces(host_layer_on_cpu):
     odd.blur.pad = (2, 1)
     with pytest.raises(NotImplementedError):
         odd(xi, st)
+
+
+# ----------------------------------------------------------------------------
+@pytest.mark.parametrize('c_shape', ['N1HW', '11HW', 'HW'])
+def test_fma_rows_route_against_the_live_reference(host_layer_on_cpu, monkeypatch, c_shape):
+    """fma (fma.py:15-58) for the shape of its one call site (networks.py:648) takes the single-pass kernel route; values and
+    gradients up to second order against the reference's fma, in fp64 through the stand-in kernel."""
+    from oracle import live_ref
+    if not live_ref.available():
+        pytest.skip('oracle/_ref is absent')
+    L = live_ref.load()
+    from torch_utils.ops import fma as F_
+    monkeypatch.setattr(F_, '_on_device', lambda a: True)
+    g = torch.Generator().manual_seed(3)
+    N, C, H, W = 3, 5, 6, 7
+    a = torch.randn(N, C, H, W, generator=g, dtype=torch.float64)
+    b = torch.randn(N, C, 1, 1, generator=g, dtype=torch.float64)
+    c = torch.randn({'N1HW': (N, 1, H, W), '11HW': (1, 1, H, W), 'HW': (H, W)}[c_shape], generator=g, dtype=torch.float64)
+    r = torch.randn(N, C, H, W, generator=g, dtype=torch.float64)
+    assert F_._rows_shape(a, b, c) and not F_._rows_shape(a, b[:, :1], c) and not F_._rows_shape(a, b, c.reshape(-1))
+
+    def run(fn):
+        ts = [t.clone().requires_grad_(True) for t in (a, b, c)]
+        y = fn(*ts)
+        first = torch.autograd.grad((y * r).sum(), ts, create_graph=True)
+        second = torch.autograd.grad(sum(t.square().sum() for t in first), ts, allow_unused=True)
+        return [y] + list(first) + [t for t in second if t is not None]
+    got, want = run(F_.fma), run(L.fma.fma)
+    assert len(got) == len(want)
+    for i, (u, v) in enumerate(zip(got, want)):
+        assert u.shape == v.shape
+        _close(u, v, 1e-12, f'fma {c_shape} output {i}')
