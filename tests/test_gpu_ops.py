@@ -859,34 +859,6 @@ def test_mixed_precision_networks_vs_the_live_reference(device):
     assert worst_mine <= 1.5 * worst_ref16 + 1e-3, (worst_mine, worst_ref16)
 
 
-# ------------------------------------------------------------------------------------------------ fma (row a6)
-@pytest.mark.parametrize('c_shape', ['N1HW', '11HW', 'HW', 'general'])
-def test_fma_vs_oracle(ops, device, c_shape):
-    """fma.fma (fma.py:15-58) on the device against the oracle: the shape of its one call site (networks.py:648: activations x
-    per-sample channel scale + a noise plane) runs gg_fma_rows_f32 -- vectorised and (odd width) scalar variant --, any other broadcast
-    pattern the reference's torch.addcmul; gradients incl. the unbroadcast sums, and a second-order gradient."""
-    g = torch.Generator().manual_seed(3)
-    for N, C, H, W in ((3, 5, 8, 12), (2, 4, 5, 7)):
-        a = torch.randn(N, C, H, W, generator=g)
-        b = torch.randn(N, C, 1, 1, generator=g) if c_shape != 'general' else torch.randn(1, C, 1, W, generator=g)
-        c = torch.randn({'N1HW': (N, 1, H, W), '11HW': (1, 1, H, W), 'HW': (H, W), 'general': (N, C, 1, 1)}[c_shape], generator=g)
-        r = torch.randn(N, C, H, W, generator=g)
-        assert ops.fma._rows_shape(a.to(device), b.to(device), c.to(device)) == (c_shape != 'general')
-
-        def run(fn, dev):
-            ts = [t.to(dev).requires_grad_(True) for t in (a, b, c)]
-            y = fn(*ts)
-            first = torch.autograd.grad((y * r.to(dev)).sum(), ts, create_graph=True)
-            second = torch.autograd.grad(sum(t.square().sum() for t in first), ts, allow_unused=True)
-            return [y] + list(first) + [t for t in second if t is not None]
-        n0 = ops.custom_ops.launch_count()
-        got, want = run(ops.fma.fma, device), run(R.fma, 'cpu')
-        assert (ops.custom_ops.launch_count() > n0) == (c_shape != 'general')
-        assert len(got) == len(want)
-        for i, (u, v) in enumerate(zip(got, want)):
-            assert_close(u, v, 1e-5, f'fma {c_shape} {N}x{C}x{H}x{W} output {i}')
-
-
 # ------------------------------------------------------------------------------------------------ rosinality adapter (row f4)
 @pytest.mark.parametrize('fused_layers', [True, False])
 def test_rosinality_networks_vs_the_unmodified_module(device, fused_layers):
@@ -942,6 +914,34 @@ def test_rosinality_networks_vs_the_unmodified_module(device, fused_layers):
         errs = sorted((max_rel_err(got[k], want[k]), k) for k in want if float(want[k].abs().max()) > 0)
         assert errs[-1][0] <= 5e-2, (nm, errs[-3:])
         assert errs[int(0.9 * (len(errs) - 1))][0] <= 5e-4, (nm, errs[int(0.9 * (len(errs) - 1))], errs[-3:])
+
+
+# ------------------------------------------------------------------------------------------------ fma (row a6)
+@pytest.mark.parametrize('c_shape', ['N1HW', '11HW', 'HW', 'general'])
+def test_fma_vs_oracle(ops, device, c_shape):
+    """fma.fma (fma.py:15-58) on the device against the oracle: the shape of its one call site (networks.py:648: activations x
+    per-sample channel scale + a noise plane) runs gg_fma_rows_f32 -- vectorised and (odd width) scalar variant --, any other broadcast
+    pattern the reference's torch.addcmul; gradients incl. the unbroadcast sums, and a second-order gradient."""
+    g = torch.Generator().manual_seed(3)
+    for N, C, H, W in ((3, 5, 8, 12), (2, 4, 5, 7)):
+        a = torch.randn(N, C, H, W, generator=g)
+        b = torch.randn(N, C, 1, 1, generator=g) if c_shape != 'general' else torch.randn(1, C, 1, W, generator=g)
+        c = torch.randn({'N1HW': (N, 1, H, W), '11HW': (1, 1, H, W), 'HW': (H, W), 'general': (N, C, 1, 1)}[c_shape], generator=g)
+        r = torch.randn(N, C, H, W, generator=g)
+        assert ops.fma._rows_shape(a.to(device), b.to(device), c.to(device)) == (c_shape != 'general')
+
+        def run(fn, dev):
+            ts = [t.to(dev).requires_grad_(True) for t in (a, b, c)]
+            y = fn(*ts)
+            first = torch.autograd.grad((y * r.to(dev)).sum(), ts, create_graph=True)
+            second = torch.autograd.grad(sum(t.square().sum() for t in first), ts, allow_unused=True)
+            return [y] + list(first) + [t for t in second if t is not None]
+        n0 = ops.custom_ops.launch_count()
+        got, want = run(ops.fma.fma, device), run(R.fma, 'cpu')
+        assert (ops.custom_ops.launch_count() > n0) == (c_shape != 'general')
+        assert len(got) == len(want)
+        for i, (u, v) in enumerate(zip(got, want)):
+            assert_close(u, v, 1e-5, f'fma {c_shape} {N}x{C}x{H}x{W} output {i}')
 
 
 @pytest.mark.parametrize('case', [
