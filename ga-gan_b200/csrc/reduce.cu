@@ -192,23 +192,22 @@ extern "C" GG_API int gg_scale_rows_f32(const float* x, const float* s, float* y
 // (training/networks.py:648, torch_utils/ops/fma.py:15-16) for callers that keep that formulation (this build's own modulated_conv2d
 // carries both terms inside the convolution kernel).  z is one [P] plane shared by the batch (zbs == 0) or one per sample (zbs == P).
 namespace {
-__global__ void __launch_bounds__(256) fma_rows_vec4(const float4* __restrict__ x, const float* __restrict__ s, const float4* __restrict__ z,
-                                                     float4* __restrict__ y, int64_t total4, int64_t P4, int64_t C, int64_t zbs4) {
-    const int64_t stride = (int64_t)gridDim.x * 256;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total4; i += stride) {
-        const int64_t r = i / P4;
-        const float f = __ldg(s + r);
-        const float4 v = __ldg(x + i);
-        const float4 w = __ldg(z + (r / C) * zbs4 + (i - r * P4));
-        y[i] = make_float4(fmaf(f, v.x, w.x), fmaf(f, v.y, w.y), fmaf(f, v.z, w.z), fmaf(f, v.w, w.w));
-    }
-}
-__global__ void __launch_bounds__(256) fma_rows_scalar(const float* __restrict__ x, const float* __restrict__ s, const float* __restrict__ z,
-                                                       float* __restrict__ y, int64_t total, int64_t P, int64_t C, int64_t zbs) {
-    const int64_t stride = (int64_t)gridDim.x * 256;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) {
-        const int64_t r = i / P;
-        y[i] = fmaf(__ldg(s + r), __ldg(x + i), __ldg(z + (r / C) * zbs + (i - r * P)));
+// one row (= one (sample, channel) plane) per blockIdx.x, its columns spread over blockIdx.y: no per-element index division
+template <typename V>
+__global__ void __launch_bounds__(256) fma_rows_kernel(const V* __restrict__ x, const float* __restrict__ s, const V* __restrict__ z,
+                                                       V* __restrict__ y, int PV, int C, int zbsV) {
+    const int r = blockIdx.x;
+    const float f = __ldg(s + r);
+    const V* xr = x + (int64_t)r * PV;
+    const V* zr = z + (int64_t)(r / C) * zbsV;
+    V* yr = y + (int64_t)r * PV;
+    for (int64_t p = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; p < PV; p += (int64_t)gridDim.y * blockDim.x) {
+        if constexpr (sizeof(V) == 16) {
+            const float4 v = __ldg(xr + p), w = __ldg(zr + p);
+            yr[p] = make_float4(fmaf(f, v.x, w.x), fmaf(f, v.y, w.y), fmaf(f, v.z, w.z), fmaf(f, v.w, w.w));
+        } else {
+            yr[p] = fmaf(f, __ldg(xr + p), __ldg(zr + p));
+        }
     }
 }
 }  // namespace
@@ -216,18 +215,20 @@ __global__ void __launch_bounds__(256) fma_rows_scalar(const float* __restrict__
 extern "C" GG_API int gg_fma_rows_f32(const float* x, const float* s, const float* z, int64_t z_batch_stride, float* y, int64_t rows, int64_t C,
                                       int64_t P, gg_stream_t stream) {
     GG_REQUIRE(x && s && z && y, "fma_rows: null pointer");
-    GG_REQUIRE(rows >= 0 && P >= 0 && C >= 1 && rows % C == 0 && (rows == 0 || P <= 0x7fffffffLL * 4 / rows), "fma_rows: bad extents or tensor too large");
+    GG_REQUIRE(rows >= 0 && P >= 0 && C >= 1 && rows % C == 0 && rows <= 0x7fffffffLL && P <= 0x7fffffffLL &&
+               (rows == 0 || P <= 0x7fffffffLL * 4 / rows), "fma_rows: bad extents or tensor too large");
     GG_REQUIRE(z_batch_stride == 0 || z_batch_stride == P, "fma_rows: z is one [P] plane (stride 0) or one per sample (stride P)");
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t total = rows * P;
-    if (total == 0) return GG_OK;
+    if (rows * P == 0) return GG_OK;
     const bool vec = P % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(z)) & 15) == 0;
-    const int64_t work = vec ? total / 4 : total;
-    int64_t blocks = (work + 255) / 256;
-    if (blocks > (int64_t)GG_NUM_SMS * 16) blocks = (int64_t)GG_NUM_SMS * 16;
-    if (vec) fma_rows_vec4<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(x), s, reinterpret_cast<const float4*>(z),
-                                                            reinterpret_cast<float4*>(y), total / 4, P / 4, C, z_batch_stride / 4);
-    else fma_rows_scalar<<<(unsigned)blocks, 256, 0, st>>>(x, s, z, y, total, P, C, z_batch_stride);
+    const int64_t PV = vec ? P / 4 : P;
+    const int threads = (int)(PV >= 256 ? 256 : (PV + 31) / 32 * 32);
+    int64_t chunks = (PV + threads - 1) / threads;
+    if (chunks > 4096) chunks = 4096;
+    const dim3 grid((unsigned)rows, (unsigned)chunks);
+    if (vec) fma_rows_kernel<float4><<<grid, threads, 0, st>>>(reinterpret_cast<const float4*>(x), s, reinterpret_cast<const float4*>(z),
+                                                               reinterpret_cast<float4*>(y), (int)PV, (int)C, (int)(z_batch_stride / 4));
+    else fma_rows_kernel<float><<<grid, threads, 0, st>>>(x, s, z, y, (int)PV, (int)C, (int)z_batch_stride);
     return gg::check_launch("fma_rows");
 }
 
