@@ -64,6 +64,38 @@ def test_cabi_library_loads_and_exports_header_symbols():
     assert rc == -1 and b'upsampling factor' in lib.gg_last_error()
 
 
+def test_cabi_argument_validation_precedes_any_cuda_call():
+    """Error behaviour at the boundary (TORCH_CHECK -> RuntimeError becomes a negative code + gg_last_error()):
+    every entry point validates its arguments before it touches the device, so the checks run on a box without a GPU.  The
+    32-bit indexing limit of the reference (upfirdn2d.cpp:34,36, bias_act.cpp:40) is among them."""
+    lib = custom_ops.load_library()
+    P = ctypes.c_void_p(4096)                            # never dereferenced: every call below must fail validation first
+    big = 1 << 16
+
+    def expect(rc, needle):
+        msg = lib.gg_last_error() or b''
+        assert rc < 0 and needle in msg, (rc, msg)
+
+    expect(lib.gg_bias_act_f32(P, None, None, None, None, P, None, 0, 3, 0.2, 1.0, -1.0, 1 << 31, 1, 1, None), b'too large')
+    expect(lib.gg_bias_act_f32(P, None, None, None, None, P, None, 3, 3, 0.2, 1.0, -1.0, 16, 1, 1, None), b'grad must be')
+    expect(lib.gg_bias_act_f32(P, None, None, None, None, P, None, 0, 11, 0.2, 1.0, -1.0, 16, 1, 1, None), b'activation')
+    expect(lib.gg_upfirdn2d_f32(P, P, P, big, big, 4, 4, 4, 4, 1, 1, 1, 1, 0, 0, 0, 0, 0, 1.0, 1, 1, None), b'too large')
+    expect(lib.gg_upfirdn2d_f32(P, P, P, 1, 1, 8, 8, 4, 4, 1, 1, 1, 1, 0, 0, 0, 0, 0, 1.0, 6, 5, None), b'output size mismatch')
+    expect(lib.gg_upfirdn2d_f32(P, P, P, 1, 1, 2, 2, 4, 4, 1, 1, 1, 1, 0, 0, 0, 0, 0, 1.0, 1, 1, None), b'at least 1x1')
+    expect(lib.gg_upfirdn2d_f32(P, P, P, 1, 1, 8, 8, 4, 4, 1, 1, 0, 1, 0, 0, 0, 0, 0, 1.0, 5, 5, None), b'downsampling factor')
+    used = ctypes.c_int(0)
+    expect(lib.gg_conv2d_f32(P, P, P, big, 512, 64, 64, 512, 3, 3, 64, 64, 1, 1, 1, 0, 0, None, None, -1, ctypes.byref(used), None), b'too large')
+    expect(lib.gg_conv2d_f32(P, P, P, 1, 8, 16, 16, 8, 3, 3, 17, 16, 2, 1, 1, 0, 0, None, None, -1, ctypes.byref(used), None), b'output size mismatch')
+    expect(lib.gg_conv2d_f32(P, P, P, 1, 8, 16, 16, 8, 3, 3, 16, 16, 1, -1, 1, 0, 0, None, None, -1, ctypes.byref(used), None), b'stride/padding')
+    expect(lib.gg_conv2d_f32(P, P, P, 1, 8, 16, 16, 8, 3, 3, 16, 16, 1, 1, 1, 0, 0, None, None, 77, ctypes.byref(used), None), b'prec')
+    expect(lib.gg_conv2d_wgrad_f32(P, P, P, 1, 8, 16, 16, 8, 16, 16, 0, 3, 1, 1, 1, 0, 0, None, None, -1, ctypes.byref(used), None), b'bad shape')
+    expect(lib.gg_conv2d_wgrad_f32(P, P, P, big, 512, 64, 64, 8, 16, 16, 3, 3, 1, 1, 1, 0, 0, None, None, -1, ctypes.byref(used), None), b'too large')
+    expect(lib.gg_fma_rows_f32(P, P, P, 7, P, 15, 5, 96, None), b'one [P] plane')
+    expect(lib.gg_fma_rows_f32(P, P, P, 0, P, 14, 5, 96, None), b'bad extents')
+    expect(lib.gg_scale_rows_f32(P, None, P, 4, 4, None), b'null pointer')
+    assert lib.gg_fma_rows_f32(P, P, P, 0, P, 0, 5, 96, None) == 0          # empty tensors are a no-op, not an error
+
+
 def test_no_cpu_fallback_and_no_ref_impl():
     x = torch.randn(2, 3, 8, 8)
     f = upfirdn2d.setup_filter([1, 3, 3, 1])
