@@ -130,7 +130,7 @@ def test_upfirdn2d_errors(ops, device):
     with pytest.raises(RuntimeError, match='at least 1x1'):
         ops.upfirdn2d.upfirdn2d(x, f, padding=0)          # 2 - 4 + 1 < 1
     with pytest.raises(RuntimeError, match='fp32'):
-        ops.upfirdn2d.upfirdn2d(x.double(), f, padding=1)          # float64 is not served (float16 is: test_gpu_mixed_precision.py)
+        ops.upfirdn2d.upfirdn2d(x.double(), f, padding=1)          # float64 is not served (float16 is: the mixed-precision tests below)
 
 
 # ------------------------------------------------------------------------------------------------ bias_act
