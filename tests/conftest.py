@@ -15,6 +15,22 @@ def pytest_configure(config):
 @pytest.fixture(scope='session')
 def device():
     import torch
+    if os.environ.get('GG_DRYRUN'):
+        # Authoring aid for a box without a GPU: `GG_DRYRUN=1 pytest tests -m gpu` runs the PYTHON paths of the GPU tests on CPU
+        # tensors with every kernel replaced by the torch stand-in (tests/fake_plugin.py).  Tests that probe kernel-level behaviour
+        # (argument validation of the C ABI wrappers, precision modes, launch counters, torch.cuda calls) fail in this mode by
+        # design; everything else must pass -- it catches host-layer and test-code regressions before GPU time is spent.
+        from tests.fake_plugin import FakePlugin
+        from torch_utils.ops import conv2d_gradfix as cg, bias_act as BA, upfirdn2d as U, fma as FM
+        from torch_utils import custom_ops
+        fp = FakePlugin()
+        cg._plugin = fp; BA._plugin = fp; U._plugin = fp
+        for name in ('bias_act_plugin', 'upfirdn2d_plugin', 'conv2d_plugin'):
+            custom_ops._cached_plugins[name] = fp
+        for mod in (cg, U, BA):
+            mod._check_input = lambda t: None
+        FM._on_device = lambda a: True
+        return torch.device('cpu')
     if not torch.cuda.is_available():
         pytest.skip('no CUDA device')
     torch.backends.cuda.matmul.allow_tf32 = False
