@@ -5,8 +5,10 @@
     round -- two ranks with half the batch each must end with the SAME parameters as one process with the whole batch;
   * GA population evaluation shards by individual (i % world) with ONE all_gather of the fitness slices.
 
-The CUDA ops have no CPU path, so the ranks run stand-in networks with the same module interface (mapping / synthesis /
-D(img, c)); what is under test is the partitioning, the sync flags and the collectives, not the kernels.
+The CUDA ops have no CPU path, so the first two tests run stand-in networks with the same module interface (mapping /
+synthesis / D(img, c)): under test are the partitioning, the sync flags and the collectives.  The third runs the REFERENCE's
+networks and loss on this build's host layer with the kernels replaced by the torch stand-in (tests/fake_plugin.py): the CPU
+twin of tests/test_gpu_multigpu.py.
 """
 import os
 import socket
@@ -172,3 +174,104 @@ def test_ga_population_eval_shards_by_individual_with_one_all_gather():
     assert torch.allclose(r0['fit'], one['fit'], rtol=1e-6, atol=1e-7)
     assert not torch.isnan(r0['fit']).any()
     assert len(set(np.round(one['fit'].numpy(), 6))) > 1                  # the offsets do change the fitness
+
+
+# ----------------------------------------------------------------------------
+# The same two workloads on the REFERENCE's networks (the installed checkout) over this build's host layer, kernels replaced by the
+# torch stand-in: the CPU twin of tests/test_gpu_multigpu.py (2 NCCL ranks on 2 GPUs).
+
+def _host_layer_on_cpu():
+    from tests.fake_plugin import FakePlugin
+    from torch_utils.ops import conv2d_gradfix as cg, bias_act as BA, upfirdn2d as U
+    from torch_utils import custom_ops
+    fp = FakePlugin()
+    cg._plugin = fp; BA._plugin = fp; U._plugin = fp
+    for name in ('bias_act_plugin', 'upfirdn2d_plugin', 'conv2d_plugin'):
+        custom_ops._cached_plugins[name] = fp
+    for mod in (cg, U, BA):
+        mod._check_input = lambda t: None
+
+
+def _run_real_networks(rank, world, port, out_dir):
+    import tests.util as U_                                   # installs the drop-in in this process
+    _host_layer_on_cpu()
+    from training import networks, loss as loss_mod
+    from gagan_b200.training import ga_eval
+    torch.set_num_threads(2)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    dev = torch.device('cpu')
+
+    def build(ga=False):
+        extra = dict(use_domain_modulation=True, domain_modulation_parametrization='additive') if ga else {}
+        torch.manual_seed(0)
+        G = U_.quiet(networks.Generator, z_dim=16, c_dim=0, w_dim=16, img_resolution=16, img_channels=3, mapping_kwargs=dict(num_layers=2),
+                     synthesis_kwargs=dict(channel_base=256, channel_max=16, **extra))
+        D = U_.quiet(networks.Discriminator, c_dim=0, img_resolution=16, img_channels=3, channel_base=256, channel_max=16,
+                     epilogue_kwargs=dict(mbstd_num_channels=0))     # minibatch-std statistics are per-rank by design (networks.py:1284-1301)
+        return G, D
+    G, D = build()
+    G.mapping.w_avg_beta = None
+    gen = torch.Generator().manual_seed(7)
+    batch = 8
+    real = torch.rand(batch, 3, 16, 16, generator=gen) * 2 - 1
+    z = torch.randn(batch, 16, generator=gen)
+    c = torch.zeros(batch, 0)
+
+    def phase_grads(G_map, G_syn, D_, sl, phase, net):
+        for m in (G, D):
+            m.requires_grad_(False)
+            for p in m.parameters():
+                p.grad = None
+        net.requires_grad_(True)
+        L = loss_mod.StyleGAN2Loss(device=dev, G_mapping=G_map, G_synthesis=G_syn, D=D_, style_mixing_prob=0, r1_gamma=1.0, pl_weight=2.0)
+        L.accumulate_gradients(phase=phase, real_img=real[sl], real_c=c[sl], gen_z=z[sl], gen_c=c[sl], sync=True, gain=1)
+        return {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None and 'noise_strength' not in k}
+
+    phases = (('Dmain', D), ('Dreg', D), ('Gmain', G))
+    full = {phase: phase_grads(G.mapping, G.synthesis, D, slice(0, batch), phase, net) for phase, net in phases}
+    ddp = {}
+    for name, module in (('G_mapping', G.mapping), ('G_synthesis', G.synthesis), ('D', D)):
+        module.requires_grad_(True)
+        ddp[name] = torch.nn.parallel.DistributedDataParallel(module, broadcast_buffers=False)      # training_loop.py:270-285
+        module.requires_grad_(False)
+    per = batch // world
+    sl = slice(rank * per, (rank + 1) * per)
+    worst = {}
+    for phase, net in phases:
+        got = phase_grads(ddp['G_mapping'], ddp['G_synthesis'], ddp['D'], sl, phase, net)
+        assert set(got) == set(full[phase])
+        w = 0.0
+        for k, g in got.items():
+            want = full[phase][k]
+            denom = float(want.abs().max())
+            if denom > 0:
+                w = max(w, float((g - want).abs().max()) / denom)
+        worst[phase] = w
+
+    Gg, Dg = build(ga=True)
+    pop = ga_eval.init_population(Gg, size=7, scale=0.1, seed=5)
+    zz = torch.randn(4, 16, generator=torch.Generator().manual_seed(9))
+    fit = ga_eval.evaluate_population(Gg, Dg, pop, zz, rank=rank, world=world)
+    fit1 = ga_eval.evaluate_population(Gg, Dg, pop, zz, rank=0, world=1)
+    torch.save(dict(worst=worst, fit=fit, fit1=fit1), os.path.join(out_dir, f'real_r{rank}.pt'))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ddp_gradients_and_ga_sharding_on_the_reference_networks_over_gloo():
+    """Two gloo ranks with half of the batch each, the reference's mapping / synthesis / discriminator wrapped in
+    DistributedDataParallel where the reference wraps them, end a loss phase (Dmain, Dreg with its double backward, Gmain) with the
+    gradients of one process that saw the whole batch; the GA population evaluation gives every rank the single-process fitness
+    vector.  Host layer of this build, stand-in kernels."""
+    if not tests.util.HAVE_CHECKOUT:
+        pytest.skip('baseline/_ref/DissimilarDomains is absent')
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_run_real_networks, args=(2, _free_port(), d), nprocs=2, join=True)
+        r0 = torch.load(os.path.join(d, 'real_r0.pt')); r1 = torch.load(os.path.join(d, 'real_r1.pt'))
+    for r in (r0, r1):
+        for phase, w in r['worst'].items():
+            assert w <= 2e-4, (phase, w)
+    assert torch.equal(r0['fit'], r1['fit'])
+    assert torch.allclose(r0['fit'], r0['fit1'], rtol=1e-5, atol=1e-6)
