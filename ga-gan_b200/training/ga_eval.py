@@ -13,7 +13,11 @@ from its pieces (SURVEY.md section 8(d) cfg 4):
     sharding     = individual i -> rank i % world (individuals are independent); every rank holds a full G/D replica and
                    the shared latent batch; ONE all_gather of the per-rank fitness slices, nothing else crosses ranks.
 
-Selection / crossover / mutation on the gathered [P] vector is host-side work outside the hot path.
+    generation   = selection on the gathered [P] vector, the reference's crossover / mutation operators
+                   (GA/crossover_mutation.py:4-7 gaussian_crossover, :16-19 dynamic_mutation) on the genomes -- host-side, a few
+                   KB per individual, drawn on rank 0 -- and ONE broadcast of the new [P, genome] population (1.9 MB at
+                   64 x 7424), so that every rank starts the next evaluation from the same genomes: `next_generation`,
+                   `evolve`.
 """
 import torch
 import torch.distributed as dist
@@ -129,3 +133,60 @@ def evaluate_population(G, D, population, z, c=None, rank=0, world=1, fitness_fn
     out = gather_fitness(local, population.shape[0], rank, world, device)
     G.train(was_training[0]); D.train(was_training[1])
     return out
+
+
+# ----------------------------------------------------------------------------
+# One GA generation on top of the evaluation: selection, the reference's operators, one broadcast.
+
+def gaussian_crossover(parent1, parent2, generator=None):
+    """GA/crossover_mutation.py:4-7: child = mu * p1 + (1 - mu) * p2 with mu ~ N(0, 1) per gene."""
+    mu = torch.randn(parent1.shape, generator=generator, dtype=parent1.dtype)
+    return mu * parent1 + (1 - mu) * parent2
+
+
+def dynamic_mutation(genomes, mutation_rate=0.1, generator=None):
+    """GA/crossover_mutation.py:16-19: genomes + mutation_rate * N(0, 1)."""
+    return genomes + mutation_rate * torch.randn(genomes.shape, generator=generator, dtype=genomes.dtype)
+
+
+def next_generation(population, fitness, rank=0, world=1, elite=None, mutation_rate=0.1, seed=0, device=None):
+    """[P, genome] -> [P, genome]: the `elite` fittest individuals survive unchanged (default P // 4, at least one), every other
+    slot is dynamic_mutation(gaussian_crossover(a, b)) of two distinct parents drawn uniformly from the fitter half.  The random
+    draws happen on rank 0 (seeded: a run is reproducible whatever the number of ranks) and the result is broadcast -- the one
+    collective of a generation besides the all_gather of the fitness.  `device`: where the broadcast buffer lives (the rank's GPU
+    under NCCL; None = CPU / gloo).  NaN fitness (an individual that diverged) ranks last."""
+    P = int(population.shape[0])
+    assert fitness.shape == (P,)
+    elite = max(1, P // 4) if elite is None else int(elite)
+    assert 1 <= elite <= P
+    new = torch.empty_like(population)
+    if rank == 0:
+        gen = torch.Generator().manual_seed(seed)
+        order = torch.argsort(torch.nan_to_num(fitness.detach().float().cpu(), nan=float('-inf')), descending=True)
+        parents = order[:max(2, P // 2)] if P >= 2 else order
+        new[:elite] = population[order[:elite]]
+        n_child = P - elite
+        if n_child:
+            ia = torch.randint(len(parents), [n_child], generator=gen)
+            if len(parents) > 1:                                 # a distinct second parent: a non-zero cyclic shift
+                ib = (ia + torch.randint(1, len(parents), [n_child], generator=gen)) % len(parents)
+            else:
+                ib = ia
+            children = gaussian_crossover(population[parents[ia]], population[parents[ib]], generator=gen)
+            new[elite:] = dynamic_mutation(children, mutation_rate, generator=gen)
+    if world > 1:
+        buf = new.to(device) if device is not None else new
+        dist.broadcast(buf, src=0)
+        new = buf.to(population.device)
+    return new
+
+
+def evolve(G, D, population, z, generations, rank=0, world=1, seed=0, **kw):
+    """`generations` rounds of evaluate_population -> next_generation; returns (final population, [fitness per generation])."""
+    history = []
+    for g in range(int(generations)):
+        fit = evaluate_population(G, D, population, z, rank=rank, world=world, **{k: v for k, v in kw.items() if k in ('c', 'fitness_fn', 'cuda_graph')})
+        history.append(fit.detach().cpu())
+        population = next_generation(population, fit, rank=rank, world=world, seed=seed + g, device=(z.device if z.device.type == 'cuda' else None),
+                                     **{k: v for k, v in kw.items() if k in ('elite', 'mutation_rate')})
+    return population, history

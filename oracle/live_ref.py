@@ -103,3 +103,16 @@ def load_rosinality():
         sys.modules.update(saved)
     _sd_cache = mod
     return mod
+
+
+def load_ga_operators():
+    """GA/crossover_mutation.py of the reference (gaussian_crossover, simulated_binary_crossover, dynamic_mutation), loaded from
+    oracle/_ref/GA by file path -- the GA package itself cannot be imported (GA/__init__.py:5)."""
+    import importlib.util
+    path = os.path.join(ROOT, 'oracle', '_ref', 'GA', 'crossover_mutation.py')
+    if not os.path.isfile(path):
+        return None
+    spec = importlib.util.spec_from_file_location('_oracle_ref_ga_crossover_mutation', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

@@ -95,7 +95,9 @@ def _worker(rank, world, port, out_dir):
     zz = torch.randn(4, 64, generator=torch.Generator().manual_seed(9)).to(dev)
     fit = ga_eval.evaluate_population(Gg, Dg, pop, zz, rank=rank, world=world)
     fit1 = ga_eval.evaluate_population(Gg, Dg, pop, zz, rank=0, world=1)
-    torch.save(dict(worst=worst, fit=fit.cpu(), fit1=fit1.cpu()), os.path.join(out_dir, f'r{rank}.pt'))
+    # two GA generations: the new population is drawn on rank 0 and broadcast over NCCL (ga_eval.next_generation)
+    pop2, hist = ga_eval.evolve(Gg, Dg, pop, zz, generations=2, rank=rank, world=world, seed=3)
+    torch.save(dict(worst=worst, fit=fit.cpu(), fit1=fit1.cpu(), pop2=pop2.cpu(), hist=[h.cpu() for h in hist]), os.path.join(out_dir, f'r{rank}.pt'))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -114,3 +116,5 @@ def test_ddp_gradients_and_ga_sharding_over_nccl():
             assert w <= 2e-4, (phase, w)
     assert torch.equal(r0['fit'], r1['fit'])
     assert torch.allclose(r0['fit'], r0['fit1'], rtol=1e-5, atol=1e-6)
+    assert torch.equal(r0['pop2'], r1['pop2']) and all(torch.equal(a, b) for a, b in zip(r0['hist'], r1['hist']))
+    assert float(r0['hist'][1].max()) >= float(r0['hist'][0].max()) - 1e-6            # elitism

@@ -275,3 +275,78 @@ def test_ddp_gradients_and_ga_sharding_on_the_reference_networks_over_gloo():
             assert w <= 2e-4, (phase, w)
     assert torch.equal(r0['fit'], r1['fit'])
     assert torch.allclose(r0['fit'], r0['fit1'], rtol=1e-5, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------
+# One GA generation: selection on the gathered fitness, the reference's operators, one broadcast of the new population.
+
+def test_ga_operators_match_the_reference_on_shared_draws():
+    """gaussian_crossover / dynamic_mutation of ga_eval against GA/crossover_mutation.py:4-7,16-19 with the random draws routed
+    through one seeded generator on both sides; next_generation keeps the elite, breeds from the fitter half and ranks NaN last."""
+    from oracle import live_ref
+    from gagan_b200.training import ga_eval
+    ref = live_ref.load_ga_operators()
+    if ref is None:
+        pytest.skip('oracle/_ref/GA is absent')
+    g = torch.Generator().manual_seed(1)
+    p1, p2 = torch.randn(5, 33, generator=g), torch.randn(5, 33, generator=g)
+    with tests.util.patched_randn(4):
+        want_c = ref.gaussian_crossover(p1, p2)
+        want_m = ref.dynamic_mutation(want_c, mutation_rate=0.07)
+    with tests.util.patched_randn(4):
+        got_c = ga_eval.gaussian_crossover(p1, p2)
+        got_m = ga_eval.dynamic_mutation(got_c, mutation_rate=0.07)
+    assert torch.equal(got_c, want_c) and torch.equal(got_m, want_m)
+
+    pop = torch.randn(8, 33, generator=g)
+    fit = torch.tensor([0.3, float('nan'), 2.0, -1.0, 0.9, 0.1, 1.5, -0.2])
+    new = ga_eval.next_generation(pop, fit, elite=2, mutation_rate=0.0, seed=3)
+    assert torch.equal(new[0], pop[2]) and torch.equal(new[1], pop[6])                 # the two fittest survive unchanged, in order
+    assert torch.equal(new, ga_eval.next_generation(pop, fit, elite=2, mutation_rate=0.0, seed=3))        # reproducible
+    assert not torch.equal(new[2:], ga_eval.next_generation(pop, fit, elite=2, mutation_rate=0.0, seed=4)[2:])
+    # the children are bred from the fitter half {2, 6, 4, 0} only: changing the genomes of the weaker half (and of the NaN
+    # individual) changes nothing
+    other = pop.clone()
+    other[[1, 3, 5, 7]] = torch.randn(4, 33, generator=g)
+    assert torch.equal(ga_eval.next_generation(other, fit, elite=2, mutation_rate=0.0, seed=3), new)
+    assert torch.isfinite(new).all()
+    # mutation adds mutation_rate * N(0,1) on top of the same children
+    mut = ga_eval.next_generation(pop, fit, elite=2, mutation_rate=0.05, seed=3)
+    assert torch.equal(mut[:2], new[:2]) and 0.02 < float((mut[2:] - new[2:]).std()) < 0.1
+
+
+def _run_generation(rank, world, port, out_dir):
+    from gagan_b200.training import ga_eval
+    if world > 1:
+        os.environ['MASTER_ADDR'] = '127.0.0.1'
+        os.environ['MASTER_PORT'] = str(port)
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                                          # the ranks' own RNG streams differ on purpose
+    G, D = _G(), _D()
+    G.load_state_dict(torch.load(os.path.join(out_dir, 'G0.pt'))); D.load_state_dict(torch.load(os.path.join(out_dir, 'D0.pt')))
+    pop = ga_eval.init_population(G, size=7, scale=0.1, seed=5)
+    z = torch.randn(4, 8, generator=torch.Generator().manual_seed(9))
+    final, history = ga_eval.evolve(G, D, pop, z, generations=3, rank=rank, world=world, seed=11, elite=2)
+    torch.save(dict(final=final, history=history), os.path.join(out_dir, f'gen_w{world}_r{rank}.pt'))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_ga_generations_broadcast_one_population_to_every_rank():
+    """Three generations (evaluate -> select -> crossover -> mutate -> broadcast) on two gloo ranks whose own RNG streams differ: both
+    ranks hold the same population after every generation, equal to the single-process run (the draws happen on rank 0), and the
+    elite's fitness never decreases."""
+    with tempfile.TemporaryDirectory() as d:
+        torch.manual_seed(0)
+        torch.save(_G().state_dict(), os.path.join(d, 'G0.pt')); torch.save(_D().state_dict(), os.path.join(d, 'D0.pt'))
+        _run_generation(0, 1, 0, d)
+        mp.spawn(_run_generation, args=(2, _free_port(), d), nprocs=2, join=True)
+        one = torch.load(os.path.join(d, 'gen_w1_r0.pt'))
+        r0 = torch.load(os.path.join(d, 'gen_w2_r0.pt')); r1 = torch.load(os.path.join(d, 'gen_w2_r1.pt'))
+    assert torch.equal(r0['final'], r1['final'])
+    assert torch.allclose(r0['final'], one['final'], rtol=0, atol=0)
+    for a, b, c in zip(one['history'], r0['history'], r1['history']):
+        assert torch.equal(b, c) and torch.allclose(a, b, rtol=1e-6, atol=1e-7)
+    best = [float(h.max()) for h in one['history']]
+    assert best == sorted(best), best                                       # elitism: the best fitness is monotone

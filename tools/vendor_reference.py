@@ -77,6 +77,10 @@ def vendor(reference='/root/reference', verbose=True):
             os.makedirs(os.path.dirname(dst), exist_ok=True)
             if not os.path.isfile(dst) or open(src, 'rb').read() != open(dst, 'rb').read():
                 shutil.copy2(src, dst)
+        ga_src = os.path.join(reference, 'GA', 'crossover_mutation.py')            # the GA operators (19 lines; the package around
+        if os.path.isfile(ga_src) and target.startswith('oracle'):                 # them is un-importable)
+            os.makedirs(os.path.join(ROOT, target, 'GA'), exist_ok=True)
+            shutil.copy2(ga_src, os.path.join(ROOT, target, 'GA', 'crossover_mutation.py'))
         if verbose:
             print(f'vendor_reference: {dst_root} up to date')
     return True
