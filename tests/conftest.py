@@ -20,10 +20,13 @@ def device():
         # tensors with every kernel replaced by the torch stand-in (tests/fake_plugin.py).  Tests that probe kernel-level behaviour
         # (argument validation of the C ABI wrappers, precision modes, launch counters, torch.cuda calls) fail in this mode by
         # design; everything else must pass -- it catches host-layer and test-code regressions before GPU time is spent.
+        # GG_DRYRUN=2 (3, 4, ...): the stand-in additionally sums its channels in a permuted order (seed = the value): the same
+        # mathematics with another fp32 rounding, which is what the GPU kernels are to a tolerance written on the CPU.
         from tests.fake_plugin import FakePlugin
         from torch_utils.ops import conv2d_gradfix as cg, bias_act as BA, upfirdn2d as U, fma as FM
         from torch_utils import custom_ops
-        fp = FakePlugin()
+        level = int(os.environ['GG_DRYRUN'])
+        fp = FakePlugin(permute_seed=(level if level > 1 else None))
         cg._plugin = fp; BA._plugin = fp; U._plugin = fp
         for name in ('bias_act_plugin', 'upfirdn2d_plugin', 'conv2d_plugin'):
             custom_ops._cached_plugins[name] = fp

@@ -14,9 +14,19 @@ class FakePlugin:
     last_conv_prec = 0
     last_wgrad_prec = 0
 
+    def __init__(self, permute_seed=None):
+        """permute_seed: sum the contracted channels of every convolution in a (seeded) permuted order -- the same mathematics with
+        another fp32 rounding, i.e. what a second correct implementation (the GPU kernels) looks like to a test.  Used to calibrate
+        the bounds of GPU tests that cannot be run where they are written (leaky-ReLU sign flips, ill-conditioned R1 gradients)."""
+        self.permute_seed = permute_seed
+
     def conv2d(self, x, w, stride=1, padding=(0, 0), transposed=False, output_padding=(0, 0), flip_w=False, in_scale=None, out_scale=None,
                prec=None, out_hw=None, flop_scale=1.0, epilogue=None):
         assert epilogue is None
+        if self.permute_seed is not None:
+            perm = torch.randperm(int(x.shape[1]), generator=torch.Generator().manual_seed(self.permute_seed + int(x.shape[1])))
+            x, w = x[:, perm].contiguous(), (w[perm] if transposed else w[:, perm]).contiguous()
+            in_scale = in_scale[:, perm] if in_scale is not None else None
         if stride != 1:                      # the generic strided route (conv2d_gradfix._conv2d_gradfix): no scales, no free extents
             assert in_scale is None and out_scale is None and out_hw is None
             v = w.flip([2, 3]) if flip_w else w
