@@ -128,6 +128,25 @@ def _run_wgrad(grad_output, input, weight_shape, transpose, stride, padding, gro
 
 _conv2d_s1_cache = dict()
 
+pad_unaligned_rows = False          # module switch.  The tensor-core kernels read their input through TMA, whose row pitch must be a multiple
+                                    # of 16 bytes: an input whose width is not a multiple of 4 (cropped / odd-size images; never the networks'
+                                    # power-of-two maps) falls to the exact FFMA kernel at 7-15 TFLOP/s (conv_tc.cu::conv2d_tc_eligible).  With
+                                    # stride 1 the output extent is a free parameter, so zero columns appended to the input rows change nothing:
+                                    # True pads such inputs to the next multiple of 4 (one extra pass over x) and keeps them on tcgen05.  Pinned
+                                    # on the CPU (tests/test_autograd_algebra.py); its GPU test was written after the round's GPU budget was
+                                    # spent -- default off until that test has run on a B200.
+
+
+def _tma_rows(x, w_shape):
+    """x with its rows zero-padded to a multiple of 4 floats when `pad_unaligned_rows` is on and the tensor-core path would otherwise
+    lose the call (>= 16 channels on both sides, square kernel of at most 3, maps of at least 64 columns)."""
+    W = int(x.shape[3])
+    if not pad_unaligned_rows or W % 4 == 0 or W < 64:
+        return x
+    if min(int(w_shape[0]), int(w_shape[1])) < 16 or int(w_shape[2]) != int(w_shape[3]) or int(w_shape[2]) > 3:
+        return x
+    return torch.nn.functional.pad(x, (0, 4 - W % 4))
+
 
 FUSABLE_ACTS = ('linear', 'relu', 'lrelu')          # the activations the convolution kernels apply in their store loop
 fuse_epilogue = False                               # module switch.  Measured on the 1024^2 step: neutral (47.2 vs 47.3 img/s) -- the activation
@@ -229,6 +248,7 @@ def _scaled_conv2d_s1(weight_shape, padding, out_hw, io, flip, live, pm, has_a, 
     wg_kw = dict(stride=1, padding=padding, flip_w=flip, out_layout=(1 if io else 0), flop_scale=live, pm=pm)
 
     def kernel(x, w, a, b, pad, hw, io_, flip_):
+        x = _tma_rows(x, w.shape)
         if not io_:
             return _plugin.conv2d(x, w, stride=1, padding=pad, transposed=False, flip_w=flip_, out_hw=hw, flop_scale=live,
                                   in_scale=a, out_scale=b)
@@ -472,6 +492,7 @@ def _conv_act_s1(weight_shape, padding, out_hw, io, flip, live, pm, has_a, has_b
     invertible = clamp < 0 and gain != 0 and (act == 'linear' or (act == 'lrelu' and alpha != 0))
 
     def kernel(x, w, a, b, pad, hw, io_, flip_, epi=None):
+        x = _tma_rows(x, w.shape)
         if not io_:
             return _plugin.conv2d(x, w, stride=1, padding=pad, transposed=False, flip_w=flip_, out_hw=hw, flop_scale=live,
                                   in_scale=a, out_scale=b, epilogue=epi)
@@ -565,6 +586,7 @@ def _conv2d_s1(weight_shape, padding, out_hw, io, flip, live=1.0, pm=None):
     dpad = (kh - 1 - padding[0], kw - 1 - padding[1])
 
     def run(x, w):
+        x = _tma_rows(x, w.shape)
         if not io:
             return _plugin.conv2d(x, w, stride=1, padding=padding, transposed=False, flip_w=flip, out_hw=out_hw, flop_scale=live)
         return _plugin.conv2d(x, w, stride=1, padding=dpad, transposed=True, flip_w=(not flip), out_hw=out_hw, flop_scale=live)

@@ -719,3 +719,42 @@ def test_fma_rows_route_against_the_live_reference(host_layer_on_cpu, monkeypatc
     for i, (u, v) in enumerate(zip(got, want)):
         assert u.shape == v.shape
         _close(u, v, 1e-12, f'fma {c_shape} output {i}')
+
+
+# ----------------------------------------------------------------------------
+@pytest.mark.parametrize('io,flip,scales', [(False, False, ''), (True, True, ''), (False, False, 'ab'), (True, False, 'a')])
+def test_unaligned_rows_are_padded_for_the_tensor_core_path(fake_plugin, monkeypatch, io, flip, scales):
+    """conv2d_gradfix.pad_unaligned_rows: inputs whose width is not a multiple of 4 reach the kernel zero-padded to the next multiple
+    (the TMA row pitch), and nothing changes -- output, first- and second-order gradients -- because the output extent of the
+    stride-1 primitive is a free parameter.  Narrow maps, thin layers and large kernels are left alone."""
+    seen = []
+    plain = type(fake_plugin).conv2d
+
+    def spy(self, x, w, **kw):
+        seen.append((int(x.shape[3]), tuple(w.shape)))
+        return plain(self, x, w, **kw)
+    monkeypatch.setattr(type(fake_plugin), 'conv2d', spy)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 16, 9, 67, generator=g, dtype=torch.float64)
+    w = torch.randn(16, 16, 3, 3, generator=g, dtype=torch.float64) / 12
+    a = torch.randn(2, 16, generator=g, dtype=torch.float64) * 0.5 + 1 if 'a' in scales else None
+    b = torch.randn(2, 16, generator=g, dtype=torch.float64) * 0.5 + 1 if 'b' in scales else None
+    r = torch.randn(2, 16, 9, 67, generator=g, dtype=torch.float64)
+    results = {}
+    for on in (False, True):
+        monkeypatch.setattr(cg, 'pad_unaligned_rows', on)
+        seen.clear()
+        y, first, second, third, second_plain = _orders(lambda x_, w_, a_, b_: _mine(x_, w_, a_, b_, 1, io, flip), x, w, a, b, r, which=(0, 1))
+        results[on] = [y] + list(first) + [t for t in second if t is not None]
+        widths = {wd for wd, ws in seen}
+        assert widths == ({68} if on else {67}), (on, widths)           # every launch (forward, dx, second order) saw aligned rows
+    for u, v in zip(results[True], results[False]):
+        _close(u, v, 1e-12, 'padded vs unpadded rows')
+    # left alone: narrow maps, thin layers, 5x5 kernels
+    monkeypatch.setattr(cg, 'pad_unaligned_rows', True)
+    assert cg._tma_rows(torch.zeros(1, 16, 4, 33), (16, 16, 3, 3)).shape[3] == 33
+    assert cg._tma_rows(torch.zeros(1, 3, 4, 67), (16, 3, 3, 3)).shape[3] == 67
+    assert cg._tma_rows(torch.zeros(1, 16, 4, 67), (16, 16, 5, 5)).shape[3] == 67
+    assert cg._tma_rows(torch.zeros(1, 16, 4, 67), (16, 16, 1, 1)).shape[3] == 68
+    assert cg._tma_rows(torch.zeros(1, 16, 4, 68), (16, 16, 3, 3)).shape[3] == 68
+

@@ -955,6 +955,41 @@ def test_fma_vs_oracle(ops, device, c_shape):
             assert_close(u, v, 1e-5, f'fma {c_shape} {N}x{C}x{H}x{W} output {i}')
 
 
+# ------------------------------------------------------------------------------------------------ unaligned conv rows on tcgen05
+@pytest.mark.parametrize('case', [
+    # N, I, O, H, W, k, pad, transposed  -- widths that are not multiples of 4: the TMA row pitch rule sends them to the FFMA kernel
+    (2, 32, 32, 40, 67, 3, 1, False), (1, 64, 64, 70, 130, 3, 1, False), (2, 16, 128, 33, 65, 1, 0, False), (1, 128, 64, 20, 66, 3, 1, True),
+])
+def test_unaligned_conv_rows_stay_on_the_tensor_cores_when_padded(ops, device, case):
+    """conv2d_gradfix.pad_unaligned_rows (default off): with the switch on, such inputs are zero-padded to a multiple
+    of 4 columns on the host and run on the tcgen05 kernels (last_conv_prec == 3xTF32) with the results of the FFMA path."""
+    N, I, O, H, W, k, pad, transposed = case
+    g = torch.Generator().manual_seed(N * 100 + W)
+    x = torch.randn(N, I, H, W, generator=g)
+    w = torch.randn(*((I, O, k, k) if transposed else (O, I, k, k)), generator=g) / np.sqrt(I * k * k)
+    xc, wc = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    want = _conv_oracle(xc, wc, 1, pad, transposed)
+    dy = torch.randn(want.shape, generator=g)
+    wdx, wdw = torch.autograd.grad(want, [xc, wc], dy)
+    fn = ops.conv2d_gradfix.conv_transpose2d if transposed else ops.conv2d_gradfix.conv2d
+    plugin = ops.custom_ops.get_plugin('conv2d_plugin')
+    used = {}
+    for on in (False, True):
+        ops.conv2d_gradfix.pad_unaligned_rows = on
+        try:
+            xg, wg = x.to(device).requires_grad_(True), w.to(device).requires_grad_(True)
+            got = fn(xg, wg, padding=pad)
+            used[on] = plugin.last_conv_prec
+            assert got.shape == want.shape
+            assert_close(got, want, 2e-5, f'fwd (padded={on})')
+            gdx, gdw = torch.autograd.grad(got, [xg, wg], dy.to(device))
+            assert_close(gdx, wdx, 2e-5, f'dgrad (padded={on})')
+            assert_close(gdw, wdw, 1e-4, f'wgrad (padded={on})')
+        finally:
+            ops.conv2d_gradfix.pad_unaligned_rows = False
+    assert used[False] == ops.custom_ops.PREC_FP32_SIMT and used[True] == ops.custom_ops.PREC_TF32X3, used
+
+
 @pytest.mark.parametrize('case', [
     # name, shape, pad -- unit-rate filters on rows that are not 16-byte multiples, wide enough for the shared-memory row exchange of
     # fir_stream (coalesced input window from 256 output columns, coalesced output segments from 384).  The same code path ran the
