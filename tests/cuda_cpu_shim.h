@@ -1,0 +1,88 @@
+// TEST INFRASTRUCTURE: a minimal CUDA execution-model shim for running SIMT kernel SOURCE on the CPU (g++ -std=c++20 -pthread).
+//
+// One std::thread per CUDA thread of a block, blocks one after the other.  __syncthreads() / __syncwarp() are real barriers over the
+// block's / the warp's threads, __shared__ variables are function-local statics (one block at a time), blockIdx / threadIdx are
+// thread-local.  Between two barriers the threads interleave freely -- as the lanes of a warp may since independent thread
+// scheduling -- so a missing __syncwarp() is a data race that ThreadSanitizer reports (build the test with -fsanitize=thread).
+// Covers kernels written with: __global__/__device__ functions and lambdas, __shared__ arrays, __ldg, float2/float4, barriers.
+// Not covered: warp shuffles / votes, atomics, TMA, mbarriers, tensor cores.
+#pragma once
+#include <algorithm>
+#include <barrier>
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <thread>
+#include <vector>
+
+struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float2 make_float2(float a, float b) { float2 v; v.x = a; v.y = b; return v; }
+static inline float4 make_float4(float a, float b, float c, float d) { float4 v; v.x = a; v.y = b; v.z = c; v.w = d; return v; }
+using std::max;
+using std::min;
+
+static thread_local dim3 blockIdx, threadIdx;
+static dim3 blockDim, gridDim;
+static std::barrier<>* shim_block_barrier = nullptr;
+static std::vector<std::unique_ptr<std::barrier<>>> shim_warp_barriers;
+static inline void __syncthreads() { shim_block_barrier->arrive_and_wait(); }
+static inline void __syncwarp() { shim_warp_barriers[threadIdx.x / 32]->arrive_and_wait(); }
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+#define __launch_bounds__(...)
+template <class T> static inline T __ldg(const T* p) { return *p; }
+
+typedef void* cudaStream_t;
+typedef void* gg_stream_t;
+#define GG_API
+#define GG_OK 0
+#define GG_EINVAL (-1)
+#define GG_NUM_SMS 148
+static char shim_err[512];
+namespace gg {
+static inline void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(shim_err, sizeof shim_err, fmt, ap); va_end(ap); }
+static inline int check_launch(const char*) { return GG_OK; }
+}  // namespace gg
+#define GG_REQUIRE(cond, ...) do { if (!(cond)) { gg::set_error(__VA_ARGS__); return GG_EINVAL; } } while (0)
+
+static long shim_blocks_launched = 0, shim_block_threads = 0;
+
+// SHIM_LAUNCH((kernel<...>), grid, block, args...): what `kernel<...><<<grid, block, 0, stream>>>(args...)` does
+template <class K, class... A>
+static void shim_launch(K kernel, dim3 grid, dim3 block, A... args) {
+    gridDim = grid; blockDim = block;
+    shim_blocks_launched = (long)grid.x * grid.y * grid.z;
+    shim_block_threads = block.x;
+    const unsigned nt = block.x * block.y * block.z;
+    for (unsigned by = 0; by < grid.y; ++by)
+        for (unsigned bx = 0; bx < grid.x; ++bx) {
+            std::barrier<> bb(nt);
+            shim_block_barrier = &bb;
+            shim_warp_barriers.clear();
+            for (unsigned w = 0; w * 32 < nt; ++w) shim_warp_barriers.emplace_back(new std::barrier<>(std::min(32u, nt - w * 32)));
+            std::vector<std::thread> threads;
+            for (unsigned t = 0; t < nt; ++t)
+                threads.emplace_back([=, &bb]() {
+                    blockIdx = dim3(bx, by, 0);
+                    threadIdx = dim3(t % block.x, t / block.x, 0);
+                    kernel(args...);
+                    shim_warp_barriers[t / 32]->arrive_and_drop();       // a thread that has returned no longer takes part in barriers
+                    bb.arrive_and_drop();
+                });
+            for (auto& th : threads) th.join();
+        }
+}
+#define SHIM_LAUNCH(kernel, grid, block, ...) shim_launch(kernel, dim3(grid), dim3(block), __VA_ARGS__)
+extern "C" long shim_blocks() { return shim_blocks_launched; }
+extern "C" long shim_threads() { return shim_block_threads; }
+extern "C" const char* shim_error() { return shim_err; }
