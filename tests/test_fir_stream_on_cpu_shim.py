@@ -43,18 +43,28 @@ def _source():
     return '#include "cuda_cpu_shim.h"\n' + body + DRIVER
 
 
-def _build(tsan):
+_built = {}
+
+
+def _build(tsan, sanitizer='thread'):
+    key = (tsan, sanitizer)
+    if key not in _built:
+        _built[key] = _build_once(tsan, sanitizer)
+    return _built[key]
+
+
+def _build_once(tsan, sanitizer):
     d = tempfile.mkdtemp(prefix='fir_shim_')
     cpp = os.path.join(d, 'fir_stream_shim.cpp')
     with open(cpp, 'w') as f:
         f.write(_source())
-    out = os.path.join(d, 'fir_stream_tsan' if tsan else 'fir_stream_shim.so')
+    out = os.path.join(d, 'fir_stream_' + sanitizer if tsan else 'fir_stream_shim.so')
     flags = ['-std=c++20', '-O1', '-pthread', '-w', '-I', os.path.join(ROOT, 'tests')]
     if tsan:
         cpp_main = os.path.join(d, 'main.cpp')
         with open(cpp_main, 'w') as f:
             f.write(_source() + TSAN_MAIN)
-        cmd = ['g++'] + flags + ['-g', '-fsanitize=thread', '-o', out, cpp_main]
+        cmd = ['g++'] + flags + ['-g', '-fno-omit-frame-pointer', '-fsanitize=' + sanitizer, '-o', out, cpp_main]
     else:
         cmd = ['g++'] + flags + ['-shared', '-fPIC', '-o', out, cpp]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -120,15 +130,18 @@ int main(int argc, char** argv) {
     // argv: N C inH inW padx0 padx1 pady0 pady1 flip
     int a[9]; for (int i = 0; i < 9; ++i) a[i] = atoi(argv[1 + i]);
     const int N = a[0], C = a[1], H = a[2], W = a[3], outH = H + a[6] + a[7] - 3, outW = W + a[4] + a[5] - 3;
-    std::vector<float> x((size_t)N * C * H * W + 4), y((size_t)N * C * outH * outW + 4, 0.f);
-    alignas(16) float f[16];
-    for (size_t i = 0; i < x.size(); ++i) x[i] = (float)((i * 2654435761u) % 1000) / 500.f - 1.f;
+    // exact-size, 16-byte aligned heap tensors: under AddressSanitizer the red zones start right behind the last element
+    const size_t nx = (size_t)N * C * H * W, ny = (size_t)N * C * outH * outW;
+    float* xa = (float*)aligned_alloc(16, (nx * 4 + 15) / 16 * 16);
+    float* ya = (float*)aligned_alloc(16, (ny * 4 + 15) / 16 * 16);
+    float* f = (float*)aligned_alloc(16, 64);
+    for (size_t i = 0; i < nx; ++i) xa[i] = (float)((i * 2654435761u) % 1000) / 500.f - 1.f;
+    for (size_t i = 0; i < ny; ++i) ya[i] = 0.f;
     for (int i = 0; i < 16; ++i) f[i] = (float)((i % 4 == 0 || i % 4 == 3 ? 1 : 3) * (i / 4 == 0 || i / 4 == 3 ? 1 : 3)) / 64.f;
-    float* xa = x.data(); while ((uintptr_t)xa & 15) ++xa;
-    float* ya = y.data(); while ((uintptr_t)ya & 15) ++ya;
     int rc = run_fir_stream(xa, f, ya, N, C, H, W, a[4], a[6], a[8], 1.f, outH, outW);
-    double s = 0; for (size_t i = 0; i < (size_t)N * C * outH * outW; ++i) s += ya[i];
+    double s = 0; for (size_t i = 0; i < ny; ++i) s += ya[i];
     printf("rc %d checksum %.6f blocks %ld\n", rc, s, shim_blocks());
+    free(xa); free(ya); free(f);
     return rc;
 }
 '''
@@ -155,6 +168,24 @@ def test_fir_stream_exchange_buffers_are_race_free_under_thread_sanitizer(shape)
     assert res.returncode == 0 and 'rc 0' in res.stdout, res.stdout[-2000:]
 
 
+@pytest.mark.parametrize('shape', [
+    (1, 1, 12, 259, 1, 1, 1, 1, 0), (1, 2, 10, 388, 0, 3, 2, 1, 1), (1, 1, 9, 392, 1, 0, 3, 0, 0), (2, 1, 7, 131, 3, 0, 0, 3, 1),
+    (1, 1, 35, 1025, 1, 1, 2, 0, 0), (1, 3, 4, 8, 2, 1, 1, 2, 0), (1, 1, 33, 257, 1, 1, 1, 1, 0),
+], ids=['in+out', 'aligned', 'out-only', 'narrow', 'w1025', 'tiny-aligned', 'w257'])
+def test_fir_stream_touches_no_byte_outside_its_tensors_under_address_sanitizer(shape):
+    """The memcheck of this kernel family: input, filter and output are exact-size heap blocks, every global load and store of every
+    thread is instrumented -- the guarded halo loads, the 128-bit loads at the row ends, the parked lanes of the last warp, the
+    per-lane row pointers of the output exchange."""
+    try:
+        exe = _build(tsan=True, sanitizer='address')
+    except AssertionError as e:
+        pytest.skip('g++ -fsanitize=address is not available: ' + str(e)[-200:])
+    res = subprocess.run([exe] + [str(v) for v in shape], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                         env=dict(os.environ, ASAN_OPTIONS='detect_leaks=0'), timeout=600)
+    assert 'AddressSanitizer' not in res.stdout, res.stdout[-4000:]
+    assert res.returncode == 0 and 'rc 0' in res.stdout, res.stdout[-2000:]
+
+
 def test_thread_sanitizer_sees_a_removed_syncwarp():
     """The checker checks: with the barrier between the coalesced window write and the per-lane read taken out of the source, the same
     run must report a data race."""
@@ -174,3 +205,22 @@ def test_thread_sanitizer_sees_a_removed_syncwarp():
     if 'FATAL: ThreadSanitizer' in run.stdout and 'data race' not in run.stdout:
         pytest.skip('ThreadSanitizer cannot run in this container')
     assert 'data race' in run.stdout
+
+
+def test_address_sanitizer_sees_a_widened_guard():
+    """The checker checks: with the column guard of the coalesced input window widened by one (`col <= inW`), the run at a width whose
+    last row ends exactly at the end of the tensor must report a heap-buffer-overflow."""
+    old = "in[i] = (row_ok && col >= 0 && col < p.inW) ? __ldg(roww + col) : 0.f;"
+    src = _source() + TSAN_MAIN
+    assert src.count(old) == 1
+    d = tempfile.mkdtemp(prefix='fir_shim_mut_')
+    with open(os.path.join(d, 'm.cpp'), 'w') as f:
+        f.write(src.replace(old, old.replace('col < p.inW', 'col <= p.inW')))
+    exe = os.path.join(d, 'm')
+    res = subprocess.run(['g++', '-std=c++20', '-O1', '-pthread', '-w', '-g', '-fsanitize=address', '-I', os.path.join(ROOT, 'tests'), '-o', exe,
+                          os.path.join(d, 'm.cpp')], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        pytest.skip('g++ -fsanitize=address is not available')
+    run = subprocess.run([exe] + '1 1 12 259 1 1 1 1 0'.split(), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                         env=dict(os.environ, ASAN_OPTIONS='detect_leaks=0'), timeout=600)
+    assert 'heap-buffer-overflow' in run.stdout, run.stdout[-2000:]
