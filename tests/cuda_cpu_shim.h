@@ -4,10 +4,13 @@
 // block's / the warp's threads, __shared__ variables are function-local statics (one block at a time), blockIdx / threadIdx are
 // thread-local.  Between two barriers the threads interleave freely -- as the lanes of a warp may since independent thread
 // scheduling -- so a missing __syncwarp() is a data race that ThreadSanitizer reports (build the test with -fsanitize=thread).
-// Covers kernels written with: __global__/__device__ functions and lambdas, __shared__ arrays, __ldg, float2/float4, barriers.
-// Not covered: warp shuffles / votes, atomics, TMA, mbarriers, tensor cores.
+// Covers kernels written with: __global__/__device__ functions and lambdas, __shared__ arrays, __ldg, float2/float4, barriers,
+// full-mask __shfl_xor_sync (an exchange through a per-warp scratch line between two warp barriers: a lane that does not take part
+// hangs the run, as a divergent full-mask shuffle would be undefined on the device) and float atomicAdd (std::atomic_ref).
+// Not covered: votes, partial-mask shuffles, TMA, mbarriers, tensor cores.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <barrier>
 #include <cmath>
 #include <cstdarg>
@@ -31,6 +34,17 @@ static std::barrier<>* shim_block_barrier = nullptr;
 static std::vector<std::unique_ptr<std::barrier<>>> shim_warp_barriers;
 static inline void __syncthreads() { shim_block_barrier->arrive_and_wait(); }
 static inline void __syncwarp() { shim_warp_barriers[threadIdx.x / 32]->arrive_and_wait(); }
+
+static float shim_shfl_line[32][32];          // [warp of the block][lane]
+static inline float __shfl_xor_sync(unsigned /*mask: full*/, float v, int lane_mask) {
+    const unsigned w = threadIdx.x / 32, l = threadIdx.x % 32;
+    shim_shfl_line[w][l] = v;
+    __syncwarp();
+    const float r = shim_shfl_line[w][l ^ (unsigned)lane_mask];
+    __syncwarp();
+    return r;
+}
+static inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
 
 #define __global__
 #define __device__
