@@ -35,6 +35,7 @@ static std::vector<std::unique_ptr<std::barrier<>>> shim_warp_barriers;
 static inline void __syncthreads() { shim_block_barrier->arrive_and_wait(); }
 static inline void __syncwarp() { shim_warp_barriers[threadIdx.x / 32]->arrive_and_wait(); }
 
+static float shim_dynamic_smem[12288];         // what `extern __shared__ float name[];` is bound to (48 KB)
 static float shim_shfl_line[32][32];          // [warp of the block][lane]
 static inline float __shfl_xor_sync(unsigned /*mask: full*/, float v, int lane_mask) {
     const unsigned w = threadIdx.x / 32, l = threadIdx.x % 32;
