@@ -73,3 +73,90 @@ def aligned(a):
     view = raw[skew: skew + a.size].reshape(a.shape)
     view[...] = a
     return view, raw
+
+
+def _balanced(text, i, open_ch, close_ch):
+    """Index just behind the bracket that closes the one at text[i]."""
+    assert text[i] == open_ch
+    depth = 0
+    for j in range(i, len(text)):
+        if text[j] == open_ch:
+            depth += 1
+        elif text[j] == close_ch:
+            depth -= 1
+            if depth == 0:
+                return j + 1
+    raise AssertionError('unbalanced ' + open_ch)
+
+
+def _split_top(text):
+    """Split at commas that are outside every bracket."""
+    parts, depth, cur = [], 0, ''
+    for ch in text:
+        if ch in '([{':
+            depth += 1
+        elif ch in ')]}':
+            depth -= 1
+        if ch == ',' and depth == 0:
+            parts.append(cur.strip())
+            cur = ''
+        else:
+            cur += ch
+    parts.append(cur.strip())
+    return parts
+
+
+def translate_unit(cu_text, expect_launches, helpers=True):
+    """A whole .cu translation unit for the shim: everything behind its `#include "common.cuh"`, with EVERY
+    `kernel<T...><<<grid, block, smem, stream>>>(args...)` rewritten into SHIM_LAUNCH((kernel<T...>), grid, block, args...) by a
+    bracket-matching pass (any grid / block expression, any argument list), `extern __shared__` bound to the shim's buffer.
+    Nothing else of the source is touched: entry points, argument checks, launch arithmetic and kernels are the shipped text."""
+    body = cu_text[cu_text.index('#include "common.cuh"') + len('#include "common.cuh"'):]
+    out, pos, n = '', 0, 0
+    while True:
+        k = body.find('<<<', pos)
+        if k < 0:
+            break
+        # the kernel expression in front of <<<: an identifier, optionally with one template argument list
+        j = k
+        if body[j - 1] == '>':
+            depth = 0
+            while True:
+                j -= 1
+                if body[j] == '>':
+                    depth += 1
+                elif body[j] == '<':
+                    depth -= 1
+                    if depth == 0:
+                        break
+        m = re.search(r'[\w:]+$', body[:j])
+        start = m.start()
+        kernel = body[start:k]
+        e = body.index('>>>', k)
+        cfg = _split_top(body[k + 3:e])
+        assert len(cfg) in (2, 3, 4), cfg
+        a0 = e + 3
+        assert body[a0] == '(', body[a0:a0 + 20]
+        a1 = _balanced(body, a0, '(', ')')
+        out += body[pos:start] + f'SHIM_LAUNCH(({kernel}), {cfg[0]}, {cfg[1]}, {body[a0 + 1:a1 - 1]})'
+        pos = a1
+        n += 1
+    out += body[pos:]
+    assert n == expect_launches, f'expected {expect_launches} kernel launches, rewrote {n}'
+    out = re.sub(r'extern __shared__ float (\w+)\[\];', r'float* \1 = shim_dynamic_smem;', out)
+    return '#include "cuda_cpu_shim.h"\n' + (device_helpers() if helpers else '') + out
+
+
+def load(so):
+    import ctypes
+    lib = ctypes.CDLL(so)
+    lib.shim_blocks.restype = ctypes.c_long
+    lib.shim_blocks_since_reset.restype = ctypes.c_long
+    lib.shim_threads.restype = ctypes.c_long
+    lib.shim_error.restype = ctypes.c_char_p
+    return lib
+
+
+def fptr(a):
+    import ctypes
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)) if a is not None else None

@@ -16,6 +16,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <memory>
 #include <thread>
 #include <vector>
@@ -59,9 +60,14 @@ template <class T> static inline T __ldg(const T* p) { return *p; }
 
 typedef void* cudaStream_t;
 typedef void* gg_stream_t;
+typedef int cudaError_t;
+#define cudaSuccess 0
+static inline const char* cudaGetErrorString(cudaError_t) { return "shim"; }
+static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t) { memset(p, v, bytes); return cudaSuccess; }
 #define GG_API
 #define GG_OK 0
 #define GG_EINVAL (-1)
+#define GG_ECUDA (-2)
 #define GG_NUM_SMS 148
 static char shim_err[512];
 namespace gg {
@@ -69,16 +75,19 @@ static inline void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fm
 static inline int check_launch(const char*) { return GG_OK; }
 }  // namespace gg
 #define GG_REQUIRE(cond, ...) do { if (!(cond)) { gg::set_error(__VA_ARGS__); return GG_EINVAL; } } while (0)
+#define GG_CUDA(call) do { if ((call) != cudaSuccess) return GG_ECUDA; } while (0)
 
-static long shim_blocks_launched = 0, shim_block_threads = 0;
+static long shim_blocks_launched = 0, shim_blocks_total = 0, shim_block_threads = 0;
 
 // SHIM_LAUNCH((kernel<...>), grid, block, args...): what `kernel<...><<<grid, block, 0, stream>>>(args...)` does
 template <class K, class... A>
 static void shim_launch(K kernel, dim3 grid, dim3 block, A... args) {
     gridDim = grid; blockDim = block;
-    shim_blocks_launched = (long)grid.x * grid.y * grid.z;
+    shim_blocks_launched = (long)grid.x * grid.y * grid.z;      // of the last launch
+    shim_blocks_total += shim_blocks_launched;                  // of all launches since shim_reset()
     shim_block_threads = block.x;
     const unsigned nt = block.x * block.y * block.z;
+    for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
         for (unsigned bx = 0; bx < grid.x; ++bx) {
             std::barrier<> bb(nt);
@@ -88,7 +97,7 @@ static void shim_launch(K kernel, dim3 grid, dim3 block, A... args) {
             std::vector<std::thread> threads;
             for (unsigned t = 0; t < nt; ++t)
                 threads.emplace_back([=, &bb]() {
-                    blockIdx = dim3(bx, by, 0);
+                    blockIdx = dim3(bx, by, bz);
                     threadIdx = dim3(t % block.x, t / block.x, 0);
                     kernel(args...);
                     shim_warp_barriers[t / 32]->arrive_and_drop();       // a thread that has returned no longer takes part in barriers
@@ -97,7 +106,12 @@ static void shim_launch(K kernel, dim3 grid, dim3 block, A... args) {
             for (auto& th : threads) th.join();
         }
 }
-#define SHIM_LAUNCH(kernel, grid, block, ...) shim_launch(kernel, dim3(grid), dim3(block), __VA_ARGS__)
+// the kernel is called by NAME inside a generic lambda, so that overload resolution and argument-dependent lookup see what the
+// `<<<>>>` call of the source sees (conv_thin.cu launches a kernel that shares its name with the host function around the launch)
+#define SHIM_UNPAREN(...) __VA_ARGS__
+#define SHIM_LAUNCH(kernel, grid, block, ...) shim_launch([=](auto... shim_a) { SHIM_UNPAREN kernel(shim_a...); }, dim3(grid), dim3(block), __VA_ARGS__)
 extern "C" long shim_blocks() { return shim_blocks_launched; }
+extern "C" long shim_blocks_since_reset() { return shim_blocks_total; }
+extern "C" void shim_reset() { shim_blocks_launched = shim_blocks_total = 0; shim_err[0] = 0; }
 extern "C" long shim_threads() { return shim_block_threads; }
 extern "C" const char* shim_error() { return shim_err; }
