@@ -56,7 +56,7 @@ def build(name, source, kind, main=''):
 
 def run_sanitized(exe, args, timeout=900):
     """Run a sanitizer build; returns its output, or None if the sanitizer cannot run in this container."""
-    env = dict(os.environ, TSAN_OPTIONS='halt_on_error=0 exitcode=66', ASAN_OPTIONS='detect_leaks=0')
+    env = dict(os.environ, TSAN_OPTIONS='halt_on_error=0 exitcode=66 history_size=7', ASAN_OPTIONS='detect_leaks=0')
     res = subprocess.run([exe] + [str(v) for v in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=timeout)
     if 'FATAL: ThreadSanitizer' in res.stdout and 'data race' not in res.stdout:
         return None
@@ -160,3 +160,62 @@ def load(so):
 def fptr(a):
     import ctypes
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)) if a is not None else None
+
+
+def tc_common_tail():
+    """The PTX-free part of csrc/tc_common.cuh, verbatim: instruction descriptor, the 3xTF32 split, rz_compensation, the fused epilogue."""
+    t = open(os.path.join(CSRC, 'tc_common.cuh')).read()
+    tail = t[t.index('// UMMA shared-memory descriptor, SWIZZLE_NONE'):t.index("// host: point this translation unit's watchdog")]
+    assert 'asm' not in tail
+    return 'namespace ggtc {\n' + tail + '}  // namespace ggtc\n'
+
+
+def translate_tc_unit(cu_text, expect_launches):
+    """A tcgen05 translation unit for tests/tc_cpu_shim.h: everything behind its `#include "tc_common.cuh"`.  Rewritten: the `<<<>>>`
+    launches (the dynamic shared-memory size becomes the size of the CTA's heap block), `extern __shared__`, and the unit's own inline
+    PTX -- `setmaxnreg` (dropped: register allocation has no CPU counterpart), `bar.sync id, n` (the shim's named barrier) and
+    `ld.shared.v4.f32` (a plain 16-byte read).  Everything else -- warp roles, pipelines, descriptors, index arithmetic, host code -- is
+    the shipped text."""
+    body = cu_text[cu_text.index('#include "tc_common.cuh"') + len('#include "tc_common.cuh"'):]
+    body = re.sub(r'asm volatile\("setmaxnreg\.[a-z]+\.sync\.aligned\.u32 \d+;"\);', '', body)
+    body = re.sub(r'asm volatile\("bar\.sync %0, %1;" ::"r"\((\w+)\), "r"\((\w+)\) : "memory"\);', r'shim_named_barrier(\1, \2);', body)
+    body = re.sub(r'asm volatile\("ld\.shared\.v4\.f32 \{%0, %1, %2, %3\}, \[%4\];" : "=f"\((\w+)\.x\), "=f"\(\1\.y\), "=f"\(\1\.z\), "=f"\(\1\.w\) : "r"\(smem_u32\((\w+)\)\)\);',
+                  r'\1 = *reinterpret_cast<const float4*>(\2);', body)
+    assert 'asm' not in body, body[body.index('asm') - 200: body.index('asm') + 200]
+    out, pos, n = '', 0, 0
+    while True:
+        k = body.find('<<<', pos)
+        if k < 0:
+            break
+        j = k
+        if body[j - 1] == '>':
+            j = _rfind_template_open(body, j)
+        start = re.search(r'[\w:]+$', body[:j]).start()
+        kernel = body[start:k]
+        e = body.index('>>>', k)
+        cfg = _split_top(body[k + 3:e])
+        a0 = e + 3
+        a1 = _balanced(body, a0, '(', ')')
+        launch = f'SHIM_LAUNCH(({kernel}), {cfg[0]}, {cfg[1]}, {body[a0 + 1:a1 - 1]})'
+        if len(cfg) > 2 and cfg[2] != '0':
+            launch = f'(shim_set_smem({cfg[2]}), {launch})'
+        out += body[pos:start] + launch
+        pos = a1
+        n += 1
+    out += body[pos:]
+    assert n == expect_launches, f'expected {expect_launches} kernel launches, rewrote {n}'
+    out, m = re.subn(r'extern __shared__ __align__\(\d+\) uint8_t (\w+)\[\];', r'uint8_t* \1 = shim_tc_smem;', out)
+    assert m >= 1
+    return '#include "tc_cpu_shim.h"\n' + device_helpers() + tc_common_tail() + out
+
+
+def _rfind_template_open(body, j):
+    depth = 0
+    while True:
+        j -= 1
+        if body[j] == '>':
+            depth += 1
+        elif body[j] == '<':
+            depth -= 1
+            if depth == 0:
+                return j

@@ -68,7 +68,9 @@ static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStre
 #define GG_OK 0
 #define GG_EINVAL (-1)
 #define GG_ECUDA (-2)
+#ifndef GG_NUM_SMS
 #define GG_NUM_SMS 148
+#endif
 static char shim_err[512];
 namespace gg {
 static inline void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(shim_err, sizeof shim_err, fmt, ap); va_end(ap); }
@@ -78,6 +80,7 @@ static inline int check_launch(const char*) { return GG_OK; }
 #define GG_CUDA(call) do { if ((call) != cudaSuccess) return GG_ECUDA; } while (0)
 
 static long shim_blocks_launched = 0, shim_blocks_total = 0, shim_block_threads = 0;
+static void (*shim_block_hook)() = nullptr;         // called after every block (tc_cpu_shim.h resets its per-CTA objects there)
 
 // SHIM_LAUNCH((kernel<...>), grid, block, args...): what `kernel<...><<<grid, block, 0, stream>>>(args...)` does
 template <class K, class... A>
@@ -104,6 +107,7 @@ static void shim_launch(K kernel, dim3 grid, dim3 block, A... args) {
                     bb.arrive_and_drop();
                 });
             for (auto& th : threads) th.join();
+            if (shim_block_hook) shim_block_hook();
         }
 }
 // the kernel is called by NAME inside a generic lambda, so that overload resolution and argument-dependent lookup see what the

@@ -1,0 +1,354 @@
+// TEST INFRASTRUCTURE: a functional model of the Blackwell primitives the tcgen05 kernels are written with, for running their SOURCE on
+// the CPU on top of cuda_cpu_shim.h (one std::thread per CUDA thread).  It stands in for csrc/tc_common.cuh's PTX wrappers:
+//
+//   mbarrier         64-bit word in shared memory: phase, arrival count, pending arrivals, pending transaction bytes; init / arrive /
+//                    arrive.expect_tx / complete_tx / try_wait.parity with the hardware's parity rule (a wait on parity P returns once
+//                    the phase whose parity is P has completed).  Implemented with acquire / release atomics on the word itself, so
+//                    ThreadSanitizer derives the same happens-before edges the hardware guarantees -- and nothing more: a consumer
+//                    that reads a stage it did not wait for, a producer that refills a slot whose release it did not wait for, or a
+//                    parity alias (the ring-ownership bug of DESIGN section 6) shows up as a data race or an over-arrival abort.
+//   TMA              cuTensorMapEncodeTiled (own CUtensorMap layout; the driver's argument rules are checked), cp.async.bulk.tensor.4d
+//                    box loads with zero fill outside the tensor, SWIZZLE_NONE / SWIZZLE_128B, 1-D cp.async.bulk; the copy runs in the
+//                    issuing thread and ends with complete_tx on the barrier.
+//   tensor memory    128 lanes x 512 columns; tcgen05.alloc / dealloc, tcgen05.ld / st 32x32b.x16 with the lane-quarter rule
+//                    (warp w touches lanes 32 (w % 4) ..), enforced.
+//   tcgen05.mma      kind::tf32, cta_group::1, M = 128, K = 8: operands read through UMMA shared-memory descriptors (K-major,
+//                    SWIZZLE_NONE and SWIZZLE_128B canonical layouts; start / LBO / SBO fields decoded as the hardware does, the 128-byte
+//                    swizzle applied to absolute shared-memory address bits) or from tensor memory (the .ts form), inputs cut to tf32,
+//                    fp32 accumulate (round to nearest: the truncation of the real accumulator is below the tolerances used here).
+//                    Executed in the issuing thread at issue; tcgen05.commit is then an arrive with release semantics.
+//   bar.sync id, n   named barriers.
+// Shared-memory addresses are 32-bit offsets from the CTA's dynamic shared memory, which is a heap block of EXACTLY the launch's size
+// (AddressSanitizer sees every byte past it); every descriptor / TMA / mbarrier address is range-checked against that size as well.
+// Not modelled: proxy fences and tcgen05 fences (no-ops), instruction latencies, setmaxnreg, the accumulator's truncation.
+#pragma once
+#include "cuda_cpu_shim.h"
+#include <chrono>
+#include <cstdlib>
+#include <climits>
+#include <map>
+#include <mutex>
+
+#define __grid_constant__
+#define GG_EUNSUPPORTED (-3)
+#define GG_PREC_TF32X1 1
+#define GG_PREC_TF32X3 3
+
+[[noreturn]] static void shim_die(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    fprintf(stderr, "TC SHIM ABORT (block %u thread %u): ", blockIdx.x, threadIdx.x);
+    vfprintf(stderr, fmt, ap); fprintf(stderr, "\n"); va_end(ap);
+    fflush(stderr);
+    _Exit(97);
+}
+
+// ------------------------------------------------------------------------------------------------ dynamic shared memory
+static uint8_t* shim_tc_smem = nullptr;
+static size_t shim_tc_smem_bytes = 0;
+static constexpr uint32_t SHIM_SMEM_ORIGIN = 1024;        // where dynamic shared memory starts in the 32-bit shared window
+#if defined(__SANITIZE_ADDRESS__)
+extern "C" void __asan_poison_memory_region(void const volatile*, size_t);
+extern "C" void __asan_unpoison_memory_region(void const volatile*, size_t);
+#endif
+static size_t shim_tc_smem_alloc = 0;
+static inline int shim_set_smem(size_t bytes) {
+    if (bytes > 227 * 1024) shim_die("launch asks for %zu bytes of dynamic shared memory (limit 227 KB)", bytes);
+#if defined(__SANITIZE_ADDRESS__)
+    if (shim_tc_smem) __asan_unpoison_memory_region(shim_tc_smem, shim_tc_smem_alloc);
+#endif
+    free(shim_tc_smem);
+    shim_tc_smem_alloc = (bytes + 1023) / 1024 * 1024;
+    shim_tc_smem = (uint8_t*)aligned_alloc(1024, shim_tc_smem_alloc);
+    memset(shim_tc_smem, 0xA5, shim_tc_smem_alloc);              // shared memory is not zero at kernel start
+    // exact size for AddressSanitizer: the rounding tail is poisoned by hand when the build has ASan
+#if defined(__SANITIZE_ADDRESS__)
+    __asan_poison_memory_region(shim_tc_smem + bytes, shim_tc_smem_alloc - bytes);
+#endif
+    shim_tc_smem_bytes = bytes;
+    return 0;
+}
+static inline uint8_t* shim_smem_ptr(uint32_t addr, size_t bytes, const char* what) {
+    if (addr < SHIM_SMEM_ORIGIN || (size_t)(addr - SHIM_SMEM_ORIGIN) + bytes > shim_tc_smem_bytes)
+        shim_die("%s: shared-memory range [%u, +%zu) is outside the CTA's %zu bytes", what, addr - SHIM_SMEM_ORIGIN, bytes, shim_tc_smem_bytes);
+    return shim_tc_smem + (addr - SHIM_SMEM_ORIGIN);
+}
+
+// ------------------------------------------------------------------------------------------------ small intrinsics
+static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline unsigned atomicOr(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_or(v, std::memory_order_relaxed); }
+static uint32_t shim_xchg_line[32][32];
+static inline uint32_t __shfl_sync(unsigned /*full*/, uint32_t v, int src) {
+    const unsigned w = threadIdx.x / 32, l = threadIdx.x % 32;
+    shim_xchg_line[w][l] = v;
+    __syncwarp();
+    const uint32_t r = shim_xchg_line[w][src & 31];
+    __syncwarp();
+    return r;
+}
+static inline int __shfl_sync(unsigned m, int v, int src) { return (int)__shfl_sync(m, (uint32_t)v, src); }
+static inline unsigned __ballot_sync(unsigned /*full*/, bool pred) {
+    const unsigned w = threadIdx.x / 32, l = threadIdx.x % 32;
+    shim_xchg_line[w][l] = pred ? 1u : 0u;
+    __syncwarp();
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) r |= shim_xchg_line[w][i] << i;
+    __syncwarp();
+    return r;
+}
+static std::mutex shim_named_mu;
+static std::map<int, std::unique_ptr<std::barrier<>>> shim_named;       // cleared by shim_tc_block_reset()
+static inline void shim_named_barrier(int id, int nthreads) {
+    std::barrier<>* b;
+    {
+        std::lock_guard<std::mutex> g(shim_named_mu);
+        auto& slot = shim_named[id];
+        if (!slot) slot.reset(new std::barrier<>(nthreads));
+        b = slot.get();
+    }
+    b->arrive_and_wait();
+}
+
+// ------------------------------------------------------------------------------------------------ host runtime stubs
+typedef int CUresult;
+#define CUDA_SUCCESS 0
+typedef unsigned long long cuuint64_t;
+typedef unsigned int cuuint32_t;
+enum CUtensorMapDataType { CU_TENSOR_MAP_DATA_TYPE_FLOAT32 = 7 };
+enum CUtensorMapInterleave { CU_TENSOR_MAP_INTERLEAVE_NONE = 0 };
+enum CUtensorMapSwizzle { CU_TENSOR_MAP_SWIZZLE_NONE = 0, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_SWIZZLE_128B };
+enum CUtensorMapL2promotion { CU_TENSOR_MAP_L2_PROMOTION_NONE = 0, CU_TENSOR_MAP_L2_PROMOTION_L2_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B };
+enum CUtensorMapFloatOOBfill { CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE = 0, CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA };
+struct alignas(64) CUtensorMap {
+    const uint8_t* base; uint32_t rank, swizzle;
+    uint64_t dim[4]; uint64_t stride[4];       // stride[0] = element size; bytes
+    uint32_t box[4];
+};
+static_assert(sizeof(CUtensorMap) <= 128, "the real CUtensorMap is 128 bytes");
+// the driver's documented argument rules (cuTensorMapEncodeTiled): a violation returns CUDA_ERROR_INVALID_VALUE
+static CUresult shim_encode_tiled(CUtensorMap* m, CUtensorMapDataType dt, cuuint32_t rank, void* base, const cuuint64_t* gdim, const cuuint64_t* gstr,
+                                  const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapInterleave il, CUtensorMapSwizzle sw, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill) {
+    if (dt != CU_TENSOR_MAP_DATA_TYPE_FLOAT32 || rank != 4 || il != CU_TENSOR_MAP_INTERLEAVE_NONE) return 1;
+    if (((uintptr_t)base & 15) != 0) return 1;
+    if (sw != CU_TENSOR_MAP_SWIZZLE_NONE && sw != CU_TENSOR_MAP_SWIZZLE_128B) return 1;
+    for (int i = 0; i < 4; ++i) {
+        if (gdim[i] < 1 || gdim[i] > (1ull << 32) || box[i] < 1 || box[i] > 256 || estr[i] != 1) return 1;
+        if (i < 3 && (gstr[i] % 16 != 0 || gstr[i] >= (1ull << 40))) return 1;
+    }
+    if ((box[0] * 4) % 16 != 0) return 1;
+    if (sw == CU_TENSOR_MAP_SWIZZLE_128B && box[0] * 4 > 128) return 1;     // the inner box dimension must fit the swizzle span
+    m->base = (const uint8_t*)base; m->rank = rank; m->swizzle = (uint32_t)sw;
+    m->stride[0] = 4;
+    for (int i = 0; i < 4; ++i) { m->dim[i] = gdim[i]; m->box[i] = box[i]; if (i < 3) m->stride[i + 1] = gstr[i]; }
+    return CUDA_SUCCESS;
+}
+typedef int cudaDriverEntryPointQueryResult;
+#define cudaDriverEntryPointSuccess 0
+#define cudaEnableDefault 0
+static inline cudaError_t cudaGetDriverEntryPoint(const char* name, void** fn, int, cudaDriverEntryPointQueryResult* q) {
+    if (strcmp(name, "cuTensorMapEncodeTiled") != 0) return 1;
+    *fn = (void*)&shim_encode_tiled; *q = cudaDriverEntryPointSuccess;
+    return cudaSuccess;
+}
+typedef void* cudaMemPool_t;
+#define cudaMemPoolAttrReleaseThreshold 0
+#define cudaFuncAttributeMaxDynamicSharedMemorySize 0
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* p, int) { *p = nullptr; return cudaSuccess; }
+static inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, int, void*) { return cudaSuccess; }
+template <class K> static inline cudaError_t cudaFuncSetAttribute(K, int, int) { return cudaSuccess; }
+static std::atomic<long> shim_scratch_live{0};
+template <class T> static inline cudaError_t cudaMallocAsync(T** p, size_t bytes, cudaStream_t) {
+    *p = (T*)aligned_alloc(16, (bytes + 15) / 16 * 16);           // exact size up to the 16-byte grain of the bulk copies
+    ++shim_scratch_live;
+    return *p ? cudaSuccess : 1;
+}
+static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); --shim_scratch_live; return cudaSuccess; }
+extern "C" long shim_scratch_blocks_live() { return shim_scratch_live.load(); }
+namespace gg {
+static inline bool done_on_this_device(const std::atomic<uint64_t>& f) { return f.load() != 0; }
+static inline void mark_done_on_this_device(std::atomic<uint64_t>& f) { f.store(1); }
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn();
+}  // namespace gg
+
+namespace ggtc {
+
+static inline uint32_t smem_u32(const void* p) {
+    const ptrdiff_t off = (const uint8_t*)p - shim_tc_smem;
+    if (off < 0 || (size_t)off > shim_tc_smem_bytes + 1024) shim_die("smem_u32 of a pointer outside dynamic shared memory");
+    return (uint32_t)off + SHIM_SMEM_ORIGIN;
+}
+static inline bool elect_one() { return threadIdx.x % 32 == 0; }
+static inline void fence_barrier_init() {}
+static inline void fence_proxy_async() {}
+static inline void tc_fence_before() {}
+static inline void tc_fence_after() {}
+static inline void wd_arm() {}
+
+// ---- mbarrier: [63:56] phase  [55:44] arrival count  [43:32] pending arrivals  [31:0] pending transaction bytes
+static inline std::atomic_ref<uint64_t> shim_bar(uint32_t bar, const char* what) {
+    if (bar & 7) shim_die("%s: mbarrier address %u is not 8-byte aligned", what, bar);
+    return std::atomic_ref<uint64_t>(*reinterpret_cast<uint64_t*>(shim_smem_ptr(bar, 8, what)));
+}
+static inline void mbar_init(uint32_t bar, uint32_t count) {
+    if (count < 1 || count > 4095) shim_die("mbarrier.init: count %u", count);
+    shim_bar(bar, "mbarrier.init").store(((uint64_t)count << 44) | ((uint64_t)count << 32), std::memory_order_release);
+}
+static inline void shim_bar_update(uint32_t bar, int arrivals, int64_t tx, const char* what) {
+    auto b = shim_bar(bar, what);
+    uint64_t old = b.load(std::memory_order_relaxed), neu;
+    do {
+        uint64_t phase = old >> 56, count = (old >> 44) & 0xFFF, pend = (old >> 32) & 0xFFF;
+        int64_t bytes = (int64_t)(int32_t)(uint32_t)old + tx;
+        if (count == 0) shim_die("%s on an mbarrier that was never initialised (address %u)", what, bar - SHIM_SMEM_ORIGIN);
+        if ((int64_t)pend < arrivals) shim_die("%s: over-arrival on mbarrier %u (phase %llu: count %llu, %llu pending)", what, bar - SHIM_SMEM_ORIGIN,
+                                                (unsigned long long)phase, (unsigned long long)count, (unsigned long long)pend);
+        if (bytes < 0 || bytes > INT32_MAX) shim_die("%s: transaction count of mbarrier %u out of range (%lld)", what, bar - SHIM_SMEM_ORIGIN, (long long)bytes);
+        pend -= arrivals;
+        if (pend == 0 && bytes == 0) { phase = (phase + 1) & 0xFF; pend = count; }
+        neu = (phase << 56) | (count << 44) | (pend << 32) | (uint32_t)bytes;
+    } while (!b.compare_exchange_weak(old, neu, std::memory_order_acq_rel, std::memory_order_relaxed));
+}
+static inline void mbar_arrive(uint32_t bar) { shim_bar_update(bar, 1, 0, "mbarrier.arrive"); }
+static inline void mbar_expect_tx(uint32_t bar, uint32_t bytes) { shim_bar_update(bar, 1, bytes, "mbarrier.arrive.expect_tx"); }
+static inline void shim_complete_tx(uint32_t bar, uint32_t bytes) { shim_bar_update(bar, 0, -(int64_t)bytes, "complete_tx"); }
+static inline void umma_commit(uint32_t bar) { shim_bar_update(bar, 1, 0, "tcgen05.commit"); }     // the MMAs of this thread ran at issue
+static inline void mbar_wait(uint32_t bar, uint32_t parity) {
+    auto b = shim_bar(bar, "mbarrier.try_wait");
+    const auto t0 = std::chrono::steady_clock::now();
+    static const long limit_s = getenv("SHIM_WAIT_TIMEOUT_S") ? atol(getenv("SHIM_WAIT_TIMEOUT_S")) : 240;      // the model's watchdog
+    for (uint32_t it = 0;; ++it) {
+        if (((b.load(std::memory_order_acquire) >> 56) & 1) != (parity & 1)) return;
+        std::this_thread::yield();
+        if ((it & 0xFFF) == 0xFFF && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(limit_s))
+            shim_die("mbarrier wait timed out: barrier %u parity %u -- the pipeline is deadlocked", bar - SHIM_SMEM_ORIGIN, parity);
+    }
+}
+static inline void mbar_wait_spin(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+
+// ---- TMA
+static inline uint32_t shim_swizzle128(uint32_t addr) { return addr ^ (((addr >> 7) & 7u) << 4); }
+static inline void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+    const int c[4] = {c0, c1, c2, c3};
+    const size_t bytes = (size_t)m->box[0] * m->box[1] * m->box[2] * m->box[3] * 4;
+    if (dst & (m->swizzle == CU_TENSOR_MAP_SWIZZLE_128B ? 1023u : 127u))
+        shim_die("cp.async.bulk.tensor: destination %u is not %s aligned", dst - SHIM_SMEM_ORIGIN, m->swizzle ? "1024-byte (SWIZZLE_128B)" : "128-byte");
+    if (((int64_t)c0 * 4) % 16 != 0) shim_die("cp.async.bulk.tensor: innermost coordinate %d is not on a 16-byte boundary", c0);
+    uint8_t* out = shim_smem_ptr(dst, bytes, "cp.async.bulk.tensor");
+    size_t lin = 0;
+    for (uint32_t i3 = 0; i3 < m->box[3]; ++i3)
+        for (uint32_t i2 = 0; i2 < m->box[2]; ++i2)
+            for (uint32_t i1 = 0; i1 < m->box[1]; ++i1)
+                for (uint32_t i0 = 0; i0 < m->box[0]; ++i0, lin += 4) {
+                    const int64_t g[4] = {c[0] + (int64_t)i0, c[1] + (int64_t)i1, c[2] + (int64_t)i2, c[3] + (int64_t)i3};
+                    bool in = true;
+                    size_t off = 0;
+                    for (int d = 0; d < 4; ++d) { in = in && g[d] >= 0 && (uint64_t)g[d] < m->dim[d]; off += (size_t)g[d] * m->stride[d]; }
+                    float v = 0.f;
+                    if (in) memcpy(&v, m->base + off, 4);
+                    const uint32_t a = m->swizzle == CU_TENSOR_MAP_SWIZZLE_128B ? shim_swizzle128(dst + (uint32_t)lin) - dst : (uint32_t)lin;
+                    memcpy(out + a, &v, 4);
+                }
+    shim_complete_tx(bar, (uint32_t)bytes);
+}
+static inline void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    if ((dst & 15) || ((uintptr_t)src & 15) || (bytes & 15) || bytes == 0) shim_die("cp.async.bulk: dst / src / size must be multiples of 16 bytes");
+    memcpy(shim_smem_ptr(dst, bytes, "cp.async.bulk"), src, bytes);
+    shim_complete_tx(bar, bytes);
+}
+
+// ---- tensor memory
+static uint32_t shim_tmem[128][512];
+static uint32_t shim_tmem_cols = 0;             // columns currently allocated (one allocation per CTA in these kernels)
+static inline void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {     // .sync.aligned: the whole warp executes it, one lane acts
+    if (threadIdx.x % 32 != 0) return;
+    if (ncols < 32 || ncols > 512 || (ncols & (ncols - 1))) shim_die("tcgen05.alloc: %u columns (must be a power of two in 32 .. 512)", ncols);
+    if (shim_tmem_cols != 0) shim_die("tcgen05.alloc while the CTA already holds an allocation");
+    shim_tmem_cols = ncols;
+    const uint32_t taddr = 0;
+    memcpy(shim_smem_ptr(dst_smem, 4, "tcgen05.alloc"), &taddr, 4);
+}
+static inline void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    if (threadIdx.x % 32 != 0) return;
+    if (taddr != 0 || ncols != shim_tmem_cols) shim_die("tcgen05.dealloc of %u columns at %u: not what was allocated (%u)", ncols, taddr, shim_tmem_cols);
+    shim_tmem_cols = 0;
+}
+static inline uint32_t* shim_tmem_row(uint32_t taddr, uint32_t ncols, const char* what) {
+    const uint32_t lane0 = taddr >> 16, col = taddr & 0xFFFF, warp = threadIdx.x / 32;
+    if (lane0 != 32 * (warp % 4)) shim_die("%s: warp %u addresses tensor-memory lanes from %u (it may only touch lanes %u ..)", what, warp, lane0, 32 * (warp % 4));
+    if (col + ncols > shim_tmem_cols) shim_die("%s: columns [%u, +%u) are outside the allocation of %u", what, col, ncols, shim_tmem_cols);
+    return &shim_tmem[lane0 + threadIdx.x % 32][col];
+}
+static inline void tmem_ld16_nowait(uint32_t taddr, uint32_t* v) { memcpy(v, shim_tmem_row(taddr, 16, "tcgen05.ld"), 64); }
+static inline void tmem_wait_ld() {}
+static inline void tmem_ld16(uint32_t taddr, uint32_t* v) { tmem_ld16_nowait(taddr, v); }
+static inline void tmem_st16(uint32_t taddr, const uint32_t* v) { memcpy(shim_tmem_row(taddr, 16, "tcgen05.st"), v, 64); }
+static inline void tmem_wait_st() {}
+
+// ---- tcgen05.mma kind::tf32
+struct ShimDesc { uint32_t start, lbo, sbo, layout; };
+static inline ShimDesc shim_decode(uint64_t d) {
+    if (((d >> 46) & 3) != 1) shim_die("UMMA descriptor: version field is %u (sm_100 needs 1)", (unsigned)((d >> 46) & 3));
+    if (((d >> 49) & 7) != 0) shim_die("UMMA descriptor: non-zero base offset");
+    ShimDesc s{(uint32_t)(d & 0x3FFF) << 4, (uint32_t)((d >> 16) & 0x3FFF) << 4, (uint32_t)((d >> 32) & 0x3FFF) << 4, (uint32_t)(d >> 61) & 7};
+    if (s.layout != 0 && s.layout != 2) shim_die("UMMA descriptor: layout type %u is not modelled (0 = no swizzle, 2 = 128-byte swizzle)", s.layout);
+    return s;
+}
+// K-major operand element (row r, tf32 element k of this instruction's 8): canonical layouts of cute/arch/mma_sm100_desc.hpp
+static inline float shim_operand(const ShimDesc& s, int r, int k) {
+    uint32_t a;
+    if (s.layout == 0) a = s.start + (uint32_t)(r & 7) * 16 + (uint32_t)(r >> 3) * s.sbo + (uint32_t)(k >> 2) * s.lbo + (uint32_t)(k & 3) * 4;
+    else a = shim_swizzle128(s.start + (uint32_t)(r >> 3) * s.sbo + (uint32_t)(r & 7) * 128 + (uint32_t)k * 4);
+    uint32_t u;
+    memcpy(&u, shim_smem_ptr(a, 4, "tcgen05.mma operand"), 4);
+    return __uint_as_float(u & 0xFFFFE000u);                      // the tensor core reads 19 bits
+}
+static inline void shim_idesc(uint32_t idesc, int& M, int& N) {
+    if (((idesc >> 4) & 3) != 1 || ((idesc >> 7) & 7) != 2 || ((idesc >> 10) & 7) != 2) shim_die("instruction descriptor: not f32 += tf32 x tf32");
+    if (((idesc >> 15) & 1) || ((idesc >> 16) & 1)) shim_die("instruction descriptor: MN-major operands are not modelled");
+    N = (int)((idesc >> 17) & 0x3F) << 3; M = (int)((idesc >> 24) & 0x1F) << 4;
+    if (M != 128 || N < 16 || N > 256 || N % 16) shim_die("instruction descriptor: M = %d, N = %d is not a legal cta_group::1 shape", M, N);
+}
+static std::atomic<long> shim_mma_count{0};
+static inline void shim_mma(uint32_t tmem_d, const ShimDesc* a, uint32_t tmem_a, const ShimDesc& b, uint32_t idesc, uint32_t accumulate) {
+    int M, N; shim_idesc(idesc, M, N);
+    const uint32_t dcol = tmem_d & 0xFFFF;
+    if ((tmem_d >> 16) != 0 || dcol + (uint32_t)N > shim_tmem_cols) shim_die("tcgen05.mma: accumulator columns [%u, +%d) outside the allocation of %u", dcol, N, shim_tmem_cols);
+    if (!a && ((tmem_a >> 16) != 0 || (tmem_a & 0xFFFF) + 8 > shim_tmem_cols)) shim_die("tcgen05.mma: A operand columns outside the tensor-memory allocation");
+    shim_mma_count.fetch_add(1, std::memory_order_relaxed);
+    float bt[256][8];
+    for (int n = 0; n < N; ++n) for (int k = 0; k < 8; ++k) bt[n][k] = shim_operand(b, n, k);
+    for (int m = 0; m < M; ++m) {
+        float av[8];
+        for (int k = 0; k < 8; ++k) av[k] = a ? shim_operand(*a, m, k) : __uint_as_float(shim_tmem[m][(tmem_a & 0xFFFF) + k] & 0xFFFFE000u);
+        for (int n = 0; n < N; ++n) {
+            double s = 0;
+            for (int k = 0; k < 8; ++k) s += (double)av[k] * (double)bt[n][k];
+            uint32_t& d = shim_tmem[m][dcol + n];
+            d = __float_as_uint(accumulate ? __uint_as_float(d) + (float)s : (float)s);
+        }
+    }
+}
+static inline void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const ShimDesc a = shim_decode(adesc), b = shim_decode(bdesc);
+    shim_mma(tmem_d, &a, 0, b, idesc, accumulate);
+}
+static inline void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const ShimDesc b = shim_decode(bdesc);
+    shim_mma(tmem_d, nullptr, tmem_a, b, idesc, accumulate);
+}
+
+}  // namespace ggtc
+
+extern "C" long shim_mma_instructions() { return ggtc::shim_mma_count.load(); }
+// per CTA: named barriers are per-CTA objects, tensor memory must have been given back
+static inline void shim_tc_block_reset() {
+    shim_named.clear();
+    if (ggtc::shim_tmem_cols != 0) shim_die("a CTA exited without tcgen05.dealloc");
+}
+static const int shim_tc_hook_installed = (shim_block_hook = shim_tc_block_reset, 0);
