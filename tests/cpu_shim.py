@@ -206,6 +206,7 @@ def translate_tc_unit(cu_text, expect_launches):
     assert n == expect_launches, f'expected {expect_launches} kernel launches, rewrote {n}'
     out, m = re.subn(r'extern __shared__ __align__\(\d+\) uint8_t (\w+)\[\];', r'uint8_t* \1 = shim_tc_smem;', out)
     assert m >= 1
+    out = out.replace('#include <cuda.h>', '')
     return '#include "tc_cpu_shim.h"\n' + device_helpers() + tc_common_tail() + out
 
 

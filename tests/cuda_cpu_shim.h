@@ -72,17 +72,28 @@ static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStre
 #define GG_NUM_SMS 148
 #endif
 static char shim_err[512];
+#ifdef SHIM_MULTI_UNIT      // several translation units linked into one library (tests/emulated_lib.py): api.cu's own definitions are used
+namespace gg {
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+static inline int check_launch(const char*) { g_launches.fetch_add(1, std::memory_order_relaxed); return GG_OK; }
+}  // namespace gg
+#else
 namespace gg {
 static inline void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(shim_err, sizeof shim_err, fmt, ap); va_end(ap); }
 static inline int check_launch(const char*) { return GG_OK; }
 }  // namespace gg
+#endif
 #define GG_REQUIRE(cond, ...) do { if (!(cond)) { gg::set_error(__VA_ARGS__); return GG_EINVAL; } } while (0)
 #define GG_CUDA(call) do { if ((call) != cudaSuccess) return GG_ECUDA; } while (0)
 
 static long shim_blocks_launched = 0, shim_blocks_total = 0, shim_block_threads = 0;
 static void (*shim_block_hook)() = nullptr;         // called after every block (tc_cpu_shim.h resets its per-CTA objects there)
 
-// SHIM_LAUNCH((kernel<...>), grid, block, args...): what `kernel<...><<<grid, block, 0, stream>>>(args...)` does
+// SHIM_LAUNCH((kernel<...>), grid, block, args...): what `kernel<...><<<grid, block, 0, stream>>>(args...)` does.  The block's threads are
+// created once per launch and walk the blocks together (two rendezvous per block instead of a thread spawn per CUDA thread); the
+// block / warp barriers are fresh objects for every block, because a thread that has returned from the kernel drops out of them.
+static std::unique_ptr<std::barrier<>> shim_block_barrier_owner;
 template <class K, class... A>
 static void shim_launch(K kernel, dim3 grid, dim3 block, A... args) {
     gridDim = grid; blockDim = block;
@@ -90,32 +101,41 @@ static void shim_launch(K kernel, dim3 grid, dim3 block, A... args) {
     shim_blocks_total += shim_blocks_launched;                  // of all launches since shim_reset()
     shim_block_threads = block.x;
     const unsigned nt = block.x * block.y * block.z;
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-        for (unsigned bx = 0; bx < grid.x; ++bx) {
-            std::barrier<> bb(nt);
-            shim_block_barrier = &bb;
-            shim_warp_barriers.clear();
-            for (unsigned w = 0; w * 32 < nt; ++w) shim_warp_barriers.emplace_back(new std::barrier<>(std::min(32u, nt - w * 32)));
-            std::vector<std::thread> threads;
-            for (unsigned t = 0; t < nt; ++t)
-                threads.emplace_back([=, &bb]() {
-                    blockIdx = dim3(bx, by, bz);
-                    threadIdx = dim3(t % block.x, t / block.x, 0);
-                    kernel(args...);
-                    shim_warp_barriers[t / 32]->arrive_and_drop();       // a thread that has returned no longer takes part in barriers
-                    bb.arrive_and_drop();
-                });
-            for (auto& th : threads) th.join();
-            if (shim_block_hook) shim_block_hook();
-        }
+    if (shim_blocks_launched == 0 || nt == 0) return;
+    auto fresh = [nt]() {
+        shim_block_barrier_owner.reset(new std::barrier<>(nt));
+        shim_block_barrier = shim_block_barrier_owner.get();
+        shim_warp_barriers.clear();
+        for (unsigned w = 0; w * 32 < nt; ++w) shim_warp_barriers.emplace_back(new std::barrier<>(std::min(32u, nt - w * 32)));
+    };
+    fresh();
+    std::barrier<> rendezvous(nt);
+    std::vector<std::thread> threads;
+    for (unsigned t = 0; t < nt; ++t)
+        threads.emplace_back([=, &rendezvous, &fresh]() {
+            for (unsigned bz = 0; bz < grid.z; ++bz)
+                for (unsigned by = 0; by < grid.y; ++by)
+                    for (unsigned bx = 0; bx < grid.x; ++bx) {
+                        blockIdx = dim3(bx, by, bz);
+                        threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+                        kernel(args...);
+                        shim_warp_barriers[t / 32]->arrive_and_drop();       // a thread that has returned no longer takes part in barriers
+                        shim_block_barrier->arrive_and_drop();
+                        rendezvous.arrive_and_wait();                        // the whole block is done
+                        if (t == 0) { if (shim_block_hook) shim_block_hook(); fresh(); }
+                        rendezvous.arrive_and_wait();                        // fresh barriers, __shared__ statics free for the next block
+                    }
+        });
+    for (auto& th : threads) th.join();
 }
 // the kernel is called by NAME inside a generic lambda, so that overload resolution and argument-dependent lookup see what the
 // `<<<>>>` call of the source sees (conv_thin.cu launches a kernel that shares its name with the host function around the launch)
 #define SHIM_UNPAREN(...) __VA_ARGS__
 #define SHIM_LAUNCH(kernel, grid, block, ...) shim_launch([=](auto... shim_a) { SHIM_UNPAREN kernel(shim_a...); }, dim3(grid), dim3(block), __VA_ARGS__)
+#ifndef SHIM_MULTI_UNIT
 extern "C" long shim_blocks() { return shim_blocks_launched; }
 extern "C" long shim_blocks_since_reset() { return shim_blocks_total; }
 extern "C" void shim_reset() { shim_blocks_launched = shim_blocks_total = 0; shim_err[0] = 0; }
 extern "C" long shim_threads() { return shim_block_threads; }
 extern "C" const char* shim_error() { return shim_err; }
+#endif

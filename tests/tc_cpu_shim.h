@@ -31,8 +31,11 @@
 
 #define __grid_constant__
 #define GG_EUNSUPPORTED (-3)
+#define GG_PREC_FP32_SIMT 0
 #define GG_PREC_TF32X1 1
 #define GG_PREC_TF32X3 3
+#define GG_PREC_AUTO (-1)
+#define GG_PREC_AUTO_FAST (-2)
 
 [[noreturn]] static void shim_die(const char* fmt, ...) {
     va_list ap; va_start(ap, fmt);
@@ -167,7 +170,9 @@ template <class T> static inline cudaError_t cudaMallocAsync(T** p, size_t bytes
     return *p ? cudaSuccess : 1;
 }
 static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); --shim_scratch_live; return cudaSuccess; }
+#ifndef SHIM_MULTI_UNIT
 extern "C" long shim_scratch_blocks_live() { return shim_scratch_live.load(); }
+#endif
 namespace gg {
 static inline bool done_on_this_device(const std::atomic<uint64_t>& f) { return f.load() != 0; }
 static inline void mark_done_on_this_device(std::atomic<uint64_t>& f) { f.store(1); }
@@ -345,7 +350,9 @@ static inline void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc
 
 }  // namespace ggtc
 
+#ifndef SHIM_MULTI_UNIT
 extern "C" long shim_mma_instructions() { return ggtc::shim_mma_count.load(); }
+#endif
 // per CTA: named barriers are per-CTA objects, tensor memory must have been given back
 static inline void shim_tc_block_reset() {
     shim_named.clear();
