@@ -229,7 +229,7 @@ static inline void mbar_wait(uint32_t bar, uint32_t parity) {
     static const long limit_s = getenv("SHIM_WAIT_TIMEOUT_S") ? atol(getenv("SHIM_WAIT_TIMEOUT_S")) : 240;      // the model's watchdog
     for (uint32_t it = 0;; ++it) {
         if (((b.load(std::memory_order_acquire) >> 56) & 1) != (parity & 1)) return;
-        std::this_thread::yield();
+        if (it < 64) std::this_thread::yield(); else std::this_thread::sleep_for(std::chrono::microseconds(it < 1024 ? 20 : 200));      // 384 threads per CTA share a few cores
         if ((it & 0xFFF) == 0xFFF && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(limit_s))
             shim_die("mbarrier wait timed out: barrier %u parity %u -- the pipeline is deadlocked", bar - SHIM_SMEM_ORIGIN, parity);
     }
