@@ -220,3 +220,18 @@ def _rfind_template_open(body, j):
             depth -= 1
             if depth == 0:
                 return j
+
+
+FULL = os.environ.get('GG_SANITIZE_ALL') == '1'
+
+
+def subset(params, default_ids, id_of=lambda p: p[0]):
+    """pytest params for a list of cases: the ones named in `default_ids` always run, the others only with GG_SANITIZE_ALL=1 (the whole
+    matrix takes ~10 minutes of host time; the default CPU suite keeps one representative per kernel and mechanism)."""
+    import pytest
+    out = []
+    for p in params:
+        i = id_of(p)
+        marks = [] if (FULL or i in default_ids) else [pytest.mark.skip(reason='runs with GG_SANITIZE_ALL=1')]
+        out.append(pytest.param(*p, id=i, marks=marks) if isinstance(p, tuple) else pytest.param(p, id=i, marks=marks))
+    return out

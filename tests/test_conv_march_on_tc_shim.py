@@ -142,8 +142,11 @@ def test_conv_march_eligibility_source(lib):
 SAN_CASES = [('nt32', (2, 16, 12, 64, 32, 1)), ('nt64_weight_ring', (1, 64, 20, 72, 48, 1)), ('pad2_many_units', (3, 16, 24, 132, 16, 2))]
 
 
-@pytest.mark.parametrize('kind', ['thread', 'address'])
-@pytest.mark.parametrize('case', SAN_CASES, ids=lambda c: c[0])
+SAN_RUNS = [(kind, c) for c in SAN_CASES for kind in ('thread', 'address')]
+SAN_DEFAULT = {'thread-nt64_weight_ring', 'thread-pad2_many_units', 'address-nt64_weight_ring', 'thread-nt32'}
+
+
+@pytest.mark.parametrize('kind,case', S.subset(SAN_RUNS, SAN_DEFAULT, id_of=lambda p: p[0] + '-' + p[1][0]))
 def test_conv_march_pipeline_under_sanitizers(kind, case):
     exe = S.build('conv_march_unit', _source(), kind, SAN_MAIN)
     out = S.run_sanitized(exe, case[1], timeout=1500)
@@ -159,7 +162,7 @@ MUTANTS = [
 ]
 
 
-@pytest.mark.parametrize('name,old,new', MUTANTS, ids=[m[0] for m in MUTANTS])
+@pytest.mark.parametrize('name,old,new', S.subset(MUTANTS, {'issuer-does-not-wait-for-the-converter'}))
 def test_the_racecheck_does_report_a_broken_marching_pipeline(name, old, new):
     src = _source()
     assert src.count(old) == 1, old

@@ -173,8 +173,11 @@ SAN_CASES = [('nt32', (2, 48, 20, 20, 32, 3, 1, 0)), ('nt64_sparse', (2, 64, 20,
              ('k2', (1, 48, 12, 12, 32, 2, 1, 0))]
 
 
-@pytest.mark.parametrize('kind', ['thread', 'address'])
-@pytest.mark.parametrize('case', SAN_CASES, ids=lambda c: c[0])
+SAN_RUNS = [(kind, c) for c in SAN_CASES for kind in ('thread', 'address')]
+SAN_DEFAULT = {'thread-nt64_sparse', 'thread-nt32_chunks_span_k_blocks', 'thread-nt256', 'address-nt256', 'address-k2', 'thread-k1'}
+
+
+@pytest.mark.parametrize('kind,case', S.subset(SAN_RUNS, SAN_DEFAULT, id_of=lambda p: p[0] + '-' + p[1][0]))
 def test_conv_tc_pipeline_under_sanitizers(kind, case):
     """ThreadSanitizer = racecheck of the four mbarrier rings (raw box, converted tile, weight stage, accumulator set) over several tiles
     per CTA and >= 3 K-blocks per tile, so that every ring wraps; AddressSanitizer = memcheck of global tensors, the weight scratch and
@@ -195,7 +198,7 @@ MUTANTS = [
 ]
 
 
-@pytest.mark.parametrize('name,old,new,args', MUTANTS, ids=[m[0] for m in MUTANTS])
+@pytest.mark.parametrize('name,old,new,args', S.subset(MUTANTS, {'converter-does-not-wait-for-the-mma'}))
 def test_the_racecheck_does_report_a_broken_pipeline(name, old, new, args):
     """Mutation check: with one wait of the pipeline removed, the ThreadSanitizer run must report a data race (or the model must abort
     on an over-arrival / deadlock) -- the run above is not vacuous.  (A consumer that merely runs AHEAD of its producer -- the MMA issuer
