@@ -32,26 +32,41 @@ def translate(cu_text, expect_launches):
 _built = {}
 
 
-def build(name, source, kind, main=''):
-    """kind: 'lib' (shared object for ctypes) or a -fsanitize= value ('thread', 'address': an executable from source + main)."""
-    key = (name, kind)
-    if key in _built:
-        return _built[key]
-    d = tempfile.mkdtemp(prefix=name + '_shim_')
+def _compile(name, source, kind, main):
+    """One g++ run; the result is kept on disk under a name derived from the source text, so a repeated session compiles nothing."""
+    import hashlib
+    text = source if kind == 'lib' else source + main
+    hdrs = b''.join(open(os.path.join(ROOT, 'tests', h), 'rb').read() for h in ('cuda_cpu_shim.h', 'tc_cpu_shim.h'))
+    d = os.path.join(tempfile.gettempdir(), 'gagan_shim_' + hashlib.sha256(text.encode() + hdrs + kind.encode()).hexdigest()[:20])
+    out = os.path.join(d, name + ('.so' if kind == 'lib' else '_' + kind))
+    if os.path.isfile(out):
+        return out
+    os.makedirs(d, exist_ok=True)
     cpp = os.path.join(d, name + '.cpp')
+    open(cpp, 'w').write(text)
     flags = ['g++', '-std=c++20', '-O1', '-pthread', '-w', '-I', os.path.join(ROOT, 'tests')]
-    if kind == 'lib':
-        open(cpp, 'w').write(source)
-        out = os.path.join(d, name + '.so')
-        cmd = flags + ['-shared', '-fPIC', '-o', out, cpp]
-    else:
-        open(cpp, 'w').write(source + main)
-        out = os.path.join(d, name + '_' + kind)
-        cmd = flags + ['-g', '-fno-omit-frame-pointer', '-fsanitize=' + kind, '-o', out, cpp]
+    tmp = out + '.tmp%d' % os.getpid()
+    cmd = flags + (['-shared', '-fPIC'] if kind == 'lib' else ['-g', '-fno-omit-frame-pointer', '-fsanitize=' + kind]) + ['-o', tmp, cpp]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert res.returncode == 0, res.stdout[-3000:]
-    _built[key] = out
+    os.replace(tmp, out)
     return out
+
+
+def build(name, source, kind, main=''):
+    """kind: 'lib' (shared object for ctypes) or a -fsanitize= value ('thread', 'address': an executable from source + main)."""
+    key = (name, kind, hash(source), hash(main) if kind != 'lib' else 0)
+    if key not in _built:
+        _built[key] = _compile(name, source, kind, main)
+    return _built[key]
+
+
+def build_all(name, source, main):
+    """The three builds of a unit (library, ThreadSanitizer, AddressSanitizer executables) side by side: the compiles dominate the
+    wall time of these tests."""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=3) as ex:
+        list(ex.map(lambda kind: build(name, source, kind, main), ('lib', 'thread', 'address')))
 
 
 def run_sanitized(exe, args, timeout=900):

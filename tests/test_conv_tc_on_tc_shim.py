@@ -63,6 +63,11 @@ def _source():
     return '#define GG_NUM_SMS 3\n' + S.translate_tc_unit(open(os.path.join(S.CSRC, 'conv_tc.cu')).read(), expect_launches=2) + EXPORTS
 
 
+@pytest.fixture(scope='module', autouse=True)
+def _prebuilt():
+    S.build_all('conv_tc_unit', _source(), SAN_MAIN)
+
+
 @pytest.fixture(scope='module')
 def lib():
     so = S.load(S.build('conv_tc_unit', _source(), 'lib'))

@@ -58,6 +58,11 @@ def _source():
     return S.translate_unit(open(os.path.join(S.CSRC, 'conv_thin.cu')).read(), expect_launches=3) + EXPORTS
 
 
+@pytest.fixture(scope='module', autouse=True)
+def _prebuilt():
+    S.build_all('conv_thin_unit', _source(), SAN_MAIN)
+
+
 @pytest.fixture(scope='module')
 def lib():
     so = S.load(S.build('conv_thin_unit', _source(), 'lib'))

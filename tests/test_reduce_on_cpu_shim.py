@@ -49,6 +49,11 @@ def _source():
     return S.translate_unit(open(os.path.join(S.CSRC, 'reduce.cu')).read(), expect_launches=8)
 
 
+@pytest.fixture(scope='module', autouse=True)
+def _prebuilt():
+    S.build_all('reduce_unit', _source(), SAN_MAIN)
+
+
 @pytest.fixture(scope='module')
 def lib():
     so = S.load(S.build('reduce_unit', _source(), 'lib'))

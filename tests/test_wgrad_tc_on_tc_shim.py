@@ -55,6 +55,11 @@ def _source():
     return '#define GG_NUM_SMS 3\n' + src + EXPORTS
 
 
+@pytest.fixture(scope='module', autouse=True)
+def _prebuilt():
+    S.build_all('wgrad_tc_unit', _source(), SAN_MAIN)
+
+
 @pytest.fixture(scope='module')
 def lib():
     so = S.load(S.build('wgrad_tc_unit', _source(), 'lib'))
