@@ -205,7 +205,20 @@ static inline void mbar_init(uint32_t bar, uint32_t count) {
     if (count < 1 || count > 4095) shim_die("mbarrier.init: count %u", count);
     shim_bar(bar, "mbarrier.init").store(((uint64_t)count << 44) | ((uint64_t)count << 32), std::memory_order_release);
 }
+// Schedule perturbation (optional): SHIM_SLOW_WARPS="lo-hi:usec" delays every mbarrier operation of warps lo..hi by `usec` microseconds,
+// SHIM_JITTER="usec" delays every mbarrier operation of every thread by a pseudo-random 0..usec.  The model's natural schedule has a slow
+// tensor core and fast converter warps; these knobs let a run explore the opposite regimes.
+static inline void shim_perturb() {
+    static const struct Cfg { int lo = -1, hi = -1; long usec = 0, jitter = 0; Cfg() {
+        if (const char* e = getenv("SHIM_SLOW_WARPS")) sscanf(e, "%d-%d:%ld", &lo, &hi, &usec);
+        if (const char* e = getenv("SHIM_JITTER")) jitter = atol(e); } } cfg;
+    const int warp = (int)(threadIdx.x / 32);
+    long d = (warp >= cfg.lo && warp <= cfg.hi) ? cfg.usec : 0;
+    if (cfg.jitter > 0) { static thread_local uint32_t r = 12345u + threadIdx.x * 2654435761u; r = r * 1664525u + 1013904223u; d += (long)((r >> 8) % (uint32_t)(cfg.jitter + 1)); }
+    if (d > 0) std::this_thread::sleep_for(std::chrono::microseconds(d));
+}
 static inline void shim_bar_update(uint32_t bar, int arrivals, int64_t tx, const char* what) {
+    shim_perturb();
     auto b = shim_bar(bar, what);
     uint64_t old = b.load(std::memory_order_relaxed), neu;
     do {
@@ -225,6 +238,7 @@ static inline void mbar_expect_tx(uint32_t bar, uint32_t bytes) { shim_bar_updat
 static inline void shim_complete_tx(uint32_t bar, uint32_t bytes) { shim_bar_update(bar, 0, -(int64_t)bytes, "complete_tx"); }
 static inline void umma_commit(uint32_t bar) { shim_bar_update(bar, 1, 0, "tcgen05.commit"); }     // the MMAs of this thread ran at issue
 static inline void mbar_wait(uint32_t bar, uint32_t parity) {
+    shim_perturb();
     auto b = shim_bar(bar, "mbarrier.try_wait");
     const auto t0 = std::chrono::steady_clock::now();
     static const long limit_s = getenv("SHIM_WAIT_TIMEOUT_S") ? atol(getenv("SHIM_WAIT_TIMEOUT_S")) : 240;      // the model's watchdog
