@@ -250,3 +250,20 @@ def subset(params, default_ids, id_of=lambda p: p[0]):
         marks = [] if (FULL or i in default_ids) else [pytest.mark.skip(reason='runs with GG_SANITIZE_ALL=1')]
         out.append(pytest.param(*p, id=i, marks=marks) if isinstance(p, tuple) else pytest.param(p, id=i, marks=marks))
     return out
+
+
+def mutant_is_reported(exe, args, attempts=({}, {'SHIM_JITTER': '100'}, {'SHIM_SLOW_WARPS': '0-3:200'}, {'SHIM_JITTER': '500'}, {'SHIM_SLOW_WARPS': '4-19:200'})):
+    """Run a mutant (one wait / barrier removed) under ThreadSanitizer until one run reports it: a data race, or the model's abort on an
+    over-arrival / deadlock.  Whether the two unordered accesses of a removed wait meet inside the sanitizer's history depends on the
+    schedule, so the later attempts perturb it (tests/tc_cpu_shim.h: SHIM_JITTER, SHIM_SLOW_WARPS).  Returns (reported, last output);
+    reported is None when the sanitizer runtime cannot start in this container."""
+    out = ''
+    for knobs in attempts:
+        env = dict(os.environ, TSAN_OPTIONS='halt_on_error=1 exitcode=66 history_size=7', SHIM_WAIT_TIMEOUT_S='8', **knobs)
+        res = subprocess.run([exe] + [str(v) for v in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=900)
+        out = res.stdout
+        if 'FATAL: ThreadSanitizer' in out and 'data race' not in out:
+            return None, out
+        if res.returncode != 0 and ('data race' in out or 'TC SHIM ABORT' in out):
+            return True, out
+    return False, out

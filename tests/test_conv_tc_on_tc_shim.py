@@ -212,8 +212,7 @@ def test_the_racecheck_does_report_a_broken_pipeline(name, old, new, args):
     src = _source()
     assert src.count(old) == 1, old
     exe = S.build('conv_tc_mutant_' + name.replace('-', '_'), src.replace(old, new), 'thread', SAN_MAIN)
-    env = dict(os.environ, TSAN_OPTIONS='halt_on_error=1 exitcode=66 history_size=7', SHIM_WAIT_TIMEOUT_S='8')
-    res = subprocess.run([exe] + [str(v) for v in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=900)
-    if 'FATAL: ThreadSanitizer' in res.stdout and 'data race' not in res.stdout:
+    reported, out = S.mutant_is_reported(exe, args)
+    if reported is None:
         pytest.skip('the sanitizer runtime cannot start in this container')
-    assert res.returncode != 0 and ('data race' in res.stdout or 'TC SHIM ABORT' in res.stdout), res.stdout[-2000:]
+    assert reported, out[-2000:]

@@ -179,8 +179,11 @@ def test_the_sanitizer_runs_do_report_a_broken_kernel(kind, old, new, args, repo
     assert src.count(old) >= 1
     exe = S.build('reduce_mutant_' + kind, src.replace(old, new, 1), kind, SAN_MAIN)
     import subprocess
-    env = dict(os.environ, TSAN_OPTIONS='halt_on_error=1 exitcode=66', ASAN_OPTIONS='detect_leaks=0')
-    res = subprocess.run([exe] + [str(v) for v in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=600)
-    if 'FATAL: ThreadSanitizer' in res.stdout and 'data race' not in res.stdout:
-        pytest.skip('the sanitizer runtime cannot start in this container')
-    assert report in res.stdout and res.returncode != 0
+    env = dict(os.environ, TSAN_OPTIONS='halt_on_error=1 exitcode=66 history_size=7', ASAN_OPTIONS='detect_leaks=0')
+    for attempt in range(4):                # whether ThreadSanitizer sees the two unordered accesses meet depends on the schedule
+        res = subprocess.run([exe] + [str(v) for v in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=600)
+        if 'FATAL: ThreadSanitizer' in res.stdout and 'data race' not in res.stdout:
+            pytest.skip('the sanitizer runtime cannot start in this container')
+        if report in res.stdout and res.returncode != 0:
+            return
+    assert False, res.stdout[-2000:]
